@@ -1,0 +1,74 @@
+"""Drop-in for the reference's all-pairs correlation block and its tensor helpers.
+
+Mirrors:
+  * CorrBlock                       model/corr.py:12-60
+  * bilinear_sampler, coords_grid, upflow8   model/model_utils.py:7-32
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ops
+
+
+def _default_precision(D: int, H: int, W: int) -> str:
+    env = os.environ.get("EEMFLOW_B200_CORR_PRECISION")
+    if env:
+        return env
+    return "tf32" if ops.tf32_supported(D, H, W) else "fp32"
+
+
+class CorrBlock:
+    """RAFT all-pairs correlation: volume + avg-pool pyramid at construction, window lookup on call.
+
+    `corr_pyramid` keeps the reference's attribute contract: a list of `[B*H*W, 1, H_l, W_l]`
+    float32 tensors.  `precision` ("tf32" | "fp32") is the one extra knob: tcgen05 TF32 tensor
+    cores (default where the shape allows) or exact fp32 FMA.
+    """
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, precision=None):
+        self.num_levels = num_levels
+        self.radius = radius
+        batch, dim, ht, wd = fmap1.shape
+        if precision is None:
+            precision = _default_precision(dim, ht, wd)
+        self.precision = precision
+        with torch.no_grad():
+            self.corr_pyramid = ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision)
+
+    def __call__(self, coords):
+        with torch.no_grad():
+            return ops.corr_lookup(self.corr_pyramid, coords, self.radius)
+
+    @staticmethod
+    def corr(fmap1, fmap2, precision=None):
+        batch, dim, ht, wd = fmap1.shape
+        if precision is None:
+            precision = _default_precision(dim, ht, wd)
+        with torch.no_grad():
+            (vol,) = ops.corr_pyramid(fmap1, fmap2, 1, precision=precision)
+        return vol.view(batch, ht, wd, 1, ht, wd)
+
+
+def bilinear_sampler(img, coords, mode='bilinear', mask=False):
+    """ Wrapper for grid_sample, uses pixel coordinates """
+    if mode != 'bilinear':
+        raise NotImplementedError("eemflow_b200.bilinear_sampler implements mode='bilinear' only")
+    with torch.no_grad():
+        return ops.bilinear_sample(img, coords, mask=mask)
+
+
+def coords_grid(batch, ht, wd):
+    coords = torch.meshgrid(torch.arange(ht), torch.arange(wd), indexing='ij')
+    coords = torch.stack(coords[::-1], dim=0).float()
+    return coords[None].repeat(batch, 1, 1, 1)
+
+
+def upflow8(flow, mode='bilinear'):
+    if mode != 'bilinear':
+        raise NotImplementedError("eemflow_b200.upflow8 implements mode='bilinear' only")
+    new_size = (8 * flow.shape[2], 8 * flow.shape[3])
+    with torch.no_grad():
+        return ops.bilinear_resize(flow, new_size, align_corners=True, scale0=8.0, scale1=8.0, scale_rest=8.0)

@@ -1,0 +1,72 @@
+// Shared host/device helpers for libeemflow_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/eemflow_b200.h"
+
+namespace eem {
+
+// Thread-local last-error text (eem_last_error_string).  Defined in api.cu.
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+inline cudaStream_t as_stream(eem_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs of the current device, cached per device.  Defined in api.cu.
+int sm_count();
+
+#define EEM_CHECK_ARG(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return ::eem::fail(EEM_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define EEM_CHECK_ALIGNED(ptr, bytes)                                                           \
+  do {                                                                                          \
+    if ((reinterpret_cast<uintptr_t>(ptr) % (bytes)) != 0)                                      \
+      return ::eem::fail(EEM_ERR_MISALIGNED, "%s must be %d-byte aligned", #ptr, (int)(bytes)); \
+  } while (0)
+
+// Call after every launch: picks up launch-configuration errors without synchronising.
+#define EEM_CHECK_LAUNCH(name)                                                              \
+  do {                                                                                      \
+    cudaError_t e_ = cudaGetLastError();                                                    \
+    if (e_ != cudaSuccess)                                                                  \
+      return ::eem::fail(EEM_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e_));             \
+  } while (0)
+
+#define EEM_CHECK_CUDA(expr)                                                                \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return ::eem::fail(EEM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));            \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device helpers -----------------------------------------------------------------------
+
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void st_stream(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+}  // namespace eem

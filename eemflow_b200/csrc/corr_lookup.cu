@@ -1,0 +1,193 @@
+// K5 multi-level correlation window lookup + K4 2x2 average pooling, sm_100a.
+//
+// Reference semantics (model/corr.py:29-50, model/model_utils.py:7-15):
+//   for level l: centre = coords / 2^l; window offsets d in [-r, r]^2 (unit spacing);
+//   out[b, l*(2r+1)^2 + a*(2r+1) + c, y, x] = bilinear(level_l[b*P + y*W + x], (cx + a - r, cy + c - r))
+//   where the first window index moves x and the second moves y (RAFT's transposed meshgrid),
+//   sampling goes through  g = 2*p/(S-1) - 1  and grid_sample(align_corners=True, zeros padding).
+//
+// A CTA owns 32 consecutive positions of one sample.  Per level it gathers each position's
+// (2r+2)^2 tap window once into shared memory (every 32-byte sector of the volume is fetched
+// once per position), then warp `a` / lane `position` produces the 2r+1 outputs of window column
+// `a`, so every store instruction writes 32 consecutive positions of one output channel (128 B).
+#include "common.cuh"
+
+namespace eem {
+namespace {
+
+constexpr int kMaxLevels = 8;
+constexpr int kPosPerBlock = 32;
+
+struct LookupParams {
+  const float* level[kMaxLevels];
+  int h[kMaxLevels], w[kMaxLevels];
+  int B, H, W, L;
+  const float* coords;
+  float* out;
+};
+
+// The reference's coordinate round trip: pixel -> [-1,1] (bilinear_sampler) -> pixel (grid_sample,
+// align_corners=True), in fp32 with the same operation order.
+__device__ __forceinline__ float roundtrip(float p, int size) {
+  const float s1 = (float)(size - 1);
+  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, p), s1), 1.0f);
+  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), s1);
+}
+
+template <int R>
+__global__ void __launch_bounds__((2 * R + 1) * 32)
+corr_lookup_kernel(const __grid_constant__ LookupParams p) {
+  constexpr int K = 2 * R + 1;   // window size
+  constexpr int T = K + 1;       // taps per dimension
+  constexpr int TT = T * T;
+  constexpr int kStride = TT | 1;  // odd stride: lanes (positions) hit distinct banks
+  constexpr int kThreads = K * 32;
+
+  __shared__ float taps[kPosPerBlock * kStride];
+  __shared__ float tx[kPosPerBlock][K];  // per-position, per-window-column horizontal fraction
+  __shared__ float ty[kPosPerBlock][K];
+  __shared__ int org[kPosPerBlock][2];   // window origin (tap [0][0]) in level pixels
+
+  const int P = p.H * p.W;
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * kPosPerBlock;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npos = min(kPosPerBlock, P - i0);
+
+  float cx = 0.f, cy = 0.f;
+  if (threadIdx.x < npos) {
+    cx = p.coords[((int64_t)b * 2 + 0) * P + i0 + threadIdx.x];
+    cy = p.coords[((int64_t)b * 2 + 1) * P + i0 + threadIdx.x];
+  }
+
+  for (int l = 0; l < p.L; ++l) {
+    const int hl = p.h[l], wl = p.w[l];
+    const int64_t plane = (int64_t)hl * wl;
+    if (plane == 0) {  // level pooled away: grid_sample over an empty map contributes zeros
+      if (lane < npos) {
+        for (int c = 0; c < K; ++c)
+          st_stream(p.out + ((int64_t)b * p.L * K * K + (int64_t)l * K * K + warp * K + c) * P + i0 + lane, 0.f);
+      }
+      continue;
+    }
+    // 1) per-position window geometry
+    if (threadIdx.x < npos) {
+      const float inv = 1.0f / (float)(1 << l);
+      const float lx = cx * inv, ly = cy * inv;  // exact: power-of-two scaling
+      // Clamp far-away / non-finite centres so the integer origin stays representable; every tap
+      // of such a window is out of the map and reads as zero either way.
+      const float ox = floorf(fminf(fmaxf(roundtrip(lx - (float)R, wl), -1.0e6f), 1.0e6f));
+      const float oy = floorf(fminf(fmaxf(roundtrip(ly - (float)R, hl), -1.0e6f), 1.0e6f));
+      org[threadIdx.x][0] = (int)ox;
+      org[threadIdx.x][1] = (int)oy;
+#pragma unroll
+      for (int a = 0; a < K; ++a) {
+        // fraction relative to tap column a of the shared window; equals the reference's
+        // (ix - floor(ix)) except on knife-edge roundings, where it extrapolates by <= 1 ulp.
+        tx[threadIdx.x][a] = roundtrip(lx + (float)(a - R), wl) - (ox + (float)a);
+        ty[threadIdx.x][a] = roundtrip(ly + (float)(a - R), hl) - (oy + (float)a);
+      }
+    }
+    __syncthreads();
+    // 2) gather taps: consecutive threads walk a window row, so a row costs 1-2 sectors
+    const float* lvl = p.level[l] + ((int64_t)b * P + i0) * plane;
+    for (int t = threadIdx.x; t < npos * TT; t += kThreads) {
+      const int pos = t / TT, tap = t - pos * TT;
+      const int r = tap / T, c = tap - r * T;
+      const int x = org[pos][0] + c, y = org[pos][1] + r;
+      float v = 0.f;
+      if (x >= 0 && x < wl && y >= 0 && y < hl) v = __ldg(lvl + (int64_t)pos * plane + (int64_t)y * wl + x);
+      taps[pos * kStride + tap] = v;
+    }
+    __syncthreads();
+    // 3) warp `a` = window column (x offset), lane = position; walk down the rows reusing the
+    //    horizontal interpolation of the previous row.
+    if (lane < npos) {
+      const int a = warp;
+      const float fx = tx[lane][a];
+      const float* tp = taps + lane * kStride + a;
+      float prev = tp[0] + fx * (tp[1] - tp[0]);
+      float* o = p.out + ((int64_t)b * p.L * K * K + (int64_t)l * K * K + a * K) * P + i0 + lane;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const float* row = tp + (c + 1) * T;
+        const float cur = row[0] + fx * (row[1] - row[0]);
+        const float fy = ty[lane][c];
+        st_stream(o + (int64_t)c * P, prev + fy * (cur - prev));
+        prev = cur;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+avg_pool2x2_kernel(const float* __restrict__ in, int64_t n_planes, int h, int w, float* __restrict__ out) {
+  const int ho = h / 2, wo = w / 2;
+  const int64_t total = n_planes * ho * wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wo);
+    const int64_t r = i / wo;
+    const int y = (int)(r % ho);
+    const int64_t pl = r / ho;
+    const float* s = in + pl * h * w + (int64_t)(2 * y) * w + 2 * x;
+    // same summation order as ATen's avg_pool2d inner loop (row-major over the 2x2 window)
+    out[i] = (((s[0] + s[1]) + s[w]) + s[w + 1]) * 0.25f;
+  }
+}
+
+}  // namespace
+}  // namespace eem
+
+using namespace eem;
+
+extern "C" {
+
+int eem_corr_lookup(const float* const* levels, int B, int H, int W, int num_levels, int radius,
+                    const float* coords, float* out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(levels && coords && out, "eem_corr_lookup: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && H > 0 && W > 0, "eem_corr_lookup: sizes must be > 0");
+  EEM_CHECK_ARG(num_levels > 0 && num_levels <= kMaxLevels, "eem_corr_lookup: num_levels must be in [1,%d]", kMaxLevels);
+  EEM_CHECK_ARG(B <= 65535, "eem_corr_lookup: batch > 65535 not supported in one call");
+  LookupParams p{};
+  int h = H, w = W;
+  for (int l = 0; l < num_levels; ++l) {
+    p.level[l] = levels[l];
+    p.h[l] = h;
+    p.w[l] = w;
+    EEM_CHECK_ARG((int64_t)h * w == 0 || levels[l] != nullptr, "eem_corr_lookup: levels[%d] is NULL", l);
+    h /= 2;
+    w /= 2;
+  }
+  p.B = B; p.H = H; p.W = W; p.L = num_levels;
+  p.coords = coords;
+  p.out = out;
+  const int P = H * W;
+  dim3 grid((unsigned)ceil_div(P, kPosPerBlock), (unsigned)B);
+  cudaStream_t stream = as_stream(stream_);
+  switch (radius) {
+    case 4: corr_lookup_kernel<4><<<grid, 9 * 32, 0, stream>>>(p); break;
+    case 3: corr_lookup_kernel<3><<<grid, 7 * 32, 0, stream>>>(p); break;
+    case 2: corr_lookup_kernel<2><<<grid, 5 * 32, 0, stream>>>(p); break;
+    case 1: corr_lookup_kernel<1><<<grid, 3 * 32, 0, stream>>>(p); break;
+    default:
+      return fail(EEM_ERR_UNSUPPORTED, "eem_corr_lookup: radius %d not in {1,2,3,4}", radius);
+  }
+  EEM_CHECK_LAUNCH("corr_lookup_kernel");
+  return EEM_OK;
+}
+
+int eem_avg_pool2x2(const float* in, int64_t n_planes, int h, int w, float* out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(in && out, "eem_avg_pool2x2: NULL pointer");
+  EEM_CHECK_ARG(n_planes > 0 && h > 0 && w > 0, "eem_avg_pool2x2: sizes must be > 0");
+  const int64_t total = n_planes * (h / 2) * (w / 2);
+  if (total == 0) return EEM_OK;
+  int64_t blocks = ceil_div(total, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (cap > 0 && blocks > cap) blocks = cap;
+  avg_pool2x2_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(in, n_planes, h, w, out);
+  EEM_CHECK_LAUNCH("avg_pool2x2_kernel");
+  return EEM_OK;
+}
+
+}  // extern "C"

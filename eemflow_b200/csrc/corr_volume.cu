@@ -1,0 +1,513 @@
+// K3 all-pairs correlation pyramid for sm_100a.
+//
+// Reference semantics (model/corr.py:13-27, 52-60):
+//   corr[b,i,j]   = (1/sqrt(D)) * sum_d fmap1[b,d,i] * fmap2[b,d,j]          i,j in [0,P), P = H*W
+//   level_{l+1}   = avg_pool2d(level_l viewed [B*P,1,H_l,W_l], 2, stride 2)    (floor)
+// avg_pool2d is linear and touches only the j axis, so
+//   level_l[b,i,:] = (1/sqrt(D)) * fmap1[b,:,i]^T . pool^l(fmap2)[b]
+// and the whole pyramid is ONE batched GEMM against [fmap2 | pool(fmap2) | pool^2(fmap2) | ...]:
+// the level-0 volume (867 MB per HREM sample) is never re-read to build the coarser levels.
+//
+// Two arithmetic paths behind one entry point:
+//   EEM_CORR_FP32  CUDA-core FFMA, 64x64x16 shared-memory tiles.  Exact-fp32 parity path.
+//   EEM_CORR_TF32  tcgen05.mma kind::tf32 reading the fp32 NCHW feature maps directly:
+//                  both operands are "MN-major" (positions contiguous, channels strided), which
+//                  is exactly how TMA lands a [32 channels x 32 positions] fp32 box with
+//                  SWIZZLE_128B, so no transpose/convert pre-pass over the features is needed.
+//                  Accumulators live in TMEM (2 x 128 columns, double-buffered against the
+//                  epilogue); the epilogue streams TMEM -> registers -> global with one
+//                  128-byte coalesced store per output row per warp.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace eem {
+namespace {
+
+constexpr int kMaxLevels = 8;
+
+// ---------------------------------------------------------------------------------------------
+// feature pooling: out[n, y, x] = mean of the 2x2 block of in[n, :, :]; output rows are written
+// with a pitch (elements) that is a multiple of 4 so TMA can address them (16-byte row pitch).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pool_fmap_kernel(const float* __restrict__ in, int64_t n_planes, int h, int w, int64_t in_pitch,
+                 float* __restrict__ out, int64_t out_pitch) {
+  const int ho = h / 2, wo = w / 2;
+  const int64_t per = (int64_t)ho * wo, total = n_planes * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pl = i / per;
+    const int r = (int)(i - pl * per);
+    const int y = r / wo, x = r - y * wo;
+    const float* s = in + pl * in_pitch + (int64_t)(2 * y) * w + 2 * x;
+    out[pl * out_pitch + r] = (((s[0] + s[1]) + s[w]) + s[w + 1]) * 0.25f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 path: C[i,j] = scale * sum_d A[d,i] * Bm[d,j] per sample; A = fmap1[b] ([D,P], pitch P),
+// Bm = level operand ([D,P_l], pitch given).  64x64 tile, 256 threads, 4x4 outputs per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int FT = 64, FK = 16;
+
+__global__ void __launch_bounds__(256)
+corr_fp32_kernel(const float* __restrict__ f1, const float* __restrict__ f2l, int D, int P, int Pl,
+                 int64_t pitch_l, float scale, float* __restrict__ out) {
+  __shared__ __align__(16) float As[FK][FT];
+  __shared__ __align__(16) float Bs[FK][FT];
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * FT, j0 = blockIdx.x * FT;
+  const float* A = f1 + (int64_t)b * D * P;
+  const float* Bm = f2l + (int64_t)b * D * pitch_l;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int d0 = 0; d0 < D; d0 += FK) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < FK * FT; t += 256) {
+      const int k = t / FT, c = t % FT;
+      const int d = d0 + k;
+      As[k][c] = (d < D && i0 + c < P) ? __ldg(A + (int64_t)d * P + i0 + c) : 0.f;
+      Bs[k][c] = (d < D && j0 + c < Pl) ? __ldg(Bm + (int64_t)d * pitch_l + j0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty * 4 + r;
+    if (i >= P) continue;
+    float* o = out + ((int64_t)b * P + i) * Pl + j0 + tx * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (j0 + tx * 4 + c < Pl) o[c] = acc[r][c] * scale;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TF32 tcgen05 path
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 128;       // MMA M: positions j of the (pooled) fmap2 level -> TMEM lanes
+constexpr int BN = 128;       // MMA N: positions i of fmap1                    -> TMEM columns
+constexpr int BK = 32;        // channels per pipeline stage (one 128-byte-swizzled TMA box row count)
+constexpr int UK = 8;         // K of one tcgen05.mma kind::tf32
+constexpr int kStages = 4;    // fmap1 (streamed operand) ring depth
+constexpr int kMaxKB = 8;     // resident-operand capacity: D <= kMaxKB * BK = 256
+constexpr int kBoxBytes = 32 * BK * 4;          // one TMA box: 32 positions x BK channels fp32 = 4 KiB
+constexpr int kTileKBytes = (BM / 32) * kBoxBytes;  // 16 KiB: 128 positions x BK channels
+constexpr int kTmemCols = 2 * BN;               // two accumulator buffers
+constexpr int kTf32Threads = 192;               // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer
+
+struct Tf32Params {
+  CUtensorMap map_f1;                 // [B*D, P] fp32, box 32 x BK, SWIZZLE_128B
+  CUtensorMap map_lvl[kMaxLevels];    // level operands [B*D, P_l] (pitch multiple of 4)
+  float* out[kMaxLevels];
+  int Pl[kMaxLevels];
+  int mt_cum[kMaxLevels + 1];         // cumulative 128-row tile counts over levels
+  int B, D, P, L;
+  int n_tiles;                        // ceil(P / BN)
+  int64_t total_tiles;                // B * mt_cum[L] * n_tiles
+  float scale;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor for an MN-major fp32 operand stored as TMA SWIZZLE_128B boxes:
+// a box is [BK channel rows][32 positions = 128 B]; 8 consecutive rows form one 1024-byte swizzle
+// atom.  In the canonical MN-major SW128 layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) [uint128 units]
+// the leading-byte offset steps between 32-position chunks (= one box, 4 KiB here) and the
+// stride-byte offset between 8-channel groups (1 KiB).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);             // start address
+  d |= (uint64_t)((kBoxBytes >> 4) & 0x3fff) << 16;       // leading byte offset: next 32-position chunk
+  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;            // stride byte offset: next 8-channel group
+  d |= (uint64_t)1 << 46;                                 // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
+  return d;
+}
+
+// kind::tf32 instruction descriptor: fp32 accumulate, A and B tf32, both MN-major, M=128, N=BN.
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TileCoord {
+  int b, l, m0, n0;
+  int64_t item;  // (b, l, m-tile) id: tiles of one item share the resident operand
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const Tf32Params& p, int64_t t) {
+  TileCoord c;
+  c.item = t / p.n_tiles;
+  c.n0 = (int)(t - c.item * p.n_tiles) * BN;
+  const int ipb = p.mt_cum[p.L];
+  c.b = (int)(c.item / ipb);
+  const int r = (int)(c.item - (int64_t)c.b * ipb);
+  int l = 0;
+  while (l + 1 < p.L && r >= p.mt_cum[l + 1]) ++l;
+  c.l = l;
+  c.m0 = (r - p.mt_cum[l]) * BM;
+  return c;
+}
+
+struct __align__(1024) Tf32Smem {
+  uint8_t resident[kMaxKB * kTileKBytes];   // pooled-fmap2 panel of the current item: 128 KiB
+  uint8_t ring[kStages * kTileKBytes];      // fmap1 stages: 64 KiB
+  uint64_t full[kStages], empty[kStages];
+  uint64_t res_free[kMaxKB];                // resident k-block may be overwritten
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kTf32Threads, 1)
+corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Tf32Smem& s = *reinterpret_cast<Tf32Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.D / BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < kMaxKB; ++i) mbar_init(&s.res_free[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+
+  // Contiguous tile range per CTA: balanced to +-1 tile, at most one extra resident reload.
+  const int64_t t_begin = p.total_tiles * blockIdx.x / gridDim.x;
+  const int64_t t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t prev_item = -1;
+      uint32_t items_done = 0;
+      for (int64_t t = t_begin; t < t_end; ++t) {
+        const TileCoord c = decode_tile(p, t);
+        const bool new_item = c.item != prev_item;
+        for (int kb = 0; kb < KB; ++kb) {
+          if (new_item && items_done > 0) mbar_wait(&s.res_free[kb], (items_done - 1) & 1);
+          mbar_wait(&s.empty[stage], phase ^ 1);
+          mbar_expect_tx(&s.full[stage], new_item ? 2 * kTileKBytes : kTileKBytes);
+          const int row = c.b * p.D + kb * BK;
+          if (new_item) {
+            uint8_t* dst = s.resident + kb * kTileKBytes;
+#pragma unroll
+            for (int ch = 0; ch < BM / 32; ++ch) tma_load_2d(dst + ch * kBoxBytes, &p.map_lvl[c.l], c.m0 + ch * 32, row, &s.full[stage]);
+          }
+          uint8_t* dst = s.ring + stage * kTileKBytes;
+#pragma unroll
+          for (int ch = 0; ch < BN / 32; ++ch) tma_load_2d(dst + ch * kBoxBytes, &p.map_f1, c.n0 + ch * 32, row, &s.full[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (new_item) { ++items_done; prev_item = c.item; }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_count = 0;
+      for (int64_t t = t_begin; t < t_end; ++t) {
+        const int64_t item = t / p.n_tiles;
+        const bool last_of_item = (t + 1 == t_end) || ((t + 1) / p.n_tiles != item);
+        const uint32_t acc = tile_count & 1;
+        mbar_wait(&s.acc_empty[acc], ((tile_count >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + acc * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s.resident + kb * kTileKBytes);
+          const uint32_t b_addr = smem_u32(s.ring + stage * kTileKBytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / UK; ++ks) {
+            // one 8-channel group = one 1024-byte swizzle atom per 32-position chunk
+            tc_mma_tf32(d_tmem, make_desc(a_addr + ks * 1024), make_desc(b_addr + ks * 1024), kIdesc, (kb | ks) != 0);
+          }
+          tc_commit(&s.empty[stage]);
+          if (last_of_item) tc_commit(&s.res_free[kb]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&s.acc_full[acc]);
+        ++tile_count;
+      }
+    }
+  } else {
+    // ===== epilogue warps 0-3: TMEM lanes [32*warp, 32*warp+32) =====
+    uint32_t tile_count = 0;
+    for (int64_t t = t_begin; t < t_end; ++t) {
+      const TileCoord c = decode_tile(p, t);
+      const uint32_t acc = tile_count & 1;
+      mbar_wait(&s.acc_full[acc], (tile_count >> 1) & 1);
+      tc_fence_after();
+      const int Pl = p.Pl[c.l];
+      const int j = c.m0 + warp * 32 + lane;
+      const bool j_ok = j < Pl;
+      float* obase = p.out[c.l] + ((int64_t)c.b * p.P) * Pl + j;
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + cc * 32));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int i_base = c.n0 + cc * 32;
+        if (j_ok) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int i = i_base + r;
+            // lanes = 32 consecutive j of output row i: one 128-byte store per row per warp
+            if (i < p.P) st_stream(obase + (int64_t)i * Pl, __uint_as_float(v[r]) * p.scale);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
+      ++tile_count;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static std::mutex mu;
+  static EncodeTiledFn fn = nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch `pitch` elements; box = 32 cols x BK rows, 128B swizzle.
+int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(EEM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EEM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return EEM_OK;
+}
+
+struct LevelDims {
+  int h[kMaxLevels], w[kMaxLevels];
+  int64_t pitch[kMaxLevels];   // element pitch of the pooled operand rows (level 0: P)
+  size_t ws_off[kMaxLevels];   // workspace offset of pooled operand l (l >= 1)
+  size_t ws_total;
+};
+
+LevelDims level_dims(int B, int D, int H, int W, int L) {
+  LevelDims d{};
+  int h = H, w = W;
+  size_t off = 0;
+  for (int l = 0; l < L; ++l) {
+    d.h[l] = h;
+    d.w[l] = w;
+    const int64_t pl = (int64_t)h * w;
+    d.pitch[l] = l == 0 ? pl : (int64_t)align_up((size_t)(pl > 0 ? pl : 1), 4);
+    d.ws_off[l] = off;
+    if (l > 0) off = align_up(off + (size_t)B * D * d.pitch[l] * sizeof(float), 256);
+    h /= 2;
+    w /= 2;
+  }
+  d.ws_total = off;
+  return d;
+}
+
+}  // namespace
+}  // namespace eem
+
+using namespace eem;
+
+extern "C" {
+
+size_t eem_corr_pyramid_workspace_bytes(int B, int D, int H, int W, int num_levels) {
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || num_levels <= 0 || num_levels > kMaxLevels) return 0;
+  return level_dims(B, D, H, W, num_levels).ws_total;
+}
+
+int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int num_levels,
+                     float* const* levels, int precision, void* workspace, size_t workspace_bytes,
+                     eem_stream_t stream_) {
+  EEM_CHECK_ARG(fmap1 && fmap2 && levels, "eem_corr_pyramid: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, "eem_corr_pyramid: sizes must be > 0");
+  EEM_CHECK_ARG(num_levels > 0 && num_levels <= kMaxLevels, "eem_corr_pyramid: num_levels must be in [1,%d]", kMaxLevels);
+  EEM_CHECK_ARG(precision == EEM_CORR_FP32 || precision == EEM_CORR_TF32, "eem_corr_pyramid: unknown precision %d", precision);
+  EEM_CHECK_ARG(B <= 65535, "eem_corr_pyramid: batch > 65535 not supported in one call");
+  EEM_CHECK_ALIGNED(fmap1, 16);
+  EEM_CHECK_ALIGNED(fmap2, 16);
+  const LevelDims ld = level_dims(B, D, H, W, num_levels);
+  if (ld.ws_total > 0) {
+    if (workspace == nullptr || workspace_bytes < ld.ws_total)
+      return fail(EEM_ERR_WORKSPACE, "eem_corr_pyramid: workspace of %zu bytes required, got %zu", ld.ws_total, workspace_bytes);
+    EEM_CHECK_ALIGNED(workspace, 256);
+  }
+  cudaStream_t stream = as_stream(stream_);
+  const int P = H * W;
+  const float scale = 1.0f / sqrtf((float)D);
+  const int64_t planes = (int64_t)B * D;
+
+  // pooled fmap2 operands (level l from level l-1)
+  const float* op[kMaxLevels];
+  op[0] = fmap2;
+  for (int l = 1; l < num_levels; ++l) {
+    float* dst = reinterpret_cast<float*>(static_cast<char*>(workspace) + ld.ws_off[l]);
+    op[l] = dst;
+    const int64_t total = planes * ld.h[l] * ld.w[l];
+    if (total == 0) continue;
+    int64_t blocks = ceil_div(total, 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (cap > 0 && blocks > cap) blocks = cap;
+    pool_fmap_kernel<<<(unsigned)blocks, 256, 0, stream>>>(op[l - 1], planes, ld.h[l - 1], ld.w[l - 1], ld.pitch[l - 1], dst, ld.pitch[l]);
+    EEM_CHECK_LAUNCH("pool_fmap_kernel");
+  }
+  for (int l = 0; l < num_levels; ++l)
+    EEM_CHECK_ARG((int64_t)ld.h[l] * ld.w[l] == 0 || levels[l] != nullptr, "eem_corr_pyramid: levels[%d] is NULL", l);
+
+  // The tensor-core path needs TMA-addressable operands (16-byte row pitch) and whole K blocks.
+  const bool tf32_ok = (P % 4 == 0) && (D % BK == 0) && (D <= kMaxKB * BK);
+  if (precision == EEM_CORR_TF32 && !tf32_ok)
+    return fail(EEM_ERR_UNSUPPORTED,
+                "eem_corr_pyramid(TF32): needs H*W %% 4 == 0, D %% %d == 0 and D <= %d (got H*W=%d, D=%d); use EEM_CORR_FP32",
+                BK, kMaxKB * BK, P, D);
+
+  if (precision == EEM_CORR_FP32) {
+    for (int l = 0; l < num_levels; ++l) {
+      const int Pl = ld.h[l] * ld.w[l];
+      if (Pl == 0) continue;
+      dim3 grid((unsigned)ceil_div(Pl, FT), (unsigned)ceil_div(P, FT), (unsigned)B);
+      corr_fp32_kernel<<<grid, 256, 0, stream>>>(fmap1, op[l], D, P, Pl, ld.pitch[l], scale, levels[l]);
+      EEM_CHECK_LAUNCH("corr_fp32_kernel");
+    }
+    return EEM_OK;
+  }
+
+  Tf32Params p{};
+  int rc = encode_map(&p.map_f1, fmap1, planes, P, P);
+  if (rc != EEM_OK) return rc;
+  int nl = 0;
+  p.mt_cum[0] = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int Pl = ld.h[l] * ld.w[l];
+    if (Pl == 0) break;  // all coarser levels are empty too
+    rc = encode_map(&p.map_lvl[l], op[l], planes, Pl, ld.pitch[l]);
+    if (rc != EEM_OK) return rc;
+    p.out[l] = levels[l];
+    p.Pl[l] = Pl;
+    p.mt_cum[l + 1] = p.mt_cum[l] + (int)ceil_div(Pl, BM);
+    nl = l + 1;
+  }
+  p.B = B; p.D = D; p.P = P; p.L = nl;
+  p.n_tiles = (int)ceil_div(P, BN);
+  p.total_tiles = (int64_t)B * p.mt_cum[nl] * p.n_tiles;
+  p.scale = scale;
+  const size_t smem = sizeof(Tf32Smem) + 1024;
+  static std::mutex attr_mu;
+  {
+    std::lock_guard<std::mutex> lock(attr_mu);
+    EEM_CHECK_CUDA(cudaFuncSetAttribute(corr_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  int64_t grid = sm_count();
+  if (grid <= 0) return fail(EEM_ERR_CUDA, "eem_corr_pyramid: cannot query SM count");
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  corr_tf32_kernel<<<(unsigned)grid, kTf32Threads, smem, stream>>>(p);
+  EEM_CHECK_LAUNCH("corr_tf32_kernel");
+  return EEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,614 @@
+// K1 event voxelization + K2 voxel-grid normalisation for sm_100a.
+//
+// Reference semantics (utils/transformers.py:56-122, EventSequenceToVoxelGrid_Pytorch.__call__):
+//   ts   = (nb-1) * (t - t_first) / dT          float64, multiply then divide, dT==0 -> 1.0
+//   x,y  = trunc(ev[1]), trunc(ev[2])           int64
+//   pol  = float(ev[3]); pol==0 -> -1
+//   ti   = floor(ts); dt = float(ts - ti)
+//   grid[x + y*W + ti*W*H]     += pol*(1-dt)    if 0 <= ti < nb          ("left" vote)
+//   grid[x + y*W + (ti+1)*W*H] += pol*dt        if 0 <= ti, ti+1 < nb    ("right" vote)
+//   optional: mean / unbiased std over non-zero voxels, v = (v-mean)/std on them.
+//
+// Data layout in HBM: events stay in the reference's [N,4] float64 row format (32 B/event); one
+// 256-bit LDG per event row, so a warp reads 1 KiB contiguous per instruction.  The grid is
+// zero-filled with a memset and updated with fire-and-forget RED.ADD.F32 resolved in L2 (the 55 MB
+// HREM grid is L2-resident on B200), so HBM sees 32*N bytes in and 4*nb*H*W bytes out.
+#include "common.cuh"
+
+namespace eem {
+namespace {
+
+constexpr int kVoteThreads = 256;
+constexpr int kVoteEventsPerThread = 4;
+
+struct EventRow {
+  double t, x, y, p;
+};
+
+// One 32-byte event row per load (LDG.E.256 on sm_100a), streaming: rows are read exactly once.
+__device__ __forceinline__ EventRow load_event(const double* ev, int64_t i) {
+  EventRow r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.t), "=d"(r.x), "=d"(r.y), "=d"(r.p)
+               : "l"(ev + 4 * i));
+  return r;
+}
+
+struct Vote {
+  int64_t idx_left, idx_right;  // flat index inside the window's grid, or -1 when the vote is skipped
+  float val_left, val_right;
+  bool oob_left, oob_right;     // vote addressed a voxel outside the grid (reference: IndexError)
+};
+
+__device__ __forceinline__ Vote make_vote(const EventRow& e, double t_first, double dT, int nb,
+                                          int64_t W, int64_t HW, int64_t total) {
+  Vote v;
+  // float64, multiply first, then divide -- the reference's evaluation order.
+  const double ts = __ddiv_rn(__dmul_rn((double)(nb - 1), __dsub_rn(e.t, t_first)), dT);
+  const int64_t xi = (int64_t)e.x;  // .long(): truncation toward zero
+  const int64_t yi = (int64_t)e.y;
+  float pol = (float)e.p;
+  if (pol == 0.0f) pol = -1.0f;
+  const double tf = floor(ts);
+  const float dt = (float)__dsub_rn(ts, tf);
+  v.val_left = __fmul_rn(pol, __fsub_rn(1.0f, dt));
+  v.val_right = __fmul_rn(pol, dt);
+  const bool nonneg = tf >= 0.0;
+  const bool ok_left = nonneg && tf < (double)nb;
+  const bool ok_right = nonneg && (tf + 1.0) < (double)nb;
+  const int64_t ti = ok_left ? (int64_t)tf : 0;
+  const int64_t base = xi + yi * W + ti * HW;
+  v.idx_left = -1;
+  v.idx_right = -1;
+  v.oob_left = v.oob_right = false;
+  if (ok_left) {
+    if (base >= 0 && base < total) v.idx_left = base; else v.oob_left = true;
+  }
+  if (ok_right) {
+    const int64_t r = base + HW;
+    if (r >= 0 && r < total) v.idx_right = r; else v.oob_right = true;
+  }
+  return v;
+}
+
+struct WindowTimes {
+  double t_first, dT;
+};
+
+__device__ __forceinline__ WindowTimes window_times(const double* ev, int64_t begin, int64_t end) {
+  WindowTimes w;
+  w.t_first = __ldg(ev + 4 * begin);
+  const double t_last = __ldg(ev + 4 * (end - 1));
+  w.dT = __dsub_rn(t_last, w.t_first);
+  if (w.dT == 0.0) w.dT = 1.0;
+  return w;
+}
+
+// ---- atomic mode ------------------------------------------------------------------------------
+// grid = (ceil(max_events / (threads*EPT)), n_windows).  Loads of a thread's EPT rows are issued
+// back to back before any vote so each thread keeps EPT 32-byte requests in flight.
+__global__ void __launch_bounds__(kVoteThreads)
+voxel_vote_atomic_kernel(const double* __restrict__ ev, const int64_t* __restrict__ offsets, int nb,
+                         int H, int W, float* __restrict__ grid, int64_t* __restrict__ dropped) {
+  const int w = blockIdx.y;
+  const int64_t begin = offsets[w], end = offsets[w + 1];
+  const int64_t n = end - begin;
+  const int64_t first = (int64_t)blockIdx.x * (kVoteThreads * kVoteEventsPerThread) + threadIdx.x;
+  if (first - threadIdx.x >= n) return;
+  const WindowTimes wt = window_times(ev, begin, end);
+  const int64_t HW = (int64_t)H * W, total = HW * nb;
+  float* g = grid + (int64_t)w * total;
+
+  EventRow rows[kVoteEventsPerThread];
+#pragma unroll
+  for (int k = 0; k < kVoteEventsPerThread; ++k) {
+    const int64_t i = first + (int64_t)k * kVoteThreads;
+    if (i < n) rows[k] = load_event(ev, begin + i);
+  }
+  int ndrop = 0;
+#pragma unroll
+  for (int k = 0; k < kVoteEventsPerThread; ++k) {
+    const int64_t i = first + (int64_t)k * kVoteThreads;
+    if (i < n) {
+      const Vote v = make_vote(rows[k], wt.t_first, wt.dT, nb, W, HW, total);
+      if (v.idx_left >= 0) red_add_f32(g + v.idx_left, v.val_left);
+      if (v.idx_right >= 0) red_add_f32(g + v.idx_right, v.val_right);
+      ndrop += (int)v.oob_left + (int)v.oob_right;
+    }
+  }
+  if (dropped != nullptr && ndrop != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(dropped), (unsigned long long)ndrop);
+}
+
+// ---- deterministic mode -------------------------------------------------------------------------
+// Votes are materialised as (global voxel key, value) pairs in the reference's accumulation order
+// -- all left votes in event order, then all right votes in event order -- and sorted by key with
+// a STABLE least-significant-digit radix sort (8-bit digits).  Each voxel's votes then sit
+// contiguously in reference order and are summed sequentially in fp32 by one thread, which
+// reproduces the CPU reference's two index_add_ passes bit for bit.
+constexpr int kSortWarpsPerBlock = 8;
+constexpr int kSortSegment = 2048;  // keys owned by one warp per pass (kept in order)
+constexpr int kRadix = 256;
+
+__global__ void __launch_bounds__(kVoteThreads)
+voxel_vote_pairs_kernel(const double* __restrict__ ev, const int64_t* __restrict__ offsets, int nb,
+                        int H, int W, int64_t n_total, uint32_t invalid_key,
+                        uint32_t* __restrict__ keys, float* __restrict__ vals,
+                        int64_t* __restrict__ dropped) {
+  const int w = blockIdx.y;
+  const int64_t begin = offsets[w], end = offsets[w + 1];
+  const int64_t n = end - begin;
+  const int64_t i = (int64_t)blockIdx.x * kVoteThreads + threadIdx.x;
+  if (i >= n) return;
+  const WindowTimes wt = window_times(ev, begin, end);
+  const int64_t HW = (int64_t)H * W, total = HW * nb;
+  const EventRow e = load_event(ev, begin + i);
+  const Vote v = make_vote(e, wt.t_first, wt.dT, nb, W, HW, total);
+  const int64_t g = begin + i;  // global event rank: concatenation order == per-window event order
+  const int64_t wbase = (int64_t)w * total;
+  keys[g] = v.idx_left >= 0 ? (uint32_t)(wbase + v.idx_left) : invalid_key;
+  vals[g] = v.val_left;
+  keys[n_total + g] = v.idx_right >= 0 ? (uint32_t)(wbase + v.idx_right) : invalid_key;
+  vals[n_total + g] = v.val_right;
+  const int ndrop = (int)v.oob_left + (int)v.oob_right;
+  if (dropped != nullptr && ndrop != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(dropped), (unsigned long long)ndrop);
+}
+
+// counts[d * n_segs + seg] = number of keys of segment `seg` whose current digit is d.
+__global__ void __launch_bounds__(kSortWarpsPerBlock * 32)
+radix_count_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int64_t n_segs,
+                   uint32_t* __restrict__ counts) {
+  __shared__ uint32_t hist[kSortWarpsPerBlock][kRadix];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * kSortWarpsPerBlock + warp;
+  for (int d = lane; d < kRadix; d += 32) hist[warp][d] = 0;
+  __syncwarp();
+  if (seg < n_segs) {
+    const int64_t s0 = seg * kSortSegment;
+#pragma unroll 4
+    for (int c = 0; c < kSortSegment / 32; ++c) {
+      const int64_t i = s0 + c * 32 + lane;
+      if (i < n) atomicAdd(&hist[warp][(keys[i] >> shift) & (kRadix - 1)], 1u);
+    }
+    __syncwarp();
+    for (int d = lane; d < kRadix; d += 32) counts[(int64_t)d * n_segs + seg] = hist[warp][d];
+  }
+}
+
+// Exclusive scan of `counts` (m entries) in three steps: per-block sums, scan of block sums, apply.
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;  // entries per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem_warp, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t ws = lane < (blockDim.x >> 5) ? smem_warp[lane] : 0;
+    uint32_t winc = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    smem_warp[lane] = winc - ws;
+    if (lane == 31) smem_warp[32] = winc;
+  }
+  __syncthreads();
+  const uint32_t r = inc - v + smem_warp[warp];
+  if (total) *total = smem_warp[32];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_block_sums_kernel(const uint32_t* __restrict__ in, int64_t m, uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t sw[33];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (base + k < m) s += in[base + k];
+  uint32_t total;
+  block_exclusive_scan(s, sw, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_of_block_sums_kernel(uint32_t* __restrict__ block_sums, int64_t nblocks) {
+  __shared__ uint32_t sw[33];
+  uint32_t carry = 0;
+  for (int64_t base = 0; base < nblocks; base += kScanThreads) {
+    const int64_t i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? block_sums[i] : 0;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, sw, &total);
+    if (i < nblocks) block_sums[i] = ex + carry;
+    carry += total;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(uint32_t* __restrict__ data, int64_t m, const uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t sw[33];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = base + k < m ? data[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t ex = block_exclusive_scan(s, sw, nullptr) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < m) data[base + k] = ex;
+    ex += v[k];
+  }
+}
+
+// Stable scatter: a warp walks its segment in order, 32 keys at a time.  Lanes holding the same
+// digit are ranked by lane id (match.any), so equal digits keep their input order.
+__global__ void __launch_bounds__(kSortWarpsPerBlock * 32)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const float* __restrict__ vals_in,
+                     int64_t n, int shift, int64_t n_segs, const uint32_t* __restrict__ offsets,
+                     uint32_t* __restrict__ keys_out, float* __restrict__ vals_out) {
+  __shared__ uint32_t offs[kSortWarpsPerBlock][kRadix];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * kSortWarpsPerBlock + warp;
+  if (seg >= n_segs) return;
+  for (int d = lane; d < kRadix; d += 32) offs[warp][d] = offsets[(int64_t)d * n_segs + seg];
+  __syncwarp();
+  const int64_t s0 = seg * kSortSegment;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int c = 0; c < kSortSegment / 32; ++c) {
+    const int64_t i = s0 + c * 32 + lane;
+    if (s0 + c * 32 >= n) break;
+    const bool valid = i < n;
+    const uint32_t key = valid ? keys_in[i] : 0u;
+    const float val = valid ? vals_in[i] : 0.0f;
+    // Lanes past the end get a private pseudo-digit so they never share a peer group.
+    const uint32_t d = valid ? ((key >> shift) & (kRadix - 1)) : (uint32_t)(kRadix + lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t rank = __popc(peers & lt_mask);
+    uint32_t base = 0;
+    if (valid) base = offs[warp][d];
+    __syncwarp();
+    if (valid && rank == 0) offs[warp][d] = base + __popc(peers);
+    __syncwarp();
+    if (valid) {
+      keys_out[base + rank] = key;
+      vals_out[base + rank] = val;
+    }
+  }
+}
+
+// One thread per segment head; sequential fp32 accumulation in sorted (= reference) order.
+__global__ void __launch_bounds__(256)
+segmented_sum_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ vals, int64_t n,
+                     uint32_t invalid_key, float* __restrict__ grid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = keys[i];
+  if (k == invalid_key) return;
+  if (i > 0 && keys[i - 1] == k) return;
+  float acc = 0.0f;
+  int64_t j = i;
+  do {
+    acc = __fadd_rn(acc, vals[j]);
+    ++j;
+  } while (j < n && keys[j] == k);
+  grid[k] = acc;
+}
+
+// ---- K2 normalisation -----------------------------------------------------------------------
+constexpr int kStatThreads = 256;
+constexpr int kStatBlocksPerWindowMax = 256;
+
+struct StatPartial {
+  double count, sum, sumsq;
+};
+
+__device__ __forceinline__ void accum_stat(float v, double& c, double& s, double& q) {
+  if (v != 0.0f) {
+    c += 1.0;
+    s += (double)v;
+    q += (double)v * (double)v;
+  }
+}
+
+// grid = (blocks_per_window, n_windows).  Partials are combined in block order by the last block
+// to finish (ticket counter), so mean/std do not depend on scheduling.
+__global__ void __launch_bounds__(kStatThreads)
+voxel_stats_kernel(const float* __restrict__ grid, int64_t vox, StatPartial* __restrict__ partials,
+                   unsigned int* __restrict__ tickets, float* __restrict__ mean_std,
+                   double* __restrict__ stats_out) {
+  __shared__ double red[3][kStatThreads / 32];
+  __shared__ bool is_last;
+  const int w = blockIdx.y;
+  const float* g = grid + (int64_t)w * vox;
+  double c = 0, s = 0, q = 0;
+  const int64_t stride = (int64_t)gridDim.x * kStatThreads;
+  const int64_t tid = (int64_t)blockIdx.x * kStatThreads + threadIdx.x;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  const int64_t nvec = vec_ok ? vox / 4 : 0;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = tid; i < nvec; i += stride) {
+    const float4 v = g4[i];
+    accum_stat(v.x, c, s, q);
+    accum_stat(v.y, c, s, q);
+    accum_stat(v.z, c, s, q);
+    accum_stat(v.w, c, s, q);
+  }
+  for (int64_t i = nvec * 4 + tid; i < vox; i += stride) accum_stat(g[i], c, s, q);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    red[0][warp] = c;
+    red[1][warp] = s;
+    red[2][warp] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bc = 0, bs = 0, bq = 0;
+    for (int k = 0; k < kStatThreads / 32; ++k) {
+      bc += red[0][k];
+      bs += red[1][k];
+      bq += red[2][k];
+    }
+    StatPartial p{bc, bs, bq};
+    partials[(int64_t)w * gridDim.x + blockIdx.x] = p;
+    __threadfence();
+    const unsigned int t = atomicAdd(&tickets[w], 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double tc = 0, ts = 0, tq = 0;
+    for (unsigned int k = 0; k < gridDim.x; ++k) {
+      const StatPartial p = partials[(int64_t)w * gridDim.x + k];
+      tc += p.count;
+      ts += p.sum;
+      tq += p.sumsq;
+    }
+    // mean and unbiased std, rounded to fp32 like the 0-dim fp32 tensors of the reference.
+    float mean = 0.0f, sd = 0.0f;
+    if (tc > 0) {
+      const double m = ts / tc;
+      mean = (float)m;
+      if (tc > 1) {
+        double var = (tq - ts * m) / (tc - 1.0);
+        if (var < 0) var = 0;
+        sd = (float)sqrt(var);
+      } else {
+        sd = __int_as_float(0x7fc00000);  // torch: std of one element is NaN -> "v - mean" branch
+      }
+    }
+    mean_std[2 * w + 0] = mean;
+    mean_std[2 * w + 1] = sd;
+    if (stats_out) {
+      stats_out[3 * w + 0] = tc;
+      stats_out[3 * w + 1] = (double)mean;
+      stats_out[3 * w + 2] = (double)sd;
+    }
+    tickets[w] = 0;  // leave the workspace reusable without a memset
+  }
+}
+
+__device__ __forceinline__ float normalize_one(float v, float mean, float sd, bool divide) {
+  if (v == 0.0f) return v;
+  const float c = __fsub_rn(v, mean);
+  return divide ? __fdiv_rn(c, sd) : c;
+}
+
+__global__ void __launch_bounds__(256)
+voxel_apply_kernel(float* __restrict__ grid, int64_t vox, const float* __restrict__ mean_std) {
+  const int w = blockIdx.y;
+  float* g = grid + (int64_t)w * vox;
+  const float mean = mean_std[2 * w + 0], sd = mean_std[2 * w + 1];
+  const bool divide = sd > 0.0f;  // false for NaN, matching "if std > 0"
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  const int64_t nvec = vec_ok ? vox / 4 : 0;
+  float4* g4 = reinterpret_cast<float4*>(g);
+  for (int64_t i = tid; i < nvec; i += stride) {
+    float4 v = g4[i];
+    v.x = normalize_one(v.x, mean, sd, divide);
+    v.y = normalize_one(v.y, mean, sd, divide);
+    v.z = normalize_one(v.z, mean, sd, divide);
+    v.w = normalize_one(v.w, mean, sd, divide);
+    g4[i] = v;
+  }
+  for (int64_t i = nvec * 4 + tid; i < vox; i += stride) g[i] = normalize_one(g[i], mean, sd, divide);
+}
+
+int bit_length(uint64_t v) {
+  int b = 0;
+  while (v) {
+    ++b;
+    v >>= 1;
+  }
+  return b;
+}
+
+struct DetLayout {
+  size_t keys_a, keys_b, vals_a, vals_b, counts, block_sums, total;
+  int64_t n_votes, n_segs, n_counts, n_scan_blocks;
+};
+
+DetLayout det_layout(int64_t n_total) {
+  DetLayout L{};
+  L.n_votes = 2 * n_total;
+  L.n_segs = ceil_div(L.n_votes > 0 ? L.n_votes : 1, kSortSegment);
+  L.n_counts = L.n_segs * kRadix;
+  L.n_scan_blocks = ceil_div(L.n_counts, kScanTile);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t nv = (size_t)(L.n_votes > 0 ? L.n_votes : 1);
+  L.keys_a = take(nv * 4);
+  L.keys_b = take(nv * 4);
+  L.vals_a = take(nv * 4);
+  L.vals_b = take(nv * 4);
+  L.counts = take((size_t)L.n_counts * 4);
+  L.block_sums = take((size_t)L.n_scan_blocks * 4);
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+}  // namespace eem
+
+using namespace eem;
+
+extern "C" {
+
+size_t eem_voxelize_workspace_bytes(int64_t n_total, int n_windows, int num_bins, int height,
+                                    int width, int mode) {
+  (void)n_windows; (void)num_bins; (void)height; (void)width;
+  if (mode != EEM_VOXEL_DETERMINISTIC || n_total < 0) return 0;
+  return det_layout(n_total).total;
+}
+
+int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, int64_t n_total,
+                 int64_t max_events_per_window, int num_bins, int height, int width, int mode,
+                 float* grid, int64_t* dropped, void* workspace, size_t workspace_bytes,
+                 eem_stream_t stream_) {
+  EEM_CHECK_ARG(n_windows > 0, "eem_voxelize: n_windows must be > 0 (got %d)", n_windows);
+  EEM_CHECK_ARG(num_bins > 0, "eem_voxelize: num_bins must be > 0 (got %d)", num_bins);
+  EEM_CHECK_ARG(height > 0 && width > 0, "eem_voxelize: height/width must be > 0 (got %dx%d)", height, width);
+  EEM_CHECK_ARG(n_total >= 0 && max_events_per_window >= 0 && max_events_per_window <= n_total,
+                "eem_voxelize: bad event counts (n_total=%lld, max_per_window=%lld)",
+                (long long)n_total, (long long)max_events_per_window);
+  EEM_CHECK_ARG(grid != nullptr && offsets != nullptr, "eem_voxelize: NULL grid/offsets");
+  EEM_CHECK_ARG(n_total == 0 || events != nullptr, "eem_voxelize: NULL events");
+  EEM_CHECK_ARG(mode == EEM_VOXEL_ATOMIC || mode == EEM_VOXEL_DETERMINISTIC,
+                "eem_voxelize: unknown mode %d", mode);
+  EEM_CHECK_ALIGNED(events, 32);
+  EEM_CHECK_ALIGNED(grid, 4);
+  cudaStream_t stream = as_stream(stream_);
+  const int64_t vox = (int64_t)num_bins * height * width;
+  const int64_t total_vox = vox * n_windows;
+  EEM_CHECK_CUDA(cudaMemsetAsync(grid, 0, (size_t)total_vox * sizeof(float), stream));
+  if (n_total == 0 || max_events_per_window == 0) return EEM_OK;
+
+  if (mode == EEM_VOXEL_ATOMIC) {
+    const int64_t per_block = (int64_t)kVoteThreads * kVoteEventsPerThread;
+    dim3 g((unsigned)ceil_div(max_events_per_window, per_block), (unsigned)n_windows);
+    voxel_vote_atomic_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height,
+                                                             width, grid, dropped);
+    EEM_CHECK_LAUNCH("voxel_vote_atomic_kernel");
+    return EEM_OK;
+  }
+
+  // deterministic: vote pairs -> stable LSD radix sort by global voxel key -> sequential sums
+  if (total_vox >= (int64_t)0xffffffffLL)
+    return fail(EEM_ERR_UNSUPPORTED,
+                "eem_voxelize(deterministic): %lld voxels in one call exceed the 32-bit key space; split the batch",
+                (long long)total_vox);
+  if (2 * n_total >= (int64_t)0x7fffffffLL)
+    return fail(EEM_ERR_UNSUPPORTED, "eem_voxelize(deterministic): too many events in one call (%lld)", (long long)n_total);
+  const DetLayout L = det_layout(n_total);
+  if (workspace == nullptr || workspace_bytes < L.total)
+    return fail(EEM_ERR_WORKSPACE, "eem_voxelize(deterministic): workspace of %zu bytes required, got %zu",
+                L.total, workspace_bytes);
+  EEM_CHECK_ALIGNED(workspace, 256);
+  char* ws = static_cast<char*>(workspace);
+  uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(ws + L.keys_a), reinterpret_cast<uint32_t*>(ws + L.keys_b)};
+  float* vals[2] = {reinterpret_cast<float*>(ws + L.vals_a), reinterpret_cast<float*>(ws + L.vals_b)};
+  uint32_t* counts = reinterpret_cast<uint32_t*>(ws + L.counts);
+  uint32_t* block_sums = reinterpret_cast<uint32_t*>(ws + L.block_sums);
+  const uint32_t invalid_key = (uint32_t)total_vox;
+
+  {
+    dim3 g((unsigned)ceil_div(max_events_per_window, kVoteThreads), (unsigned)n_windows);
+    voxel_vote_pairs_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width,
+                                                            n_total, invalid_key, keys[0], vals[0], dropped);
+    EEM_CHECK_LAUNCH("voxel_vote_pairs_kernel");
+  }
+  const int key_bits = bit_length((uint64_t)invalid_key);
+  const int passes = (key_bits + 7) / 8;
+  const unsigned sort_blocks = (unsigned)ceil_div(L.n_segs, kSortWarpsPerBlock);
+  int cur = 0;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    radix_count_kernel<<<sort_blocks, kSortWarpsPerBlock * 32, 0, stream>>>(keys[cur], L.n_votes, shift, L.n_segs, counts);
+    EEM_CHECK_LAUNCH("radix_count_kernel");
+    scan_block_sums_kernel<<<(unsigned)L.n_scan_blocks, kScanThreads, 0, stream>>>(counts, L.n_counts, block_sums);
+    EEM_CHECK_LAUNCH("scan_block_sums_kernel");
+    scan_of_block_sums_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, L.n_scan_blocks);
+    EEM_CHECK_LAUNCH("scan_of_block_sums_kernel");
+    scan_apply_kernel<<<(unsigned)L.n_scan_blocks, kScanThreads, 0, stream>>>(counts, L.n_counts, block_sums);
+    EEM_CHECK_LAUNCH("scan_apply_kernel");
+    radix_scatter_kernel<<<sort_blocks, kSortWarpsPerBlock * 32, 0, stream>>>(
+        keys[cur], vals[cur], L.n_votes, shift, L.n_segs, counts, keys[cur ^ 1], vals[cur ^ 1]);
+    EEM_CHECK_LAUNCH("radix_scatter_kernel");
+    cur ^= 1;
+  }
+  segmented_sum_kernel<<<(unsigned)ceil_div(L.n_votes, 256), 256, 0, stream>>>(keys[cur], vals[cur], L.n_votes,
+                                                                             invalid_key, grid);
+  EEM_CHECK_LAUNCH("segmented_sum_kernel");
+  return EEM_OK;
+}
+
+static int stat_blocks(int64_t vox) {
+  int64_t b = ceil_div(vox, (int64_t)kStatThreads * 4 * 8);
+  if (b < 1) b = 1;
+  if (b > kStatBlocksPerWindowMax) b = kStatBlocksPerWindowMax;
+  return (int)b;
+}
+
+size_t eem_voxel_normalize_workspace_bytes(int n_windows, int64_t voxels_per_window) {
+  if (n_windows <= 0 || voxels_per_window <= 0) return 0;
+  const size_t nb = (size_t)stat_blocks(voxels_per_window);
+  size_t bytes = align_up((size_t)n_windows * nb * sizeof(StatPartial), 256);
+  bytes += align_up((size_t)n_windows * sizeof(unsigned int), 256);  // tickets (must start zeroed)
+  bytes += align_up((size_t)n_windows * 2 * sizeof(float), 256);     // mean, std
+  return bytes;
+}
+
+int eem_voxel_normalize(float* grid, int n_windows, int64_t voxels_per_window, double* stats_out,
+                        void* workspace, size_t workspace_bytes, eem_stream_t stream_) {
+  EEM_CHECK_ARG(grid != nullptr, "eem_voxel_normalize: NULL grid");
+  EEM_CHECK_ARG(n_windows > 0 && voxels_per_window > 0, "eem_voxel_normalize: sizes must be > 0");
+  const size_t need = eem_voxel_normalize_workspace_bytes(n_windows, voxels_per_window);
+  if (workspace == nullptr || workspace_bytes < need)
+    return fail(EEM_ERR_WORKSPACE, "eem_voxel_normalize: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+  EEM_CHECK_ALIGNED(workspace, 256);
+  cudaStream_t stream = as_stream(stream_);
+  const int nb = stat_blocks(voxels_per_window);
+  char* ws = static_cast<char*>(workspace);
+  StatPartial* partials = reinterpret_cast<StatPartial*>(ws);
+  size_t off = align_up((size_t)n_windows * nb * sizeof(StatPartial), 256);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + off);
+  off += align_up((size_t)n_windows * sizeof(unsigned int), 256);
+  float* mean_std = reinterpret_cast<float*>(ws + off);
+  // Tickets are reset by the kernel itself after use; the memset makes a fresh workspace valid.
+  EEM_CHECK_CUDA(cudaMemsetAsync(tickets, 0, (size_t)n_windows * sizeof(unsigned int), stream));
+  dim3 g((unsigned)nb, (unsigned)n_windows);
+  voxel_stats_kernel<<<g, kStatThreads, 0, stream>>>(grid, voxels_per_window, partials, tickets, mean_std, stats_out);
+  EEM_CHECK_LAUNCH("voxel_stats_kernel");
+  voxel_apply_kernel<<<g, 256, 0, stream>>>(grid, voxels_per_window, mean_std);
+  EEM_CHECK_LAUNCH("voxel_apply_kernel");
+  return EEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// K7 backward warp (+ validity mask, + fused CDC blend), K8 bilinear resize, K9 replicate pad.
+// All are HBM-bound gathers: thread = output pixel with x fastest (128 B coalesced stores),
+// texture-free bilinear interpolation, sample geometry computed once per pixel and reused over
+// the channel loop.
+//
+// Coordinate conventions are the reference's, kept bug-for-bug (trap 5):
+//   g  = 2*(px+u)/max(W-1,1) - 1                          every warp variant (tools.py:2289-2290)
+//   EXACT   ix = (g+1)/2*(W-1)       grid_sample(align_corners=True)   EEMFlow+.py:145-148
+//   HALFPIX ix = ((g+1)*W-1)/2       grid_sample default (False)       tools.py:2295, cdc_utils.py:71
+// Bilinear weights and accumulation order follow ATen's grid_sampler_2d (nw, ne, sw, se).
+#include "common.cuh"
+
+namespace eem {
+namespace {
+
+struct Bilin {
+  int x0, y0;             // north-west tap
+  float nw, ne, sw, se;   // weights
+  bool in_nw, in_ne, in_sw, in_se;
+};
+
+__device__ __forceinline__ float unnormalize(float g, int size, int convention) {
+  if (convention == EEM_WARP_EXACT) return ((g + 1.f) / 2.f) * (float)(size - 1);
+  return ((g + 1.f) * (float)size - 1.f) / 2.f;
+}
+
+__device__ __forceinline__ Bilin make_bilin(float px, float py, int H, int W, int convention) {
+  const float gx = 2.0f * px / (float)max(W - 1, 1) - 1.0f;
+  const float gy = 2.0f * py / (float)max(H - 1, 1) - 1.0f;
+  const float ix = unnormalize(gx, W, convention);
+  const float iy = unnormalize(gy, H, convention);
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  Bilin s;
+  // keep the integer conversion defined for wild flows; such samples are fully out of bounds
+  s.x0 = (int)fminf(fmaxf(fx0, -2.0e9f), 2.0e9f);
+  s.y0 = (int)fminf(fmaxf(fy0, -2.0e9f), 2.0e9f);
+  const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+  s.nw = (fx1 - ix) * (fy1 - iy);
+  s.ne = (ix - fx0) * (fy1 - iy);
+  s.sw = (fx1 - ix) * (iy - fy0);
+  s.se = (ix - fx0) * (iy - fy0);
+  const bool xin0 = s.x0 >= 0 && s.x0 < W, xin1 = s.x0 + 1 >= 0 && s.x0 + 1 < W;
+  const bool yin0 = s.y0 >= 0 && s.y0 < H, yin1 = s.y0 + 1 >= 0 && s.y0 + 1 < H;
+  const bool finite = (fx0 == fx0) && (fy0 == fy0) && fabsf(fx0) < 1.0e9f && fabsf(fy0) < 1.0e9f;
+  s.in_nw = finite && xin0 && yin0;
+  s.in_ne = finite && xin1 && yin0;
+  s.in_sw = finite && xin0 && yin1;
+  s.in_se = finite && xin1 && yin1;
+  return s;
+}
+
+__device__ __forceinline__ float sample(const float* __restrict__ plane, const Bilin& s, int W) {
+  const float* p = plane + (int64_t)s.y0 * W + s.x0;
+  float acc = 0.f;
+  if (s.in_nw) acc += __ldg(p) * s.nw;
+  if (s.in_ne) acc += __ldg(p + 1) * s.ne;
+  if (s.in_sw) acc += __ldg(p + W) * s.sw;
+  if (s.in_se) acc += __ldg(p + W + 1) * s.se;
+  return acc;
+}
+
+__device__ __forceinline__ float ones_sample(const Bilin& s) {
+  float acc = 0.f;
+  if (s.in_nw) acc += s.nw;
+  if (s.in_ne) acc += s.ne;
+  if (s.in_sw) acc += s.sw;
+  if (s.in_se) acc += s.se;
+  return acc;
+}
+
+constexpr int kWarpChunk = 8;  // channels per thread; grid.z = B * ceil(C / kWarpChunk)
+
+__global__ void __launch_bounds__(256)
+backwarp_kernel(const float* __restrict__ x, const float* __restrict__ flow, int B, int C, int H, int W,
+                int convention, int mask_mode, float* __restrict__ out, float* __restrict__ mask_out) {
+  const int px = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int py = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (px >= W || py >= H) return;
+  const int chunks = (C + kWarpChunk - 1) / kWarpChunk;
+  const int b = blockIdx.z / chunks, c0 = (blockIdx.z % chunks) * kWarpChunk;
+  const int64_t plane = (int64_t)H * W, pix = (int64_t)py * W + px;
+  const float u = flow[((int64_t)b * 2 + 0) * plane + pix];
+  const float v = flow[((int64_t)b * 2 + 1) * plane + pix];
+  const Bilin s = make_bilin((float)px + u, (float)py + v, H, W, convention);
+  float m = 1.f;
+  if (mask_mode != EEM_MASK_NONE) {
+    const float ms = ones_sample(s);
+    m = (mask_mode == EEM_MASK_GE1) ? (ms >= 1.0f ? 1.f : 0.f) : (ms < 0.9999f ? 0.f : 1.f);
+    if (mask_out != nullptr && c0 == 0) mask_out[(int64_t)b * plane + pix] = m;
+  }
+  const int c1 = min(C, c0 + kWarpChunk);
+  for (int c = c0; c < c1; ++c) {
+    const int64_t off = ((int64_t)b * C + c) * plane;
+    float r = sample(x + off, s, W);
+    if (mask_mode != EEM_MASK_NONE) r *= m;
+    st_stream(out + off + pix, r);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+warp_blend_kernel(const float* __restrict__ flow_init, const float* __restrict__ inter, const float* __restrict__ mk,
+                  int B, int H, int W, float* __restrict__ out) {
+  const int px = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int py = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (px >= W || py >= H) return;
+  const int64_t plane = (int64_t)H * W, pix = (int64_t)py * W + px;
+  const float u = inter[((int64_t)b * 2 + 0) * plane + pix];
+  const float v = inter[((int64_t)b * 2 + 1) * plane + pix];
+  const Bilin s = make_bilin((float)px + u, (float)py + v, H, W, EEM_WARP_HALFPIX);
+  const float m = mk[(int64_t)b * plane + pix];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int64_t off = ((int64_t)b * 2 + c) * plane;
+    const float w = sample(flow_init + off, s, W);
+    const float f = flow_init[off + pix];
+    out[off + pix] = w * (1.f - m) + f * m;
+  }
+}
+
+// ATen area_pixel_compute_source_index (UpSample.h), fp32.
+__device__ __forceinline__ void source_index(int dst, int in_size, int out_size, int align_corners,
+                                             int& i0, int& i1, float& l0, float& l1) {
+  float src;
+  if (align_corners) {
+    const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+    src = scale * (float)dst;
+  } else {
+    const float scale = (float)in_size / (float)out_size;
+    src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256)
+bilinear_resize_kernel(const float* __restrict__ in, int B, int C, int h, int w, float* __restrict__ out,
+                       int H, int W, int align_corners, float scale0, float scale1, float scale_rest) {
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (X >= W || Y >= H) return;
+  int x0, x1, y0, y1;
+  float lx0, lx1, ly0, ly1;
+  source_index(X, w, W, align_corners, x0, x1, lx0, lx1);
+  source_index(Y, h, H, align_corners, y0, y1, ly0, ly1);
+  const int64_t ip = (int64_t)h * w, op = (int64_t)H * W;
+  for (int bc = blockIdx.z; bc < B * C; bc += gridDim.z) {
+    const int c = bc % C;
+    const float* s = in + (int64_t)bc * ip;
+    const float v = ly0 * (lx0 * __ldg(s + (int64_t)y0 * w + x0) + lx1 * __ldg(s + (int64_t)y0 * w + x1)) +
+                    ly1 * (lx0 * __ldg(s + (int64_t)y1 * w + x0) + lx1 * __ldg(s + (int64_t)y1 * w + x1));
+    const float sc = c == 0 ? scale0 : (c == 1 ? scale1 : scale_rest);
+    st_stream(out + (int64_t)bc * op + (int64_t)Y * W + X, v * sc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scale_uv_kernel(float* __restrict__ flow, int B, int C, int64_t plane, float s0, float s1) {
+  const int64_t total = (int64_t)B * 2 * plane;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / (2 * plane), r = i % (2 * plane);
+    const int c = (int)(r / plane);
+    float* p = flow + ((int64_t)b * C + c) * plane + (r % plane);
+    *p = *p * (c == 0 ? s0 : s1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+replicate_pad_kernel(const float* __restrict__ in, int64_t n_planes, int H, int W, int left, int top,
+                     int Ho, int Wo, float* __restrict__ out) {
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (X >= Wo || Y >= Ho) return;
+  const int sx = min(max(X - left, 0), W - 1), sy = min(max(Y - top, 0), H - 1);
+  for (int64_t pl = blockIdx.z; pl < n_planes; pl += gridDim.z)
+    out[pl * Ho * Wo + (int64_t)Y * Wo + X] = __ldg(in + pl * H * W + (int64_t)sy * W + sx);
+}
+
+// bilinear_sampler (model/model_utils.py:7-15): img [N,C,H,W], coords [N,Ho,Wo,2] in pixels, sampled
+// through the reference's normalise / grid_sample(align_corners=True) round trip, zeros outside.
+__global__ void __launch_bounds__(256)
+bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ coords, int N, int C, int H, int W,
+                       int Ho, int Wo, float* __restrict__ out, float* __restrict__ mask_out) {
+  const int64_t per = (int64_t)Ho * Wo, total = (int64_t)N * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / per, r = i - n * per;
+    const float cx = coords[2 * i + 0], cy = coords[2 * i + 1];
+    const float gx = 2.f * cx / (float)(W - 1) - 1.f, gy = 2.f * cy / (float)(H - 1) - 1.f;
+    const float ix = ((gx + 1.f) / 2.f) * (float)(W - 1), iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    Bilin s;
+    s.x0 = (int)fminf(fmaxf(fx0, -2.0e9f), 2.0e9f);
+    s.y0 = (int)fminf(fmaxf(fy0, -2.0e9f), 2.0e9f);
+    const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+    s.nw = (fx1 - ix) * (fy1 - iy);
+    s.ne = (ix - fx0) * (fy1 - iy);
+    s.sw = (fx1 - ix) * (iy - fy0);
+    s.se = (ix - fx0) * (iy - fy0);
+    const bool xin0 = s.x0 >= 0 && s.x0 < W, xin1 = s.x0 + 1 >= 0 && s.x0 + 1 < W;
+    const bool yin0 = s.y0 >= 0 && s.y0 < H, yin1 = s.y0 + 1 >= 0 && s.y0 + 1 < H;
+    const bool finite = (fx0 == fx0) && (fy0 == fy0) && fabsf(fx0) < 1.0e9f && fabsf(fy0) < 1.0e9f;
+    s.in_nw = finite && xin0 && yin0;
+    s.in_ne = finite && xin1 && yin0;
+    s.in_sw = finite && xin0 && yin1;
+    s.in_se = finite && xin1 && yin1;
+    for (int c = 0; c < C; ++c)
+      out[((int64_t)n * C + c) * per + r] = sample(img + ((int64_t)n * C + c) * H * W, s, W);
+    if (mask_out) mask_out[i] = (gx > -1.f && gy > -1.f && gx < 1.f && gy < 1.f) ? 1.f : 0.f;
+  }
+}
+
+}  // namespace
+}  // namespace eem
+
+using namespace eem;
+
+extern "C" {
+
+int eem_backwarp(const float* x, const float* flow, int B, int C, int H, int W, int convention,
+                 int mask_mode, float* out, float* mask_out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(x && flow && out, "eem_backwarp: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "eem_backwarp: sizes must be > 0");
+  EEM_CHECK_ARG(convention == EEM_WARP_EXACT || convention == EEM_WARP_HALFPIX, "eem_backwarp: unknown convention %d", convention);
+  EEM_CHECK_ARG(mask_mode >= EEM_MASK_NONE && mask_mode <= EEM_MASK_9999, "eem_backwarp: unknown mask_mode %d", mask_mode);
+  const int64_t gz = (int64_t)B * ceil_div(C, kWarpChunk);
+  EEM_CHECK_ARG(gz <= 65535, "eem_backwarp: B*ceil(C/%d) = %lld exceeds 65535; split the batch", kWarpChunk, (long long)gz);
+  dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)gz);
+  backwarp_kernel<<<grid, 256, 0, as_stream(stream_)>>>(x, flow, B, C, H, W, convention, mask_mode, out, mask_out);
+  EEM_CHECK_LAUNCH("backwarp_kernel");
+  return EEM_OK;
+}
+
+int eem_warp_blend(const float* flow_init, const float* inter_flow, const float* m, int B, int H,
+                   int W, float* out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(flow_init && inter_flow && m && out, "eem_warp_blend: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && H > 0 && W > 0 && B <= 65535, "eem_warp_blend: bad sizes");
+  EEM_CHECK_ARG(out != flow_init, "eem_warp_blend: out must not alias flow_init (it is gathered from)");
+  dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)B);
+  warp_blend_kernel<<<grid, 256, 0, as_stream(stream_)>>>(flow_init, inter_flow, m, B, H, W, out);
+  EEM_CHECK_LAUNCH("warp_blend_kernel");
+  return EEM_OK;
+}
+
+int eem_bilinear_resize(const float* in, int B, int C, int h, int w, float* out, int H, int W,
+                        int align_corners, float scale0, float scale1, float scale_rest, eem_stream_t stream_) {
+  EEM_CHECK_ARG(in && out, "eem_bilinear_resize: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "eem_bilinear_resize: sizes must be > 0");
+  const int64_t bc = (int64_t)B * C;
+  dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)(bc < 65535 ? bc : 65535));
+  bilinear_resize_kernel<<<grid, 256, 0, as_stream(stream_)>>>(in, B, C, h, w, out, H, W, align_corners ? 1 : 0, scale0, scale1, scale_rest);
+  EEM_CHECK_LAUNCH("bilinear_resize_kernel");
+  return EEM_OK;
+}
+
+int eem_scale_uv_inplace(float* flow, int B, int C, int h, int w, float scale0, float scale1,
+                         eem_stream_t stream_) {
+  EEM_CHECK_ARG(flow != nullptr, "eem_scale_uv_inplace: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && C >= 2 && h > 0 && w > 0, "eem_scale_uv_inplace: need C >= 2 and positive sizes");
+  const int64_t total = (int64_t)B * 2 * h * w;
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > 4096) blocks = 4096;
+  scale_uv_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(flow, B, C, (int64_t)h * w, scale0, scale1);
+  EEM_CHECK_LAUNCH("scale_uv_kernel");
+  return EEM_OK;
+}
+
+int eem_replicate_pad(const float* in, int B, int C, int H, int W, int left, int right, int top,
+                      int bottom, float* out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(in && out, "eem_replicate_pad: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "eem_replicate_pad: sizes must be > 0");
+  EEM_CHECK_ARG(left >= 0 && right >= 0 && top >= 0 && bottom >= 0, "eem_replicate_pad: negative padding");
+  const int Ho = H + top + bottom, Wo = W + left + right;
+  const int64_t planes = (int64_t)B * C;
+  dim3 grid((unsigned)ceil_div(Wo, 32), (unsigned)ceil_div(Ho, 8), (unsigned)(planes < 65535 ? planes : 65535));
+  replicate_pad_kernel<<<grid, 256, 0, as_stream(stream_)>>>(in, planes, H, W, left, top, Ho, Wo, out);
+  EEM_CHECK_LAUNCH("replicate_pad_kernel");
+  return EEM_OK;
+}
+
+int eem_bilinear_sample(const float* img, const float* coords, int N, int C, int H, int W, int Ho, int Wo,
+                        float* out, float* mask_out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(img && coords && out, "eem_bilinear_sample: NULL pointer");
+  EEM_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "eem_bilinear_sample: sizes must be > 0");
+  const int64_t total = (int64_t)N * Ho * Wo;
+  int64_t blocks = ceil_div(total, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (cap > 0 && blocks > cap) blocks = cap;
+  bilinear_sample_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(img, coords, N, C, H, W, Ho, Wo, out, mask_out);
+  EEM_CHECK_LAUNCH("bilinear_sample_kernel");
+  return EEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+"""Drop-in replacements for the reference's event container and voxel encoder.
+
+Mirrors (same names, arguments, return types, assertion behaviour):
+  * EventSequence                    loader/loader_utils.py:352-397 (dup utils_luo/event_utils.py:255-300)
+  * EventSequenceToVoxelGrid_Pytorch utils/transformers.py:18-124 (identical copies in
+                                     utils_luo/event_utils.py:145-253, loader/loader_utils.py:429-537)
+
+The voting and normalisation run in the sm_100a kernels of csrc/voxelize.cu through the C ABI.
+There is no CPU implementation here: with gpu=False the grid is still computed on the GPU and
+only the *returned tensor* is moved to the CPU, which is the device contract of the reference.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy
+import torch
+
+from . import ops
+
+
+class EventSequence(object):
+    """[N,4] float64 (ts, x, y, p) events + sensor size; loader/loader_utils.py:352-397."""
+
+    def __init__(self, dataframe, params, features=None, timestamp_multiplier=None, convert_to_relative=False):
+        if _is_dataframe(dataframe):
+            self.feature_names = dataframe.columns.values
+            self.features = dataframe.to_numpy()
+        else:
+            self.feature_names = numpy.array(['ts', 'x', 'y', 'p'], dtype=object)
+            if features is None:
+                self.features = numpy.zeros([1, 4])
+            else:
+                self.features = features
+        self.image_height = params['height']
+        self.image_width = params['width']
+        if not self.is_sorted():
+            self.sort_by_timestamp()
+        if timestamp_multiplier is not None:
+            self.features[:, 0] *= timestamp_multiplier
+        if convert_to_relative:
+            self.absolute_time_to_relative()
+
+    def get_sequence_only(self):
+        return self.features
+
+    def __len__(self):
+        return len(self.features)
+
+    def __add__(self, sequence):
+        return EventSequence(dataframe=None,
+                             features=numpy.concatenate([self.features, sequence.features]),
+                             params={'height': self.image_height, 'width': self.image_width})
+
+    def is_sorted(self):
+        return numpy.all(self.features[:-1, 0] <= self.features[1:, 0])
+
+    def sort_by_timestamp(self):
+        if len(self.features[:, 0]) > 0:
+            sort_indices = numpy.argsort(self.features[:, 0])
+            self.features = self.features[sort_indices]
+
+    def absolute_time_to_relative(self):
+        """Transforms absolute time to time relative to the first event."""
+        start_ts = self.features[:, 0].min()
+        assert (start_ts == self.features[0, 0])
+        self.features[:, 0] -= start_ts
+
+
+def _is_dataframe(obj) -> bool:
+    try:
+        import pandas
+    except ImportError:  # pandas is optional: only the DataFrame constructor path needs it
+        return False
+    return isinstance(obj, pandas.DataFrame)
+
+
+def _upload_events(arrays: Sequence[numpy.ndarray], device: torch.device):
+    """Concatenate [N_i,4] float64 windows in pinned host memory and copy them to the device."""
+    counts = [int(a.shape[0]) for a in arrays]
+    total = sum(counts)
+    host = torch.empty((total, 4), dtype=torch.float64, pin_memory=True)
+    pos = 0
+    for a, n in zip(arrays, counts):
+        host[pos:pos + n].numpy()[...] = a  # astype('float') + from_numpy of the reference, in one copy
+        pos += n
+    offsets = torch.zeros(len(arrays) + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(torch.tensor(counts, dtype=torch.int64), 0)
+    ev = host.to(device, non_blocking=True)
+    off = offsets.pin_memory().to(device, non_blocking=True)
+    return ev, off, max(counts) if counts else 0
+
+
+class EventSequenceToVoxelGrid_Pytorch(object):
+    """Time-bilinear polarity voxel grid; signature of utils/transformers.py:20.
+
+    Extra keyword arguments (all optional, defaults keep the reference behaviour):
+      deterministic  sort-by-voxel mode, bit-exact against the reference's CPU result
+      strict         raise IndexError (after a sync) if a vote fell outside the grid, like the
+                     reference's index_add_ does
+      compute_device CUDA device the kernels run on when gpu=False (default cuda:gpu_nr)
+    """
+
+    def __init__(self, num_bins, gpu=False, gpu_nr=0, normalize=True, forkserver=True,
+                 deterministic=False, strict=False, compute_device=None):
+        if forkserver:
+            try:
+                torch.multiprocessing.set_start_method('forkserver')
+            except RuntimeError:
+                pass
+        self.num_bins = num_bins
+        self.normalize = normalize
+        self.deterministic = deterministic
+        self.strict = strict
+        self.compute_device = torch.device(compute_device if compute_device is not None else 'cuda:' + str(gpu_nr))
+        if gpu:
+            self.device = torch.device('cuda:' + str(gpu_nr))
+        else:
+            self.device = torch.device('cpu')
+
+    def __call__(self, event_sequence):
+        """event_sequence.features: [N x 4] NumPy array, rows [timestamp, x, y, polarity] -> float32 [bins,H,W]."""
+        return self.voxelize_batch([event_sequence])[0]
+
+    def voxelize_batch(self, event_sequences):
+        """Voxelize several windows of the same sensor size in one launch -> [n, bins, H, W]."""
+        assert len(event_sequences) > 0
+        width = event_sequences[0].image_width
+        height = event_sequences[0].image_height
+        arrays = []
+        for seq in event_sequences:
+            events = seq.features
+            assert (events.shape[1] == 4)
+            assert seq.image_width == width and seq.image_height == height
+            if events.shape[0] == 0:
+                raise IndexError("index -1 is out of bounds for dimension 0 with size 0")  # events_torch[-1, 0]
+            arrays.append(events)
+        assert (self.num_bins > 0)
+        assert (width > 0)
+        assert (height > 0)
+        with torch.no_grad():
+            ev, off, max_n = _upload_events(arrays, self.compute_device)
+            dropped = torch.zeros(1, dtype=torch.int64, device=self.compute_device) if self.strict else None
+            grid = ops.voxelize(ev, off, max_n, self.num_bins, height, width, normalize=self.normalize,
+                                deterministic=self.deterministic, dropped=dropped)
+            if self.strict and int(dropped.item()) != 0:
+                raise IndexError(f"index out of range in self ({int(dropped.item())} votes fell outside the voxel grid)")
+        if grid.device != self.device:
+            grid = grid.to(self.device)
+        return grid

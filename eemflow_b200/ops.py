@@ -1,0 +1,245 @@
+"""Functional torch-tensor front end of the C ABI (one function per kernel family).
+
+Every function takes CUDA tensors, allocates the output with torch (caller-owned memory, as the
+ABI requires), launches on torch's current stream and returns without synchronising.  The
+reference-shaped classes in event_utils.py / corr.py / correlation.py / warp.py are thin
+wrappers over these.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _dev(t: torch.Tensor) -> torch.device:
+    return t.device
+
+
+# ------------------------------------------------------------------------------------------ K1/K2
+def voxelize(events: torch.Tensor, offsets: torch.Tensor, max_events: int, num_bins: int, height: int,
+             width: int, *, normalize: bool = True, deterministic: bool = False,
+             dropped: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Voxelize concatenated event windows.
+
+    events  : CUDA float64 [N, 4] rows (ts, x, y, p)  -- the reference's EventSequence.features layout
+    offsets : CUDA int64 [n_windows + 1]
+    returns : CUDA float32 [n_windows, num_bins, height, width]
+    Follows utils/transformers.py:56-122 per window.
+    """
+    assert events.dim() == 2 and events.shape[1] == 4, "events must be [N, 4]"
+    assert num_bins > 0
+    assert width > 0
+    assert height > 0
+    assert events.dtype == torch.float64, "Timestamps must be float64!"
+    events = L.require_cuda(events, "events", torch.float64)
+    offsets = L.require_cuda(offsets, "offsets", torch.int64)
+    dev = _dev(events)
+    n_windows = offsets.numel() - 1
+    n_total = events.shape[0]
+    if out is None:
+        out = torch.empty((n_windows, num_bins, height, width), dtype=torch.float32, device=dev)
+    else:
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+        assert out.numel() == n_windows * num_bins * height * width
+    lib = L.lib()
+    mode = L.VOXEL_DETERMINISTIC if deterministic else L.VOXEL_ATOMIC
+    with torch.cuda.device(dev):
+        ws_bytes = lib.eem_voxelize_workspace_bytes(n_total, n_windows, num_bins, height, width, mode)
+        ws = L.workspace.get(dev, ws_bytes, "voxel")
+        L.check(lib.eem_voxelize(events.data_ptr(), offsets.data_ptr(), n_windows, n_total, int(max_events),
+                                 num_bins, height, width, mode, out.data_ptr(), L.ptr(dropped),
+                                 L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
+        if normalize:
+            voxel_normalize_(out)
+    return out
+
+
+def voxel_normalize_(grid: torch.Tensor, stats_out: torch.Tensor | None = None) -> torch.Tensor:
+    """In-place non-zero mean/std normalisation of [n_windows, ...] grids (utils/transformers.py:114-122)."""
+    grid = L.require_cuda(grid, "grid")
+    dev = _dev(grid)
+    n_windows = grid.shape[0]
+    vox = grid.numel() // max(n_windows, 1)
+    lib = L.lib()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.eem_voxel_normalize_workspace_bytes(n_windows, vox)
+        ws = L.workspace.get(dev, ws_bytes, "norm")
+        L.check(lib.eem_voxel_normalize(grid.data_ptr(), n_windows, vox, L.ptr(stats_out), L.ptr(ws), ws_bytes,
+                                        L.stream_ptr(dev)))
+    return grid
+
+
+# ------------------------------------------------------------------------------------------ K3/K4
+def pyramid_level_shapes(h: int, w: int, num_levels: int) -> list[tuple[int, int]]:
+    shapes = []
+    for _ in range(num_levels):
+        shapes.append((h, w))
+        h, w = h // 2, w // 2
+    return shapes
+
+
+def corr_pyramid(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4, *, precision: str = "tf32",
+                 out: Sequence[torch.Tensor] | None = None) -> list[torch.Tensor]:
+    """All-pairs correlation pyramid (model/corr.py:13-27): list of [B*H*W, 1, H_l, W_l] float32."""
+    fmap1 = L.require_cuda(fmap1, "fmap1")
+    fmap2 = L.require_cuda(fmap2, "fmap2")
+    assert fmap1.shape == fmap2.shape and fmap1.dim() == 4
+    B, D, H, W = fmap1.shape
+    dev = _dev(fmap1)
+    shapes = pyramid_level_shapes(H, W, num_levels)
+    if out is None:
+        out = [torch.empty((B * H * W, 1, h, w), dtype=torch.float32, device=dev) for (h, w) in shapes]
+    prec = {"fp32": L.CORR_FP32, "tf32": L.CORR_TF32}[precision]
+    lib = L.lib()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.eem_corr_pyramid_workspace_bytes(B, D, H, W, num_levels)
+        ws = L.workspace.get(dev, ws_bytes, "corr")
+        L.check(lib.eem_corr_pyramid(fmap1.data_ptr(), fmap2.data_ptr(), B, D, H, W, num_levels, L.ptr_array(out),
+                                     prec, L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
+    return list(out)
+
+
+def tf32_supported(D: int, H: int, W: int) -> bool:
+    """Shapes the tcgen05 path takes (others use the fp32 kernel): see eem_corr_pyramid."""
+    return (H * W) % 4 == 0 and D % 32 == 0 and D <= 256
+
+
+def avg_pool2x2(x: torch.Tensor) -> torch.Tensor:
+    """F.avg_pool2d(x, 2, stride=2) for [N, C, h, w] (model/corr.py:25-27)."""
+    x = L.require_cuda(x, "x")
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, h // 2, w // 2), dtype=torch.float32, device=x.device)
+    if out.numel():
+        with torch.cuda.device(x.device):
+            L.check(L.lib().eem_avg_pool2x2(x.data_ptr(), n * c, h, w, out.data_ptr(), L.stream_ptr(x.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K5
+def corr_lookup(pyramid: Sequence[torch.Tensor], coords: torch.Tensor, radius: int = 4,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """CorrBlock.__call__ (model/corr.py:29-50): coords [B,2,H,W] -> [B, L*(2r+1)^2, H, W]."""
+    coords = L.require_cuda(coords, "coords")
+    B, two, H, W = coords.shape
+    assert two == 2
+    num_levels = len(pyramid)
+    for lvl in pyramid:
+        if lvl.numel():
+            assert lvl.is_cuda and lvl.dtype == torch.float32 and lvl.is_contiguous()
+    assert pyramid[0].shape[0] == B * H * W, "pyramid does not match coords"
+    k = (2 * radius + 1) ** 2
+    if out is None:
+        out = torch.empty((B, num_levels * k, H, W), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        L.check(L.lib().eem_corr_lookup(L.ptr_array(pyramid), B, H, W, num_levels, radius, coords.data_ptr(),
+                                        out.data_ptr(), L.stream_ptr(coords.device)))
+    return out
+
+
+def bilinear_sample(img: torch.Tensor, coords: torch.Tensor, mask: bool = False):
+    """bilinear_sampler (model/model_utils.py:7-21): img [N,C,H,W], coords [N,Ho,Wo,2] pixels -> [N,C,Ho,Wo]."""
+    img = L.require_cuda(img, "img")
+    coords = L.require_cuda(coords, "coords")
+    N, Cc, H, W = img.shape
+    n2, Ho, Wo, two = coords.shape
+    assert n2 == N and two == 2
+    out = torch.empty((N, Cc, Ho, Wo), dtype=torch.float32, device=img.device)
+    m = torch.empty((N, Ho, Wo, 1), dtype=torch.float32, device=img.device) if mask else None
+    with torch.cuda.device(img.device):
+        L.check(L.lib().eem_bilinear_sample(img.data_ptr(), coords.data_ptr(), N, Cc, H, W, Ho, Wo, out.data_ptr(),
+                                            L.ptr(m), L.stream_ptr(img.device)))
+    return (out, m) if mask else out
+
+
+# ------------------------------------------------------------------------------------------ K6
+def local_corr(f1: torch.Tensor, f2: torch.Tensor, max_disp: int = 4, index: Sequence[int] | None = None,
+               scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Local (2*md+1)^2 correlation, optional fused channel select and scale -> [B, n_out, H, W]."""
+    f1 = L.require_cuda(f1, "f1")
+    f2 = L.require_cuda(f2, "f2")
+    assert f1.shape == f2.shape and f1.dim() == 4
+    B, Cc, H, W = f1.shape
+    nd = (2 * max_disp + 1) ** 2
+    if index is None:
+        n_out, idx = nd, None
+    else:
+        n_out = len(index)
+        idx = (C.c_int * n_out)(*[int(v) for v in index])
+    if out is None:
+        out = torch.empty((B, n_out, H, W), dtype=torch.float32, device=f1.device)
+    with torch.cuda.device(f1.device):
+        L.check(L.lib().eem_local_corr(f1.data_ptr(), f2.data_ptr(), B, Cc, H, W, max_disp, idx, n_out,
+                                       float(scale), out.data_ptr(), L.stream_ptr(f1.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K7
+def backwarp(x: torch.Tensor, flow: torch.Tensor, convention: int, mask_mode: int = L.MASK_NONE,
+             return_mask: bool = False):
+    x = L.require_cuda(x, "x")
+    flow = L.require_cuda(flow, "flow")
+    B, Cc, H, W = x.shape
+    assert flow.shape == (B, 2, H, W), f"flow must be [B,2,H,W] matching x, got {tuple(flow.shape)}"
+    out = torch.empty_like(x)
+    mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device) if return_mask else None
+    with torch.cuda.device(x.device):
+        L.check(L.lib().eem_backwarp(x.data_ptr(), flow.data_ptr(), B, Cc, H, W, convention, mask_mode,
+                                     out.data_ptr(), L.ptr(mask), L.stream_ptr(x.device)))
+    return (out, mask) if return_mask else out
+
+
+def warp_blend(flow_init: torch.Tensor, inter_flow: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """torch_warp(flow_init, inter_flow) * (1 - mask) + flow_init * mask  (cdc_utils.py:173)."""
+    flow_init = L.require_cuda(flow_init, "flow_init")
+    inter_flow = L.require_cuda(inter_flow, "inter_flow")
+    mask = L.require_cuda(mask, "mask")
+    B, two, H, W = flow_init.shape
+    assert two == 2 and inter_flow.shape == flow_init.shape and mask.shape == (B, 1, H, W)
+    out = torch.empty_like(flow_init)
+    with torch.cuda.device(flow_init.device):
+        L.check(L.lib().eem_warp_blend(flow_init.data_ptr(), inter_flow.data_ptr(), mask.data_ptr(), B, H, W,
+                                       out.data_ptr(), L.stream_ptr(flow_init.device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K8/K9
+def bilinear_resize(x: torch.Tensor, size: tuple[int, int], align_corners: bool, scale0: float = 1.0,
+                    scale1: float = 1.0, scale_rest: float = 1.0) -> torch.Tensor:
+    x = L.require_cuda(x, "x")
+    B, Cc, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().eem_bilinear_resize(x.data_ptr(), B, Cc, h, w, out.data_ptr(), H, W, int(bool(align_corners)),
+                                            float(scale0), float(scale1), float(scale_rest), L.stream_ptr(x.device)))
+    return out
+
+
+def scale_uv_(flow: torch.Tensor, scale0: float, scale1: float) -> torch.Tensor:
+    assert flow.is_cuda and flow.dtype == torch.float32 and flow.is_contiguous()
+    B, Cc, h, w = flow.shape
+    with torch.cuda.device(flow.device):
+        L.check(L.lib().eem_scale_uv_inplace(flow.data_ptr(), B, Cc, h, w, float(scale0), float(scale1),
+                                             L.stream_ptr(flow.device)))
+    return flow
+
+
+def replicate_pad(x: torch.Tensor, pad: Sequence[int]) -> torch.Tensor:
+    """F.pad(x, [left, right, top, bottom], mode='replicate') for [B,C,H,W]."""
+    x = L.require_cuda(x, "x")
+    B, Cc, H, W = x.shape
+    left, right, top, bottom = (int(v) for v in pad)
+    out = torch.empty((B, Cc, H + top + bottom, W + left + right), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().eem_replicate_pad(x.data_ptr(), B, Cc, H, W, left, right, top, bottom, out.data_ptr(),
+                                          L.stream_ptr(x.device)))
+    return out
+
+
+def inv_sqrt_dim(d: int) -> float:
+    return 1.0 / math.sqrt(float(d))

@@ -1,0 +1,114 @@
+"""Drop-ins for the reference's backward-warp, flow-resize and padding helpers.
+
+Mirrors (names and argument meaning kept; every quirk of the sampling conventions kept, see
+SURVEY.md section 0 trap 5):
+  * warp(x, flo)                        EEMFlow_cdc.warp           model/EEMFlow/EEMFlow+.py:137-149
+  * tensor_tools.torch_warp(x, flo)     utils_luo/tools.py:2262-2306
+  * tensor_tools.torch_warp_mask(x,flo) utils_luo/tools.py:2217-2259
+  * WarpingLayer_no_div()(x, flow)      model/EEMFlow/cdc_utils.py:50-78
+  * upsample2d_flow_as(inputs, target_as, mode, if_rate)   model/EEMFlow/cdc_utils.py:80-103
+  * upsample_flow(flow, orig_size)      EEMFlow.upsample_flow      model/EEMFlow/EEMFlow.py:118-120
+  * cdc_blend(flow_init, inter_flow, inter_mask)           model/EEMFlow/cdc_utils.py:173
+  * InputPadder                         utils/image_utils.py:126-145
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+
+def warp(x, flo):
+    """Bilinear sample of x at (px+u, py+v), zeros outside, exact pixel positions (align_corners=True)."""
+    with torch.no_grad():
+        return ops.backwarp(x, flo, L.WARP_EXACT)
+
+
+class tensor_tools:
+    """The two classmethods of utils_luo/tools.py::tensor_tools that sit on the hot path."""
+
+    @classmethod
+    def torch_warp(cls, x, flo):
+        """warp an image/tensor (im2) back to im1, according to the optical flow; x [B,C,H,W], flo [B,2,H,W].
+
+        Keeps the reference's convention: (W-1) normalisation + grid_sample's default
+        align_corners=False, i.e. the sample lands at px'*W/(W-1) - 0.5.
+        """
+        with torch.no_grad():
+            return ops.backwarp(x, flo, L.WARP_HALFPIX)
+
+    @classmethod
+    def torch_warp_mask(cls, x, flo):
+        with torch.no_grad():
+            out, mask = ops.backwarp(x, flo, L.WARP_HALFPIX, mask_mode=L.MASK_9999, return_mask=True)
+        return out, mask.expand_as(out)
+
+
+torch_warp = tensor_tools.torch_warp
+torch_warp_mask = tensor_tools.torch_warp_mask
+
+
+class WarpingLayer_no_div(nn.Module):
+    def __init__(self):
+        super(WarpingLayer_no_div, self).__init__()
+
+    def forward(self, x, flow):
+        with torch.no_grad():
+            return ops.backwarp(x, flow, L.WARP_HALFPIX, mask_mode=L.MASK_GE1)
+
+
+def upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate=False):
+    """Resize `inputs` to target_as's spatial size (align_corners=True); with if_rate scale u by w/w_ and
+    v by h/h_ -- and, like the reference (cdc_utils.py:85-86), scale `inputs` itself IN PLACE."""
+    if mode != "bilinear":
+        raise NotImplementedError("eemflow_b200.upsample2d_flow_as implements mode='bilinear' only")
+    _, _, h, w = target_as.shape
+    with torch.no_grad():
+        if if_rate:
+            _, _, h_, w_ = inputs.shape
+            u_scale, v_scale = (w / w_), (h / h_)
+            res = ops.bilinear_resize(inputs, (h, w), align_corners=True, scale0=u_scale, scale1=v_scale)
+            if inputs.is_contiguous() and inputs.dtype == torch.float32:
+                ops.scale_uv_(inputs, u_scale, v_scale)
+            else:  # keep the side effect for exotic views as well
+                inputs[:, 0, :, :] *= u_scale
+                inputs[:, 1, :, :] *= v_scale
+            return res
+        return ops.bilinear_resize(inputs, (h, w), align_corners=True)
+
+
+def upsample_flow(flow, orig_size):
+    """Meshflow -> dense flow: bilinear, align_corners=False, no magnitude rescale."""
+    with torch.no_grad():
+        return ops.bilinear_resize(flow, tuple(orig_size), align_corners=False)
+
+
+def cdc_blend(flow_init, inter_flow, inter_mask):
+    """torch_warp(flow_init, inter_flow) * (1 - inter_mask) + flow_init * inter_mask, fused."""
+    with torch.no_grad():
+        return ops.warp_blend(flow_init, inter_flow, inter_mask)
+
+
+class InputPadder:
+    """ Pads images such that dimensions are divisible by eval_pad_rate (replicate padding) """
+
+    def __init__(self, dims, mode='sintel', eval_pad_rate=32):
+        self.eval_pad_rate = eval_pad_rate
+        self.ht, self.wd = dims[-2:]
+        pad_ht = (((self.ht // eval_pad_rate) + 1) * eval_pad_rate - self.ht) % eval_pad_rate
+        pad_wd = (((self.wd // eval_pad_rate) + 1) * eval_pad_rate - self.wd) % eval_pad_rate
+        if mode == 'sintel':
+            self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, pad_ht // 2, pad_ht - pad_ht // 2]
+        else:
+            self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, 0, pad_ht]
+
+    def pad(self, *inputs):
+        with torch.no_grad():
+            return [ops.replicate_pad(x, self._pad) for x in inputs]
+
+    def unpad(self, x):
+        ht, wd = x.shape[-2:]
+        c = [self._pad[2], ht - self._pad[3], self._pad[0], wd - self._pad[1]]
+        return x[..., c[0]:c[1], c[2]:c[3]]

@@ -1,0 +1,196 @@
+/*
+ * eemflow_b200.h -- C ABI of libeemflow_b200.so
+ *
+ * B200 (sm_100a) kernels for the data-parallel hot path of boomluo02/EEMFlow:
+ * event voxelization -> correlation (all-pairs pyramid + local 9x9) -> window
+ * lookup -> backward warp / flow upsampling.  Every entry point takes raw DEVICE
+ * pointers, plain sizes and a CUDA stream; the caller owns all memory (inputs,
+ * outputs and workspaces).  Nothing here allocates, frees or retains memory,
+ * and nothing synchronises the stream.  All functions return 0 on success and
+ * a negative eem_status otherwise; eem_last_error_string() describes the last
+ * failure on the calling thread.
+ *
+ * The "replaces" notes cite the reference (paths relative to the EEMFlow tree)
+ * so a maintainer can see which Python/ATen code each call stands in for.
+ * INTEGRATION.md shows the ctypes binding used by the Python drop-in classes.
+ */
+#ifndef EEMFLOW_B200_H_
+#define EEMFLOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EEM_API __attribute__((visibility("default")))
+#else
+#define EEM_API
+#endif
+
+/* cudaStream_t / CUstream, passed as an opaque pointer (NULL = legacy default stream). */
+typedef void* eem_stream_t;
+
+enum eem_status {
+  EEM_OK = 0,
+  EEM_ERR_BAD_ARG = -1,       /* non-positive size, NULL pointer, unsupported flag       */
+  EEM_ERR_MISALIGNED = -2,    /* pointer not aligned as documented                       */
+  EEM_ERR_WORKSPACE = -3,     /* workspace NULL or smaller than *_workspace_bytes()      */
+  EEM_ERR_CUDA = -4,          /* CUDA runtime/driver error (message holds the CUDA text) */
+  EEM_ERR_UNSUPPORTED = -5    /* shape outside what the kernel family implements         */
+};
+
+EEM_API int eem_version(void);
+EEM_API const char* eem_last_error_string(void);
+/* Number of SMs of the current device (used by callers to size benches); <0 on error. */
+EEM_API int eem_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  event voxelization (time-bilinear polarity voting)
+ * replaces: utils/transformers.py:56-112 (EventSequenceToVoxelGrid_Pytorch.__call__, voting
+ *           part; identical copies utils_luo/event_utils.py:185-241, loader/loader_utils.py:469-525)
+ *
+ * events : [n_total, 4] float64 rows (ts, x, y, p) exactly as EventSequence.features holds them,
+ *          32-byte aligned.  Windows are concatenated; window w owns rows
+ *          [offsets[w], offsets[w+1]).  offsets is a DEVICE array of n_windows+1 int64.
+ * grid   : [n_windows, num_bins, height, width] float32.  The call zero-fills it first.
+ * mode   : EEM_VOXEL_ATOMIC        fp32 red.global.add, order of adds not defined
+ *          EEM_VOXEL_DETERMINISTIC stable sort by voxel, sequential fp32 adds in the reference's
+ *                                  order (all "left" votes in event order, then all "right"
+ *                                  votes): bit-exact against the CPU reference.
+ * max_events_per_window : host-side upper bound of offsets[w+1]-offsets[w] (sizes the launch).
+ * dropped : optional DEVICE int64 counter (may be NULL); incremented once per vote whose flat
+ *           index x + y*W + bin*W*H falls outside the grid (the reference raises IndexError
+ *           there).  In-range flat indices are voted exactly like the reference, including its
+ *           row wrap-around for x >= width.
+ * ------------------------------------------------------------------------------------------ */
+enum { EEM_VOXEL_ATOMIC = 0, EEM_VOXEL_DETERMINISTIC = 1 };
+
+EEM_API size_t eem_voxelize_workspace_bytes(int64_t n_total, int n_windows, int num_bins,
+                                            int height, int width, int mode);
+EEM_API int eem_voxelize(const double* events, const int64_t* offsets, int n_windows,
+                         int64_t n_total, int64_t max_events_per_window, int num_bins,
+                         int height, int width, int mode, float* grid, int64_t* dropped,
+                         void* workspace, size_t workspace_bytes, eem_stream_t stream);
+
+/* K2  voxel-grid normalisation: per window, mean / unbiased std over the NON-ZERO voxels, then
+ *     v = (v - mean) / std on the non-zero voxels (v - mean when !(std > 0), which includes the
+ *     NaN std of a single non-zero voxel).  In place.
+ * replaces: utils/transformers.py:114-122
+ * stats_out: optional DEVICE [n_windows, 3] float64 (count, mean, std) for inspection; may be NULL. */
+EEM_API size_t eem_voxel_normalize_workspace_bytes(int n_windows, int64_t voxels_per_window);
+EEM_API int eem_voxel_normalize(float* grid, int n_windows, int64_t voxels_per_window,
+                                double* stats_out, void* workspace, size_t workspace_bytes,
+                                eem_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  all-pairs correlation pyramid
+ * replaces: model/corr.py:13-27 (CorrBlock.__init__) and :52-60 (CorrBlock.corr)
+ *
+ * fmap1, fmap2 : [B, D, H, W] float32 contiguous (NCHW), 16-byte aligned.
+ * levels[l]    : DEVICE pointer to level l, [B*H*W, H_l*W_l] float32 with H_0=H, W_0=W and
+ *                H_{l+1} = H_l/2, W_{l+1} = W_l/2 (floor), l < num_levels (<= 8).  `levels` itself
+ *                is a HOST array of num_levels device pointers.  A level with H_l*W_l == 0 is skipped.
+ *     level_l[b*P + i, j] = (1/sqrt(D)) * sum_d fmap1[b,d,i] * pool^l(fmap2)[b,d,j]
+ *   which equals avg_pool2d(2,2) applied l times to level 0 (pooling is linear and acts on j only).
+ * precision    : EEM_CORR_FP32  CUDA-core fp32 FMA (<= 1e-5 abs against the reference)
+ *                EEM_CORR_TF32  tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators
+ * ------------------------------------------------------------------------------------------ */
+enum { EEM_CORR_FP32 = 0, EEM_CORR_TF32 = 1 };
+
+EEM_API size_t eem_corr_pyramid_workspace_bytes(int B, int D, int H, int W, int num_levels);
+EEM_API int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W,
+                             int num_levels, float* const* levels, int precision,
+                             void* workspace, size_t workspace_bytes, eem_stream_t stream);
+
+/* K4  avg_pool2d(kernel 2, stride 2, floor) over planes: in [n_planes, h, w] -> out [n_planes, h/2, w/2].
+ * replaces: model/corr.py:25-27 when a caller pools an existing volume itself. */
+EEM_API int eem_avg_pool2x2(const float* in, int64_t n_planes, int h, int w, float* out,
+                            eem_stream_t stream);
+
+/* K5  multi-level (2r+1)^2 bilinear window lookup
+ * replaces: model/corr.py:29-50 (CorrBlock.__call__) + model/model_utils.py:7-15 (bilinear_sampler)
+ *
+ * levels : HOST array of num_levels DEVICE pointers laid out as K3 writes them.
+ * coords : [B, 2, H, W] float32 (channel 0 = x, channel 1 = y), pixel units of level 0.
+ * out    : [B, num_levels*(2r+1)^2, H, W] float32 contiguous;
+ *          channel l*(2r+1)^2 + a*(2r+1) + b samples level l at (x/2^l + a - r, y/2^l + b - r)
+ *          (the reference's transposed window: a moves x, b moves y), zeros outside the map. */
+EEM_API int eem_corr_lookup(const float* const* levels, int B, int H, int W, int num_levels,
+                            int radius, const float* coords, float* out, eem_stream_t stream);
+
+/* K5b generic pixel-coordinate bilinear sampler
+ * replaces: bilinear_sampler (model/model_utils.py:7-21) = normalise with (S-1) + F.grid_sample(align_corners=True)
+ * img [N,C,H,W], coords [N,Ho,Wo,2] (x, y) in pixels -> out [N,C,Ho,Wo]; mask_out (optional, [N,Ho,Wo,1])
+ * is the reference's strict-interior mask (model_utils.py:17-19). */
+EEM_API int eem_bilinear_sample(const float* img, const float* coords, int N, int C, int H, int W,
+                                int Ho, int Wo, float* out, float* mask_out, eem_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  local (2*max_disp+1)^2 correlation with fused 1/C and fused channel selection
+ * replaces: spatial_correlation_sampler.SpatialCorrelationSampler(1, 9, 1, 0, 1) as called from
+ *           model/EEMFlow/EEMFlow.py:14-23 / EEMFlow+.py:16-25, the "/ c" there, and the
+ *           torch.index_select that follows (EEMFlow.py:160, EEMFlow+.py:178,190,202,214,226)
+ *
+ * f1, f2 : [B, C, H, W] float32.
+ * out    : [B, n_out, H, W];  out[b,k,y,x] = scale * sum_c f1[b,c,y,x] * f2[b,c,y+dy,x+dx]
+ *          with channel id ch = (dy+md)*(2md+1) + (dx+md), zero outside f2;
+ *          index == NULL: n_out must be (2md+1)^2 and k = ch; else ch = index[k] (HOST array).
+ * scale  : 1.0f for the raw sampler output, 1.0f/C for Correlation.forward. */
+EEM_API int eem_local_corr(const float* f1, const float* f2, int B, int C, int H, int W,
+                           int max_disp, const int* index, int n_out, float scale, float* out,
+                           eem_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7  backward warp (bilinear, zero padding)
+ * replaces: EEMFlow_cdc.warp (model/EEMFlow/EEMFlow+.py:137-149)          -> EEM_WARP_EXACT
+ *           tensor_tools.torch_warp (utils_luo/tools.py:2262-2306)         -> EEM_WARP_HALFPIX
+ *           WarpingLayer_no_div.forward (model/EEMFlow/cdc_utils.py:50-78) -> EEM_WARP_HALFPIX + EEM_MASK_GE1
+ *           tensor_tools.torch_warp_mask (utils_luo/tools.py:2217-2259)    -> EEM_WARP_HALFPIX + EEM_MASK_9999
+ *
+ * Both conventions normalise with (W-1): g = 2*(px+u)/max(W-1,1) - 1.  EXACT un-normalises with
+ * align_corners=True ((g+1)/2*(W-1)); HALFPIX with align_corners=False (((g+1)*W-1)/2), i.e.
+ * the reference's effective sample position px'*W/(W-1) - 0.5.
+ * x    : [B, C, H, W], flow : [B, 2, H, W] (u, v), out : [B, C, H, W].
+ * mask_out : optional [B, 1, H, W] receiving the 0/1 validity mask (may be NULL). */
+enum { EEM_WARP_EXACT = 0, EEM_WARP_HALFPIX = 1 };
+enum { EEM_MASK_NONE = 0, EEM_MASK_GE1 = 1, EEM_MASK_9999 = 2 };
+
+EEM_API int eem_backwarp(const float* x, const float* flow, int B, int C, int H, int W,
+                         int convention, int mask_mode, float* out, float* mask_out,
+                         eem_stream_t stream);
+
+/* K7b fused CDC blend: out = warp_HALFPIX(flow_init, inter_flow) * (1 - m) + flow_init * m
+ * replaces: model/EEMFlow/cdc_utils.py:173.  flow_init, inter_flow, out: [B,2,H,W]; m: [B,1,H,W]. */
+EEM_API int eem_warp_blend(const float* flow_init, const float* inter_flow, const float* m,
+                           int B, int H, int W, float* out, eem_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K8  bilinear resize of flow / meshflow maps
+ * replaces: upsample2d_flow_as (model/EEMFlow/cdc_utils.py:80-103; utils_luo/tools.py:3215-3229)
+ *             -> align_corners = 1, scale0 = W/w, scale1 = H/h when if_rate else 1
+ *           EEMFlow.upsample_flow (model/EEMFlow/EEMFlow.py:118-120), HREM ground-truth upsample
+ *           (loader/HREM.py:264-268), upflow8 (model/model_utils.py:30-32)
+ *             -> align_corners = 0 (resp. 1 with scale 8)
+ * in : [B, C, h, w] -> out : [B, C, H, W]; channel 0 is multiplied by scale0, channel 1 by
+ * scale1, further channels by scale_rest. */
+EEM_API int eem_bilinear_resize(const float* in, int B, int C, int h, int w, float* out, int H,
+                                int W, int align_corners, float scale0, float scale1,
+                                float scale_rest, eem_stream_t stream);
+
+/* In-place per-channel scale of channels 0 and 1 of [B, C, h, w]; reproduces the side effect of
+ * upsample2d_flow_as(if_rate=True) on its input (model/EEMFlow/cdc_utils.py:85-86). */
+EEM_API int eem_scale_uv_inplace(float* flow, int B, int C, int h, int w, float scale0,
+                                 float scale1, eem_stream_t stream);
+
+/* K9  replicate padding.  replaces: InputPadder.pad (utils/image_utils.py:126-139, F.pad 'replicate')
+ * in [B,C,H,W] -> out [B,C,H+top+bottom,W+left+right]. */
+EEM_API int eem_replicate_pad(const float* in, int B, int C, int H, int W, int left, int right,
+                              int top, int bottom, float* out, eem_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEMFLOW_B200_H_ */

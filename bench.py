@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""Benchmark of the EEMFlow hot path on B200: frame-pairs/s for voxelize + corr + lookup + warp.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" is one pass of the hot path over one batch of synthetic frame pairs, BASELINE.json
+configs[1] (MVSEC dt1 shape) per GPU:
+  * 2*B event windows (260x346, 30 000 events each, [N,4] float64 rows) -> 5-bin voxel grids, normalised
+  * CorrBlock on [B,256,36,44] feature maps: 4-level all-pairs pyramid (TF32 tcgen05) + `lookups`
+    (default 12 = ERAFT's iterations, model/eraft.py:140) radius-4 window lookups
+  * the EEMFlow_cdc op sequence on its 5 pyramid levels at the padded 320x384 size: local 9x9
+    correlation (53 kept channels), upsample2d_flow_as, WarpingLayer_no_div, CDC blend, warp, and the 5
+    final flow upsamples to 260x346 (model/EEMFlow/EEMFlow+.py:158-234 without the cuDNN convs)
+Weak scaling: every rank processes its own B pairs (independent units, no data-path collective);
+at N > 1 the per-step result flows are all-gathered over NCCL and a metric accumulator all-reduced.
+
+`value` times device-resident inputs with CUDA events; `e2e` runs the same step through the public
+reference-shaped API from HOST buffers (numpy events, pinned feature maps) including H2D and D2H.
+`--impl reference` times the CPU oracle port (the reference's own ATen calls, all host threads) on
+a bounded sample of the same workload.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+H, W, NB = 260, 346, 5                 # MVSEC sensor, a_meshflow / mvsec configs use 5 bins
+EVENTS_PER_WINDOW = 30_000             # MVSEC dt1
+FH, FW, FD = 36, 44, 256               # ERAFT feature map of the 288x352 padded input
+LEVELS, RADIUS = 4, 4
+# EEMFlow_cdc pyramid (C, h, w) for the 320x384 padded MVSEC input, coarse -> fine
+EEM_LEVELS = [(64, 5, 6), (64, 10, 12), (64, 20, 24), (64, 40, 48), (32, 80, 96)]
+# the 53 correlation channels EEMFlow_cdc keeps (model/EEMFlow/EEMFlow+.py:89-97)
+EEMFLOW_CDC_INDEX = [0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 21, 22, 23, 24, 26, 28, 29, 30, 31, 32, 33, 34, 36, 38, 39, 40,
+                     41, 42, 44, 46, 47, 48, 49, 50, 51, 52, 54, 56, 57, 58, 59, 60, 62, 64, 66, 68, 70, 72, 74, 76, 78, 80]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frame pairs per GPU per step")
+    ap.add_argument("--lookups", type=int, default=12, help="CorrBlock lookups per pair (ERAFT iterations)")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="frame pairs per CPU-baseline sample step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs (seeded)
+# ------------------------------------------------------------------------------------------------
+def make_events(rng, n, h, w):
+    t = np.sort(rng.uniform(0.0, 0.05, size=n)) * 1e6
+    t -= t[0]
+    return np.stack([t, rng.integers(0, w, size=n).astype(np.float64), rng.integers(0, h, size=n).astype(np.float64),
+                     2.0 * rng.integers(0, 2, size=n) - 1.0], axis=1)
+
+
+def make_host_inputs(B: int, lookups: int, seed: int, pin: bool):
+    rng = np.random.default_rng(seed)
+    g = torch.Generator().manual_seed(seed)
+
+    def t(*shape, scale=1.0):
+        x = torch.randn(*shape, generator=g) * scale
+        return x.pin_memory() if pin else x
+
+    inp = {"events": [make_events(rng, EVENTS_PER_WINDOW, H, W) for _ in range(2 * B)]}
+    inp["f1"], inp["f2"] = t(B, FD, FH, FW), t(B, FD, FH, FW)
+    base = torch.stack(torch.meshgrid(torch.arange(FH), torch.arange(FW), indexing="ij")[::-1], 0).float()
+    inp["coords"] = [(base[None] + t(B, 2, FH, FW, scale=3.0)) for _ in range(lookups)]
+    if pin:
+        inp["coords"] = [c.pin_memory() for c in inp["coords"]]
+    inp["eem"] = []
+    for (c, h, w) in EEM_LEVELS:
+        inp["eem"].append({"f1": t(B, c, h, w), "f2": t(B, c, h, w), "p1": t(B, 32, h, w), "p2": t(B, 32, h, w),
+                           "inter": t(B, 2, h, w, scale=1.5), "mask": torch.sigmoid(t(B, 1, h, w)),
+                           "flow": t(B, 2, h, w, scale=2.0)})
+    if pin:
+        for lv in inp["eem"]:
+            for k in lv:
+                lv[k] = lv[k].pin_memory()
+    return inp
+
+
+def h2d_bytes(inp) -> int:
+    n = sum(e.nbytes for e in inp["events"]) + inp["f1"].numel() * 4 * 2 + sum(c.numel() * 4 for c in inp["coords"])
+    for lv in inp["eem"]:
+        n += sum(v.numel() * 4 for v in lv.values())
+    return n
+
+
+# ------------------------------------------------------------------------------------------------
+# the step, B200 arm
+# ------------------------------------------------------------------------------------------------
+class B200Step:
+    def __init__(self, inp, dev, lookups):
+        import eemflow_b200 as E
+        from eemflow_b200 import ops
+        from eemflow_b200.correlation import EEMFLOW_CDC_INDEX
+        self.E, self.ops, self.index = E, ops, EEMFLOW_CDC_INDEX
+        self.dev, self.lookups = dev, lookups
+        self.host = inp
+        self.B = inp["f1"].shape[0]
+        self.target = torch.empty(self.B, 1, H, W, device=dev)
+        self.enc = E.EventSequenceToVoxelGrid_Pytorch(NB, gpu=True, gpu_nr=dev.index or 0, normalize=True, forkserver=False)
+        self.seqs = [E.EventSequence(None, {"height": H, "width": W}, features=e) for e in inp["events"]]
+        # device-resident copies for the kernel-only number
+        ev = np.concatenate(inp["events"], 0)
+        self.d_events = torch.from_numpy(ev).to(dev)
+        counts = [e.shape[0] for e in inp["events"]]
+        self.d_offsets = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int64, device=dev)
+        self.max_n = max(counts)
+        self.d = {"f1": inp["f1"].to(dev), "f2": inp["f2"].to(dev), "coords": [c.to(dev) for c in inp["coords"]],
+                  "eem": [{k: v.to(dev) for k, v in lv.items()} for lv in inp["eem"]]}
+        self.out_host = None
+        self.flow_host = None
+
+    def _model_side(self, d, marks=None):
+        """CorrBlock + EEMFlow_cdc op sequence on device tensors; returns (last lookup, final flows)."""
+        E = self.E
+        blk = E.CorrBlock(d["f1"], d["f2"], num_levels=LEVELS, radius=RADIUS, precision="tf32")
+        if marks is not None:
+            marks.append(self._mark())
+        out = None
+        for c in d["coords"]:
+            out = blk(c)
+        if marks is not None:
+            marks.append(self._mark())
+        flows = []
+        lv = d["eem"][0]
+        E.correlation_select(lv["f1"], lv["f2"], self.index)
+        flow = lv["flow"]
+        flows.append(flow)
+        for lv in d["eem"][1:]:
+            flow_up = E.upsample2d_flow_as(flow.clone(), lv["p1"], mode="bilinear", if_rate=True)
+            E.WarpingLayer_no_div()(lv["p2"], flow_up)
+            flow_up = E.cdc_blend(flow_up, lv["inter"], lv["mask"])
+            f2w = E.warp(lv["f2"], flow_up)
+            E.correlation_select(lv["f1"], f2w, self.index)
+            flow = flow_up
+            flows.append(flow)
+        finals = [E.upsample2d_flow_as(f.clone(), self.target, mode="bilinear", if_rate=True) for f in flows]
+        if marks is not None:
+            marks.append(self._mark())
+        return out, finals[-1]
+
+    def _mark(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def resident(self, marks=None):
+        """Inputs already in HBM."""
+        if marks is not None:
+            marks.append(self._mark())
+        self.ops.voxelize(self.d_events, self.d_offsets, self.max_n, NB, H, W, normalize=True)
+        if marks is not None:
+            marks.append(self._mark())
+        return self._model_side(self.d, marks)
+
+    def end_to_end(self):
+        """Same step through the public API from HOST buffers: numpy events, pinned feature maps in,
+        last correlation features + final flow out to pinned host memory."""
+        dev = self.dev
+        self.enc.voxelize_batch(self.seqs)
+        hi = self.host
+        d = {"f1": hi["f1"].to(dev, non_blocking=True), "f2": hi["f2"].to(dev, non_blocking=True),
+             "coords": [c.to(dev, non_blocking=True) for c in hi["coords"]],
+             "eem": [{k: v.to(dev, non_blocking=True) for k, v in lv.items()} for lv in hi["eem"]]}
+        out, flow = self._model_side(d)
+        if self.out_host is None:
+            self.out_host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            self.flow_host = torch.empty(flow.shape, dtype=flow.dtype, pin_memory=True)
+        self.out_host.copy_(out, non_blocking=True)
+        self.flow_host.copy_(flow, non_blocking=True)
+        return flow
+
+    def d2h_bytes(self):
+        return (self.out_host.numel() + self.flow_host.numel()) * 4 if self.out_host is not None else 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the step, CPU reference arm (oracle port: the reference's own ATen calls)
+# ------------------------------------------------------------------------------------------------
+def reference_step(inp, lookups):
+    from oracle import ref_ops as R
+    idx = EEMFLOW_CDC_INDEX
+    for e in inp["events"]:
+        R.voxelize(e, NB, H, W, normalize=True)
+    pyr = R.corr_pyramid(inp["f1"], inp["f2"], LEVELS)
+    for c in inp["coords"][:lookups]:
+        R.corr_lookup(pyr, c, RADIUS)
+    B = inp["f1"].shape[0]
+    target = torch.empty(B, 1, H, W)
+    lv = inp["eem"][0]
+    R.correlation(lv["f1"], lv["f2"], 4, index=idx)
+    flow = lv["flow"]
+    flows = [flow]
+    for lv in inp["eem"][1:]:
+        flow_up = R.upsample2d_flow_as(flow.clone(), lv["p1"], if_rate=True)
+        R.warping_layer_no_div(lv["p2"], flow_up)
+        flow_up = R.cdc_blend(flow_up, lv["inter"], lv["mask"])
+        f2w = R.warp_exact(lv["f2"], flow_up)
+        R.correlation(lv["f1"], f2w, 4, index=idx)
+        flow = flow_up
+        flows.append(flow)
+    return [R.upsample2d_flow_as(f.clone(), target, if_rate=True) for f in flows][-1]
+
+
+def time_reference(cpu_batch, lookups, steps, warmup, budget_s=25.0):
+    torch.set_num_threads(os.cpu_count() or 1)
+    inp = make_host_inputs(cpu_batch, lookups, seed=1234, pin=False)
+    for _ in range(max(1, min(warmup, 2))):
+        reference_step(inp, lookups)
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        reference_step(inp, lookups)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 3:
+            break
+    return times
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if r[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def lookup_algorithmic_bytes(B):
+    """per position 4*L*81 written + 8 coords + 4*sum_l min((2r+2)^2, P_l) volume taps read."""
+    P = FH * FW
+    taps, h, w = 0, FH, FW
+    for _ in range(LEVELS):
+        taps += min((2 * RADIUS + 2) ** 2, h * w)
+        h, w = h // 2, w // 2
+    return B * P * (4 * LEVELS * (2 * RADIUS + 1) ** 2 + 8 + 4 * taps)
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        p = json.loads(f.read_text())
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "mvsec_dt1_260x346_batch32_voxelize+corrblock4x4+eemflow_cdc_ops",
+              "pairs_per_gpu": args.batch, "windows_per_pair": 2, "events_per_window": EVENTS_PER_WINDOW,
+              "voxel": f"{NB}x{H}x{W}", "fmap": f"{FD}x{FH}x{FW}", "corr_levels": LEVELS, "radius": RADIUS,
+              "lookups_per_pair": args.lookups, "eemflow_levels": EEM_LEVELS,
+              "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
+              "l2": "no explicit flush: a step streams ~1.3 GB (425 MB volume written then gathered 12x) >> 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        times = time_reference(args.cpu_batch, args.lookups, args.steps, args.warmup, budget_s=120.0)
+        ms = 1e3 * statistics.mean(times)
+        val = args.cpu_batch / statistics.mean(times)
+        cores = os.cpu_count() or 1
+        sample = f"{args.cpu_batch} frame pairs per step (of the {args.batch}-pair batch), {len(times)} timed steps"
+        line = {"impl": "reference", "metric": "frame-pairs/sec (voxelize+corr+lookup+warp)", "value": val, "unit": "frame-pairs/s",
+                "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 event times)", "data": "synthetic",
+                "config": dict(config, pairs_per_step=args.cpu_batch),
+                "cpu_baseline": {"value": val, "unit": "frame-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    from eemflow_b200 import _lib
+    from eemflow_b200 import dist as edist
+    assert torch.cuda.is_available(), "bench.py (b200 arm) needs a CUDA device; there is no CPU fallback"
+    rank, world, local_rank = edist.init_from_env("nccl")
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    lib = _lib.lib()
+
+    inp = make_host_inputs(args.batch, args.lookups, seed=100 + rank, pin=True)
+    step = B200Step(inp, dev, args.lookups)
+    metric_acc = torch.zeros(2, device=dev, dtype=torch.float64)
+
+    def full_step(marks=None):
+        out, flow = step.resident(marks)
+        if world > 1:                       # result + metric gather only; nothing on the data path
+            edist.gather_batch(flow)
+            metric_acc[0] = flow.abs().sum()
+            metric_acc[1] = flow.numel()
+            edist.reduce_metrics(metric_acc)
+        return out, flow
+
+    for _ in range(max(3, args.warmup)):
+        full_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    marks = []
+    launches0 = lib.eem_launch_count()
+    torch.cuda.synchronize()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        full_step(marks)
+    t_stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    elapsed_ms = edist.max_over_ranks(t_start.elapsed_time(t_stop), dev)
+    launches = lib.eem_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-family device time from the event marks: [start, voxel, corr_build, lookups, eemflow] per step
+    fam = {"voxelize": 0.0, "corr_pyramid": 0.0, "corr_lookup": 0.0, "eemflow_ops": 0.0}
+    for s in range(args.steps):
+        m = marks[5 * s: 5 * s + 5]
+        for k, name in enumerate(fam):
+            fam[name] += m[k].elapsed_time(m[k + 1])
+    total_fam = sum(fam.values())
+    lookup_ms = fam["corr_lookup"] / (args.steps * args.lookups)
+    peak, peak_src = peaks()
+    algo = lookup_algorithmic_bytes(args.batch)
+    achieved = algo / (lookup_ms * 1e-3) / 1e9
+    roofline = {"kernel": "corr_lookup_kernel<4>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                "avg_launch_ms": lookup_ms, "share_of_step": fam["corr_lookup"] / total_fam,
+                "family_ms_per_step": {k: v / args.steps for k, v in fam.items()}}
+
+    value = args.batch * world * args.steps / (elapsed_ms * 1e-3)
+
+    # end to end through the public API from host buffers
+    e2e = None
+    if not args.no_e2e:
+        k = max(3, args.steps // 4)
+        for _ in range(2):
+            step.end_to_end()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            flow = step.end_to_end()
+            if world > 1:
+                edist.gather_batch(flow)
+        torch.cuda.synchronize()
+        dt = edist.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e = {"value": args.batch * world * k / dt, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d_bytes(inp),
+               "d2h_bytes_per_step": step.d2h_bytes(), "steps": k, "ms_per_step": 1e3 * dt / k,
+               "timer": "host perf_counter around synchronize (host staging + H2D + kernels + D2H)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times = time_reference(args.cpu_batch, args.lookups, steps=12, warmup=1, budget_s=20.0)
+        cpu = {"value": args.cpu_batch / statistics.mean(times), "unit": "frame-pairs/s", "cores": os.cpu_count() or 1,
+               "kind": "port", "sample": f"{args.cpu_batch} frame pairs per step x {len(times)} steps of the same workload, "
+                                         f"oracle/ref_ops.py (the reference's ATen calls), torch threads = {torch.get_num_threads()}"}
+
+    if rank == 0:
+        line = {"metric": "frame-pairs/sec (voxelize+corr+lookup+warp)", "value": value, "unit": "frame-pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core volume, f64 event times)",
+                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

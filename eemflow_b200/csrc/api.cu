@@ -1,4 +1,5 @@
 // Library-level entry points: version, error text, device query.
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -7,6 +8,9 @@
 namespace eem {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -48,6 +52,8 @@ extern "C" {
 int eem_version(void) { return 100; }
 
 const char* eem_last_error_string(void) { return eem::g_err; }
+
+long long eem_launch_count(void) { return eem::g_launches.load(std::memory_order_relaxed); }
 
 int eem_sm_count(void) {
   int n = eem::sm_count();

@@ -18,6 +18,9 @@ inline cudaStream_t as_stream(eem_stream_t s) { return reinterpret_cast<cudaStre
 // Number of SMs of the current device, cached per device.  Defined in api.cu.
 int sm_count();
 
+// Kernel launches issued by this library in this process (eem_launch_count).  Defined in api.cu.
+void count_launch();
+
 #define EEM_CHECK_ARG(cond, ...)                                   \
   do {                                                             \
     if (!(cond)) return ::eem::fail(EEM_ERR_BAD_ARG, __VA_ARGS__); \
@@ -32,6 +35,7 @@ int sm_count();
 // Call after every launch: picks up launch-configuration errors without synchronising.
 #define EEM_CHECK_LAUNCH(name)                                                              \
   do {                                                                                      \
+    ::eem::count_launch();                                                                  \
     cudaError_t e_ = cudaGetLastError();                                                    \
     if (e_ != cudaSuccess)                                                                  \
       return ::eem::fail(EEM_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e_));             \

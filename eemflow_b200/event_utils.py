@@ -75,20 +75,41 @@ def _is_dataframe(obj) -> bool:
     return isinstance(obj, pandas.DataFrame)
 
 
-def _upload_events(arrays: Sequence[numpy.ndarray], device: torch.device):
-    """Concatenate [N_i,4] float64 windows in pinned host memory and copy them to the device."""
-    counts = [int(a.shape[0]) for a in arrays]
-    total = sum(counts)
-    host = torch.empty((total, 4), dtype=torch.float64, pin_memory=True)
-    pos = 0
-    for a, n in zip(arrays, counts):
-        host[pos:pos + n].numpy()[...] = a  # astype('float') + from_numpy of the reference, in one copy
-        pos += n
-    offsets = torch.zeros(len(arrays) + 1, dtype=torch.int64)
-    offsets[1:] = torch.cumsum(torch.tensor(counts, dtype=torch.int64), 0)
-    ev = host.to(device, non_blocking=True)
-    off = offsets.pin_memory().to(device, non_blocking=True)
-    return ev, off, max(counts) if counts else 0
+class _PinnedStage:
+    """Grow-only pinned staging buffer for the host->device copy of event rows.
+
+    cudaHostAlloc costs milliseconds, so the buffer is kept between calls; an event recorded after
+    each async copy guards it against being refilled while the previous copy is still in flight.
+    """
+
+    def __init__(self):
+        self.buf = None
+        self.off = None
+        self.done = None
+
+    def upload(self, arrays: Sequence[numpy.ndarray], device: torch.device):
+        counts = [int(a.shape[0]) for a in arrays]
+        total = sum(counts)
+        if self.done is not None:
+            self.done.synchronize()
+        if self.buf is None or self.buf.shape[0] < total:
+            self.buf = torch.empty((max(total, 1024), 4), dtype=torch.float64, pin_memory=True)
+        if self.off is None or self.off.numel() < len(arrays) + 1:
+            self.off = torch.empty(max(len(arrays) + 1, 64), dtype=torch.int64, pin_memory=True)
+        host = self.buf.numpy()
+        pos = 0
+        for a, n in zip(arrays, counts):
+            host[pos:pos + n] = a  # astype('float') + from_numpy of the reference, in one copy
+            pos += n
+        off_host = self.off.numpy()
+        off_host[0] = 0
+        numpy.cumsum(counts, out=off_host[1:len(arrays) + 1])
+        with torch.cuda.device(device):
+            ev = self.buf[:total].to(device, non_blocking=True)
+            off = self.off[:len(arrays) + 1].to(device, non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record()
+        return ev, off, max(counts) if counts else 0
 
 
 class EventSequenceToVoxelGrid_Pytorch(object):
@@ -113,6 +134,7 @@ class EventSequenceToVoxelGrid_Pytorch(object):
         self.deterministic = deterministic
         self.strict = strict
         self.compute_device = torch.device(compute_device if compute_device is not None else 'cuda:' + str(gpu_nr))
+        self._stage = _PinnedStage()
         if gpu:
             self.device = torch.device('cuda:' + str(gpu_nr))
         else:
@@ -139,7 +161,7 @@ class EventSequenceToVoxelGrid_Pytorch(object):
         assert (width > 0)
         assert (height > 0)
         with torch.no_grad():
-            ev, off, max_n = _upload_events(arrays, self.compute_device)
+            ev, off, max_n = self._stage.upload(arrays, self.compute_device)
             dropped = torch.zeros(1, dtype=torch.int64, device=self.compute_device) if self.strict else None
             grid = ops.voxelize(ev, off, max_n, self.num_bins, height, width, normalize=self.normalize,
                                 deterministic=self.deterministic, dropped=dropped)

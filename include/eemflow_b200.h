@@ -46,6 +46,9 @@ EEM_API int eem_version(void);
 EEM_API const char* eem_last_error_string(void);
 /* Number of SMs of the current device (used by callers to size benches); <0 on error. */
 EEM_API int eem_sm_count(void);
+/* Number of CUDA kernels this library has launched in this process so far (bench.py reports the
+ * difference over its timed region as "gpu_launches"). */
+EEM_API long long eem_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * K1  event voxelization (time-bilinear polarity voting)

@@ -1,0 +1,162 @@
+"""GPU parity: all-pairs correlation pyramid (csrc/corr_volume.cu) and window lookup
+(csrc/corr_lookup.cu) against the real reference's golden vectors and the CPU oracle.
+
+Gates: fp32 path <= 1e-5 abs on unit-variance volumes (stated per assert); TF32 tensor-core path
+<= 1e-2*sigma per element (sigma = std of the reference volume) and <= 2e-3*sigma RMS.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+@pytest.fixture(scope="module")
+def E():
+    import eemflow_b200
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device is visible"
+    return eemflow_b200
+
+
+@pytest.mark.parametrize("name", ["even", "odd", "wide", "degenerate"])
+def test_golden_fp32_pyramid_and_lookup(golden, E, name):
+    g = golden("corr")
+    f1, f2, coords = _t(g[f"{name}__f1"]).cuda(), _t(g[f"{name}__f2"]).cuda(), _t(g[f"{name}__coords"]).cuda()
+    L = int(g[f"{name}__levels"])
+    blk = E.CorrBlock(f1, f2, num_levels=L, radius=4, precision="fp32")
+    assert len(blk.corr_pyramid) == L
+    for l, lvl in enumerate(blk.corr_pyramid):
+        ref = g[f"{name}__pyr{l}"]
+        assert tuple(lvl.shape) == ref.shape and lvl.dtype == torch.float32
+        err = np.abs(lvl.cpu().numpy() - ref).max()
+        assert err <= 1e-5, (name, l, err)
+    vol = E.CorrBlock.corr(f1, f2, precision="fp32")
+    assert tuple(vol.shape) == g[f"{name}__corr"].shape
+    assert np.abs(vol.cpu().numpy() - g[f"{name}__corr"]).max() <= 1e-5
+    out = blk(coords)
+    ref = g[f"{name}__lookup"]
+    assert tuple(out.shape) == ref.shape and out.is_contiguous()
+    got = out.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), name       # degenerate 1-row level: NaN like the reference
+    err = np.nanmax(np.abs(got - ref))
+    assert err <= 2e-5, (name, err)                                 # 1e-5 from the volume + 1e-5 interpolation
+
+
+@pytest.mark.parametrize("name", ["even", "wide"])
+def test_golden_tf32_pyramid(golden, E, name):
+    g = golden("corr")
+    f1, f2 = _t(g[f"{name}__f1"]).cuda(), _t(g[f"{name}__f2"]).cuda()
+    L = int(g[f"{name}__levels"])
+    blk = E.CorrBlock(f1, f2, num_levels=L, radius=4, precision="tf32")
+    for l, lvl in enumerate(blk.corr_pyramid):
+        ref = g[f"{name}__pyr{l}"]
+        sigma = ref.std()
+        d = lvl.cpu().numpy() - ref
+        assert np.abs(d).max() <= 1e-2 * sigma, (name, l, np.abs(d).max(), sigma)
+        assert np.sqrt((d ** 2).mean()) <= 2e-3 * sigma, (name, l)
+
+
+@pytest.mark.parametrize("B,D,H,W", [(2, 256, 36, 44), (1, 256, 32, 32), (1, 128, 23, 40), (3, 64, 17, 20)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_oracle_parity_mvsec_shapes(E, B, D, H, W, precision):
+    """ERAFT feature-map shapes (260x346 -> 36x44, 256x256 crop -> 32x32) and ragged ones
+    (P not a multiple of the 128-position tiles, odd level sizes)."""
+    gen = torch.Generator().manual_seed(B * 1000 + H)
+    f1 = torch.randn(B, D, H, W, generator=gen)
+    f2 = torch.randn(B, D, H, W, generator=gen)
+    coords = ref_ops.coords_grid(B, H, W) + 3.0 * torch.randn(B, 2, H, W, generator=gen)
+    ref_pyr = ref_ops.corr_pyramid(f1, f2, 4)
+    blk = E.CorrBlock(f1.cuda(), f2.cuda(), num_levels=4, radius=4, precision=precision)
+    tol_abs = 1e-5 if precision == "fp32" else None
+    for l, (lvl, ref) in enumerate(zip(blk.corr_pyramid, ref_pyr)):
+        d = (lvl.cpu() - ref).abs()
+        if tol_abs is not None:
+            assert d.max().item() <= tol_abs, (l, d.max().item())
+        else:
+            sigma = ref.std().item()
+            assert d.max().item() <= 1e-2 * sigma, (l, d.max().item(), sigma)
+    # lookup on OUR pyramid vs the oracle lookup on the SAME pyramid isolates the gather kernel
+    ours = blk(coords.cuda()).cpu()
+    ref = ref_ops.corr_lookup([lvl.cpu() for lvl in blk.corr_pyramid], coords, 4)
+    err = (ours - ref).abs().max().item()
+    assert err <= 1e-5, err
+    assert tuple(ours.shape) == (B, 324, H, W)
+
+
+def test_lookup_radius_and_level_variants(E):
+    gen = torch.Generator().manual_seed(7)
+    f1 = torch.randn(1, 32, 12, 20, generator=gen)
+    f2 = torch.randn(1, 32, 12, 20, generator=gen)
+    coords = ref_ops.coords_grid(1, 12, 20) + 2.0 * torch.randn(1, 2, 12, 20, generator=gen)
+    for L, r in ((1, 4), (2, 3), (3, 2), (2, 1)):
+        blk = E.CorrBlock(f1.cuda(), f2.cuda(), num_levels=L, radius=r, precision="fp32")
+        ours = blk(coords.cuda()).cpu()
+        ref = ref_ops.corr_lookup(ref_ops.corr_pyramid(f1, f2, L), coords, r)
+        assert tuple(ours.shape) == tuple(ref.shape) == (1, L * (2 * r + 1) ** 2, 12, 20)
+        assert (ours - ref).abs().max().item() <= 2e-5, (L, r)
+
+
+def test_full_size_hrem_volume_properties(E):
+    """HREM size (P = 92*160 = 14720, D = 256; 867 MB level 0): too big for the CPU oracle in seconds,
+    so check size-independent properties: (1) rows sampled at random against an fp64 dot product,
+    (2) pooling consistency level_{l+1} == avg_pool2d(level_l), (3) bilinearity in fmap1."""
+    B, D, H, W = 1, 256, 92, 160
+    gen = torch.Generator().manual_seed(11)
+    f1 = torch.randn(B, D, H, W, generator=gen).cuda()
+    f2 = torch.randn(B, D, H, W, generator=gen).cuda()
+    blk = E.CorrBlock(f1, f2, num_levels=4, radius=4, precision="tf32")
+    P = H * W
+    lv0 = blk.corr_pyramid[0].view(P, P)
+    rows = torch.randint(0, P, (64,), generator=gen).cuda()
+    ref_rows = (f1.view(D, P)[:, rows].double().t() @ f2.view(D, P).double()) / 16.0
+    d = (lv0[rows].double() - ref_rows).abs()
+    assert d.max().item() <= 1e-2, d.max().item()                       # sigma == 1 for unit-variance features
+    for l in range(3):
+        a = blk.corr_pyramid[l][:4096]
+        pooled = torch.nn.functional.avg_pool2d(a, 2, stride=2)
+        dd = (pooled - blk.corr_pyramid[l + 1][:4096]).abs().max().item()
+        assert dd <= 1e-2, (l, dd)
+    blk2 = E.CorrBlock(2.0 * f1, f2, num_levels=1, radius=4, precision="tf32")
+    assert torch.allclose(blk2.corr_pyramid[0].view(P, P)[rows], 2.0 * lv0[rows], atol=1e-6)   # exact scaling by 2
+    coords = (ref_ops.coords_grid(B, H, W) + 3.0 * torch.randn(B, 2, H, W, generator=gen)).cuda()
+    out = blk(coords)
+    assert tuple(out.shape) == (1, 324, H, W) and torch.isfinite(out).all()
+    # spot-check the lookup at 32 positions against the oracle fed with those rows only
+    pos = torch.randint(0, P, (32,), generator=gen)
+    sub = [lvl[pos.cuda()].cpu() for lvl in blk.corr_pyramid]
+    c = coords.view(2, P)[:, pos.cuda()].cpu().view(1, 2, 1, 32)
+    ref = ref_ops.corr_lookup(sub, c, 4)                                 # [1, 324, 1, 32]
+    got = out.view(324, P)[:, pos.cuda()].cpu().view(1, 324, 1, 32)
+    assert (got - ref).abs().max().item() <= 1e-5
+
+
+def test_bilinear_sampler_coords_grid_upflow8(golden, E):
+    g = golden("corr")
+    s, m = E.bilinear_sampler(_t(g["bs_img"]).cuda(), _t(g["bs_coords"]).cuda(), mask=True)
+    assert np.abs(s.cpu().numpy() - g["bs_out"]).max() <= 1e-5
+    assert np.array_equal(m.cpu().numpy(), g["bs_mask"])
+    up = E.upflow8(_t(g["up8_in"]).cuda())
+    assert np.abs(up.cpu().numpy() - g["up8_out"]).max() <= 1e-5
+    assert torch.equal(E.coords_grid(2, 5, 7), ref_ops.coords_grid(2, 5, 7))
+
+
+def test_avg_pool_kernel(E):
+    from eemflow_b200 import ops
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(37, 1, 9, 13, generator=gen)
+    ref = torch.nn.functional.avg_pool2d(x, 2, stride=2)
+    assert (ops.avg_pool2x2(x.cuda()).cpu() - ref).abs().max().item() <= 1e-6
+
+
+def test_tf32_unsupported_shape_is_loud(E):
+    f = torch.randn(1, 16, 9, 13).cuda()
+    with pytest.raises(NotImplementedError):
+        E.CorrBlock(f, f, precision="tf32")
+    blk = E.CorrBlock(f, f, num_levels=3)          # default picks fp32 for this shape
+    assert blk.precision == "fp32"

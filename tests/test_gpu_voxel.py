@@ -1,0 +1,156 @@
+"""GPU parity: voxelization kernels (csrc/voxelize.cu) against the golden vectors of the real
+reference and against the CPU oracle on seeded inputs.  Run with `-m gpu` on a B200.
+
+Gates: vote addresses bit-exact; raw grid bit-exact in deterministic mode and
+<= 1e-5 relative (|a-b| <= 1e-5*max(|b|,1)) in atomic mode; normalised grid <= 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, ref_ops
+from tests.conftest import cases_of
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_close(a, b, tol=1e-5):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) <= tol * np.maximum(np.abs(b), 1.0)
+
+
+class Seq:
+    def __init__(self, features, h, w):
+        self.features, self.image_height, self.image_width = features, h, w
+
+
+def make_events(rng, n, h, w, clustered=False):
+    t = np.sort(rng.uniform(0.0, 0.05, size=n)) * 1e6
+    t -= t[0]
+    if clustered:  # 80 % of the events in a few Gaussian blobs (~5 % of the pixels)
+        k = int(0.8 * n)
+        centres = rng.uniform([0, 0], [w, h], size=(8, 2))
+        which = rng.integers(0, 8, size=k)
+        sig = 0.035 * min(h, w)
+        xy = centres[which] + rng.normal(0, sig, size=(k, 2))
+        x = np.concatenate([np.clip(np.round(xy[:, 0]), 0, w - 1), rng.integers(0, w, size=n - k)])
+        y = np.concatenate([np.clip(np.round(xy[:, 1]), 0, h - 1), rng.integers(0, h, size=n - k)])
+        perm = rng.permutation(n)
+        x, y = x[perm], y[perm]
+    else:
+        x = rng.integers(0, w, size=n).astype(np.float64)
+        y = rng.integers(0, h, size=n).astype(np.float64)
+    p = 2.0 * rng.integers(0, 2, size=n) - 1.0
+    return np.stack([t, x.astype(np.float64), y.astype(np.float64), p], axis=1)
+
+
+@pytest.fixture(scope="module")
+def V():
+    import eemflow_b200
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device is visible"
+    return eemflow_b200.EventSequenceToVoxelGrid_Pytorch
+
+
+def test_golden_raw_atomic_and_deterministic(golden, V):
+    g = golden("voxel")
+    for name in cases_of(g):
+        nb, h, w = (int(v) for v in g[f"{name}__shape"])
+        ev = g[f"{name}__events"]
+        ref = g[f"{name}__raw"]
+        out_a = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev.copy(), h, w)).cpu().numpy()
+        assert out_a.shape == ref.shape and out_a.dtype == np.float32
+        assert rel_close(out_a, ref).all(), (name, np.abs(out_a - ref).max())
+        out_d = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True)(Seq(ev.copy(), h, w)).cpu().numpy()
+        assert np.array_equal(out_d, ref), (name, np.abs(out_d - ref).max())     # bit-exact
+
+
+def test_golden_normalized(golden, V):
+    g = golden("voxel")
+    for name in cases_of(g):
+        nb, h, w = (int(v) for v in g[f"{name}__shape"])
+        ev = g[f"{name}__events"]
+        ref = g[f"{name}__norm"]
+        for det in (False, True):
+            out = V(nb, gpu=True, normalize=True, forkserver=False, deterministic=det)(Seq(ev.copy(), h, w)).cpu().numpy()
+            assert rel_close(out, ref).all(), (name, det, np.abs(out - ref).max())
+
+
+@pytest.mark.parametrize("n,nb,h,w,clustered", [
+    (30_000, 5, 260, 346, False),      # MVSEC dt1 window
+    (120_000, 5, 260, 346, True),      # MVSEC dt4, clustered
+    (1_000_000, 15, 720, 1280, False),  # HREM-shaped, 1M events
+    (600_000, 15, 720, 1280, True),
+])
+def test_oracle_parity(V, n, nb, h, w, clustered):
+    rng = np.random.default_rng(n + nb)
+    ev = make_events(rng, n, h, w, clustered)
+    ref_raw, dropped, _ = c_oracle.voxelize(ev, nb, h, w, normalize=False)
+    assert dropped == 0
+    out_d = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True)(Seq(ev, h, w)).cpu().numpy()
+    assert np.array_equal(out_d, ref_raw)                                       # bit-exact
+    out_a = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
+    assert rel_close(out_a, ref_raw).all(), np.abs(out_a - ref_raw).max()
+    ref_norm = ref_ops.voxelize(ev, nb, h, w, normalize=True).numpy()
+    out_n = V(nb, gpu=True, normalize=True, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
+    assert rel_close(out_n, ref_norm).all(), np.abs(out_n - ref_norm).max()
+
+
+def test_batched_windows_ragged(V):
+    rng = np.random.default_rng(5)
+    h, w, nb = 64, 96, 5
+    seqs = [Seq(make_events(rng, n, h, w), h, w) for n in (1, 2, 777, 5000, 31, 12345)]
+    enc = V(nb, gpu=True, normalize=True, forkserver=False)
+    batch = enc.voxelize_batch(seqs).cpu().numpy()
+    assert batch.shape == (len(seqs), nb, h, w)
+    for k, s in enumerate(seqs):
+        ref = ref_ops.voxelize(s.features, nb, h, w, normalize=True).numpy()
+        assert rel_close(batch[k], ref).all(), k
+    det = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_batch(seqs).cpu().numpy()
+    for k, s in enumerate(seqs):
+        ref, _, _ = c_oracle.voxelize(s.features, nb, h, w, normalize=False)
+        assert np.array_equal(det[k], ref), k
+
+
+def test_full_size_hrem_checksum(V):
+    """BASELINE size (10M events, 15x720x1280): size-independent property -- the grid's total and its
+    per-bin totals equal the sums of the per-event vote weights (computed vectorised on the CPU)."""
+    rng = np.random.default_rng(9)
+    n, nb, h, w = 10_000_000, 15, 720, 1280
+    ev = make_events(rng, n, h, w)
+    out = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev, h, w))
+    v = ref_ops.voxel_votes(ev, nb, h, w)
+    per_bin = np.zeros(nb)
+    for idx, val in ((v["idx_left"], v["val_left"]), (v["idx_right"], v["val_right"])):
+        ok = idx >= 0
+        per_bin += np.bincount(idx[ok] // (h * w), weights=val[ok].astype(np.float64), minlength=nb)
+    got = out.double().sum(dim=(1, 2)).cpu().numpy()
+    assert np.allclose(got, per_bin, rtol=0, atol=2.0), (got - per_bin)   # ~1e6 fp32 adds per bin
+    # and the event count per pixel column is conserved: |votes| sum to the number of events per bin pair
+    absum = out.abs().double().sum().item()
+    assert absum <= n + 1.0
+
+
+def test_device_contract_and_errors(V):
+    rng = np.random.default_rng(3)
+    ev = make_events(rng, 1000, 32, 48)
+    out_cpu = V(5, gpu=False, normalize=True, forkserver=False)(Seq(ev, 32, 48))
+    assert out_cpu.device.type == "cpu" and out_cpu.dtype == torch.float32 and tuple(out_cpu.shape) == (5, 32, 48)
+    out_gpu = V(5, gpu=True, normalize=True, forkserver=False)(Seq(ev, 32, 48))
+    assert out_gpu.is_cuda
+    assert torch.equal(out_gpu.cpu() != 0, out_cpu != 0)
+    ev_before = ev.copy()
+    V(5, gpu=True, forkserver=False)(Seq(ev, 32, 48))
+    assert np.array_equal(ev, ev_before)                          # features are not modified
+    with pytest.raises(AssertionError):
+        V(5, gpu=True, forkserver=False)(Seq(np.zeros((10, 3)), 32, 48))
+    with pytest.raises(AssertionError):
+        V(0, gpu=True, forkserver=False)(Seq(ev, 32, 48))
+    with pytest.raises(AssertionError):
+        V(5, gpu=True, forkserver=False)(Seq(ev, 0, 48))
+    with pytest.raises(IndexError):
+        V(5, gpu=True, forkserver=False)(Seq(np.zeros((0, 4)), 32, 48))
+    bad = ev.copy()
+    bad[10, 2] = 4000.0                                           # flat index outside the grid
+    with pytest.raises(IndexError):
+        V(5, gpu=True, forkserver=False, strict=True)(Seq(bad, 32, 48))
+    V(5, gpu=True, forkserver=False)(Seq(bad, 32, 48))            # non-strict: vote dropped, no error

@@ -1,0 +1,134 @@
+"""GPU parity: local 9x9 correlation (csrc/local_corr.cu), backward warps, flow resize, blend and
+replicate padding (csrc/warp.cu) against the real reference's golden vectors and the CPU oracle.
+fp32 paths, gate <= 1e-5 abs (stated per assert).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+@pytest.fixture(scope="module")
+def E():
+    import eemflow_b200
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device is visible"
+    return eemflow_b200
+
+
+# ------------------------------------------------------------------------------------ local corr
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_local_corr_golden(golden, E, name):
+    g = golden("local_corr")
+    f1, f2 = _t(g[f"{name}__f1"]).cuda(), _t(g[f"{name}__f2"]).cuda()
+    ref = g[f"{name}__cv"]
+    b, c, h, w = f1.shape
+    out = E.Correlation(4)(f1, f2)
+    assert tuple(out.shape) == (b, 81, h, w)
+    assert np.abs(out.cpu().numpy() - ref).max() <= 1e-5
+    raw = E.SpatialCorrelationSampler(1, 9, 1, 0, 1)(f1, f2)
+    assert tuple(raw.shape) == (b, 9, 9, h, w)
+    assert np.abs(raw.view(b, 81, h, w).cpu().numpy() / c - ref).max() <= 1e-5
+    for idx in (g["index_cdc"], g["index_eemflow"]):
+        sel = E.correlation_select(f1, f2, torch.as_tensor(idx))
+        assert tuple(sel.shape) == (b, len(idx), h, w)
+        assert np.abs(sel.cpu().numpy() - ref[:, idx]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 5, 6), (2, 64, 40, 48), (1, 32, 80, 96), (1, 64, 96, 160), (1, 32, 192, 320), (1, 19, 33, 37)])
+def test_local_corr_oracle_eemflow_shapes(E, B, C, H, W):
+    """EEMFlow_cdc pyramid shapes at MVSEC (pad 320x384) and HREM (pad 768x1280), plus a ragged one."""
+    gen = torch.Generator().manual_seed(C + H)
+    f1 = torch.randn(B, C, H, W, generator=gen)
+    f2 = torch.randn(B, C, H, W, generator=gen)
+    from eemflow_b200.correlation import EEMFLOW_CDC_INDEX
+    ref = ref_ops.correlation(f1, f2, 4)
+    out = E.Correlation(4)(f1.cuda(), f2.cuda()).cpu()
+    assert (out - ref).abs().max().item() <= 1e-5
+    sel = E.correlation_select(f1.cuda(), f2.cuda(), EEMFLOW_CDC_INDEX).cpu()
+    assert torch.equal(sel, out[:, EEMFLOW_CDC_INDEX])
+
+
+# ------------------------------------------------------------------------------------ warps
+def _mask_knife_edge(x, flo):
+    """Positions where the reference's ones-sample is within 2 ulp of its threshold: the 0/1 mask there
+    depends on the rounding order of four weight products and is excluded from exact comparison."""
+    _, raw = ref_ops.warping_layer_no_div(x, flo.clone(), return_raw_mask=True)
+    return ((raw - 1.0).abs() <= 3e-7) | ((raw - 0.9999).abs() <= 3e-7)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_warp_golden(golden, E, name):
+    g = golden("warp")
+    x, flo = _t(g[f"{name}__x"]), _t(g[f"{name}__flo"])
+    xc, fc = x.cuda(), flo.cuda()
+    assert np.abs(E.warp(xc, fc).cpu().numpy() - g[f"{name}__warp_exact"]).max() <= 1e-5
+    assert np.abs(E.tensor_tools.torch_warp(xc, fc).cpu().numpy() - g[f"{name}__torch_warp"]).max() <= 1e-5
+    assert torch.equal(fc.cpu(), flo)                                          # flow is not modified
+    edge = _mask_knife_edge(x, flo).numpy()
+    o, m = E.tensor_tools.torch_warp_mask(xc, fc)
+    assert tuple(m.shape) == tuple(x.shape)
+    ok = ~edge
+    assert np.array_equal(m.cpu().numpy()[ok], g[f"{name}__torch_warp_mask_mask"][ok])
+    assert np.abs(o.cpu().numpy() - g[f"{name}__torch_warp_mask_out"])[ok].max() <= 1e-5
+    wl = E.WarpingLayer_no_div()(xc, fc).cpu().numpy()
+    assert np.abs(wl - g[f"{name}__warping_layer"])[ok].max() <= 1e-5
+    assert edge.mean() < 0.2
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 10, 12), (1, 32, 80, 96), (1, 64, 96, 160), (2, 2, 45, 80)])
+def test_warp_oracle(E, B, C, H, W):
+    gen = torch.Generator().manual_seed(H * W)
+    x = torch.randn(B, C, H, W, generator=gen)
+    flo = 2.0 * torch.randn(B, 2, H, W, generator=gen)
+    xc, fc = x.cuda(), flo.cuda()
+    assert (E.warp(xc, fc).cpu() - ref_ops.warp_exact(x, flo.clone())).abs().max().item() <= 1e-5
+    assert (E.torch_warp(xc, fc).cpu() - ref_ops.torch_warp(x, flo.clone())).abs().max().item() <= 1e-5
+    edge = _mask_knife_edge(x, flo)
+    d = (E.WarpingLayer_no_div()(xc, fc).cpu() - ref_ops.warping_layer_no_div(x, flo.clone())).abs()
+    assert d[~edge].max().item() <= 1e-5
+    # identity flow under the exact convention returns the input
+    zero = torch.zeros_like(fc)
+    assert (E.warp(xc, zero) - xc).abs().max().item() <= 1e-6
+
+
+def test_resize_blend_pad_golden(golden, E):
+    g = golden("warp")
+    tgt = torch.zeros(2, 1, 7, 9).cuda()
+    a = _t(g["up_in"]).cuda()
+    assert np.abs(E.upsample2d_flow_as(a, tgt, mode="bilinear", if_rate=False).cpu().numpy() - g["up_norate"]).max() <= 1e-5
+    assert np.array_equal(a.cpu().numpy(), g["up_in"])
+    b = _t(g["up_in"]).cuda()
+    r = E.upsample2d_flow_as(b, tgt, mode="bilinear", if_rate=True)
+    assert np.abs(r.cpu().numpy() - g["up_rate"]).max() <= 1e-5
+    assert np.abs(b.cpu().numpy() - g["up_rate_input_after"]).max() <= 1e-6     # in-place side effect reproduced
+    mesh = _t(g["mesh_in"]).cuda()
+    assert np.abs(E.upsample_flow(mesh, (45, 80)).cpu().numpy() - g["mesh_up"]).max() <= 1e-5
+    assert np.abs(E.upsample_flow(mesh, (5, 7)).cpu().numpy() - g["mesh_down"]).max() <= 1e-5
+    bl = E.cdc_blend(_t(g["blend_init"]).cuda(), _t(g["blend_inter"]).cuda(), _t(g["blend_mask"]).cuda())
+    assert np.abs(bl.cpu().numpy() - g["blend_out"]).max() <= 1e-5
+    x = _t(g["pad_in"]).cuda()
+    for mode, rate in (("chairs", 64), ("sintel", 32), ("chairs", 32)):
+        p = E.InputPadder(x.shape, mode=mode, eval_pad_rate=rate)
+        (y,) = p.pad(x)
+        assert np.array_equal(y.cpu().numpy(), g[f"pad_{mode}_{rate}"])
+        assert torch.equal(p.unpad(y), x)
+
+
+@pytest.mark.parametrize("h,w,H,W", [(24, 40, 720, 1280), (16, 16, 720, 1280), (12, 20, 24, 40), (10, 12, 260, 346), (7, 9, 7, 9)])
+def test_resize_oracle_meshflow_shapes(E, h, w, H, W):
+    gen = torch.Generator().manual_seed(h * w)
+    fl = torch.randn(2, 2, h, w, generator=gen)
+    tgt = torch.zeros(2, 1, H, W)
+    ref = ref_ops.upsample2d_flow_as(fl.clone(), tgt, if_rate=True)
+    got = E.upsample2d_flow_as(fl.clone().cuda(), tgt.cuda(), if_rate=True).cpu()
+    assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, W / w)            # values are scaled by W/w
+    ref = ref_ops.upsample_flow(fl, (H, W))
+    got = E.upsample_flow(fl.cuda(), (H, W)).cpu()
+    assert (got - ref).abs().max().item() <= 1e-5

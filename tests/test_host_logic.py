@@ -1,0 +1,120 @@
+"""CPU tests of the host side: C-ABI surface, reference-shaped containers, argument handling.
+No compute call is made (no GPU here); the GPU parity tests live in test_gpu_*.py."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "eemflow_b200.h").read_text()
+    return sorted(set(re.findall(r"EEM_API\s+[\w\s\*]+?\b(eem_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from eemflow_b200 import _lib
+    from eemflow_b200.build import build
+    build(verbose=False)                       # no-op when up to date; nvcc cross-compiles without a GPU
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    h = ctypes.CDLL(str(_lib.LIB_PATH))
+    for s in syms:
+        assert hasattr(h, s), f"{s} declared in include/eemflow_b200.h but not exported"
+    # the ctypes table binds exactly the header's surface
+    assert sorted(_lib.SIGNATURES) == syms
+    lib = _lib.lib()
+    assert lib.eem_version() >= 100
+    assert isinstance(lib.eem_last_error_string(), bytes)
+
+
+def test_workspace_queries_are_pure_host_functions():
+    from eemflow_b200 import _lib
+    lib = _lib.lib()
+    assert lib.eem_voxelize_workspace_bytes(10_000_000, 1, 15, 720, 1280, _lib.VOXEL_ATOMIC) == 0
+    det = lib.eem_voxelize_workspace_bytes(10_000_000, 1, 15, 720, 1280, _lib.VOXEL_DETERMINISTIC)
+    assert det >= 2 * 10_000_000 * 16          # two key and two value buffers over 2N votes
+    assert lib.eem_voxel_normalize_workspace_bytes(64, 5 * 260 * 346) > 0
+    assert lib.eem_corr_pyramid_workspace_bytes(32, 256, 36, 44, 1) == 0
+    ws = lib.eem_corr_pyramid_workspace_bytes(32, 256, 36, 44, 4)
+    assert ws >= 32 * 256 * (18 * 22 + 9 * 11 + 4 * 5) * 4
+
+
+def test_bad_arguments_return_status_not_crash():
+    from eemflow_b200 import _lib
+    lib = _lib.lib()
+    # argument validation happens before any CUDA call
+    rc = lib.eem_voxelize(None, None, 0, 0, 0, 5, 10, 10, 0, None, None, None, 0, None)
+    assert rc == _lib.EEM_ERR_BAD_ARG
+    assert b"n_windows" in lib.eem_last_error_string()
+    with pytest.raises(AssertionError):
+        _lib.check(rc)
+    rc = lib.eem_corr_lookup(None, 1, 4, 4, 4, 4, None, None, None)
+    assert rc == _lib.EEM_ERR_BAD_ARG
+    idx = (ctypes.c_int * 2)(3, 3)
+    rc = lib.eem_local_corr(1, 1, 1, 1, 4, 4, 4, idx, 2, 1.0, 1, None)   # dummy non-NULL pointers, repeated index
+    assert rc == _lib.EEM_ERR_UNSUPPORTED
+    with pytest.raises(NotImplementedError):
+        _lib.check(rc)
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing them elsewhere."""
+    import eemflow_b200
+    from eemflow_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.corr_pyramid(torch.zeros(1, 32, 4, 4), torch.zeros(1, 32, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        eemflow_b200.warp(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
+    with pytest.raises(NotImplementedError):
+        eemflow_b200.SpatialCorrelationSampler(3, 9, 1, 0, 1)
+
+
+def test_product_code_never_imports_the_oracle():
+    for f in (ROOT / "eemflow_b200").rglob("*.py"):
+        src = f.read_text()
+        assert "oracle" not in re.sub(r"#.*", "", src).replace("oracle of", ""), f"{f} mentions the oracle"
+    for f in (ROOT / "eemflow_b200" / "csrc").glob("*.cu*"):
+        assert "oracle" not in f.read_text()
+
+
+def test_event_sequence_container():
+    from eemflow_b200 import EventSequence
+    rng = np.random.default_rng(0)
+    f = np.stack([rng.uniform(1.0, 2.0, 50), rng.integers(0, 9, 50), rng.integers(0, 7, 50),
+                  rng.integers(0, 2, 50)], axis=1).astype(np.float64)
+    s = EventSequence(None, {"height": 7, "width": 9}, features=f.copy(), timestamp_multiplier=1e6,
+                      convert_to_relative=True)
+    assert s.is_sorted() and s.features[0, 0] == 0.0 and len(s) == 50
+    order = np.argsort(f[:, 0])
+    assert np.allclose(s.features[:, 0], (f[order, 0] * 1e6) - f[order, 0].min() * 1e6)
+    both = s + s
+    assert len(both) == 100 and both.image_height == 7
+    import pandas
+    df = pandas.DataFrame(f, columns=["ts", "x", "y", "p"])
+    s2 = EventSequence(df, {"height": 7, "width": 9})
+    assert list(s2.feature_names) == ["ts", "x", "y", "p"] and s2.is_sorted()
+
+
+def test_input_padder_geometry():
+    from eemflow_b200 import InputPadder
+    p = InputPadder((1, 5, 260, 346), mode='chairs', eval_pad_rate=64)
+    assert p._pad == [19, 19, 0, 60]                 # 260x346 -> 320x384
+    p = InputPadder((1, 5, 720, 1280), mode='chairs', eval_pad_rate=64)
+    assert p._pad == [0, 0, 0, 48]
+    p = InputPadder((1, 5, 260, 346), mode='sintel', eval_pad_rate=32)
+    assert p._pad == [3, 3, 14, 14]
+    x = torch.zeros(1, 1, 288, 352)
+    assert tuple(p.unpad(x).shape) == (1, 1, 260, 346)
+
+
+def test_pyramid_shapes_and_tf32_gate():
+    from eemflow_b200 import ops
+    assert ops.pyramid_level_shapes(36, 44, 4) == [(36, 44), (18, 22), (9, 11), (4, 5)]
+    assert ops.pyramid_level_shapes(92, 160, 4) == [(92, 160), (46, 80), (23, 40), (11, 20)]
+    assert ops.tf32_supported(256, 36, 44) and ops.tf32_supported(256, 92, 160)
+    assert not ops.tf32_supported(16, 9, 13) and not ops.tf32_supported(512, 36, 44)

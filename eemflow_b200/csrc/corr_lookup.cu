@@ -30,8 +30,8 @@ struct LookupParams {
 // align_corners=True), in fp32 with the same operation order.
 __device__ __forceinline__ float roundtrip(float p, int size) {
   const float s1 = (float)(size - 1);
-  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, p), s1), 1.0f);
-  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), s1);
+  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, p), s1), 1.0f);   // 2*x/(S-1) - 1
+  return __fmul_rn(__fadd_rn(g, 1.0f), s1 * 0.5f);                      // ATen CPU: (g+1) * ((S-1)/2)
 }
 
 template <int R>

@@ -19,6 +19,7 @@
 //                  128-byte coalesced store per output row per warp.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -118,6 +119,7 @@ struct Tf32Params {
   int n_tiles;                        // ceil(P / BN)
   int64_t total_tiles;                // B * mt_cum[L] * n_tiles
   float scale;
+  uint32_t desc_lo, desc_hi;          // constant smem-descriptor fields (desc_fields)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -166,19 +168,23 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       : "memory");
 }
 
-// Shared-memory matrix descriptor for an MN-major fp32 operand stored as TMA SWIZZLE_128B boxes:
-// a box is [BK channel rows][32 positions = 128 B]; 8 consecutive rows form one 1024-byte swizzle
-// atom.  In the canonical MN-major SW128 layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) [uint128 units]
-// the leading-byte offset steps between 32-position chunks (= one box, 4 KiB here) and the
-// stride-byte offset between 8-channel groups (1 KiB).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);             // start address
-  d |= (uint64_t)((kBoxBytes >> 4) & 0x3fff) << 16;       // leading byte offset: next 32-position chunk
-  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;            // stride byte offset: next 8-channel group
-  d |= (uint64_t)1 << 46;                                 // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
-  return d;
+// Shared-memory matrix descriptor for an MN-major fp32/tf32 operand.  For MN-major tf32 the only
+// swizzled layout tcgen05 accepts is "128B swizzle with 32B atomicity" (layout type 1; CuTe's
+// Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>): an atom is 32 positions (128 B) x 4 channel rows and
+// the four 32-byte chunks of a row are XOR-permuted with (row % 4).  TMA writes exactly that with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: a box is [BK channel rows][32 positions = 128 B], i.e. BK/4
+// atoms stacked along K.  Canonical form ((8,n),(4,k)) : ((1,LBO),(8,SBO)) in uint128 units:
+//   leading-byte offset = distance between 32-position chunks (one box, 4 KiB here)
+//   stride-byte offset  = distance between 4-channel groups   (512 B)
+// One kind::tf32 MMA consumes K = 8 channels = two such groups; the next MMA starts 1 KiB further.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lo_fields, uint32_t hi_fields) {
+  return ((uint64_t)hi_fields << 32) | (uint64_t)(lo_fields | ((smem_addr >> 4) & 0x3fff));
+}
+
+// Host-side encoding of the constant descriptor fields.
+inline void desc_fields(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type, uint32_t* lo, uint32_t* hi) {
+  *lo = ((lbo_bytes >> 4) & 0x3fff) << 16;                               // bits [16,30): leading byte offset
+  *hi = ((sbo_bytes >> 4) & 0x3fff) | (1u << 14) | (layout_type << 29);  // [32,46) SBO, [46,48) version 1, [61,64) layout
 }
 
 // kind::tf32 instruction descriptor: fp32 accumulate, A and B tf32, both MN-major, M=128, N=BN.
@@ -287,8 +293,9 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
           const uint32_t b_addr = smem_u32(s.ring + stage * kTileKBytes);
 #pragma unroll
           for (int ks = 0; ks < BK / UK; ++ks) {
-            // one 8-channel group = one 1024-byte swizzle atom per 32-position chunk
-            tc_mma_tf32(d_tmem, make_desc(a_addr + ks * 1024), make_desc(b_addr + ks * 1024), kIdesc, (kb | ks) != 0);
+            // 8 channels = 8 rows of 128 B = two 512-byte swizzle atoms per 32-position chunk
+            tc_mma_tf32(d_tmem, make_desc(a_addr + ks * 1024, p.desc_lo, p.desc_hi),
+                        make_desc(b_addr + ks * 1024, p.desc_lo, p.desc_hi), kIdesc, (kb | ks) != 0);
           }
           tc_commit(&s.empty[stage]);
           if (last_of_item) tc_commit(&s.res_free[kb]);
@@ -369,8 +376,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row pitch `pitch` elements; box = 32 cols x BK rows, 128B swizzle.
-int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch) {
+// 2-D fp32 tensor [rows, cols] with row pitch `pitch` elements; box = 32 cols x BK rows.
+int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch,
+               CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return fail(EEM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -378,7 +386,7 @@ int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, 
   cuuint32_t box[2] = {32, (cuuint32_t)BK};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(EEM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return EEM_OK;
@@ -478,14 +486,28 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   }
 
   Tf32Params p{};
-  int rc = encode_map(&p.map_f1, fmap1, planes, P, P);
+  // Layout variant: 0 is the production setting.  The others exist only so a single GPU session can
+  // A/B the descriptor encoding (EEM_TF32_VARIANT is read by scripts/debug_tf32.py runs).
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  uint32_t lbo = kBoxBytes, sbo = 512, layout = 1;
+  if (const char* v = getenv("EEM_TF32_VARIANT")) {
+    switch (atoi(v)) {
+      case 1: lbo = 512; sbo = kBoxBytes; break;
+      case 2: swz = CU_TENSOR_MAP_SWIZZLE_128B; layout = 2; sbo = 1024; break;
+      case 3: sbo = 1024; break;
+      case 4: swz = CU_TENSOR_MAP_SWIZZLE_128B; layout = 1; break;
+      default: break;
+    }
+  }
+  desc_fields(lbo, sbo, layout, &p.desc_lo, &p.desc_hi);
+  int rc = encode_map(&p.map_f1, fmap1, planes, P, P, swz);
   if (rc != EEM_OK) return rc;
   int nl = 0;
   p.mt_cum[0] = 0;
   for (int l = 0; l < num_levels; ++l) {
     const int Pl = ld.h[l] * ld.w[l];
     if (Pl == 0) break;  // all coarser levels are empty too
-    rc = encode_map(&p.map_lvl[l], op[l], planes, Pl, ld.pitch[l]);
+    rc = encode_map(&p.map_lvl[l], op[l], planes, Pl, ld.pitch[l], swz);
     if (rc != EEM_OK) return rc;
     p.out[l] = levels[l];
     p.Pl[l] = Pl;

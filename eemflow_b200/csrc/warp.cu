@@ -19,26 +19,29 @@ struct Bilin {
   bool in_nw, in_ne, in_sw, in_se;
 };
 
+// Un-normalisation exactly as ATen's CPU grid sampler evaluates it (GridSamplerKernel.cpp,
+// ComputeLocation): align_corners=True -> (g+1) * ((S-1)/2); align_corners=False ->
+// fma(g+1, S/2, -0.5) (one rounding).  Matching the rounding matters: the reference thresholds the
+// interpolated ones-tensor at 1.0 (cdc_utils.py:77), and for an interior sample that sum is
+// 1 +- 1 ulp, so the 0/1 validity mask is decided by these roundings.
 __device__ __forceinline__ float unnormalize(float g, int size, int convention) {
-  if (convention == EEM_WARP_EXACT) return ((g + 1.f) / 2.f) * (float)(size - 1);
-  return ((g + 1.f) * (float)size - 1.f) / 2.f;
+  const float g1 = __fadd_rn(g, 1.0f);
+  if (convention == EEM_WARP_EXACT) return __fmul_rn(g1, (float)(size - 1) * 0.5f);
+  return __fmaf_rn(g1, (float)size * 0.5f, -0.5f);
 }
 
-__device__ __forceinline__ Bilin make_bilin(float px, float py, int H, int W, int convention) {
-  const float gx = 2.0f * px / (float)max(W - 1, 1) - 1.0f;
-  const float gy = 2.0f * py / (float)max(H - 1, 1) - 1.0f;
-  const float ix = unnormalize(gx, W, convention);
-  const float iy = unnormalize(gy, H, convention);
+__device__ __forceinline__ void fill_bilin(Bilin& s, float ix, float iy, int H, int W) {
   const float fx0 = floorf(ix), fy0 = floorf(iy);
-  Bilin s;
   // keep the integer conversion defined for wild flows; such samples are fully out of bounds
   s.x0 = (int)fminf(fmaxf(fx0, -2.0e9f), 2.0e9f);
   s.y0 = (int)fminf(fmaxf(fy0, -2.0e9f), 2.0e9f);
-  const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
-  s.nw = (fx1 - ix) * (fy1 - iy);
-  s.ne = (ix - fx0) * (fy1 - iy);
-  s.sw = (fx1 - ix) * (iy - fy0);
-  s.se = (ix - fx0) * (iy - fy0);
+  // ATen compute_interp_params: w = x - floor(x), e = 1 - w, n = y - floor(y), s = 1 - n
+  const float w = __fsub_rn(ix, fx0), e = __fsub_rn(1.0f, w);
+  const float n = __fsub_rn(iy, fy0), so = __fsub_rn(1.0f, n);
+  s.nw = __fmul_rn(so, e);
+  s.ne = __fmul_rn(so, w);
+  s.sw = __fmul_rn(n, e);
+  s.se = __fmul_rn(n, w);
   const bool xin0 = s.x0 >= 0 && s.x0 < W, xin1 = s.x0 + 1 >= 0 && s.x0 + 1 < W;
   const bool yin0 = s.y0 >= 0 && s.y0 < H, yin1 = s.y0 + 1 >= 0 && s.y0 + 1 < H;
   const bool finite = (fx0 == fx0) && (fy0 == fy0) && fabsf(fx0) < 1.0e9f && fabsf(fy0) < 1.0e9f;
@@ -46,25 +49,33 @@ __device__ __forceinline__ Bilin make_bilin(float px, float py, int H, int W, in
   s.in_ne = finite && xin1 && yin0;
   s.in_sw = finite && xin0 && yin1;
   s.in_se = finite && xin1 && yin1;
+}
+
+__device__ __forceinline__ Bilin make_bilin(float px, float py, int H, int W, int convention) {
+  // vgrid = 2.0 * (grid + flo) / max(W-1, 1) - 1.0: multiply, true division, subtract (tools.py:2289-2290)
+  const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, px), (float)max(W - 1, 1)), 1.0f);
+  const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, py), (float)max(H - 1, 1)), 1.0f);
+  Bilin s;
+  fill_bilin(s, unnormalize(gx, W, convention), unnormalize(gy, H, convention), H, W);
   return s;
 }
 
+// nw*v_nw + ne*v_ne + sw*v_sw + se*v_se, out-of-bounds taps read as 0 (ATen masks the gather).
 __device__ __forceinline__ float sample(const float* __restrict__ plane, const Bilin& s, int W) {
   const float* p = plane + (int64_t)s.y0 * W + s.x0;
-  float acc = 0.f;
-  if (s.in_nw) acc += __ldg(p) * s.nw;
-  if (s.in_ne) acc += __ldg(p + 1) * s.ne;
-  if (s.in_sw) acc += __ldg(p + W) * s.sw;
-  if (s.in_se) acc += __ldg(p + W + 1) * s.se;
-  return acc;
+  const float v_nw = s.in_nw ? __ldg(p) : 0.f;
+  const float v_ne = s.in_ne ? __ldg(p + 1) : 0.f;
+  const float v_sw = s.in_sw ? __ldg(p + W) : 0.f;
+  const float v_se = s.in_se ? __ldg(p + W + 1) : 0.f;
+  return fmaf(v_se, s.se, fmaf(v_sw, s.sw, fmaf(v_ne, s.ne, v_nw * s.nw)));
 }
 
+// grid_sample of an all-ones tensor: the weights of the in-bounds taps, summed nw, ne, sw, se.
 __device__ __forceinline__ float ones_sample(const Bilin& s) {
-  float acc = 0.f;
-  if (s.in_nw) acc += s.nw;
-  if (s.in_ne) acc += s.ne;
-  if (s.in_sw) acc += s.sw;
-  if (s.in_se) acc += s.se;
+  float acc = s.in_nw ? s.nw : 0.f;
+  acc = __fadd_rn(acc, s.in_ne ? s.ne : 0.f);
+  acc = __fadd_rn(acc, s.in_sw ? s.sw : 0.f);
+  acc = __fadd_rn(acc, s.in_se ? s.se : 0.f);
   return acc;
 }
 
@@ -189,24 +200,11 @@ bilinear_sample_kernel(const float* __restrict__ img, const float* __restrict__ 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = i / per, r = i - n * per;
     const float cx = coords[2 * i + 0], cy = coords[2 * i + 1];
-    const float gx = 2.f * cx / (float)(W - 1) - 1.f, gy = 2.f * cy / (float)(H - 1) - 1.f;
-    const float ix = ((gx + 1.f) / 2.f) * (float)(W - 1), iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    // xgrid = 2*xgrid/(W-1) - 1 (model_utils.py:11-12), then ATen's align_corners=True un-normalisation
+    const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, cx), (float)(W - 1)), 1.f);
+    const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, cy), (float)(H - 1)), 1.f);
     Bilin s;
-    s.x0 = (int)fminf(fmaxf(fx0, -2.0e9f), 2.0e9f);
-    s.y0 = (int)fminf(fmaxf(fy0, -2.0e9f), 2.0e9f);
-    const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
-    s.nw = (fx1 - ix) * (fy1 - iy);
-    s.ne = (ix - fx0) * (fy1 - iy);
-    s.sw = (fx1 - ix) * (iy - fy0);
-    s.se = (ix - fx0) * (iy - fy0);
-    const bool xin0 = s.x0 >= 0 && s.x0 < W, xin1 = s.x0 + 1 >= 0 && s.x0 + 1 < W;
-    const bool yin0 = s.y0 >= 0 && s.y0 < H, yin1 = s.y0 + 1 >= 0 && s.y0 + 1 < H;
-    const bool finite = (fx0 == fx0) && (fy0 == fy0) && fabsf(fx0) < 1.0e9f && fabsf(fy0) < 1.0e9f;
-    s.in_nw = finite && xin0 && yin0;
-    s.in_ne = finite && xin1 && yin0;
-    s.in_sw = finite && xin0 && yin1;
-    s.in_se = finite && xin1 && yin1;
+    fill_bilin(s, unnormalize(gx, W, EEM_WARP_EXACT), unnormalize(gy, H, EEM_WARP_EXACT), H, W);
     for (int c = 0; c < C; ++c)
       out[((int64_t)n * C + c) * per + r] = sample(img + ((int64_t)n * C + c) * H * W, s, W);
     if (mask_out) mask_out[i] = (gx > -1.f && gy > -1.f && gx < 1.f && gy < 1.f) ? 1.f : 0.f;

@@ -47,7 +47,19 @@ def check(B, D, H, W, L=1, seed=0, structured=False):
 
 
 if __name__ == "__main__":
+    import os
     torch.manual_seed(0)
+    if "--sweep" in sys.argv:
+        for variant in (0, 3, 1, 4, 2):
+            os.environ["EEM_TF32_VARIANT"] = str(variant)
+            print(f"===== variant {variant}")
+            try:
+                ok = check(1, 32, 8, 16) and check(1, 64, 16, 16)
+            except Exception as exc:  # keep sweeping
+                print("  exception:", exc)
+                ok = False
+            print(f"===== variant {variant}:", "OK" if ok else "MISMATCH")
+        os.environ.pop("EEM_TF32_VARIANT", None)
     allok = True
     for args in [(1, 32, 8, 16), (1, 32, 16, 16), (1, 64, 16, 16), (1, 256, 16, 24), (2, 256, 36, 44), (1, 128, 23, 40)]:
         print("random", args)

@@ -13,3 +13,8 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; e
 tail -n 3 gpurun_out/t_voxel.log gpurun_out/t_warp.log gpurun_out/t_corr_fp32.log gpurun_out/t_corr_all.log gpurun_out/smoke.log
 tail -n 25 gpurun_out/tf32_debug.log
 tail -c 1500 gpurun_out/bench.log
+if [ "$NCU" = "1" ]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu_list rc=$?" | tee -a gpurun_out/summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:corr_lookup -s 40 -c 2 -o gpurun_out/prof_lookup python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_lookup.log 2>&1; echo "ncu_lookup rc=$?" | tee -a gpurun_out/summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:corr_tf32 -s 3 -c 1 -o gpurun_out/prof_corr python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_corr.log 2>&1; echo "ncu_corr rc=$?" | tee -a gpurun_out/summary.txt
+fi

@@ -97,9 +97,10 @@ def test_warp_oracle(E, B, C, H, W):
     assert d.max().item() <= 1e-5, f"{(d > 1e-5).sum().item()} of {d.numel()} differ (mask threshold rounding?)"
     _, m = E.torch_warp_mask(xc, fc)
     assert torch.equal(m.cpu(), ref_ops.torch_warp_mask(x, flo.clone())[1])
-    # identity flow under the exact convention returns the input
+    # identity flow under the exact convention returns the input up to the reference's own
+    # normalise/un-normalise round trip (~W * eps in the coordinate, times the local gradient)
     zero = torch.zeros_like(fc)
-    assert (E.warp(xc, zero) - xc).abs().max().item() <= 1e-6
+    assert (E.warp(xc, zero) - xc).abs().max().item() <= 1e-4
 
 
 def test_resize_blend_pad_golden(golden, E):

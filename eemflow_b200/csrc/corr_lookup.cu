@@ -6,10 +6,13 @@
 //   where the first window index moves x and the second moves y (RAFT's transposed meshgrid),
 //   sampling goes through  g = 2*p/(S-1) - 1  and grid_sample(align_corners=True, zeros padding).
 //
-// A CTA owns 32 consecutive positions of one sample.  Per level it gathers each position's
-// (2r+2)^2 tap window once into shared memory (every 32-byte sector of the volume is fetched
-// once per position), then warp `a` / lane `position` produces the 2r+1 outputs of window column
-// `a`, so every store instruction writes 32 consecutive positions of one output channel (128 B).
+// A CTA owns 32 consecutive positions of one sample.  It gathers each position's (2r+2)^2 tap
+// window of EVERY level into shared memory in one phase (every 32-byte sector of the volume is
+// fetched once per position, all loads in flight together), then warp `a` / lane `position`
+// produces the 2r+1 outputs of window column `a`, so every store instruction writes 32
+// consecutive positions of one output channel (128 B).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace eem {
@@ -34,91 +37,133 @@ __device__ __forceinline__ float roundtrip(float p, int size) {
   return __fmul_rn(__fadd_rn(g, 1.0f), s1 * 0.5f);                      // ATen CPU: (g+1) * ((S-1)/2)
 }
 
+// Shared-memory layout (dynamic): per level l
+//   taps[l][pos][kStride]   (2r+2)^2 window taps of position pos, zero outside the map
+//   fx[l][pos][K], fy[l][pos][K]   bilinear fractions per window column / row
+//   org[l][pos][2]          integer window origin
+// Phases: (1) geometry for every (position, level); (2) ONE gather phase that issues every tap
+// load of every level before anything is consumed -- thread = (position, window column), walking
+// down the rows, so consecutive lanes read consecutive addresses of a window row; (3) interpolation
+// with warp = window column, lane = position, so each store instruction writes 32 consecutive
+// positions of one output channel (128 B).  Two block barriers in total.
 template <int R>
-__global__ void __launch_bounds__((2 * R + 1) * 32)
-corr_lookup_kernel(const __grid_constant__ LookupParams p) {
-  constexpr int K = 2 * R + 1;   // window size
-  constexpr int T = K + 1;       // taps per dimension
-  constexpr int TT = T * T;
-  constexpr int kStride = TT | 1;  // odd stride: lanes (positions) hit distinct banks
-  constexpr int kThreads = K * 32;
+struct LookupSmem {
+  static constexpr int K = 2 * R + 1, T = K + 1, TT = T * T, kStride = TT | 1;
+  static constexpr int kPerLevelFloats = kPosPerBlock * kStride + 2 * kPosPerBlock * K;
+  static constexpr int kPerLevelBytes = kPerLevelFloats * 4 + kPosPerBlock * 2 * 4;
+};
 
-  __shared__ float taps[kPosPerBlock * kStride];
-  __shared__ float tx[kPosPerBlock][K];  // per-position, per-window-column horizontal fraction
-  __shared__ float ty[kPosPerBlock][K];
-  __shared__ int org[kPosPerBlock][2];   // window origin (tap [0][0]) in level pixels
+template <int R>
+__global__ void __launch_bounds__((2 * R + 2) * 32)
+corr_lookup_kernel(const __grid_constant__ LookupParams p) {
+  using S = LookupSmem<R>;
+  constexpr int K = S::K, T = S::T, kStride = S::kStride;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
 
   const int P = p.H * p.W;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * kPosPerBlock;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int npos = min(kPosPerBlock, P - i0);
+  const int L = p.L;
 
-  float cx = 0.f, cy = 0.f;
-  if (threadIdx.x < npos) {
-    cx = p.coords[((int64_t)b * 2 + 0) * P + i0 + threadIdx.x];
-    cy = p.coords[((int64_t)b * 2 + 1) * P + i0 + threadIdx.x];
-  }
+  auto taps_of = [&](int l) { return reinterpret_cast<float*>(smem_raw + (size_t)l * S::kPerLevelBytes); };
+  auto fx_of = [&](int l) { return taps_of(l) + kPosPerBlock * kStride; };
+  auto fy_of = [&](int l) { return fx_of(l) + kPosPerBlock * K; };
+  auto org_of = [&](int l) { return reinterpret_cast<int*>(fy_of(l) + kPosPerBlock * K); };
 
-  for (int l = 0; l < p.L; ++l) {
+  // 1) window geometry, one thread per (position, level)
+  for (int t = threadIdx.x; t < kPosPerBlock * L; t += blockDim.x) {
+    const int l = t / kPosPerBlock, pos = t % kPosPerBlock;
     const int hl = p.h[l], wl = p.w[l];
-    const int64_t plane = (int64_t)hl * wl;
-    if (plane == 0) {  // level pooled away: grid_sample over an empty map contributes zeros
-      if (lane < npos) {
-        for (int c = 0; c < K; ++c)
-          st_stream(p.out + ((int64_t)b * p.L * K * K + (int64_t)l * K * K + warp * K + c) * P + i0 + lane, 0.f);
-      }
-      continue;
+    float cx = 0.f, cy = 0.f;
+    if (pos < npos) {
+      cx = __ldg(p.coords + ((int64_t)b * 2 + 0) * P + i0 + pos);
+      cy = __ldg(p.coords + ((int64_t)b * 2 + 1) * P + i0 + pos);
     }
-    // 1) per-position window geometry
-    if (threadIdx.x < npos) {
-      const float inv = 1.0f / (float)(1 << l);
-      const float lx = cx * inv, ly = cy * inv;  // exact: power-of-two scaling
-      // Clamp far-away / non-finite centres so the integer origin stays representable; every tap
-      // of such a window is out of the map and reads as zero either way.
-      const float ox = floorf(fminf(fmaxf(roundtrip(lx - (float)R, wl), -1.0e6f), 1.0e6f));
-      const float oy = floorf(fminf(fmaxf(roundtrip(ly - (float)R, hl), -1.0e6f), 1.0e6f));
-      org[threadIdx.x][0] = (int)ox;
-      org[threadIdx.x][1] = (int)oy;
+    const float inv = 1.0f / (float)(1 << l);
+    const float lx = cx * inv, ly = cy * inv;  // exact: power-of-two scaling
+    // Clamp far-away / non-finite centres so the integer origin stays representable; every tap of
+    // such a window is out of the map and reads as zero either way.
+    const float ox = floorf(fminf(fmaxf(roundtrip(lx - (float)R, wl), -1.0e6f), 1.0e6f));
+    const float oy = floorf(fminf(fmaxf(roundtrip(ly - (float)R, hl), -1.0e6f), 1.0e6f));
+    org_of(l)[pos * 2 + 0] = (int)ox;
+    org_of(l)[pos * 2 + 1] = (int)oy;
 #pragma unroll
-      for (int a = 0; a < K; ++a) {
-        // fraction relative to tap column a of the shared window; equals the reference's
-        // (ix - floor(ix)) except on knife-edge roundings, where it extrapolates by <= 1 ulp.
-        tx[threadIdx.x][a] = roundtrip(lx + (float)(a - R), wl) - (ox + (float)a);
-        ty[threadIdx.x][a] = roundtrip(ly + (float)(a - R), hl) - (oy + (float)a);
+    for (int a = 0; a < K; ++a) {
+      // fraction relative to tap column a of the shared window; equals the reference's
+      // (ix - floor(ix)) except on knife-edge roundings, where it extrapolates by <= 1 ulp.
+      fx_of(l)[pos * K + a] = roundtrip(lx + (float)(a - R), wl) - (ox + (float)a);
+      fy_of(l)[pos * K + a] = roundtrip(ly + (float)(a - R), hl) - (oy + (float)a);
+    }
+  }
+  __syncthreads();
+
+  // 2) gather: thread = (position, tap column); T row loads per level, all levels back to back
+  {
+    const int pos = threadIdx.x / T, col = threadIdx.x - pos * T;
+    if (pos < npos) {
+      for (int l = 0; l < L; ++l) {
+        const int hl = p.h[l], wl = p.w[l];
+        const int64_t plane = (int64_t)hl * wl;
+        float* tp = taps_of(l) + pos * kStride + col;
+        const int x = org_of(l)[pos * 2 + 0] + col, y0 = org_of(l)[pos * 2 + 1];
+        const bool x_ok = x >= 0 && x < wl;
+        const float* src = p.level[l] + ((int64_t)b * P + i0 + pos) * plane + (int64_t)y0 * wl + x;
+        float v[T];
+#pragma unroll
+        for (int r = 0; r < T; ++r) {
+          const int y = y0 + r;
+          v[r] = (x_ok && y >= 0 && y < hl) ? __ldg(src + (int64_t)r * wl) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < T; ++r) tp[r * T] = v[r];
       }
     }
-    __syncthreads();
-    // 2) gather taps: consecutive threads walk a window row, so a row costs 1-2 sectors
-    const float* lvl = p.level[l] + ((int64_t)b * P + i0) * plane;
-    for (int t = threadIdx.x; t < npos * TT; t += kThreads) {
-      const int pos = t / TT, tap = t - pos * TT;
-      const int r = tap / T, c = tap - r * T;
-      const int x = org[pos][0] + c, y = org[pos][1] + r;
-      float v = 0.f;
-      if (x >= 0 && x < wl && y >= 0 && y < hl) v = __ldg(lvl + (int64_t)pos * plane + (int64_t)y * wl + x);
-      taps[pos * kStride + tap] = v;
-    }
-    __syncthreads();
-    // 3) warp `a` = window column (x offset), lane = position; walk down the rows reusing the
-    //    horizontal interpolation of the previous row.
-    if (lane < npos) {
-      const int a = warp;
-      const float fx = tx[lane][a];
-      const float* tp = taps + lane * kStride + a;
+  }
+  __syncthreads();
+
+  // 3) interpolate: warp = window column a (x offset), lane = position; walk down the rows reusing
+  //    the horizontal interpolation of the previous row.
+  if (warp < K && lane < npos) {
+    const int a = warp;
+    for (int l = 0; l < L; ++l) {
+      float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a * K) * P + i0 + lane;
+      if ((int64_t)p.h[l] * p.w[l] == 0) {  // level pooled away: an empty map contributes zeros
+#pragma unroll
+        for (int c = 0; c < K; ++c) st_stream(o + (int64_t)c * P, 0.f);
+        continue;
+      }
+      const float fx = fx_of(l)[lane * K + a];
+      const float* tp = taps_of(l) + lane * kStride + a;
+      const float* fy = fy_of(l) + lane * K;
       float prev = tp[0] + fx * (tp[1] - tp[0]);
-      float* o = p.out + ((int64_t)b * p.L * K * K + (int64_t)l * K * K + a * K) * P + i0 + lane;
 #pragma unroll
       for (int c = 0; c < K; ++c) {
         const float* row = tp + (c + 1) * T;
         const float cur = row[0] + fx * (row[1] - row[0]);
-        const float fy = ty[lane][c];
-        st_stream(o + (int64_t)c * P, prev + fy * (cur - prev));
+        st_stream(o + (int64_t)c * P, prev + fy[c] * (cur - prev));
         prev = cur;
       }
     }
-    __syncthreads();
   }
+}
+
+template <int R>
+int launch_lookup(const LookupParams& p, dim3 grid, cudaStream_t stream) {
+  using S = LookupSmem<R>;
+  const size_t smem = (size_t)p.L * S::kPerLevelBytes;
+  static std::mutex mu;
+  static size_t configured = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (smem > configured) {
+      EEM_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+  }
+  corr_lookup_kernel<R><<<grid, (2 * R + 2) * 32, smem, stream>>>(p);
+  return EEM_OK;
 }
 
 __global__ void __launch_bounds__(256)
@@ -165,14 +210,16 @@ int eem_corr_lookup(const float* const* levels, int B, int H, int W, int num_lev
   const int P = H * W;
   dim3 grid((unsigned)ceil_div(P, kPosPerBlock), (unsigned)B);
   cudaStream_t stream = as_stream(stream_);
+  int rc = EEM_OK;
   switch (radius) {
-    case 4: corr_lookup_kernel<4><<<grid, 9 * 32, 0, stream>>>(p); break;
-    case 3: corr_lookup_kernel<3><<<grid, 7 * 32, 0, stream>>>(p); break;
-    case 2: corr_lookup_kernel<2><<<grid, 5 * 32, 0, stream>>>(p); break;
-    case 1: corr_lookup_kernel<1><<<grid, 3 * 32, 0, stream>>>(p); break;
+    case 4: rc = launch_lookup<4>(p, grid, stream); break;
+    case 3: rc = launch_lookup<3>(p, grid, stream); break;
+    case 2: rc = launch_lookup<2>(p, grid, stream); break;
+    case 1: rc = launch_lookup<1>(p, grid, stream); break;
     default:
       return fail(EEM_ERR_UNSUPPORTED, "eem_corr_lookup: radius %d not in {1,2,3,4}", radius);
   }
+  if (rc != EEM_OK) return rc;
   EEM_CHECK_LAUNCH("corr_lookup_kernel");
   return EEM_OK;
 }

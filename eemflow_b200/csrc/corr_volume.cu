@@ -102,7 +102,7 @@ constexpr int BM = 128;       // MMA M: positions j of the (pooled) fmap2 level 
 constexpr int BN = 128;       // MMA N: positions i of fmap1                    -> TMEM columns
 constexpr int BK = 32;        // channels per pipeline stage (one 128-byte-swizzled TMA box row count)
 constexpr int UK = 8;         // K of one tcgen05.mma kind::tf32
-constexpr int kStages = 4;    // fmap1 (streamed operand) ring depth
+constexpr int kStages = 6;    // fmap1 (streamed operand) ring depth: 96 KiB in flight per SM
 constexpr int kMaxKB = 8;     // resident-operand capacity: D <= kMaxKB * BK = 256
 constexpr int kBoxBytes = 32 * BK * 4;          // one TMA box: 32 positions x BK channels fp32 = 4 KiB
 constexpr int kTileKBytes = (BM / 32) * kBoxBytes;  // 16 KiB: 128 positions x BK channels
@@ -117,7 +117,7 @@ struct Tf32Params {
   int mt_cum[kMaxLevels + 1];         // cumulative 128-row tile counts over levels
   int B, D, P, L;
   int n_tiles;                        // ceil(P / BN)
-  int64_t total_tiles;                // B * mt_cum[L] * n_tiles
+  int64_t n_items;                    // B * mt_cum[L]
   float scale;
   uint32_t desc_lo, desc_hi;          // constant smem-descriptor fields (desc_fields)
 };
@@ -146,10 +146,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+// L2 cache policies: the feature-map operands (a few MB per sample, re-read by every tile) are kept
+// with evict_last; the volume being written (hundreds of MB, not re-read by this kernel) is marked
+// evict_first so that it does not flush the operands out of the 126 MB L2.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_evict_first(float* p, float v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -196,13 +212,50 @@ struct TileCoord {
   int64_t item;  // (b, l, m-tile) id: tiles of one item share the resident operand
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const Tf32Params& p, int64_t t) {
+// Work order.  An "item" is (sample b, level l, 128-row tile of that level): its resident operand
+// is loaded once and reused for all n_tiles output tiles.  Items are numbered sample-major and
+// dealt round-robin -- in round r CTA c owns item r*G + c -- so at any moment the CTAs work on ~G
+// consecutive items, i.e. a handful of samples whose feature maps (a few MB each) stay in L2.  The
+// n_items % G leftover items are cut into single tiles and spread evenly over all CTAs, so the
+// tail costs ceil(leftover_tiles / G) tile-times instead of a whole item.
+struct TileSched {
+  int64_t cta, G, r_full, full_tiles, tail_begin, tail_end;
+  int n_tiles;
+  __device__ __forceinline__ int64_t count() const { return full_tiles + (tail_end - tail_begin); }
+  __device__ __forceinline__ void at(int64_t k, int64_t& item, int& nt) const {
+    if (k < full_tiles) {
+      const int64_t r = k / n_tiles;
+      item = r * G + cta;
+      nt = (int)(k - r * n_tiles);
+    } else {
+      const int64_t t = tail_begin + (k - full_tiles);
+      const int64_t q = t / n_tiles;
+      item = r_full * G + q;
+      nt = (int)(t - q * n_tiles);
+    }
+  }
+};
+
+__device__ __forceinline__ TileSched make_sched(const Tf32Params& p) {
+  TileSched s;
+  s.cta = blockIdx.x;
+  s.G = gridDim.x;
+  s.n_tiles = p.n_tiles;
+  s.r_full = p.n_items / s.G;
+  s.full_tiles = s.r_full * p.n_tiles;
+  const int64_t tail_tiles = (p.n_items - s.r_full * s.G) * p.n_tiles;
+  s.tail_begin = tail_tiles * s.cta / s.G;
+  s.tail_end = tail_tiles * (s.cta + 1) / s.G;
+  return s;
+}
+
+__device__ __forceinline__ TileCoord decode_tile(const Tf32Params& p, int64_t item, int nt) {
   TileCoord c;
-  c.item = t / p.n_tiles;
-  c.n0 = (int)(t - c.item * p.n_tiles) * BN;
+  c.item = item;
+  c.n0 = nt * BN;
   const int ipb = p.mt_cum[p.L];
-  c.b = (int)(c.item / ipb);
-  const int r = (int)(c.item - (int64_t)c.b * ipb);
+  c.b = (int)(item / ipb);
+  const int r = (int)(item - (int64_t)c.b * ipb);
   int l = 0;
   while (l + 1 < p.L && r >= p.mt_cum[l + 1]) ++l;
   c.l = l;
@@ -212,7 +265,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Tf32Params& p, int64_t t)
 
 struct __align__(1024) Tf32Smem {
   uint8_t resident[kMaxKB * kTileKBytes];   // pooled-fmap2 panel of the current item: 128 KiB
-  uint8_t ring[kStages * kTileKBytes];      // fmap1 stages: 64 KiB
+  uint8_t ring[kStages * kTileKBytes];      // fmap1 stages: 6 x 16 KiB
   uint64_t full[kStages], empty[kStages];
   uint64_t res_free[kMaxKB];                // resident k-block may be overwritten
   uint64_t acc_full[2], acc_empty[2];
@@ -241,19 +294,22 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
 
-  // Contiguous tile range per CTA: balanced to +-1 tile, at most one extra resident reload.
-  const int64_t t_begin = p.total_tiles * blockIdx.x / gridDim.x;
-  const int64_t t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+  const TileSched sched = make_sched(p);
+  const int64_t n_mine = sched.count();
 
   if (warp == 4) {
     // ===== TMA producer =====
     if (lane == 0) {
+      const uint64_t keep = policy_evict_last();
       int stage = 0;
       uint32_t phase = 0;
       int64_t prev_item = -1;
       uint32_t items_done = 0;
-      for (int64_t t = t_begin; t < t_end; ++t) {
-        const TileCoord c = decode_tile(p, t);
+      for (int64_t k = 0; k < n_mine; ++k) {
+        int64_t item;
+        int nt;
+        sched.at(k, item, nt);
+        const TileCoord c = decode_tile(p, item, nt);
         const bool new_item = c.item != prev_item;
         for (int kb = 0; kb < KB; ++kb) {
           if (new_item && items_done > 0) mbar_wait(&s.res_free[kb], (items_done - 1) & 1);
@@ -263,11 +319,13 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
           if (new_item) {
             uint8_t* dst = s.resident + kb * kTileKBytes;
 #pragma unroll
-            for (int ch = 0; ch < BM / 32; ++ch) tma_load_2d(dst + ch * kBoxBytes, &p.map_lvl[c.l], c.m0 + ch * 32, row, &s.full[stage]);
+            for (int ch = 0; ch < BM / 32; ++ch)
+              tma_load_2d(dst + ch * kBoxBytes, &p.map_lvl[c.l], c.m0 + ch * 32, row, &s.full[stage], keep);
           }
           uint8_t* dst = s.ring + stage * kTileKBytes;
 #pragma unroll
-          for (int ch = 0; ch < BN / 32; ++ch) tma_load_2d(dst + ch * kBoxBytes, &p.map_f1, c.n0 + ch * 32, row, &s.full[stage]);
+          for (int ch = 0; ch < BN / 32; ++ch)
+            tma_load_2d(dst + ch * kBoxBytes, &p.map_f1, c.n0 + ch * 32, row, &s.full[stage], keep);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (new_item) { ++items_done; prev_item = c.item; }
@@ -278,12 +336,14 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t tile_count = 0;
-      for (int64_t t = t_begin; t < t_end; ++t) {
-        const int64_t item = t / p.n_tiles;
-        const bool last_of_item = (t + 1 == t_end) || ((t + 1) / p.n_tiles != item);
-        const uint32_t acc = tile_count & 1;
-        mbar_wait(&s.acc_empty[acc], ((tile_count >> 1) & 1) ^ 1);
+      for (int64_t k = 0; k < n_mine; ++k) {
+        int64_t item, next_item = -1;
+        int nt, nt2;
+        sched.at(k, item, nt);
+        if (k + 1 < n_mine) sched.at(k + 1, next_item, nt2);
+        const bool last_of_item = next_item != item;
+        const uint32_t acc = (uint32_t)k & 1;
+        mbar_wait(&s.acc_empty[acc], (((uint32_t)k >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem + acc * BN;
         for (int kb = 0; kb < KB; ++kb) {
@@ -302,16 +362,18 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         tc_commit(&s.acc_full[acc]);
-        ++tile_count;
       }
     }
   } else {
     // ===== epilogue warps 0-3: TMEM lanes [32*warp, 32*warp+32) =====
-    uint32_t tile_count = 0;
-    for (int64_t t = t_begin; t < t_end; ++t) {
-      const TileCoord c = decode_tile(p, t);
-      const uint32_t acc = tile_count & 1;
-      mbar_wait(&s.acc_full[acc], (tile_count >> 1) & 1);
+    const uint64_t stream_out = policy_evict_first();
+    for (int64_t k = 0; k < n_mine; ++k) {
+      int64_t item;
+      int nt;
+      sched.at(k, item, nt);
+      const TileCoord c = decode_tile(p, item, nt);
+      const uint32_t acc = (uint32_t)k & 1;
+      mbar_wait(&s.acc_full[acc], ((uint32_t)k >> 1) & 1);
       tc_fence_after();
       const int Pl = p.Pl[c.l];
       const int j = c.m0 + warp * 32 + lane;
@@ -333,18 +395,18 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int i_base = c.n0 + cc * 32;
         if (j_ok) {
+          float* o = obase + (int64_t)i_base * Pl;
+          const int n_valid = min(32, p.P - i_base);
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
-            const int i = i_base + r;
             // lanes = 32 consecutive j of output row i: one 128-byte store per row per warp
-            if (i < p.P) st_stream(obase + (int64_t)i * Pl, __uint_as_float(v[r]) * p.scale);
+            if (r < n_valid) st_evict_first(o + (int64_t)r * Pl, __uint_as_float(v[r]) * p.scale, stream_out);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
-      ++tile_count;
     }
   }
 
@@ -516,7 +578,7 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   }
   p.B = B; p.D = D; p.P = P; p.L = nl;
   p.n_tiles = (int)ceil_div(P, BN);
-  p.total_tiles = (int64_t)B * p.mt_cum[nl] * p.n_tiles;
+  p.n_items = (int64_t)B * p.mt_cum[nl];
   p.scale = scale;
   const size_t smem = sizeof(Tf32Smem) + 1024;
   static std::mutex attr_mu;
@@ -526,7 +588,7 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   }
   int64_t grid = sm_count();
   if (grid <= 0) return fail(EEM_ERR_CUDA, "eem_corr_pyramid: cannot query SM count");
-  if (grid > p.total_tiles) grid = p.total_tiles;
+  if (grid > p.n_items * p.n_tiles) grid = p.n_items * p.n_tiles;
   corr_tf32_kernel<<<(unsigned)grid, kTf32Threads, smem, stream>>>(p);
   EEM_CHECK_LAUNCH("corr_tf32_kernel");
   return EEM_OK;

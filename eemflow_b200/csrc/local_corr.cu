@@ -11,6 +11,8 @@
 // float4 and three f2 float4 (12 consecutive columns) from shared memory and issues 36 FMAs, so
 // the loop is FMA-bound rather than LDS-bound.  Channels stream through shared memory in chunks
 // of 8 with the f2 halo (+-4) loaded once per chunk.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace eem {
@@ -34,7 +36,7 @@ struct LocalCorrParams {
 };
 
 __global__ void __launch_bounds__(kThreads)
-local_corr_kernel(const __grid_constant__ LocalCorrParams p) {
+local_corr_generic_kernel(const __grid_constant__ LocalCorrParams p) {
   __shared__ __align__(16) float s1[CC][TH][TW];
   __shared__ __align__(16) float s2[CC][F2H][F2W];
 
@@ -108,6 +110,114 @@ local_corr_kernel(const __grid_constant__ LocalCorrParams p) {
   }
 }
 
+
+// ---- fast path (W % 4 == 0, 16-byte aligned inputs) -----------------------------------------
+// Tile 8 x 32 pixels.  Warp = dy (9 warps), lane = (row 0..7, octet 0..3): a thread owns 8
+// horizontally adjacent pixels x 9 dx = 72 accumulators and per channel reads 2 float4 of f1 and
+// 4 float4 of f2 (16 consecutive columns), i.e. 6 LDS.128 per 72 FMAs.  Channel chunks of 8 are
+// staged with cp.async (16-byte copies, zero-filled outside the image) into a double buffer so the
+// loads of chunk k+1 overlap the FMAs of chunk k.  Row pitches (36 / 44 floats) are chosen so the
+// 8 lanes of an LDS.128 phase hit distinct banks.
+constexpr int VW = 32, VH = 8;
+constexpr int VC = 8;                       // channels per stage
+constexpr int S1P = 36;                     // f1 smem row pitch (floats)
+constexpr int S2W = VW + 2 * MD;            // 40 valid columns
+constexpr int S2P = 44;                     // f2 smem row pitch (floats)
+constexpr int S2H = VH + 2 * MD;            // 16
+constexpr int kS1Floats = VC * VH * S1P;    // 2304
+constexpr int kS2Floats = VC * S2H * S2P;   // 5632
+constexpr int kStageFloats = kS1Floats + kS2Floats;
+constexpr int kVec1 = VC * VH * (VW / 4);   // 512 16-byte copies of f1 per stage
+constexpr int kVec2 = VC * S2H * (S2W / 4); // 1280 of f2
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;  // src-size 0: nothing is read, the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+local_corr_vec_kernel(const __grid_constant__ LocalCorrParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * VW, y0 = blockIdx.y * VH;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = lane >> 2, oct = (lane & 3) * 8;
+  const int dy = warp - MD;
+  const int64_t plane = (int64_t)p.H * p.W;
+  const float* f1 = p.f1 + (int64_t)b * p.C * plane;
+  const float* f2 = p.f2 + (int64_t)b * p.C * plane;
+  const int n_chunks = (p.C + VC - 1) / VC;
+
+  auto issue = [&](int chunk, int buf) {
+    float* s1 = smem + buf * kStageFloats;
+    float* s2 = s1 + kS1Floats;
+    const int c0 = chunk * VC;
+    for (int v = threadIdx.x; v < kVec1 + kVec2; v += kThreads) {
+      if (v < kVec1) {
+        const int c = v >> 6, r = (v >> 3) & 7, q = v & 7;
+        const int gy = y0 + r, gx = x0 + 4 * q;
+        const bool ok = (c0 + c < p.C) && gy < p.H && gx < p.W;
+        cp_async16(s1 + (c * VH + r) * S1P + 4 * q, ok ? f1 + (int64_t)(c0 + c) * plane + (int64_t)gy * p.W + gx : f1, ok);
+      } else {
+        const int w = v - kVec1;
+        const int c = w / (S2H * (S2W / 4)), rem = w - c * (S2H * (S2W / 4));
+        const int r = rem / (S2W / 4), q = rem - r * (S2W / 4);
+        const int gy = y0 + r - MD, gx = x0 - MD + 4 * q;
+        const bool ok = (c0 + c < p.C) && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+        cp_async16(s2 + (c * S2H + r) * S2P + 4 * q, ok ? f2 + (int64_t)(c0 + c) * plane + (int64_t)gy * p.W + gx : f2, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[8][ND];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int d = 0; d < ND; ++d) acc[i][d] = 0.f;
+
+  issue(0, 0);
+  for (int k = 0; k < n_chunks; ++k) {
+    if (k + 1 < n_chunks) {
+      issue(k + 1, (k + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* s1 = smem + (k & 1) * kStageFloats;
+    const float* s2 = s1 + kS1Floats;
+#pragma unroll 1
+    for (int c = 0; c < VC; ++c) {
+      const float4* a4 = reinterpret_cast<const float4*>(s1 + (c * VH + row) * S1P + oct);
+      const float4* w4 = reinterpret_cast<const float4*>(s2 + (c * S2H + row + MD + dy) * S2P + oct);
+      const float4 a0 = a4[0], a1 = a4[1];
+      const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[i][d] = fmaf(av[i], wv[i + d], acc[i][d]);
+    }
+    __syncthreads();
+  }
+
+  const int gy = y0 + row, gx = x0 + oct;
+  if (gy >= p.H || gx >= p.W) return;
+  const bool second = gx + 4 < p.W;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const int slot = p.slot[(dy + MD) * ND + d];
+    if (slot < 0) continue;
+    float* o = p.out + ((int64_t)b * p.n_out + slot) * plane + (int64_t)gy * p.W + gx;
+    st_stream4(o, make_float4(acc[0][d] * p.scale, acc[1][d] * p.scale, acc[2][d] * p.scale, acc[3][d] * p.scale));
+    if (second)
+      st_stream4(o + 4, make_float4(acc[4][d] * p.scale, acc[5][d] * p.scale, acc[6][d] * p.scale, acc[7][d] * p.scale));
+  }
+}
+
 }  // namespace
 }  // namespace eem
 
@@ -138,8 +248,23 @@ extern "C" int eem_local_corr(const float* f1, const float* f2, int B, int C, in
       p.slot[index[k]] = (signed char)k;
     }
   }
+  const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) |
+                                        reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  if (vec_ok) {
+    const size_t smem = 2 * (size_t)kStageFloats * sizeof(float);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+      attr_err = cudaFuncSetAttribute(local_corr_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
+    if (attr_err != cudaSuccess) return fail(EEM_ERR_CUDA, "local_corr_vec_kernel attribute: %s", cudaGetErrorString(attr_err));
+    dim3 grid((unsigned)ceil_div(W, VW), (unsigned)ceil_div(H, VH), (unsigned)B);
+    local_corr_vec_kernel<<<grid, kThreads, smem, as_stream(stream_)>>>(p);
+    EEM_CHECK_LAUNCH("local_corr_vec_kernel");
+    return EEM_OK;
+  }
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)ceil_div(H, TH), (unsigned)B);
-  local_corr_kernel<<<grid, kThreads, 0, as_stream(stream_)>>>(p);
-  EEM_CHECK_LAUNCH("local_corr_kernel");
+  local_corr_generic_kernel<<<grid, kThreads, 0, as_stream(stream_)>>>(p);
+  EEM_CHECK_LAUNCH("local_corr_generic_kernel");
   return EEM_OK;
 }

@@ -159,13 +159,16 @@ bilinear_resize_kernel(const float* __restrict__ in, int B, int C, int h, int w,
   source_index(X, w, W, align_corners, x0, x1, lx0, lx1);
   source_index(Y, h, H, align_corners, y0, y1, ly0, ly1);
   const int64_t ip = (int64_t)h * w, op = (int64_t)H * W;
+  // source taps and weights are computed once per output pixel and reused over the planes
+  const int o00 = y0 * w + x0, o01 = y0 * w + x1, o10 = y1 * w + x0, o11 = y1 * w + x1;
+  const int64_t opix = (int64_t)Y * W + X;
+#pragma unroll 4
   for (int bc = blockIdx.z; bc < B * C; bc += gridDim.z) {
     const int c = bc % C;
     const float* s = in + (int64_t)bc * ip;
-    const float v = ly0 * (lx0 * __ldg(s + (int64_t)y0 * w + x0) + lx1 * __ldg(s + (int64_t)y0 * w + x1)) +
-                    ly1 * (lx0 * __ldg(s + (int64_t)y1 * w + x0) + lx1 * __ldg(s + (int64_t)y1 * w + x1));
+    const float v = ly0 * (lx0 * __ldg(s + o00) + lx1 * __ldg(s + o01)) + ly1 * (lx0 * __ldg(s + o10) + lx1 * __ldg(s + o11));
     const float sc = c == 0 ? scale0 : (c == 1 ? scale1 : scale_rest);
-    st_stream(out + (int64_t)bc * op + (int64_t)Y * W + X, v * sc);
+    st_stream(out + (int64_t)bc * op + opix, v * sc);
   }
 }
 
@@ -248,7 +251,13 @@ int eem_bilinear_resize(const float* in, int B, int C, int h, int w, float* out,
   EEM_CHECK_ARG(in && out, "eem_bilinear_resize: NULL pointer");
   EEM_CHECK_ARG(B > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "eem_bilinear_resize: sizes must be > 0");
   const int64_t bc = (int64_t)B * C;
-  dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)(bc < 65535 ? bc : 65535));
+  // enough CTAs to fill the chip (~8 per SM), the rest of the planes are looped inside the thread
+  const int64_t blocks_xy = ceil_div(W, 32) * ceil_div(H, 8);
+  int64_t gz = ceil_div((int64_t)sm_count() * 8, blocks_xy);
+  if (gz < 1) gz = 1;
+  if (gz > bc) gz = bc;
+  if (gz > 65535) gz = 65535;
+  dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)gz);
   bilinear_resize_kernel<<<grid, 256, 0, as_stream(stream_)>>>(in, B, C, h, w, out, H, W, align_corners ? 1 : 0, scale0, scale1, scale_rest);
   EEM_CHECK_LAUNCH("bilinear_resize_kernel");
   return EEM_OK;

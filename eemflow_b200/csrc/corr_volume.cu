@@ -100,17 +100,26 @@ corr_fp32_kernel(const float* __restrict__ f1, const float* __restrict__ f2l, in
 // ---------------------------------------------------------------------------------------------
 constexpr int BM = 128;       // MMA M: positions j of the (pooled) fmap2 level -> TMEM lanes
 constexpr int BN = 128;       // MMA N: positions i of fmap1                    -> TMEM columns
-constexpr int BK = 32;        // channels per pipeline stage (one 128-byte-swizzled TMA box row count)
 constexpr int UK = 8;         // K of one tcgen05.mma kind::tf32
-constexpr int kStages = 6;    // fmap1 (streamed operand) ring depth: 96 KiB in flight per SM
-constexpr int kMaxKB = 8;     // resident-operand capacity: D <= kMaxKB * BK = 256
-constexpr int kBoxBytes = 32 * BK * 4;          // one TMA box: 32 positions x BK channels fp32 = 4 KiB
-constexpr int kTileKBytes = (BM / 32) * kBoxBytes;  // 16 KiB: 128 positions x BK channels
+constexpr int kMaxD = 256;    // resident-operand capacity: 128 positions x 256 channels fp32 = 128 KiB
+constexpr int kRingBytes = 96 * 1024;           // streamed-operand ring: 96 KiB in flight per SM
 constexpr int kTmemCols = 2 * BN;               // two accumulator buffers
-constexpr int kTf32Threads = 192;               // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer
+constexpr int kEpiWarps = 8;                    // two epilogue warps per TMEM lane quarter (column halves)
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kTf32Threads = (kEpiWarps + 2) * 32; // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
+
+// BK = channels per pipeline stage.  BK = 64 (used whenever D % 64 == 0) gives the single MMA-issuing
+// thread 8 MMAs (512 tensor-pipe cycles) per mbarrier round trip; BK = 32 covers D % 32 == 0.
+template <int BK>
+struct Cfg {
+  static constexpr int kBoxBytes = 32 * BK * 4;                 // one TMA box: 32 positions x BK channels fp32
+  static constexpr int kTileKBytes = (BM / 32) * kBoxBytes;     // 128 positions x BK channels
+  static constexpr int kStages = kRingBytes / kTileKBytes;      // 6 (BK=32) or 3 (BK=64)
+  static constexpr int kMaxKB = kMaxD / BK;
+};
 
 struct Tf32Params {
-  CUtensorMap map_f1;                 // [B*D, P] fp32, box 32 x BK, SWIZZLE_128B
+  CUtensorMap map_f1;                 // [B*D, P] fp32, box 32 positions x BK channels, 128B_ATOM_32B swizzle
   CUtensorMap map_lvl[kMaxLevels];    // level operands [B*D, P_l] (pitch multiple of 4)
   float* out[kMaxLevels];
   int Pl[kMaxLevels];
@@ -120,6 +129,7 @@ struct Tf32Params {
   int64_t n_items;                    // B * mt_cum[L]
   float scale;
   uint32_t desc_lo, desc_hi;          // constant smem-descriptor fields (desc_fields)
+  uint32_t debug;                     // EEM_TF32_DEBUG bits (timing experiments only): 1 skip MMA, 2 skip stores, 4 skip streamed loads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,6 +171,16 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 }
 __device__ __forceinline__ void st_evict_first(float* p, float v, uint64_t pol) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+// Predicated form: a single @p STG, so the unrolled epilogue has no branches.
+__device__ __forceinline__ void st_evict_first_if(float* p, float v, uint64_t pol, bool pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %3, 0;\n"
+      "@q st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;\n"
+      "}\n" ::"l"(p), "f"(v), "l"(pol), "r"((int)pred)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint64_t pol) {
   asm volatile(
@@ -207,85 +227,113 @@ inline void desc_fields(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-struct TileCoord {
-  int b, l, m0, n0;
-  int64_t item;  // (b, l, m-tile) id: tiles of one item share the resident operand
-};
-
 // Work order.  An "item" is (sample b, level l, 128-row tile of that level): its resident operand
 // is loaded once and reused for all n_tiles output tiles.  Items are numbered sample-major and
 // dealt round-robin -- in round r CTA c owns item r*G + c -- so at any moment the CTAs work on ~G
 // consecutive items, i.e. a handful of samples whose feature maps (a few MB each) stay in L2.  The
 // n_items % G leftover items are cut into single tiles and spread evenly over all CTAs, so the
 // tail costs ceil(leftover_tiles / G) tile-times instead of a whole item.
-struct TileSched {
-  int64_t cta, G, r_full, full_tiles, tail_begin, tail_end;
-  int n_tiles;
-  __device__ __forceinline__ int64_t count() const { return full_tiles + (tail_end - tail_begin); }
-  __device__ __forceinline__ void at(int64_t k, int64_t& item, int& nt) const {
-    if (k < full_tiles) {
-      const int64_t r = k / n_tiles;
-      item = r * G + cta;
-      nt = (int)(k - r * n_tiles);
+// Division-free iterator over this CTA's tiles: the single TMA / MMA issuing threads walk it once
+// per tile, so it must cost a handful of instructions (an earlier version used 64-bit div/mod
+// here and spent more time in it than in the MMAs).
+struct TileIter {
+  int cta, G, n_tiles, ipb;
+  int r, r_full;          // current round / number of full rounds
+  int item, nt;           // current item and n-tile
+  int tail_left;          // tiles still to visit in the tail phase (valid once r == r_full)
+  int remaining;          // total tiles still to visit, including the current one
+  int b, l, m0;           // decoded item
+
+  __device__ __forceinline__ void decode(const Tf32Params& p) {
+    b = item / ipb;       // 32-bit, once per item (every n_tiles tiles)
+    const int rr = item - b * ipb;
+    int lv = 0;
+    while (lv + 1 < p.L && rr >= p.mt_cum[lv + 1]) ++lv;
+    l = lv;
+    m0 = (rr - p.mt_cum[lv]) * BM;
+  }
+
+  __device__ __forceinline__ void init(const Tf32Params& p) {
+    cta = blockIdx.x;
+    G = gridDim.x;
+    n_tiles = p.n_tiles;
+    ipb = p.mt_cum[p.L];
+    const int n_items = (int)p.n_items;
+    r_full = n_items / G;
+    const int tail_tiles = (n_items - r_full * G) * n_tiles;
+    const int tail_begin = (int)((int64_t)tail_tiles * cta / G);
+    const int tail_end = (int)((int64_t)tail_tiles * (cta + 1) / G);
+    tail_left = tail_end - tail_begin;
+    remaining = r_full * n_tiles + tail_left;
+    r = 0;
+    if (r_full > 0) {
+      item = cta;
+      nt = 0;
     } else {
-      const int64_t t = tail_begin + (k - full_tiles);
-      const int64_t q = t / n_tiles;
+      const int q = tail_begin / n_tiles;
       item = r_full * G + q;
-      nt = (int)(t - q * n_tiles);
+      nt = tail_begin - q * n_tiles;
     }
+    tail_begin_ = tail_begin;
+    if (remaining > 0) decode(p);
+  }
+  int tail_begin_;
+
+  __device__ __forceinline__ bool valid() const { return remaining > 0; }
+  // true when the current tile is the last one this CTA computes for the current item
+  __device__ __forceinline__ bool last_of_item() const { return nt + 1 == n_tiles || remaining == 1; }
+  __device__ __forceinline__ int n0() const { return nt * BN; }
+
+  // advance; returns true when the item changed
+  __device__ __forceinline__ bool next(const Tf32Params& p) {
+    --remaining;
+    if (remaining <= 0) return false;
+    if (++nt < n_tiles) return false;
+    nt = 0;
+    if (r < r_full) {
+      ++r;
+      if (r < r_full) {
+        item = r * G + cta;
+      } else {  // enter the tail: contiguous range of leftover tiles
+        const int q = tail_begin_ / n_tiles;
+        item = r_full * G + q;
+        nt = tail_begin_ - q * n_tiles;
+      }
+    } else {
+      ++item;
+    }
+    decode(p);
+    return true;
   }
 };
 
-__device__ __forceinline__ TileSched make_sched(const Tf32Params& p) {
-  TileSched s;
-  s.cta = blockIdx.x;
-  s.G = gridDim.x;
-  s.n_tiles = p.n_tiles;
-  s.r_full = p.n_items / s.G;
-  s.full_tiles = s.r_full * p.n_tiles;
-  const int64_t tail_tiles = (p.n_items - s.r_full * s.G) * p.n_tiles;
-  s.tail_begin = tail_tiles * s.cta / s.G;
-  s.tail_end = tail_tiles * (s.cta + 1) / s.G;
-  return s;
-}
-
-__device__ __forceinline__ TileCoord decode_tile(const Tf32Params& p, int64_t item, int nt) {
-  TileCoord c;
-  c.item = item;
-  c.n0 = nt * BN;
-  const int ipb = p.mt_cum[p.L];
-  c.b = (int)(item / ipb);
-  const int r = (int)(item - (int64_t)c.b * ipb);
-  int l = 0;
-  while (l + 1 < p.L && r >= p.mt_cum[l + 1]) ++l;
-  c.l = l;
-  c.m0 = (r - p.mt_cum[l]) * BM;
-  return c;
-}
-
+template <int BK>
 struct __align__(1024) Tf32Smem {
-  uint8_t resident[kMaxKB * kTileKBytes];   // pooled-fmap2 panel of the current item: 128 KiB
-  uint8_t ring[kStages * kTileKBytes];      // fmap1 stages: 6 x 16 KiB
-  uint64_t full[kStages], empty[kStages];
-  uint64_t res_free[kMaxKB];                // resident k-block may be overwritten
+  uint8_t resident[kMaxD * 128 * 4];          // pooled-fmap2 panel of the current item: 128 KiB
+  uint8_t ring[kRingBytes];                   // fmap1 stages
+  uint64_t full[Cfg<BK>::kStages], empty[Cfg<BK>::kStages];
+  uint64_t res_free[Cfg<BK>::kMaxKB];         // resident k-block may be overwritten
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
+template <int BK>
 __global__ void __launch_bounds__(kTf32Threads, 1)
 corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
+  constexpr int kStages = Cfg<BK>::kStages, kMaxKB = Cfg<BK>::kMaxKB;
+  constexpr int kBoxBytes = Cfg<BK>::kBoxBytes, kTileKBytes = Cfg<BK>::kTileKBytes;
   extern __shared__ uint8_t smem_raw[];
-  Tf32Smem& s = *reinterpret_cast<Tf32Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Tf32Smem<BK>& s = *reinterpret_cast<Tf32Smem<BK>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.D / BK;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     for (int i = 0; i < kMaxKB; ++i) mbar_init(&s.res_free[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -294,56 +342,54 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
 
-  const TileSched sched = make_sched(p);
-  const int64_t n_mine = sched.count();
-
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     // ===== TMA producer =====
     if (lane == 0) {
       const uint64_t keep = policy_evict_last();
+      const bool stream = !(p.debug & 4);
+      TileIter it;
+      it.init(p);
       int stage = 0;
       uint32_t phase = 0;
-      int64_t prev_item = -1;
+      bool new_item = true;
       uint32_t items_done = 0;
-      for (int64_t k = 0; k < n_mine; ++k) {
-        int64_t item;
-        int nt;
-        sched.at(k, item, nt);
-        const TileCoord c = decode_tile(p, item, nt);
-        const bool new_item = c.item != prev_item;
+      while (it.valid()) {
+        const int n0 = it.n0();
         for (int kb = 0; kb < KB; ++kb) {
           if (new_item && items_done > 0) mbar_wait(&s.res_free[kb], (items_done - 1) & 1);
           mbar_wait(&s.empty[stage], phase ^ 1);
-          mbar_expect_tx(&s.full[stage], new_item ? 2 * kTileKBytes : kTileKBytes);
-          const int row = c.b * p.D + kb * BK;
+          mbar_expect_tx(&s.full[stage], (new_item ? kTileKBytes : 0) + (stream ? kTileKBytes : 0));
+          const int row = it.b * p.D + kb * BK;
           if (new_item) {
             uint8_t* dst = s.resident + kb * kTileKBytes;
 #pragma unroll
             for (int ch = 0; ch < BM / 32; ++ch)
-              tma_load_2d(dst + ch * kBoxBytes, &p.map_lvl[c.l], c.m0 + ch * 32, row, &s.full[stage], keep);
+              tma_load_2d(dst + ch * kBoxBytes, &p.map_lvl[it.l], it.m0 + ch * 32, row, &s.full[stage], keep);
           }
-          uint8_t* dst = s.ring + stage * kTileKBytes;
+          if (stream) {
+            uint8_t* dst = s.ring + stage * kTileKBytes;
 #pragma unroll
-          for (int ch = 0; ch < BN / 32; ++ch)
-            tma_load_2d(dst + ch * kBoxBytes, &p.map_f1, c.n0 + ch * 32, row, &s.full[stage], keep);
+            for (int ch = 0; ch < BN / 32; ++ch)
+              tma_load_2d(dst + ch * kBoxBytes, &p.map_f1, n0 + ch * 32, row, &s.full[stage], keep);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (new_item) { ++items_done; prev_item = c.item; }
+        if (new_item) ++items_done;
+        new_item = it.next(p);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
+      TileIter it;
+      it.init(p);
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t k = 0; k < n_mine; ++k) {
-        int64_t item, next_item = -1;
-        int nt, nt2;
-        sched.at(k, item, nt);
-        if (k + 1 < n_mine) sched.at(k + 1, next_item, nt2);
-        const bool last_of_item = next_item != item;
-        const uint32_t acc = (uint32_t)k & 1;
-        mbar_wait(&s.acc_empty[acc], (((uint32_t)k >> 1) & 1) ^ 1);
+      uint32_t k = 0;
+      while (it.valid()) {
+        const bool last_of_item = it.last_of_item();
+        const uint32_t acc = k & 1;
+        mbar_wait(&s.acc_empty[acc], ((k >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem + acc * BN;
         for (int kb = 0; kb < KB; ++kb) {
@@ -351,37 +397,46 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
           tc_fence_after();
           const uint32_t a_addr = smem_u32(s.resident + kb * kTileKBytes);
           const uint32_t b_addr = smem_u32(s.ring + stage * kTileKBytes);
+          if (!(p.debug & 1)) {
 #pragma unroll
-          for (int ks = 0; ks < BK / UK; ++ks) {
-            // 8 channels = 8 rows of 128 B = two 512-byte swizzle atoms per 32-position chunk
-            tc_mma_tf32(d_tmem, make_desc(a_addr + ks * 1024, p.desc_lo, p.desc_hi),
-                        make_desc(b_addr + ks * 1024, p.desc_lo, p.desc_hi), kIdesc, (kb | ks) != 0);
+            for (int ks = 0; ks < BK / UK; ++ks) {
+              // 8 channels = 8 rows of 128 B = two 512-byte swizzle atoms per 32-position chunk
+              tc_mma_tf32(d_tmem, make_desc(a_addr + ks * 1024, p.desc_lo, p.desc_hi),
+                          make_desc(b_addr + ks * 1024, p.desc_lo, p.desc_hi), kIdesc, (kb | ks) != 0);
+            }
           }
           tc_commit(&s.empty[stage]);
           if (last_of_item) tc_commit(&s.res_free[kb]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         tc_commit(&s.acc_full[acc]);
+        it.next(p);
+        ++k;
       }
     }
   } else {
-    // ===== epilogue warps 0-3: TMEM lanes [32*warp, 32*warp+32) =====
+    // ===== epilogue warps 0-7: warp w reads TMEM lanes [32*(w%4), +32) and the column half w/4 =====
+    // Each SM sub-partition hosts two epilogue warps; the store loop is branch-free (one predicated
+    // STG per 128-byte row segment) so it stays far below the MMA time.
     const uint64_t stream_out = policy_evict_first();
-    for (int64_t k = 0; k < n_mine; ++k) {
-      int64_t item;
-      int nt;
-      sched.at(k, item, nt);
-      const TileCoord c = decode_tile(p, item, nt);
-      const uint32_t acc = (uint32_t)k & 1;
-      mbar_wait(&s.acc_full[acc], ((uint32_t)k >> 1) & 1);
+    const int quarter = warp & 3, half = warp >> 2;
+    const float scale = p.scale;
+    const bool do_store = !(p.debug & 2);
+    TileIter it;
+    it.init(p);
+    uint32_t k = 0;
+    while (it.valid()) {
+      const uint32_t acc = k & 1;
+      mbar_wait(&s.acc_full[acc], (k >> 1) & 1);
       tc_fence_after();
-      const int Pl = p.Pl[c.l];
-      const int j = c.m0 + warp * 32 + lane;
-      const bool j_ok = j < Pl;
-      float* obase = p.out[c.l] + ((int64_t)c.b * p.P) * Pl + j;
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * BN;
+      const int Pl = p.Pl[it.l];
+      const int j = it.m0 + quarter * 32 + lane;
+      const bool j_ok = (j < Pl) && do_store;
+      float* obase = p.out[it.l] + ((int64_t)it.b * p.P) * Pl + j;
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      const int n0 = it.n0();
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
+      for (int cc = half * (BN / 64); cc < (half + 1) * (BN / 64); ++cc) {
         uint32_t v[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -393,26 +448,29 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr + cc * 32));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int i_base = c.n0 + cc * 32;
+        const int i_base = n0 + cc * 32;
         if (j_ok) {
           float* o = obase + (int64_t)i_base * Pl;
-          const int n_valid = min(32, p.P - i_base);
+          // lanes = 32 consecutive j of output row i: one 128-byte store per row per warp
+          const int n_valid = p.P - i_base;  // >= 32 on interior tiles
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
-            // lanes = 32 consecutive j of output row i: one 128-byte store per row per warp
-            if (r < n_valid) st_evict_first(o + (int64_t)r * Pl, __uint_as_float(v[r]) * p.scale, stream_out);
+            st_evict_first_if(o, __uint_as_float(v[r]) * scale, stream_out, r < n_valid);
+            o += Pl;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.acc_empty[acc]);
+      it.next(p);
+      ++k;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
   }
@@ -438,14 +496,14 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row pitch `pitch` elements; box = 32 cols x BK rows.
+// 2-D fp32 tensor [rows, cols] with row pitch `pitch` elements; box = 32 cols x box_rows rows.
 int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch,
-               CUtensorMapSwizzle swizzle) {
+               CUtensorMapSwizzle swizzle, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return fail(EEM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
-  cuuint32_t box[2] = {32, (cuuint32_t)BK};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -530,11 +588,11 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
     EEM_CHECK_ARG((int64_t)ld.h[l] * ld.w[l] == 0 || levels[l] != nullptr, "eem_corr_pyramid: levels[%d] is NULL", l);
 
   // The tensor-core path needs TMA-addressable operands (16-byte row pitch) and whole K blocks.
-  const bool tf32_ok = (P % 4 == 0) && (D % BK == 0) && (D <= kMaxKB * BK);
+  const bool tf32_ok = (P % 4 == 0) && (D % 32 == 0) && (D <= kMaxD);
   if (precision == EEM_CORR_TF32 && !tf32_ok)
     return fail(EEM_ERR_UNSUPPORTED,
-                "eem_corr_pyramid(TF32): needs H*W %% 4 == 0, D %% %d == 0 and D <= %d (got H*W=%d, D=%d); use EEM_CORR_FP32",
-                BK, kMaxKB * BK, P, D);
+                "eem_corr_pyramid(TF32): needs H*W %% 4 == 0, D %% 32 == 0 and D <= %d (got H*W=%d, D=%d); use EEM_CORR_FP32",
+                kMaxD, P, D);
 
   if (precision == EEM_CORR_FP32) {
     for (int l = 0; l < num_levels; ++l) {
@@ -547,14 +605,20 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
     return EEM_OK;
   }
 
+  int bk = (D % 64 == 0) ? 64 : 32;
+  if (const char* v = getenv("EEM_TF32_BK")) {   // timing experiments only
+    const int forced = atoi(v);
+    if ((forced == 32 || forced == 64) && D % forced == 0) bk = forced;
+  }
+  const uint32_t box_bytes = 32u * (uint32_t)bk * 4u;
   Tf32Params p{};
   // Layout variant: 0 is the production setting.  The others exist only so a single GPU session can
   // A/B the descriptor encoding (EEM_TF32_VARIANT is read by scripts/debug_tf32.py runs).
   CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  uint32_t lbo = kBoxBytes, sbo = 512, layout = 1;
+  uint32_t lbo = box_bytes, sbo = 512, layout = 1;
   if (const char* v = getenv("EEM_TF32_VARIANT")) {
     switch (atoi(v)) {
-      case 1: lbo = 512; sbo = kBoxBytes; break;
+      case 1: lbo = 512; sbo = box_bytes; break;
       case 2: swz = CU_TENSOR_MAP_SWIZZLE_128B; layout = 2; sbo = 1024; break;
       case 3: sbo = 1024; break;
       case 4: swz = CU_TENSOR_MAP_SWIZZLE_128B; layout = 1; break;
@@ -562,14 +626,15 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
     }
   }
   desc_fields(lbo, sbo, layout, &p.desc_lo, &p.desc_hi);
-  int rc = encode_map(&p.map_f1, fmap1, planes, P, P, swz);
+  if (const char* v = getenv("EEM_TF32_DEBUG")) p.debug = (uint32_t)atoi(v);
+  int rc = encode_map(&p.map_f1, fmap1, planes, P, P, swz, bk);
   if (rc != EEM_OK) return rc;
   int nl = 0;
   p.mt_cum[0] = 0;
   for (int l = 0; l < num_levels; ++l) {
     const int Pl = ld.h[l] * ld.w[l];
     if (Pl == 0) break;  // all coarser levels are empty too
-    rc = encode_map(&p.map_lvl[l], op[l], planes, Pl, ld.pitch[l], swz);
+    rc = encode_map(&p.map_lvl[l], op[l], planes, Pl, ld.pitch[l], swz, bk);
     if (rc != EEM_OK) return rc;
     p.out[l] = levels[l];
     p.Pl[l] = Pl;
@@ -580,16 +645,25 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   p.n_tiles = (int)ceil_div(P, BN);
   p.n_items = (int64_t)B * p.mt_cum[nl];
   p.scale = scale;
-  const size_t smem = sizeof(Tf32Smem) + 1024;
-  static std::mutex attr_mu;
-  {
-    std::lock_guard<std::mutex> lock(attr_mu);
-    EEM_CHECK_CUDA(cudaFuncSetAttribute(corr_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  if (p.n_items * p.n_tiles >= (int64_t)0x7fffffff)
+    return fail(EEM_ERR_UNSUPPORTED, "eem_corr_pyramid(TF32): too many tiles in one call; split the batch");
   int64_t grid = sm_count();
   if (grid <= 0) return fail(EEM_ERR_CUDA, "eem_corr_pyramid: cannot query SM count");
   if (grid > p.n_items * p.n_tiles) grid = p.n_items * p.n_tiles;
-  corr_tf32_kernel<<<(unsigned)grid, kTf32Threads, smem, stream>>>(p);
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(corr_tf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(Tf32Smem<32>) + 1024));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(corr_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(Tf32Smem<64>) + 1024));
+  });
+  if (attr_err != cudaSuccess) return fail(EEM_ERR_CUDA, "corr_tf32_kernel attribute: %s", cudaGetErrorString(attr_err));
+  if (bk == 64)
+    corr_tf32_kernel<64><<<(unsigned)grid, kTf32Threads, sizeof(Tf32Smem<64>) + 1024, stream>>>(p);
+  else
+    corr_tf32_kernel<32><<<(unsigned)grid, kTf32Threads, sizeof(Tf32Smem<32>) + 1024, stream>>>(p);
   EEM_CHECK_LAUNCH("corr_tf32_kernel");
   return EEM_OK;
 }

@@ -6,7 +6,7 @@ python -c "import torch; print(torch.__version__, torch.cuda.get_device_name(0))
 timeout 900 python -m pytest tests/test_gpu_voxel.py -m gpu -x -q > gpurun_out/t_voxel.log 2>&1; echo "voxel rc=$?" | tee -a gpurun_out/summary.txt
 timeout 600 python -m pytest tests/test_gpu_warp.py -m gpu -x -q > gpurun_out/t_warp.log 2>&1; echo "warp rc=$?" | tee -a gpurun_out/summary.txt
 timeout 600 python -m pytest tests/test_gpu_corr.py -m gpu -q -k "fp32 or lookup or bilinear or avg_pool or loud" > gpurun_out/t_corr_fp32.log 2>&1; echo "corr_fp32 rc=$?" | tee -a gpurun_out/summary.txt
-timeout 300 python scripts/debug_tf32.py --sweep > gpurun_out/tf32_debug.log 2>&1; echo "tf32_debug rc=$?" | tee -a gpurun_out/summary.txt
+timeout 300 python scripts/debug_tf32.py > gpurun_out/tf32_debug.log 2>&1; echo "tf32_debug rc=$?" | tee -a gpurun_out/summary.txt
 timeout 600 python -m pytest tests/test_gpu_corr.py -m gpu -q > gpurun_out/t_corr_all.log 2>&1; echo "corr_all rc=$?" | tee -a gpurun_out/summary.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/summary.txt
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?" | tee -a gpurun_out/summary.txt

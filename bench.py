@@ -132,17 +132,22 @@ class B200Step:
         self.out_host = None
         self.flow_host = None
 
-    def _model_side(self, d, marks=None):
-        """CorrBlock + EEMFlow_cdc op sequence on device tensors; returns (last lookup, final flows)."""
-        E = self.E
-        blk = E.CorrBlock(d["f1"], d["f2"], num_levels=LEVELS, radius=RADIUS, precision="tf32")
-        if marks is not None:
-            marks.append(self._mark())
-        out = None
+    # ---- the four kernel families of a step; each is also captured as its own CUDA graph ----------
+    def fam_voxelize(self):
+        self.grids = self.ops.voxelize(self.d_events, self.d_offsets, self.max_n, NB, H, W, normalize=True)
+
+    def fam_corr_pyramid(self, d=None):
+        d = d or self.d
+        self.blk = self.E.CorrBlock(d["f1"], d["f2"], num_levels=LEVELS, radius=RADIUS, precision="tf32")
+
+    def fam_corr_lookup(self, d=None):
+        d = d or self.d
         for c in d["coords"]:
-            out = blk(c)
-        if marks is not None:
-            marks.append(self._mark())
+            self.out = self.blk(c)
+
+    def fam_eemflow_ops(self, d=None):
+        d = d or self.d
+        E = self.E
         flows = []
         lv = d["eem"][0]
         E.correlation_select(lv["f1"], lv["f2"], self.index)
@@ -157,23 +162,17 @@ class B200Step:
             flow = flow_up
             flows.append(flow)
         finals = [E.upsample2d_flow_as(f.clone(), self.target, mode="bilinear", if_rate=True) for f in flows]
-        if marks is not None:
-            marks.append(self._mark())
-        return out, finals[-1]
+        self.flow = finals[-1]
 
-    def _mark(self):
-        e = torch.cuda.Event(enable_timing=True)
-        e.record()
-        return e
+    FAMILIES = ("voxelize", "corr_pyramid", "corr_lookup", "eemflow_ops")
 
-    def resident(self, marks=None):
-        """Inputs already in HBM."""
-        if marks is not None:
-            marks.append(self._mark())
-        self.ops.voxelize(self.d_events, self.d_offsets, self.max_n, NB, H, W, normalize=True)
-        if marks is not None:
-            marks.append(self._mark())
-        return self._model_side(self.d, marks)
+    def resident(self):
+        """One step with inputs already in HBM; returns (last lookup, final flow)."""
+        self.fam_voxelize()
+        self.fam_corr_pyramid()
+        self.fam_corr_lookup()
+        self.fam_eemflow_ops()
+        return self.out, self.flow
 
     def end_to_end(self):
         """Same step through the public API from HOST buffers: numpy events, pinned feature maps in,
@@ -184,7 +183,10 @@ class B200Step:
         d = {"f1": hi["f1"].to(dev, non_blocking=True), "f2": hi["f2"].to(dev, non_blocking=True),
              "coords": [c.to(dev, non_blocking=True) for c in hi["coords"]],
              "eem": [{k: v.to(dev, non_blocking=True) for k, v in lv.items()} for lv in hi["eem"]]}
-        out, flow = self._model_side(d)
+        self.fam_corr_pyramid(d)
+        self.fam_corr_lookup(d)
+        self.fam_eemflow_ops(d)
+        out, flow = self.out, self.flow
         if self.out_host is None:
             self.out_host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
             self.flow_host = torch.empty(flow.shape, dtype=flow.dtype, pin_memory=True)
@@ -346,27 +348,32 @@ def main():
     step = B200Step(inp, dev, args.lookups)
     metric_acc = torch.zeros(2, device=dev, dtype=torch.float64)
 
-    def full_step(marks=None):
-        out, flow = step.resident(marks)
+    def eager_step():
+        out, flow = step.resident()
         if world > 1:                       # result + metric gather only; nothing on the data path
             edist.gather_batch(flow)
-            metric_acc[0] = flow.abs().sum()
-            metric_acc[1] = flow.numel()
-            edist.reduce_metrics(metric_acc)
         return out, flow
 
     for _ in range(max(3, args.warmup)):
-        full_step()
+        eager_step()
     torch.cuda.synchronize()
 
-    # The step is ~60 short kernels; issued one by one from Python the launch path is as long as the
-    # GPU work, so the resident step is captured once into a CUDA graph and replayed (the graph
-    # holds exactly the launches of one eager step; buffers live in the graph's private pool).
+    # The step is ~55 short kernels; issued one by one from Python the launch path is as long as the
+    # GPU work, so the resident step is captured once into a CUDA graph and replayed (the graph holds
+    # exactly the launches of one eager step; buffers live in a shared private pool).  The four kernel
+    # families are additionally captured as their own graphs for the per-family split.
+    pool = torch.cuda.graph_pool_handle()
     launches_a = lib.eem_launch_count()
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, pool=pool):
         g_out, g_flow = step.resident()
     launches_per_step = lib.eem_launch_count() - launches_a
+    fam_graphs = {}
+    for name in B200Step.FAMILIES:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
+            getattr(step, "fam_" + name)()
+        fam_graphs[name] = g
 
     def timed_step():
         graph.replay()
@@ -396,20 +403,27 @@ def main():
     elapsed_ms = edist.max_over_ranks(t_start.elapsed_time(t_stop), dev)
     launches = launches_per_step * args.steps
 
-    # Same K steps again, eagerly, with CUDA events at the kernel-family boundaries (events cannot be
-    # timed inside a replayed graph): gives the per-family split and the dominant kernel's duration.
+    # Same K steps again as four family graphs with CUDA events between the replays (events cannot be
+    # timed inside one replayed graph): per-family split and the dominant kernel's launch duration.
+    def mark():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
     marks = []
     for _ in range(args.steps):
-        full_step(marks)
+        marks.append(mark())
+        for name in B200Step.FAMILIES:
+            fam_graphs[name].replay()
+            marks.append(mark())
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-family device time from the event marks: [start, voxel, corr_build, lookups, eemflow] per step
-    fam = {"voxelize": 0.0, "corr_pyramid": 0.0, "corr_lookup": 0.0, "eemflow_ops": 0.0}
-    for s in range(args.steps):
-        m = marks[5 * s: 5 * s + 5]
-        for k, name in enumerate(fam):
-            fam[name] += m[k].elapsed_time(m[k + 1])
+    fam = {name: 0.0 for name in B200Step.FAMILIES}
+    for s_ in range(args.steps):
+        m = marks[5 * s_: 5 * s_ + 5]
+        for k_, name in enumerate(B200Step.FAMILIES):
+            fam[name] += m[k_].elapsed_time(m[k_ + 1])
     total_fam = sum(fam.values())
     lookup_ms = fam["corr_lookup"] / (args.steps * args.lookups)
     peak, peak_src = peaks()
@@ -418,7 +432,7 @@ def main():
     roofline = {"kernel": "corr_lookup_kernel<4>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                 "avg_launch_ms": lookup_ms, "share_of_step": fam["corr_lookup"] / total_fam,
-                "timing": "CUDA events around the 12 lookups of each of the K steps (eager pass over the same inputs)",
+                "timing": "CUDA events around a graph replay of the 12 lookups, K steps, same inputs as the timed region",
                 "family_ms_per_step": {k: v / args.steps for k, v in fam.items()}}
 
     value = args.batch * world * args.steps / (elapsed_ms * 1e-3)

@@ -99,27 +99,35 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
   }
   __syncthreads();
 
-  // 2) gather: thread = (position, tap column); T row loads per level, all levels back to back
+  // 2) gather: thread = (position, tap column); T row taps per level, all levels back to back.
+  //    cp.async (4-byte, zero-filling when the tap lies outside the map) moves every tap straight
+  //    from global to shared memory, so all (2r+2)*L loads of a thread are in flight at once with
+  //    no register staging; one wait + barrier afterwards.
   {
     const int pos = threadIdx.x / T, col = threadIdx.x - pos * T;
     if (pos < npos) {
       for (int l = 0; l < L; ++l) {
         const int hl = p.h[l], wl = p.w[l];
         const int64_t plane = (int64_t)hl * wl;
-        float* tp = taps_of(l) + pos * kStride + col;
+        if (plane == 0) continue;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(taps_of(l) + pos * kStride + col);
         const int x = org_of(l)[pos * 2 + 0] + col, y0 = org_of(l)[pos * 2 + 1];
         const bool x_ok = x >= 0 && x < wl;
-        const float* src = p.level[l] + ((int64_t)b * P + i0 + pos) * plane + (int64_t)y0 * wl + x;
-        float v[T];
+        const float* base = p.level[l] + ((int64_t)b * P + i0 + pos) * plane;
+        const float* src = base + (int64_t)y0 * wl + x;
 #pragma unroll
         for (int r = 0; r < T; ++r) {
           const int y = y0 + r;
-          v[r] = (x_ok && y >= 0 && y < hl) ? __ldg(src + (int64_t)r * wl) : 0.f;
+          const bool ok = x_ok && y >= 0 && y < hl;
+          const int bytes = ok ? 4 : 0;  // src-size 0: nothing is read, the word is zero-filled
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + r * T * 4),
+                       "l"(ok ? src + (int64_t)r * wl : base), "r"(bytes)
+                       : "memory");
         }
-#pragma unroll
-        for (int r = 0; r < T; ++r) tp[r * T] = v[r];
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 

@@ -58,20 +58,33 @@ local_corr_generic_kernel(const __grid_constant__ LocalCorrParams p) {
   for (int c0 = 0; c0 < p.C; c0 += CC) {
     const int nc = min(CC, p.C - c0);
     __syncthreads();
-    for (int t = threadIdx.x; t < CC * TH * TW; t += kThreads) {
+    // fixed trip counts, loads first and stores after, so the ~17 global loads of a thread overlap
+    constexpr int N1 = (CC * TH * TW + kThreads - 1) / kThreads, N2 = (CC * F2H * F2W + kThreads - 1) / kThreads;
+    float v1[N1], v2[N2];
+#pragma unroll
+    for (int k = 0; k < N1; ++k) {
+      const int t = threadIdx.x + k * kThreads;
       const int c = t / (TH * TW), r = (t / TW) % TH, x = t % TW;
       const int gy = y0 + r, gx = x0 + x;
-      float v = 0.f;
-      if (c < nc && gy < p.H && gx < p.W) v = __ldg(f1 + (int64_t)(c0 + c) * plane + (int64_t)gy * p.W + gx);
-      s1[c][r][x] = v;
+      v1[k] = (t < CC * TH * TW && c < nc && gy < p.H && gx < p.W) ? __ldg(f1 + (int64_t)(c0 + c) * plane + (int64_t)gy * p.W + gx) : 0.f;
     }
-    for (int t = threadIdx.x; t < CC * F2H * F2W; t += kThreads) {
+#pragma unroll
+    for (int k = 0; k < N2; ++k) {
+      const int t = threadIdx.x + k * kThreads;
       const int c = t / (F2H * F2W), r = (t / F2W) % F2H, x = t % F2W;
       const int gy = y0 + r - MD, gx = x0 + x - MD;
-      float v = 0.f;
-      if (c < nc && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
-        v = __ldg(f2 + (int64_t)(c0 + c) * plane + (int64_t)gy * p.W + gx);
-      s2[c][r][x] = v;
+      v2[k] = (t < CC * F2H * F2W && c < nc && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+                  ? __ldg(f2 + (int64_t)(c0 + c) * plane + (int64_t)gy * p.W + gx) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < N1; ++k) {
+      const int t = threadIdx.x + k * kThreads;
+      if (t < CC * TH * TW) (&s1[0][0][0])[t] = v1[k];
+    }
+#pragma unroll
+    for (int k = 0; k < N2; ++k) {
+      const int t = threadIdx.x + k * kThreads;
+      if (t < CC * F2H * F2W) (&s2[0][0][0])[t] = v2[k];
     }
     __syncthreads();
 #pragma unroll 2
@@ -149,24 +162,56 @@ local_corr_vec_kernel(const __grid_constant__ LocalCorrParams p) {
   const float* f2 = p.f2 + (int64_t)b * p.C * plane;
   const int n_chunks = (p.C + VC - 1) / VC;
 
+  // Per-thread copy descriptors, computed ONCE: which 16-byte vectors of a stage this thread moves
+  // (shared-memory offset, global element offset relative to the chunk's first channel, in-image
+  // flag).  Only the channel base changes from chunk to chunk, so issuing a stage is ~3
+  // instructions per vector instead of re-deriving (channel, row, column) with div/mod every time.
+  constexpr int kSlots = (kVec1 + kVec2 + kThreads - 1) / kThreads;   // 7
+  int s_off[kSlots], g_off[kSlots];
+  unsigned ch_of = 0, in_img = 0, is_f2 = 0;   // 4-bit channel index per slot / 1-bit flags per slot
+#pragma unroll
+  for (int k = 0; k < kSlots; ++k) {
+    const int v = threadIdx.x + k * kThreads;
+    int c = 0, so = 0, go = 0;
+    bool ok = false, f2v = false;
+    if (v < kVec1) {
+      c = v >> 6;
+      const int r = (v >> 3) & 7, q = v & 7;
+      const int gy = y0 + r, gx = x0 + 4 * q;
+      ok = gy < p.H && gx < p.W;
+      so = (c * VH + r) * S1P + 4 * q;
+      go = c * (int)plane + gy * p.W + gx;
+    } else if (v < kVec1 + kVec2) {
+      const int w = v - kVec1;
+      c = w / (S2H * (S2W / 4));
+      const int rem = w - c * (S2H * (S2W / 4));
+      const int r = rem / (S2W / 4), q = rem - r * (S2W / 4);
+      const int gy = y0 + r - MD, gx = x0 - MD + 4 * q;
+      ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+      so = kS1Floats + (c * S2H + r) * S2P + 4 * q;
+      go = c * (int)plane + gy * p.W + gx;
+      f2v = true;
+    } else {
+      so = -1;
+    }
+    s_off[k] = so;
+    g_off[k] = ok ? go : 0;
+    ch_of |= (unsigned)c << (4 * k);
+    in_img |= (unsigned)ok << k;
+    is_f2 |= (unsigned)f2v << k;
+  }
+
   auto issue = [&](int chunk, int buf) {
-    float* s1 = smem + buf * kStageFloats;
-    float* s2 = s1 + kS1Floats;
+    float* stage = smem + buf * kStageFloats;
     const int c0 = chunk * VC;
-    for (int v = threadIdx.x; v < kVec1 + kVec2; v += kThreads) {
-      if (v < kVec1) {
-        const int c = v >> 6, r = (v >> 3) & 7, q = v & 7;
-        const int gy = y0 + r, gx = x0 + 4 * q;
-        const bool ok = (c0 + c < p.C) && gy < p.H && gx < p.W;
-        cp_async16(s1 + (c * VH + r) * S1P + 4 * q, ok ? f1 + (int64_t)(c0 + c) * plane + (int64_t)gy * p.W + gx : f1, ok);
-      } else {
-        const int w = v - kVec1;
-        const int c = w / (S2H * (S2W / 4)), rem = w - c * (S2H * (S2W / 4));
-        const int r = rem / (S2W / 4), q = rem - r * (S2W / 4);
-        const int gy = y0 + r - MD, gx = x0 - MD + 4 * q;
-        const bool ok = (c0 + c < p.C) && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-        cp_async16(s2 + (c * S2H + r) * S2P + 4 * q, ok ? f2 + (int64_t)(c0 + c) * plane + (int64_t)gy * p.W + gx : f2, ok);
-      }
+    const int64_t cbase = (int64_t)c0 * plane;
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+      if (s_off[k] < 0) continue;
+      const int c = (ch_of >> (4 * k)) & 15;
+      const bool ok = ((in_img >> k) & 1) && (c0 + c < p.C);
+      const float* src = (((is_f2 >> k) & 1) ? f2 : f1) + (ok ? cbase + g_off[k] : 0);
+      cp_async16(stage + s_off[k], src, ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };

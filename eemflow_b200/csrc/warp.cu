@@ -99,12 +99,17 @@ backwarp_kernel(const float* __restrict__ x, const float* __restrict__ flow, int
     m = (mask_mode == EEM_MASK_GE1) ? (ms >= 1.0f ? 1.f : 0.f) : (ms < 0.9999f ? 0.f : 1.f);
     if (mask_out != nullptr && c0 == 0) mask_out[(int64_t)b * plane + pix] = m;
   }
-  const int c1 = min(C, c0 + kWarpChunk);
-  for (int c = c0; c < c1; ++c) {
-    const int64_t off = ((int64_t)b * C + c) * plane;
-    float r = sample(x + off, s, W);
-    if (mask_mode != EEM_MASK_NONE) r *= m;
-    st_stream(out + off + pix, r);
+  // fixed trip count: the 4 x kWarpChunk tap loads of a thread are issued back to back
+  float r[kWarpChunk];
+#pragma unroll
+  for (int k = 0; k < kWarpChunk; ++k) {
+    const int c = min(c0 + k, C - 1);
+    r[k] = sample(x + ((int64_t)b * C + c) * plane, s, W);
+  }
+#pragma unroll
+  for (int k = 0; k < kWarpChunk; ++k) {
+    const int c = c0 + k;
+    if (c < C) st_stream(out + ((int64_t)b * C + c) * plane + pix, mask_mode != EEM_MASK_NONE ? r[k] * m : r[k]);
   }
 }
 
@@ -162,13 +167,22 @@ bilinear_resize_kernel(const float* __restrict__ in, int B, int C, int h, int w,
   // source taps and weights are computed once per output pixel and reused over the planes
   const int o00 = y0 * w + x0, o01 = y0 * w + x1, o10 = y1 * w + x0, o11 = y1 * w + x1;
   const int64_t opix = (int64_t)Y * W + X;
+  // plane loop with running pointers and a running channel id (no div/mod, no 64-bit multiplies)
+  const int gz = gridDim.z, BC = B * C;
+  const float* s = in + (int64_t)blockIdx.z * ip;
+  float* o = out + (int64_t)blockIdx.z * op + opix;
+  const int64_t s_step = (int64_t)gz * ip, o_step = (int64_t)gz * op;
+  int c = blockIdx.z % C;
+  const int c_step = gz % C;
 #pragma unroll 4
-  for (int bc = blockIdx.z; bc < B * C; bc += gridDim.z) {
-    const int c = bc % C;
-    const float* s = in + (int64_t)bc * ip;
+  for (int bc = blockIdx.z; bc < BC; bc += gz) {
     const float v = ly0 * (lx0 * __ldg(s + o00) + lx1 * __ldg(s + o01)) + ly1 * (lx0 * __ldg(s + o10) + lx1 * __ldg(s + o11));
     const float sc = c == 0 ? scale0 : (c == 1 ? scale1 : scale_rest);
-    st_stream(out + (int64_t)bc * op + opix, v * sc);
+    st_stream(o, v * sc);
+    s += s_step;
+    o += o_step;
+    c += c_step;
+    if (c >= C) c -= C;
   }
 }
 

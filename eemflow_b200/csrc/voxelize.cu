@@ -13,6 +13,8 @@
 // 256-bit LDG per event row, so a warp reads 1 KiB contiguous per instruction.  The grid is
 // zero-filled with a memset and updated with fire-and-forget RED.ADD.F32 resolved in L2 (the 55 MB
 // HREM grid is L2-resident on B200), so HBM sees 32*N bytes in and 4*nb*H*W bytes out.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace eem {
@@ -84,17 +86,33 @@ __device__ __forceinline__ WindowTimes window_times(const double* ev, int64_t be
   return w;
 }
 
+// Events are time-sorted, so a contiguous chunk votes into only two bin planes.  CTAs are scheduled
+// roughly in blockIdx order; mapping consecutive CTAs to chunks that are far apart in time spreads the
+// concurrent REDs over all bin planes, which removes most of the same-sector serialisation in L2
+// for spatially clustered event data (ncu: 397 us -> see profiles/).  Bijective on [0, n_chunks).
+__device__ __forceinline__ int64_t interleaved_chunk(int64_t b, int64_t n_chunks, int lanes) {
+  const int64_t per = (n_chunks + lanes - 1) / lanes;       // chunks per time lane
+  const int64_t full_lanes = n_chunks - (per - 1) * lanes;   // lanes that own `per` chunks (rest own per-1)
+  const int64_t lane = b % lanes, k = b / lanes;
+  // lane l owns a contiguous run of chunks; runs of the first `full_lanes` lanes are one longer
+  const int64_t start = lane < full_lanes ? lane * per : full_lanes * per + (lane - full_lanes) * (per - 1);
+  const int64_t len = lane < full_lanes ? per : per - 1;
+  return k < len ? start + k : -1;
+}
+
 // ---- atomic mode ------------------------------------------------------------------------------
 // grid = (ceil(max_events / (threads*EPT)), n_windows).  Loads of a thread's EPT rows are issued
 // back to back before any vote so each thread keeps EPT 32-byte requests in flight.
 __global__ void __launch_bounds__(kVoteThreads)
 voxel_vote_atomic_kernel(const double* __restrict__ ev, const int64_t* __restrict__ offsets, int nb,
-                         int H, int W, float* __restrict__ grid, int64_t* __restrict__ dropped) {
+                         int H, int W, int lanes, float* __restrict__ grid, int64_t* __restrict__ dropped) {
   const int w = blockIdx.y;
   const int64_t begin = offsets[w], end = offsets[w + 1];
   const int64_t n = end - begin;
-  const int64_t first = (int64_t)blockIdx.x * (kVoteThreads * kVoteEventsPerThread) + threadIdx.x;
-  if (first - threadIdx.x >= n) return;
+  const int64_t per_block = kVoteThreads * kVoteEventsPerThread;
+  const int64_t chunk = interleaved_chunk(blockIdx.x, (n + per_block - 1) / per_block, lanes);
+  if (chunk < 0) return;
+  const int64_t first = chunk * per_block + threadIdx.x;
   const WindowTimes wt = window_times(ev, begin, end);
   const int64_t HW = (int64_t)H * W, total = HW * nb;
   float* g = grid + (int64_t)w * total;
@@ -113,6 +131,59 @@ voxel_vote_atomic_kernel(const double* __restrict__ ev, const int64_t* __restric
       const Vote v = make_vote(rows[k], wt.t_first, wt.dT, nb, W, HW, total);
       if (v.idx_left >= 0) red_add_f32(g + v.idx_left, v.val_left);
       if (v.idx_right >= 0) red_add_f32(g + v.idx_right, v.val_right);
+      ndrop += (int)v.oob_left + (int)v.oob_right;
+    }
+  }
+  if (dropped != nullptr && ndrop != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(dropped), (unsigned long long)ndrop);
+}
+
+// ---- atomic mode, pair layout (event-dominated windows) -----------------------------------------
+// L2 is the binding unit of the direct kernel above: every 4-byte RED costs a full 32-byte sector
+// operation (ncu: lts throughput 75 %, 2 sector ops per event).  When a call has at least ~2 events
+// per voxel the votes go to a scratch array S[window][bin k][pixel][2] instead, where slot
+// 0 collects the "left" weights of events with floor(ts) == k (-> bin k) and slot 1 their "right"
+// weights (-> bin k+1): ONE 8-byte vector RED (REDG.ADD.F32x2) per event, half the L2 sector ops.
+// A streaming pass then forms grid[b] = S[b][.][0] + S[b-1][.][1], optionally accumulating the
+// normalisation statistics on the fly so the separate stats pass disappears.
+__device__ __forceinline__ void red_add_f32x2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+__global__ void __launch_bounds__(kVoteThreads)
+voxel_vote_pair_kernel(const double* __restrict__ ev, const int64_t* __restrict__ offsets, int nb,
+                       int H, int W, int lanes, float* __restrict__ scratch, int64_t* __restrict__ dropped) {
+  const int w = blockIdx.y;
+  const int64_t begin = offsets[w], end = offsets[w + 1];
+  const int64_t n = end - begin;
+  const int64_t per_block = kVoteThreads * kVoteEventsPerThread;
+  const int64_t chunk = interleaved_chunk(blockIdx.x, (n + per_block - 1) / per_block, lanes);
+  if (chunk < 0) return;
+  const int64_t first = chunk * per_block + threadIdx.x;
+  const WindowTimes wt = window_times(ev, begin, end);
+  const int64_t HW = (int64_t)H * W, total = HW * nb;
+  float* S = scratch + (int64_t)w * total * 2;
+
+  EventRow rows[kVoteEventsPerThread];
+#pragma unroll
+  for (int k = 0; k < kVoteEventsPerThread; ++k) {
+    const int64_t i = first + (int64_t)k * kVoteThreads;
+    if (i < n) rows[k] = load_event(ev, begin + i);
+  }
+  int ndrop = 0;
+#pragma unroll
+  for (int k = 0; k < kVoteEventsPerThread; ++k) {
+    const int64_t i = first + (int64_t)k * kVoteThreads;
+    if (i < n) {
+      const Vote v = make_vote(rows[k], wt.t_first, wt.dT, nb, W, HW, total);
+      // flat = pix + bin*HW.  Fast path: both votes address the same pixel of adjacent bins.
+      if (v.idx_left >= 0 && (v.idx_right == v.idx_left + HW || v.idx_right < 0) && !v.oob_right) {
+        red_add_f32x2(S + 2 * v.idx_left, v.val_left, v.idx_right >= 0 ? v.val_right : 0.0f);
+      } else {  // a vote was dropped or wrapped differently: address the slots one by one
+        if (v.idx_left >= 0) red_add_f32(S + 2 * v.idx_left, v.val_left);
+        if (v.idx_right >= HW) red_add_f32(S + 2 * (v.idx_right - HW) + 1, v.val_right);
+        else if (v.idx_right >= 0) red_add_f32(S + 2 * v.idx_right, v.val_right);  // no plane below: use slot 0
+      }
       ndrop += (int)v.oob_left + (int)v.oob_right;
     }
   }
@@ -311,7 +382,7 @@ segmented_sum_kernel(const uint32_t* __restrict__ keys, const float* __restrict_
 
 // ---- K2 normalisation -----------------------------------------------------------------------
 constexpr int kStatThreads = 256;
-constexpr int kStatBlocksPerWindowMax = 256;
+constexpr int kStatBlocksPerWindowMax = 2048;
 
 struct StatPartial {
   double count, sum, sumsq;
@@ -325,30 +396,13 @@ __device__ __forceinline__ void accum_stat(float v, double& c, double& s, double
   }
 }
 
-// grid = (blocks_per_window, n_windows).  Partials are combined in block order by the last block
-// to finish (ticket counter), so mean/std do not depend on scheduling.
-__global__ void __launch_bounds__(kStatThreads)
-voxel_stats_kernel(const float* __restrict__ grid, int64_t vox, StatPartial* __restrict__ partials,
-                   unsigned int* __restrict__ tickets, float* __restrict__ mean_std,
-                   double* __restrict__ stats_out) {
-  __shared__ double red[3][kStatThreads / 32];
+// Block-reduce (count, sum, sum of squares), publish the block partial, and let the last block of the
+// window combine all partials in block order (ticket counter) so mean/std do not depend on scheduling.
+__device__ __forceinline__ void finish_stats(double c, double s, double q, int w, StatPartial* __restrict__ partials,
+                                             unsigned int* __restrict__ tickets, float* __restrict__ mean_std,
+                                             double* __restrict__ stats_out) {
+  __shared__ double red[3][32];
   __shared__ bool is_last;
-  const int w = blockIdx.y;
-  const float* g = grid + (int64_t)w * vox;
-  double c = 0, s = 0, q = 0;
-  const int64_t stride = (int64_t)gridDim.x * kStatThreads;
-  const int64_t tid = (int64_t)blockIdx.x * kStatThreads + threadIdx.x;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
-  const int64_t nvec = vec_ok ? vox / 4 : 0;
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (int64_t i = tid; i < nvec; i += stride) {
-    const float4 v = g4[i];
-    accum_stat(v.x, c, s, q);
-    accum_stat(v.y, c, s, q);
-    accum_stat(v.z, c, s, q);
-    accum_stat(v.w, c, s, q);
-  }
-  for (int64_t i = nvec * 4 + tid; i < vox; i += stride) accum_stat(g[i], c, s, q);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -364,7 +418,7 @@ voxel_stats_kernel(const float* __restrict__ grid, int64_t vox, StatPartial* __r
   __syncthreads();
   if (threadIdx.x == 0) {
     double bc = 0, bs = 0, bq = 0;
-    for (int k = 0; k < kStatThreads / 32; ++k) {
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
       bc += red[0][k];
       bs += red[1][k];
       bq += red[2][k];
@@ -376,14 +430,37 @@ voxel_stats_kernel(const float* __restrict__ grid, int64_t vox, StatPartial* __r
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last) {
+    // The last block combines the partials: thread t sums partials t, t+T, ... in index order, then a
+    // fixed shuffle/shared-memory tree -- parallel, and still independent of block scheduling.
     __threadfence();
-    double tc = 0, ts = 0, tq = 0;
-    for (unsigned int k = 0; k < gridDim.x; ++k) {
+    double pc = 0, ps = 0, pq = 0;
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
       const StatPartial p = partials[(int64_t)w * gridDim.x + k];
-      tc += p.count;
-      ts += p.sum;
-      tq += p.sumsq;
+      pc += p.count;
+      ps += p.sum;
+      pq += p.sumsq;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pc += __shfl_xor_sync(0xffffffffu, pc, o);
+      ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      pq += __shfl_xor_sync(0xffffffffu, pq, o);
+    }
+    __syncthreads();   // red[] is free again
+    if (lane == 0) {
+      red[0][warp] = pc;
+      red[1][warp] = ps;
+      red[2][warp] = pq;
+    }
+    __syncthreads();
+  }
+  if (is_last && threadIdx.x == 0) {
+    double tc = 0, ts = 0, tq = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+      tc += red[0][k];
+      ts += red[1][k];
+      tq += red[2][k];
     }
     // mean and unbiased std, rounded to fp32 like the 0-dim fp32 tensors of the reference.
     float mean = 0.0f, sd = 0.0f;
@@ -407,6 +484,57 @@ voxel_stats_kernel(const float* __restrict__ grid, int64_t vox, StatPartial* __r
     }
     tickets[w] = 0;  // leave the workspace reusable without a memset
   }
+}
+
+// grid = (blocks_per_window, n_windows).  Partials are combined in block order by the last block
+// to finish (ticket counter), so mean/std do not depend on scheduling.
+__global__ void __launch_bounds__(kStatThreads)
+voxel_stats_kernel(const float* __restrict__ grid, int64_t vox, StatPartial* __restrict__ partials,
+                   unsigned int* __restrict__ tickets, float* __restrict__ mean_std,
+                   double* __restrict__ stats_out) {
+  const int w = blockIdx.y;
+  const float* g = grid + (int64_t)w * vox;
+  double c = 0, s = 0, q = 0;
+  const int64_t stride = (int64_t)gridDim.x * kStatThreads;
+  const int64_t tid = (int64_t)blockIdx.x * kStatThreads + threadIdx.x;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  const int64_t nvec = vec_ok ? vox / 4 : 0;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = tid; i < nvec; i += stride) {
+    const float4 v = g4[i];
+    accum_stat(v.x, c, s, q);
+    accum_stat(v.y, c, s, q);
+    accum_stat(v.z, c, s, q);
+    accum_stat(v.w, c, s, q);
+  }
+  for (int64_t i = nvec * 4 + tid; i < vox; i += stride) accum_stat(g[i], c, s, q);
+  finish_stats(c, s, q, w, partials, tickets, mean_std, stats_out);
+}
+
+// grid[b][pix] = S[b][pix][0] + S[b-1][pix][1]; thread = pixel, walking the bins so every scratch
+// element is read exactly once (8-byte loads, coalesced across pixels).  With kStats the
+// normalisation statistics are accumulated on the fly.  grid = (blocks, n_windows).
+template <bool kStats>
+__global__ void __launch_bounds__(kStatThreads)
+voxel_combine_kernel(const float2* __restrict__ scratch, int nb, int64_t HW, float* __restrict__ grid,
+                     StatPartial* __restrict__ partials, unsigned int* __restrict__ tickets,
+                     float* __restrict__ mean_std, double* __restrict__ stats_out) {
+  const int w = blockIdx.y;
+  const float2* S = scratch + (int64_t)w * nb * HW;
+  float* g = grid + (int64_t)w * nb * HW;
+  double c = 0, s = 0, q = 0;
+  for (int64_t pix = (int64_t)blockIdx.x * kStatThreads + threadIdx.x; pix < HW; pix += (int64_t)gridDim.x * kStatThreads) {
+    float carry = 0.0f;
+    for (int b = 0; b < nb; ++b) {
+      float2 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(S + (int64_t)b * HW + pix));
+      const float out = __fadd_rn(v.x, carry);
+      carry = v.y;
+      g[(int64_t)b * HW + pix] = out;
+      if (kStats) accum_stat(out, c, s, q);
+    }
+  }
+  if (kStats) finish_stats(c, s, q, w, partials, tickets, mean_std, stats_out);
 }
 
 __device__ __forceinline__ float normalize_one(float v, float mean, float sd, bool divide) {
@@ -479,19 +607,89 @@ DetLayout det_layout(int64_t n_total) {
 
 using namespace eem;
 
+namespace eem {
+namespace {
+
+int stat_blocks(int64_t vox, int n_windows) {
+  // enough CTAs to fill the chip even for a single window (8 per SM), never more than the work
+  int64_t want = ceil_div((int64_t)sm_count() > 0 ? (int64_t)sm_count() * 8 : 1184, n_windows > 0 ? n_windows : 1);
+  if (want < 8) want = 8;
+  int64_t b = ceil_div(vox, (int64_t)kStatThreads * 4);
+  if (b > want) b = want;
+  if (b < 1) b = 1;
+  if (b > kStatBlocksPerWindowMax) b = kStatBlocksPerWindowMax;
+  return (int)b;
+}
+
+struct StatLayout {
+  size_t partials, tickets, mean_std, total;
+};
+
+StatLayout stat_layout(int n_windows) {
+  StatLayout L{};
+  size_t off = 0;
+  L.partials = off;
+  off = align_up(off + (size_t)n_windows * kStatBlocksPerWindowMax * sizeof(StatPartial), 256);
+  L.tickets = off;
+  off = align_up(off + (size_t)n_windows * sizeof(unsigned int), 256);
+  L.mean_std = off;
+  off = align_up(off + (size_t)n_windows * 2 * sizeof(float), 256);
+  L.total = off;
+  return L;
+}
+
+// Pair layout pays 2x grid bytes of scratch traffic (memset + combine read) and wins when the events
+// dominate: measured crossover on B200 at ~2 events per voxel (HREM dt4: 500 -> 380 us; dt1: 146 vs 163 us).
+bool use_pair_path(int64_t n_total, int64_t total_vox) {
+  if (const char* v = getenv("EEM_VOXEL_PATH")) {   // timing experiments only
+    if (v[0] == 'p') return true;
+    if (v[0] == 'd') return false;
+  }
+  return n_total >= 2 * total_vox;
+}
+
+int time_lanes(int dflt) {
+  if (const char* v = getenv("EEM_VOXEL_LANES")) {   // timing experiments only
+    const int n = atoi(v);
+    if (n >= 1 && n <= 1024) return n;
+  }
+  return dflt;
+}
+
+int launch_normalize(float* grid, int n_windows, int64_t vox, double* stats_out, char* ws, cudaStream_t stream) {
+  const StatLayout L = stat_layout(n_windows);
+  StatPartial* partials = reinterpret_cast<StatPartial*>(ws + L.partials);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + L.tickets);
+  float* mean_std = reinterpret_cast<float*>(ws + L.mean_std);
+  // Tickets are reset by the kernel itself after use; the memset makes a fresh workspace valid.
+  EEM_CHECK_CUDA(cudaMemsetAsync(tickets, 0, (size_t)n_windows * sizeof(unsigned int), stream));
+  dim3 g((unsigned)stat_blocks(vox, n_windows), (unsigned)n_windows);
+  voxel_stats_kernel<<<g, kStatThreads, 0, stream>>>(grid, vox, partials, tickets, mean_std, stats_out);
+  EEM_CHECK_LAUNCH("voxel_stats_kernel");
+  voxel_apply_kernel<<<g, 256, 0, stream>>>(grid, vox, mean_std);
+  EEM_CHECK_LAUNCH("voxel_apply_kernel");
+  return EEM_OK;
+}
+
+}  // namespace
+}  // namespace eem
+
 extern "C" {
 
 size_t eem_voxelize_workspace_bytes(int64_t n_total, int n_windows, int num_bins, int height,
-                                    int width, int mode) {
-  (void)n_windows; (void)num_bins; (void)height; (void)width;
-  if (mode != EEM_VOXEL_DETERMINISTIC || n_total < 0) return 0;
-  return det_layout(n_total).total;
+                                    int width, int mode, int normalize) {
+  if (n_total < 0 || n_windows <= 0 || num_bins <= 0 || height <= 0 || width <= 0) return 0;
+  const int64_t total_vox = (int64_t)n_windows * num_bins * height * width;
+  size_t bytes = normalize ? stat_layout(n_windows).total : 0;
+  if (mode == EEM_VOXEL_DETERMINISTIC) bytes += det_layout(n_total).total;
+  else if (use_pair_path(n_total, total_vox)) bytes += align_up((size_t)total_vox * 2 * sizeof(float), 256);
+  return bytes;
 }
 
 int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, int64_t n_total,
                  int64_t max_events_per_window, int num_bins, int height, int width, int mode,
-                 float* grid, int64_t* dropped, void* workspace, size_t workspace_bytes,
-                 eem_stream_t stream_) {
+                 int normalize, float* grid, int64_t* dropped, double* stats_out, void* workspace,
+                 size_t workspace_bytes, eem_stream_t stream_) {
   EEM_CHECK_ARG(n_windows > 0, "eem_voxelize: n_windows must be > 0 (got %d)", n_windows);
   EEM_CHECK_ARG(num_bins > 0, "eem_voxelize: num_bins must be > 0 (got %d)", num_bins);
   EEM_CHECK_ARG(height > 0 && width > 0, "eem_voxelize: height/width must be > 0 (got %dx%d)", height, width);
@@ -502,113 +700,128 @@ int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, in
   EEM_CHECK_ARG(n_total == 0 || events != nullptr, "eem_voxelize: NULL events");
   EEM_CHECK_ARG(mode == EEM_VOXEL_ATOMIC || mode == EEM_VOXEL_DETERMINISTIC,
                 "eem_voxelize: unknown mode %d", mode);
+  EEM_CHECK_ARG(n_windows <= 65535, "eem_voxelize: more than 65535 windows in one call");
   EEM_CHECK_ALIGNED(events, 32);
   EEM_CHECK_ALIGNED(grid, 4);
   cudaStream_t stream = as_stream(stream_);
   const int64_t vox = (int64_t)num_bins * height * width;
   const int64_t total_vox = vox * n_windows;
-  EEM_CHECK_CUDA(cudaMemsetAsync(grid, 0, (size_t)total_vox * sizeof(float), stream));
-  if (n_total == 0 || max_events_per_window == 0) return EEM_OK;
-
-  if (mode == EEM_VOXEL_ATOMIC) {
-    const int64_t per_block = (int64_t)kVoteThreads * kVoteEventsPerThread;
-    dim3 g((unsigned)ceil_div(max_events_per_window, per_block), (unsigned)n_windows);
-    voxel_vote_atomic_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height,
-                                                             width, grid, dropped);
-    EEM_CHECK_LAUNCH("voxel_vote_atomic_kernel");
-    return EEM_OK;
+  const size_t need = eem_voxelize_workspace_bytes(n_total, n_windows, num_bins, height, width, mode, normalize);
+  if (need > 0) {
+    if (workspace == nullptr || workspace_bytes < need)
+      return fail(EEM_ERR_WORKSPACE, "eem_voxelize: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+    EEM_CHECK_ALIGNED(workspace, 256);
   }
-
-  // deterministic: vote pairs -> stable LSD radix sort by global voxel key -> sequential sums
-  if (total_vox >= (int64_t)0xffffffffLL)
-    return fail(EEM_ERR_UNSUPPORTED,
-                "eem_voxelize(deterministic): %lld voxels in one call exceed the 32-bit key space; split the batch",
-                (long long)total_vox);
-  if (2 * n_total >= (int64_t)0x7fffffffLL)
-    return fail(EEM_ERR_UNSUPPORTED, "eem_voxelize(deterministic): too many events in one call (%lld)", (long long)n_total);
-  const DetLayout L = det_layout(n_total);
-  if (workspace == nullptr || workspace_bytes < L.total)
-    return fail(EEM_ERR_WORKSPACE, "eem_voxelize(deterministic): workspace of %zu bytes required, got %zu",
-                L.total, workspace_bytes);
-  EEM_CHECK_ALIGNED(workspace, 256);
   char* ws = static_cast<char*>(workspace);
-  uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(ws + L.keys_a), reinterpret_cast<uint32_t*>(ws + L.keys_b)};
-  float* vals[2] = {reinterpret_cast<float*>(ws + L.vals_a), reinterpret_cast<float*>(ws + L.vals_b)};
-  uint32_t* counts = reinterpret_cast<uint32_t*>(ws + L.counts);
-  uint32_t* block_sums = reinterpret_cast<uint32_t*>(ws + L.block_sums);
-  const uint32_t invalid_key = (uint32_t)total_vox;
+  char* ws_stats = ws;                                             // [stats | mode-specific]
+  char* ws_mode = ws + (normalize ? stat_layout(n_windows).total : 0);
 
-  {
-    dim3 g((unsigned)ceil_div(max_events_per_window, kVoteThreads), (unsigned)n_windows);
-    voxel_vote_pairs_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width,
-                                                            n_total, invalid_key, keys[0], vals[0], dropped);
-    EEM_CHECK_LAUNCH("voxel_vote_pairs_kernel");
+  const bool no_events = (n_total == 0 || max_events_per_window == 0);
+  const bool pair = !no_events && mode == EEM_VOXEL_ATOMIC && use_pair_path(n_total, total_vox);
+  if (!pair) EEM_CHECK_CUDA(cudaMemsetAsync(grid, 0, (size_t)total_vox * sizeof(float), stream));
+
+  if (no_events) {
+    // nothing to vote
+  } else if (mode == EEM_VOXEL_ATOMIC && !pair) {
+    const int64_t per_block = (int64_t)kVoteThreads * kVoteEventsPerThread;
+    const int64_t chunks = ceil_div(max_events_per_window, per_block);
+    const int lanes = time_lanes(64);
+    dim3 g((unsigned)(ceil_div(chunks, lanes) * lanes), (unsigned)n_windows);
+    voxel_vote_atomic_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height,
+                                                             width, lanes, grid, dropped);
+    EEM_CHECK_LAUNCH("voxel_vote_atomic_kernel");
+  } else if (pair) {
+    float* scratch = reinterpret_cast<float*>(ws_mode);
+    EEM_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)total_vox * 2 * sizeof(float), stream));
+    const int64_t per_block = (int64_t)kVoteThreads * kVoteEventsPerThread;
+    const int64_t chunks = ceil_div(max_events_per_window, per_block);
+    // the scratch is 2x the grid: keep the set of concurrently active bin planes small enough for L2
+    const int lanes = time_lanes(4);
+    dim3 g((unsigned)(ceil_div(chunks, lanes) * lanes), (unsigned)n_windows);
+    voxel_vote_pair_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width, lanes, scratch, dropped);
+    EEM_CHECK_LAUNCH("voxel_vote_pair_kernel");
+    const int64_t HW = (int64_t)height * width;
+    dim3 gc((unsigned)stat_blocks(HW * 4, n_windows), (unsigned)n_windows);
+    if (normalize) {
+      const StatLayout L = stat_layout(n_windows);
+      StatPartial* partials = reinterpret_cast<StatPartial*>(ws_stats + L.partials);
+      unsigned int* tickets = reinterpret_cast<unsigned int*>(ws_stats + L.tickets);
+      float* mean_std = reinterpret_cast<float*>(ws_stats + L.mean_std);
+      EEM_CHECK_CUDA(cudaMemsetAsync(tickets, 0, (size_t)n_windows * sizeof(unsigned int), stream));
+      voxel_combine_kernel<true><<<gc, kStatThreads, 0, stream>>>(reinterpret_cast<const float2*>(scratch), num_bins, HW, grid,
+                                                                  partials, tickets, mean_std, stats_out);
+      EEM_CHECK_LAUNCH("voxel_combine_kernel");
+      dim3 ga((unsigned)stat_blocks(vox, n_windows), (unsigned)n_windows);
+      voxel_apply_kernel<<<ga, 256, 0, stream>>>(grid, vox, mean_std);
+      EEM_CHECK_LAUNCH("voxel_apply_kernel");
+      return EEM_OK;
+    }
+    voxel_combine_kernel<false><<<gc, kStatThreads, 0, stream>>>(reinterpret_cast<const float2*>(scratch), num_bins, HW, grid,
+                                                                 nullptr, nullptr, nullptr, nullptr);
+    EEM_CHECK_LAUNCH("voxel_combine_kernel");
+    return EEM_OK;
+  } else {
+    // deterministic: vote pairs -> stable LSD radix sort by global voxel key -> sequential sums
+    if (total_vox >= (int64_t)0xffffffffLL)
+      return fail(EEM_ERR_UNSUPPORTED,
+                  "eem_voxelize(deterministic): %lld voxels in one call exceed the 32-bit key space; split the batch",
+                  (long long)total_vox);
+    if (2 * n_total >= (int64_t)0x7fffffffLL)
+      return fail(EEM_ERR_UNSUPPORTED, "eem_voxelize(deterministic): too many events in one call (%lld)", (long long)n_total);
+    const DetLayout L = det_layout(n_total);
+    uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(ws_mode + L.keys_a), reinterpret_cast<uint32_t*>(ws_mode + L.keys_b)};
+    float* vals[2] = {reinterpret_cast<float*>(ws_mode + L.vals_a), reinterpret_cast<float*>(ws_mode + L.vals_b)};
+    uint32_t* counts = reinterpret_cast<uint32_t*>(ws_mode + L.counts);
+    uint32_t* block_sums = reinterpret_cast<uint32_t*>(ws_mode + L.block_sums);
+    const uint32_t invalid_key = (uint32_t)total_vox;
+    {
+      dim3 g((unsigned)ceil_div(max_events_per_window, kVoteThreads), (unsigned)n_windows);
+      voxel_vote_pairs_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width,
+                                                              n_total, invalid_key, keys[0], vals[0], dropped);
+      EEM_CHECK_LAUNCH("voxel_vote_pairs_kernel");
+    }
+    const int key_bits = bit_length((uint64_t)invalid_key);
+    const int passes = (key_bits + 7) / 8;
+    const unsigned sort_blocks = (unsigned)ceil_div(L.n_segs, kSortWarpsPerBlock);
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+      const int shift = 8 * p;
+      radix_count_kernel<<<sort_blocks, kSortWarpsPerBlock * 32, 0, stream>>>(keys[cur], L.n_votes, shift, L.n_segs, counts);
+      EEM_CHECK_LAUNCH("radix_count_kernel");
+      scan_block_sums_kernel<<<(unsigned)L.n_scan_blocks, kScanThreads, 0, stream>>>(counts, L.n_counts, block_sums);
+      EEM_CHECK_LAUNCH("scan_block_sums_kernel");
+      scan_of_block_sums_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, L.n_scan_blocks);
+      EEM_CHECK_LAUNCH("scan_of_block_sums_kernel");
+      scan_apply_kernel<<<(unsigned)L.n_scan_blocks, kScanThreads, 0, stream>>>(counts, L.n_counts, block_sums);
+      EEM_CHECK_LAUNCH("scan_apply_kernel");
+      radix_scatter_kernel<<<sort_blocks, kSortWarpsPerBlock * 32, 0, stream>>>(
+          keys[cur], vals[cur], L.n_votes, shift, L.n_segs, counts, keys[cur ^ 1], vals[cur ^ 1]);
+      EEM_CHECK_LAUNCH("radix_scatter_kernel");
+      cur ^= 1;
+    }
+    segmented_sum_kernel<<<(unsigned)ceil_div(L.n_votes, 256), 256, 0, stream>>>(keys[cur], vals[cur], L.n_votes,
+                                                                               invalid_key, grid);
+    EEM_CHECK_LAUNCH("segmented_sum_kernel");
   }
-  const int key_bits = bit_length((uint64_t)invalid_key);
-  const int passes = (key_bits + 7) / 8;
-  const unsigned sort_blocks = (unsigned)ceil_div(L.n_segs, kSortWarpsPerBlock);
-  int cur = 0;
-  for (int p = 0; p < passes; ++p) {
-    const int shift = 8 * p;
-    radix_count_kernel<<<sort_blocks, kSortWarpsPerBlock * 32, 0, stream>>>(keys[cur], L.n_votes, shift, L.n_segs, counts);
-    EEM_CHECK_LAUNCH("radix_count_kernel");
-    scan_block_sums_kernel<<<(unsigned)L.n_scan_blocks, kScanThreads, 0, stream>>>(counts, L.n_counts, block_sums);
-    EEM_CHECK_LAUNCH("scan_block_sums_kernel");
-    scan_of_block_sums_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, L.n_scan_blocks);
-    EEM_CHECK_LAUNCH("scan_of_block_sums_kernel");
-    scan_apply_kernel<<<(unsigned)L.n_scan_blocks, kScanThreads, 0, stream>>>(counts, L.n_counts, block_sums);
-    EEM_CHECK_LAUNCH("scan_apply_kernel");
-    radix_scatter_kernel<<<sort_blocks, kSortWarpsPerBlock * 32, 0, stream>>>(
-        keys[cur], vals[cur], L.n_votes, shift, L.n_segs, counts, keys[cur ^ 1], vals[cur ^ 1]);
-    EEM_CHECK_LAUNCH("radix_scatter_kernel");
-    cur ^= 1;
-  }
-  segmented_sum_kernel<<<(unsigned)ceil_div(L.n_votes, 256), 256, 0, stream>>>(keys[cur], vals[cur], L.n_votes,
-                                                                             invalid_key, grid);
-  EEM_CHECK_LAUNCH("segmented_sum_kernel");
+  if (normalize) return launch_normalize(grid, n_windows, vox, stats_out, ws_stats, stream);
   return EEM_OK;
-}
-
-static int stat_blocks(int64_t vox) {
-  int64_t b = ceil_div(vox, (int64_t)kStatThreads * 4 * 8);
-  if (b < 1) b = 1;
-  if (b > kStatBlocksPerWindowMax) b = kStatBlocksPerWindowMax;
-  return (int)b;
 }
 
 size_t eem_voxel_normalize_workspace_bytes(int n_windows, int64_t voxels_per_window) {
   if (n_windows <= 0 || voxels_per_window <= 0) return 0;
-  const size_t nb = (size_t)stat_blocks(voxels_per_window);
-  size_t bytes = align_up((size_t)n_windows * nb * sizeof(StatPartial), 256);
-  bytes += align_up((size_t)n_windows * sizeof(unsigned int), 256);  // tickets (must start zeroed)
-  bytes += align_up((size_t)n_windows * 2 * sizeof(float), 256);     // mean, std
-  return bytes;
+  return stat_layout(n_windows).total;
 }
 
 int eem_voxel_normalize(float* grid, int n_windows, int64_t voxels_per_window, double* stats_out,
                         void* workspace, size_t workspace_bytes, eem_stream_t stream_) {
   EEM_CHECK_ARG(grid != nullptr, "eem_voxel_normalize: NULL grid");
   EEM_CHECK_ARG(n_windows > 0 && voxels_per_window > 0, "eem_voxel_normalize: sizes must be > 0");
+  EEM_CHECK_ARG(n_windows <= 65535, "eem_voxel_normalize: more than 65535 windows in one call");
   const size_t need = eem_voxel_normalize_workspace_bytes(n_windows, voxels_per_window);
   if (workspace == nullptr || workspace_bytes < need)
     return fail(EEM_ERR_WORKSPACE, "eem_voxel_normalize: workspace of %zu bytes required, got %zu", need, workspace_bytes);
   EEM_CHECK_ALIGNED(workspace, 256);
-  cudaStream_t stream = as_stream(stream_);
-  const int nb = stat_blocks(voxels_per_window);
-  char* ws = static_cast<char*>(workspace);
-  StatPartial* partials = reinterpret_cast<StatPartial*>(ws);
-  size_t off = align_up((size_t)n_windows * nb * sizeof(StatPartial), 256);
-  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + off);
-  off += align_up((size_t)n_windows * sizeof(unsigned int), 256);
-  float* mean_std = reinterpret_cast<float*>(ws + off);
-  // Tickets are reset by the kernel itself after use; the memset makes a fresh workspace valid.
-  EEM_CHECK_CUDA(cudaMemsetAsync(tickets, 0, (size_t)n_windows * sizeof(unsigned int), stream));
-  dim3 g((unsigned)nb, (unsigned)n_windows);
-  voxel_stats_kernel<<<g, kStatThreads, 0, stream>>>(grid, voxels_per_window, partials, tickets, mean_std, stats_out);
-  EEM_CHECK_LAUNCH("voxel_stats_kernel");
-  voxel_apply_kernel<<<g, 256, 0, stream>>>(grid, voxels_per_window, mean_std);
-  EEM_CHECK_LAUNCH("voxel_apply_kernel");
-  return EEM_OK;
+  return launch_normalize(grid, n_windows, voxels_per_window, stats_out, static_cast<char*>(workspace), as_stream(stream_));
 }
 
 }  // extern "C"

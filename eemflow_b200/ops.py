@@ -23,7 +23,8 @@ def _dev(t: torch.Tensor) -> torch.device:
 # ------------------------------------------------------------------------------------------ K1/K2
 def voxelize(events: torch.Tensor, offsets: torch.Tensor, max_events: int, num_bins: int, height: int,
              width: int, *, normalize: bool = True, deterministic: bool = False,
-             dropped: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+             dropped: torch.Tensor | None = None, out: torch.Tensor | None = None,
+             stats_out: torch.Tensor | None = None) -> torch.Tensor:
     """Voxelize concatenated event windows.
 
     events  : CUDA float64 [N, 4] rows (ts, x, y, p)  -- the reference's EventSequence.features layout
@@ -49,13 +50,11 @@ def voxelize(events: torch.Tensor, offsets: torch.Tensor, max_events: int, num_b
     lib = L.lib()
     mode = L.VOXEL_DETERMINISTIC if deterministic else L.VOXEL_ATOMIC
     with torch.cuda.device(dev):
-        ws_bytes = lib.eem_voxelize_workspace_bytes(n_total, n_windows, num_bins, height, width, mode)
+        ws_bytes = lib.eem_voxelize_workspace_bytes(n_total, n_windows, num_bins, height, width, mode, int(normalize))
         ws = L.workspace.get(dev, ws_bytes, "voxel")
         L.check(lib.eem_voxelize(events.data_ptr(), offsets.data_ptr(), n_windows, n_total, int(max_events),
-                                 num_bins, height, width, mode, out.data_ptr(), L.ptr(dropped),
-                                 L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
-        if normalize:
-            voxel_normalize_(out)
+                                 num_bins, height, width, mode, int(normalize), out.data_ptr(), L.ptr(dropped),
+                                 L.ptr(stats_out), L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
     return out
 
 

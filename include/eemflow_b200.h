@@ -64,6 +64,12 @@ EEM_API long long eem_launch_count(void);
  *                                  order (all "left" votes in event order, then all "right"
  *                                  votes): bit-exact against the CPU reference.
  * max_events_per_window : host-side upper bound of offsets[w+1]-offsets[w] (sizes the launch).
+ * normalize : non-zero fuses K2 (mean / unbiased std over the non-zero voxels, utils/transformers.py:114-122)
+ *           into the call; stats_out (optional DEVICE [n_windows,3] float64: count, mean, std) as for K2.
+ * Atomic mode picks between two layouts by itself: direct RED.ADD.F32 into the grid, or -- when a call
+ * has at least two events per voxel -- a scratch "pair" layout that needs ONE 8-byte vector RED
+ * per event followed by a streaming combine pass (see csrc/voxelize.cu); both need the workspace size
+ * returned by eem_voxelize_workspace_bytes for the same arguments.
  * dropped : optional DEVICE int64 counter (may be NULL); incremented once per vote whose flat
  *           index x + y*W + bin*W*H falls outside the grid (the reference raises IndexError
  *           there).  In-range flat indices are voted exactly like the reference, including its
@@ -72,11 +78,12 @@ EEM_API long long eem_launch_count(void);
 enum { EEM_VOXEL_ATOMIC = 0, EEM_VOXEL_DETERMINISTIC = 1 };
 
 EEM_API size_t eem_voxelize_workspace_bytes(int64_t n_total, int n_windows, int num_bins,
-                                            int height, int width, int mode);
+                                            int height, int width, int mode, int normalize);
 EEM_API int eem_voxelize(const double* events, const int64_t* offsets, int n_windows,
                          int64_t n_total, int64_t max_events_per_window, int num_bins,
-                         int height, int width, int mode, float* grid, int64_t* dropped,
-                         void* workspace, size_t workspace_bytes, eem_stream_t stream);
+                         int height, int width, int mode, int normalize, float* grid,
+                         int64_t* dropped, double* stats_out, void* workspace,
+                         size_t workspace_bytes, eem_stream_t stream);
 
 /* K2  voxel-grid normalisation: per window, mean / unbiased std over the NON-ZERO voxels, then
  *     v = (v - mean) / std on the non-zero voxels (v - mean when !(std > 0), which includes the

@@ -154,3 +154,40 @@ def test_device_contract_and_errors(V):
     with pytest.raises(IndexError):
         V(5, gpu=True, forkserver=False, strict=True)(Seq(bad, 32, 48))
     V(5, gpu=True, forkserver=False)(Seq(bad, 32, 48))            # non-strict: vote dropped, no error
+
+
+def test_pair_layout_path_parity(golden, V, monkeypatch):
+    """The event-dominated path (scratch pair layout, one vector RED per event, fused combine + stats) is
+    normally chosen only when a call has >= 2 events per voxel; force it and repeat the parity checks,
+    including the reference's row-wrap and dropped-vote corner cases."""
+    monkeypatch.setenv("EEM_VOXEL_PATH", "pair")
+    g = golden("voxel")
+    for name in cases_of(g):
+        nb, h, w = (int(v) for v in g[f"{name}__shape"])
+        ev = g[f"{name}__events"]
+        raw = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev.copy(), h, w)).cpu().numpy()
+        assert rel_close(raw, g[f"{name}__raw"]).all(), (name, np.abs(raw - g[f"{name}__raw"]).max())
+        norm = V(nb, gpu=True, normalize=True, forkserver=False)(Seq(ev.copy(), h, w)).cpu().numpy()
+        assert rel_close(norm, g[f"{name}__norm"]).all(), (name, np.abs(norm - g[f"{name}__norm"]).max())
+    rng = np.random.default_rng(21)
+    for n, nb, h, w, clustered in [(600_000, 15, 720, 1280, True), (200_000, 5, 260, 346, False)]:
+        ev = make_events(rng, n, h, w, clustered)
+        ref_raw, _, _ = c_oracle.voxelize(ev, nb, h, w, normalize=False)
+        out = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
+        assert rel_close(out, ref_raw).all(), np.abs(out - ref_raw).max()
+        ref_norm = ref_ops.voxelize(ev, nb, h, w, normalize=True).numpy()
+        out_n = V(nb, gpu=True, normalize=True, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
+        assert rel_close(out_n, ref_norm).all(), np.abs(out_n - ref_norm).max()
+    # ragged batch through the pair path
+    seqs = [Seq(make_events(rng, n, 64, 96), 64, 96) for n in (1, 2, 777, 5000, 31, 12345)]
+    batch = V(5, gpu=True, normalize=True, forkserver=False).voxelize_batch(seqs).cpu().numpy()
+    for k, s in enumerate(seqs):
+        assert rel_close(batch[k], ref_ops.voxelize(s.features, 5, 64, 96, normalize=True).numpy()).all(), k
+    # out-of-grid votes are dropped (and counted in strict mode) on this path too
+    bad = make_events(rng, 1000, 32, 48)
+    bad[10, 2] = 4000.0
+    bad[20, 1] = -7.0
+    bad[20, 2] = 0.0
+    with pytest.raises(IndexError):
+        V(5, gpu=True, forkserver=False, strict=True)(Seq(bad, 32, 48))
+    V(5, gpu=True, forkserver=False)(Seq(bad, 32, 48))

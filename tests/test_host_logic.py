@@ -35,8 +35,11 @@ def test_library_exports_every_declared_symbol():
 def test_workspace_queries_are_pure_host_functions():
     from eemflow_b200 import _lib
     lib = _lib.lib()
-    assert lib.eem_voxelize_workspace_bytes(10_000_000, 1, 15, 720, 1280, _lib.VOXEL_ATOMIC) == 0
-    det = lib.eem_voxelize_workspace_bytes(10_000_000, 1, 15, 720, 1280, _lib.VOXEL_DETERMINISTIC)
+    assert lib.eem_voxelize_workspace_bytes(30_000, 1, 5, 260, 346, _lib.VOXEL_ATOMIC, 0) == 0       # direct RED path
+    pair = lib.eem_voxelize_workspace_bytes(40_000_000, 1, 15, 720, 1280, _lib.VOXEL_ATOMIC, 0)  # pair-layout scratch (dt4)
+    assert lib.eem_voxelize_workspace_bytes(10_000_000, 1, 15, 720, 1280, _lib.VOXEL_ATOMIC, 0) == 0
+    assert pair >= 2 * 15 * 720 * 1280 * 4
+    det = lib.eem_voxelize_workspace_bytes(10_000_000, 1, 15, 720, 1280, _lib.VOXEL_DETERMINISTIC, 0)
     assert det >= 2 * 10_000_000 * 16          # two key and two value buffers over 2N votes
     assert lib.eem_voxel_normalize_workspace_bytes(64, 5 * 260 * 346) > 0
     assert lib.eem_corr_pyramid_workspace_bytes(32, 256, 36, 44, 1) == 0
@@ -48,7 +51,7 @@ def test_bad_arguments_return_status_not_crash():
     from eemflow_b200 import _lib
     lib = _lib.lib()
     # argument validation happens before any CUDA call
-    rc = lib.eem_voxelize(None, None, 0, 0, 0, 5, 10, 10, 0, None, None, None, 0, None)
+    rc = lib.eem_voxelize(None, None, 0, 0, 0, 5, 10, 10, 0, 0, None, None, None, None, 0, None)
     assert rc == _lib.EEM_ERR_BAD_ARG
     assert b"n_windows" in lib.eem_last_error_string()
     with pytest.raises(AssertionError):

@@ -48,13 +48,19 @@ __device__ __forceinline__ float roundtrip(float p, int size) {
 // positions of one output channel (128 B).  Two block barriers in total.
 template <int R>
 struct LookupSmem {
-  static constexpr int K = 2 * R + 1, T = K + 1, TT = T * T, kStride = TT | 1;
+  static constexpr int K = 2 * R + 1, T = K + 1, TT = T * T;
+  // tap stride per position: == T+1 (mod 32) so the T lanes of consecutive positions written by one
+  // cp.async instruction land in disjoint banks, and odd so lane = position reads are conflict-free
+  static constexpr int kStride = TT + ((T + 1 - TT % 32 + 32) % 32);
+  static constexpr int kColsPerTask = 3, kGroups = (K + kColsPerTask - 1) / kColsPerTask;
+  // threads: >= 32*T for the gather phase, and 4*kGroups warps so a 4-level pyramid is one task per warp
+  static constexpr int kThreads = 32 * (T > 4 * kGroups ? T : 4 * kGroups);
   static constexpr int kPerLevelFloats = kPosPerBlock * kStride + 2 * kPosPerBlock * K;
   static constexpr int kPerLevelBytes = kPerLevelFloats * 4 + kPosPerBlock * 2 * 4;
 };
 
 template <int R>
-__global__ void __launch_bounds__((2 * R + 2) * 32)
+__global__ void __launch_bounds__(LookupSmem<R>::kThreads)
 corr_lookup_kernel(const __grid_constant__ LookupParams p) {
   using S = LookupSmem<R>;
   constexpr int K = S::K, T = S::T, kStride = S::kStride;
@@ -105,23 +111,24 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
   //    no register staging; one wait + barrier afterwards.
   {
     const int pos = threadIdx.x / T, col = threadIdx.x - pos * T;
-    if (pos < npos) {
+    if (pos < npos) {  // (threads beyond 32*T have pos >= 32 and only take part in phase 3)
       for (int l = 0; l < L; ++l) {
         const int hl = p.h[l], wl = p.w[l];
         const int64_t plane = (int64_t)hl * wl;
         if (plane == 0) continue;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(taps_of(l) + pos * kStride + col);
         const int x = org_of(l)[pos * 2 + 0] + col, y0 = org_of(l)[pos * 2 + 1];
-        const bool x_ok = x >= 0 && x < wl;
+        const bool x_ok = (unsigned)x < (unsigned)wl;
+        // 32-bit element offsets inside this position's map (h_l*w_l < 2^31); an out-of-map tap copies
+        // 0 bytes from offset 0 (zero-fill), so every address handed to cp.async is valid.
         const float* base = p.level[l] + ((int64_t)b * P + i0 + pos) * plane;
-        const float* src = base + (int64_t)y0 * wl + x;
+        const int off0 = y0 * wl + x;
 #pragma unroll
         for (int r = 0; r < T; ++r) {
-          const int y = y0 + r;
-          const bool ok = x_ok && y >= 0 && y < hl;
-          const int bytes = ok ? 4 : 0;  // src-size 0: nothing is read, the word is zero-filled
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + r * T * 4),
-                       "l"(ok ? src + (int64_t)r * wl : base), "r"(bytes)
+          const bool ok = x_ok && (unsigned)(y0 + r) < (unsigned)hl;
+          const int off = ok ? off0 + r * wl : 0;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + r * T * 4), "l"(base + off),
+                       "r"(ok ? 4 : 0)
                        : "memory");
         }
       }
@@ -131,27 +138,49 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
   }
   __syncthreads();
 
-  // 3) interpolate: warp = window column a (x offset), lane = position; walk down the rows reusing
-  //    the horizontal interpolation of the previous row.
-  if (warp < K && lane < npos) {
-    const int a = warp;
-    for (int l = 0; l < L; ++l) {
-      float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a * K) * P + i0 + lane;
+  // 3) interpolate.  A task = (level, group of G adjacent window columns); tasks are dealt to the
+  //    warps, lane = position.  Per tap row a thread reads G+1 taps and forms G horizontal lerps
+  //    (adjacent columns share a tap), then combines with the previous row: (G+1)*T tap loads per
+  //    G*K outputs, and every store instruction writes 32 consecutive positions of one channel.
+  constexpr int G = S::kColsPerTask, kGroups = S::kGroups;
+  const int n_warps = blockDim.x >> 5;
+  if (lane < npos) {
+    for (int task = warp; task < L * kGroups; task += n_warps) {
+      const int l = task / kGroups, a0 = (task - l * kGroups) * G;
+      float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a0 * K) * P + i0 + lane;
       if ((int64_t)p.h[l] * p.w[l] == 0) {  // level pooled away: an empty map contributes zeros
 #pragma unroll
-        for (int c = 0; c < K; ++c) st_stream(o + (int64_t)c * P, 0.f);
+        for (int g = 0; g < G; ++g)
+          if (a0 + g < K)
+#pragma unroll
+            for (int c = 0; c < K; ++c) st_stream(o + (int64_t)(g * K + c) * P, 0.f);
         continue;
       }
-      const float fx = fx_of(l)[lane * K + a];
-      const float* tp = taps_of(l) + lane * kStride + a;
-      const float* fy = fy_of(l) + lane * K;
-      float prev = tp[0] + fx * (tp[1] - tp[0]);
+      const float* tp = taps_of(l) + lane * kStride + a0;
+      const float* fyp = fy_of(l) + lane * K;
+      float fx[G], prev[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) fx[g] = (a0 + g < K) ? fx_of(l)[lane * K + a0 + g] : 0.f;
+      {
+        float t[G + 1];
+#pragma unroll
+        for (int g = 0; g <= G; ++g) t[g] = (a0 + g < T) ? tp[g] : 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) prev[g] = t[g] + fx[g] * (t[g + 1] - t[g]);
+      }
 #pragma unroll
       for (int c = 0; c < K; ++c) {
         const float* row = tp + (c + 1) * T;
-        const float cur = row[0] + fx * (row[1] - row[0]);
-        st_stream(o + (int64_t)c * P, prev + fy[c] * (cur - prev));
-        prev = cur;
+        float t[G + 1];
+#pragma unroll
+        for (int g = 0; g <= G; ++g) t[g] = (a0 + g < T) ? row[g] : 0.f;
+        const float fy = fyp[c];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float cur = t[g] + fx[g] * (t[g + 1] - t[g]);
+          if (a0 + g < K) st_stream(o + (int64_t)(g * K + c) * P, prev[g] + fy * (cur - prev[g]));
+          prev[g] = cur;
+        }
       }
     }
   }
@@ -170,7 +199,7 @@ int launch_lookup(const LookupParams& p, dim3 grid, cudaStream_t stream) {
       configured = smem;
     }
   }
-  corr_lookup_kernel<R><<<grid, (2 * R + 2) * 32, smem, stream>>>(p);
+  corr_lookup_kernel<R><<<grid, S::kThreads, smem, stream>>>(p);
   return EEM_OK;
 }
 

@@ -99,24 +99,31 @@ corr_fp32_kernel(const float* __restrict__ f1, const float* __restrict__ f2l, in
 // TF32 tcgen05 path
 // ---------------------------------------------------------------------------------------------
 constexpr int BM = 128;       // MMA M: positions j of the (pooled) fmap2 level -> TMEM lanes
-constexpr int BN = 128;       // MMA N: positions i of fmap1                    -> TMEM columns
+// MMA N (positions i of fmap1 -> TMEM columns) is a template parameter: 128 or 256
 constexpr int UK = 8;         // K of one tcgen05.mma kind::tf32
 constexpr int kMaxD = 256;    // resident-operand capacity: 128 positions x 256 channels fp32 = 128 KiB
 constexpr int kRingBytes = 96 * 1024;           // streamed-operand ring: 96 KiB in flight per SM
-constexpr int kTmemCols = 2 * BN;               // two accumulator buffers
 constexpr int kEpiWarps = 8;                    // two epilogue warps per TMEM lane quarter (column halves)
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kTf32Threads = (kEpiWarps + 2) * 32; // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
 
 // BK = channels per pipeline stage.  BK = 64 (used whenever D % 64 == 0) gives the single MMA-issuing
 // thread 8 MMAs (512 tensor-pipe cycles) per mbarrier round trip; BK = 32 covers D % 32 == 0.
-template <int BK>
+template <int BK, int BN>
 struct Cfg {
   static constexpr int kBoxBytes = 32 * BK * 4;                 // one TMA box: 32 positions x BK channels fp32
-  static constexpr int kTileKBytes = (BM / 32) * kBoxBytes;     // 128 positions x BK channels
-  static constexpr int kStages = kRingBytes / kTileKBytes;      // 6 (BK=32) or 3 (BK=64)
+  static constexpr int kResKBytes = (BM / 32) * kBoxBytes;      // resident operand, one k-block: 128 positions x BK channels
+  static constexpr int kStageBytes = (BN / 32) * kBoxBytes;     // streamed operand, one stage: BN positions x BK channels
+  static constexpr int kStages = kRingBytes / kStageBytes;      // 96 KiB ring: 3 stages of 32 KiB (BK*BN = 8192) or 6 of 16 KiB
   static constexpr int kMaxKB = kMaxD / BK;
+  static constexpr int kTmemCols = 2 * BN;                      // two accumulator buffers
+  // kind::tf32 instruction descriptor: fp32 accumulate, A and B tf32, both MN-major, M = 128, N = BN
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                     ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
+
+// Timeline probe (EEM_TF32_DEBUG bit 16): CTA 0's MMA thread records clock64 around each pipeline step.
+__device__ long long g_probe[8192];
 
 struct Tf32Params {
   CUtensorMap map_f1;                 // [B*D, P] fp32, box 32 positions x BK channels, 128B_ATOM_32B swizzle
@@ -126,10 +133,12 @@ struct Tf32Params {
   int mt_cum[kMaxLevels + 1];         // cumulative 128-row tile counts over levels
   int B, D, P, L;
   int n_tiles;                        // ceil(P / BN)
-  int64_t n_items;                    // B * mt_cum[L]
+  int64_t n_items;                    // cluster-items: B * gpb
+  int gpb;                            // groups of `cluster` consecutive 128-row tiles per sample
+  int cluster;                        // CTAs per cluster sharing one fmap1 stream (1, 2 or 4)
   float scale;
   uint32_t desc_lo, desc_hi;          // constant smem-descriptor fields (desc_fields)
-  uint32_t debug;                     // EEM_TF32_DEBUG bits (timing experiments only): 1 skip MMA, 2 skip stores, 4 skip streamed loads
+  uint32_t debug;                     // EEM_TF32_DEBUG bits (timing experiments only): 1 skip MMA, 2 skip stores, 4 skip streamed loads, 8 skip TMEM loads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -188,10 +197,44 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(pol)
       : "memory");
 }
+// Multicast variant: the box lands at the same shared-memory offset in every CTA of `mask` and
+// completes bytes on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar,
+                                               uint16_t mask, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// One lane of a CONVERGED warp.  The producer / MMA warps run their loops with all 32 lanes and
+// predicate only the issuing instructions with this, so the compiler can keep descriptors and
+// addresses in uniform registers; under `if (lane == 0)` it wraps every UTCHMMA / UTMALDG in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY loop (~70 cycles per MMA issue, measured with the clock64 probe).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Arrive (once the MMAs issued so far have completed) on the mbarrier at this offset in every CTA of `mask`.
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -223,10 +266,6 @@ inline void desc_fields(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_
   *hi = ((sbo_bytes >> 4) & 0x3fff) | (1u << 14) | (layout_type << 29);  // [32,46) SBO, [46,48) version 1, [61,64) layout
 }
 
-// kind::tf32 instruction descriptor: fp32 accumulate, A and B tf32, both MN-major, M=128, N=BN.
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
 // Work order.  An "item" is (sample b, level l, 128-row tile of that level): its resident operand
 // is loaded once and reused for all n_tiles output tiles.  Items are numbered sample-major and
 // dealt round-robin -- in round r CTA c owns item r*G + c -- so at any moment the CTAs work on ~G
@@ -237,34 +276,45 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1
 // per tile, so it must cost a handful of instructions (an earlier version used 64-bit div/mod
 // here and spent more time in it than in the MMAs).
 struct TileIter {
-  int cta, G, n_tiles, ipb;
+  int cta, G, n_tiles, ipb, gpb, CL, rank, bn;   // cta = cluster id, G = number of clusters, bn = N tile
   int r, r_full;          // current round / number of full rounds
-  int item, nt;           // current item and n-tile
-  int tail_left;          // tiles still to visit in the tail phase (valid once r == r_full)
+  int item, nt;           // current cluster-item and n-tile
   int remaining;          // total tiles still to visit, including the current one
-  int b, l, m0;           // decoded item
+  int tail_begin_;
+  int b, l, m0;           // decoded item of THIS CTA (a 128-row tile of one level of sample b)
 
+  // cluster-item -> (sample b, group of CL consecutive 128-row tiles); CTA `rank` takes tile rank of
+  // the group.  A group that runs past the sample's last tile gives the surplus CTAs a dummy tile
+  // (m0 beyond the level: TMA zero-fills, nothing is stored) so the cluster stays in lock step.
   __device__ __forceinline__ void decode(const Tf32Params& p) {
-    b = item / ipb;       // 32-bit, once per item (every n_tiles tiles)
-    const int rr = item - b * ipb;
-    int lv = 0;
-    while (lv + 1 < p.L && rr >= p.mt_cum[lv + 1]) ++lv;
-    l = lv;
-    m0 = (rr - p.mt_cum[lv]) * BM;
+    b = item / gpb;       // 32-bit, once per item (every n_tiles tiles)
+    const int rr = (item - b * gpb) * CL + rank;
+    if (rr < ipb) {
+      int lv = 0;
+      while (lv + 1 < p.L && rr >= p.mt_cum[lv + 1]) ++lv;
+      l = lv;
+      m0 = (rr - p.mt_cum[lv]) * BM;
+    } else {
+      l = 0;
+      m0 = p.mt_cum[1] * BM;   // >= P_0: fully out of range
+    }
   }
 
-  __device__ __forceinline__ void init(const Tf32Params& p) {
-    cta = blockIdx.x;
-    G = gridDim.x;
+  __device__ __forceinline__ void init(const Tf32Params& p, int bn_) {
+    bn = bn_;
+    CL = p.cluster;
+    rank = blockIdx.x % CL;
+    cta = blockIdx.x / CL;
+    G = gridDim.x / CL;
     n_tiles = p.n_tiles;
     ipb = p.mt_cum[p.L];
+    gpb = p.gpb;
     const int n_items = (int)p.n_items;
     r_full = n_items / G;
     const int tail_tiles = (n_items - r_full * G) * n_tiles;
     const int tail_begin = (int)((int64_t)tail_tiles * cta / G);
     const int tail_end = (int)((int64_t)tail_tiles * (cta + 1) / G);
-    tail_left = tail_end - tail_begin;
-    remaining = r_full * n_tiles + tail_left;
+    remaining = r_full * n_tiles + (tail_end - tail_begin);
     r = 0;
     if (r_full > 0) {
       item = cta;
@@ -277,12 +327,11 @@ struct TileIter {
     tail_begin_ = tail_begin;
     if (remaining > 0) decode(p);
   }
-  int tail_begin_;
 
   __device__ __forceinline__ bool valid() const { return remaining > 0; }
   // true when the current tile is the last one this CTA computes for the current item
   __device__ __forceinline__ bool last_of_item() const { return nt + 1 == n_tiles || remaining == 1; }
-  __device__ __forceinline__ int n0() const { return nt * BN; }
+  __device__ __forceinline__ int n0() const { return nt * bn; }
 
   // advance; returns true when the item changed
   __device__ __forceinline__ bool next(const Tf32Params& p) {
@@ -307,28 +356,33 @@ struct TileIter {
   }
 };
 
-template <int BK>
+template <int BK, int BN>
 struct __align__(1024) Tf32Smem {
   uint8_t resident[kMaxD * 128 * 4];          // pooled-fmap2 panel of the current item: 128 KiB
   uint8_t ring[kRingBytes];                   // fmap1 stages
-  uint64_t full[Cfg<BK>::kStages], empty[Cfg<BK>::kStages];
-  uint64_t res_free[Cfg<BK>::kMaxKB];         // resident k-block may be overwritten
+  uint64_t full[Cfg<BK, BN>::kStages], empty[Cfg<BK, BN>::kStages];
+  uint64_t res_free[Cfg<BK, BN>::kMaxKB];     // resident k-block may be overwritten
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
-template <int BK>
+template <int BK, int BN, int CL>
 __global__ void __launch_bounds__(kTf32Threads, 1)
 corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
-  constexpr int kStages = Cfg<BK>::kStages, kMaxKB = Cfg<BK>::kMaxKB;
-  constexpr int kBoxBytes = Cfg<BK>::kBoxBytes, kTileKBytes = Cfg<BK>::kTileKBytes;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  using C = Cfg<BK, BN>;
+  constexpr int kStages = C::kStages, kMaxKB = C::kMaxKB, kTmemCols = C::kTmemCols;
+  constexpr int kBoxBytes = C::kBoxBytes, kResKBytes = C::kResKBytes, kStageBytes = C::kStageBytes;
+  constexpr uint32_t kIdesc = C::kIdesc;
   extern __shared__ uint8_t smem_raw[];
-  Tf32Smem<BK>& s = *reinterpret_cast<Tf32Smem<BK>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Tf32Smem<BK, BN>& s = *reinterpret_cast<Tf32Smem<BK, BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.D / BK;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    // empty[] collects one arrival per CTA of the cluster: a stage is refilled by multicast from every
+    // CTA, so all of them must have consumed it
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], CL); }
     for (int i = 0; i < kMaxKB; ++i) mbar_init(&s.res_free[i], 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -339,16 +393,18 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
+  const int rank = (int)(blockIdx.x % CL);
 
   if (warp == kProducerWarp) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (whole warp converged, one elected lane issues) =====
+    {
       const uint64_t keep = policy_evict_last();
       const bool stream = !(p.debug & 4);
       TileIter it;
-      it.init(p);
+      it.init(p, BN);
       int stage = 0;
       uint32_t phase = 0;
       bool new_item = true;
@@ -358,20 +414,32 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
         for (int kb = 0; kb < KB; ++kb) {
           if (new_item && items_done > 0) mbar_wait(&s.res_free[kb], (items_done - 1) & 1);
           mbar_wait(&s.empty[stage], phase ^ 1);
-          mbar_expect_tx(&s.full[stage], (new_item ? kTileKBytes : 0) + (stream ? kTileKBytes : 0));
           const int row = it.b * p.D + kb * BK;
-          if (new_item) {
-            uint8_t* dst = s.resident + kb * kTileKBytes;
+          if (elect_one()) {
+            mbar_expect_tx(&s.full[stage], (new_item ? kResKBytes : 0) + (stream ? kStageBytes : 0));
+            if (new_item) {
+              uint8_t* dst = s.resident + kb * kResKBytes;
 #pragma unroll
-            for (int ch = 0; ch < BM / 32; ++ch)
-              tma_load_2d(dst + ch * kBoxBytes, &p.map_lvl[it.l], it.m0 + ch * 32, row, &s.full[stage], keep);
-          }
-          if (stream) {
-            uint8_t* dst = s.ring + stage * kTileKBytes;
+              for (int ch = 0; ch < BM / 32; ++ch)
+                tma_load_2d(dst + ch * kBoxBytes, &p.map_lvl[it.l], it.m0 + ch * 32, row, &s.full[stage], keep);
+            }
+            if (stream) {
+              uint8_t* dst = s.ring + stage * kStageBytes;
+              if constexpr (CL == 1) {
 #pragma unroll
-            for (int ch = 0; ch < BN / 32; ++ch)
-              tma_load_2d(dst + ch * kBoxBytes, &p.map_f1, n0 + ch * 32, row, &s.full[stage], keep);
+                for (int ch = 0; ch < BN / 32; ++ch)
+                  tma_load_2d(dst + ch * kBoxBytes, &p.map_f1, n0 + ch * 32, row, &s.full[stage], keep);
+              } else {
+                // this CTA fetches 1/CL of the fmap1 stage and multicasts it to the whole cluster
+#pragma unroll
+                for (int k = 0; k < BN / 32 / CL; ++k) {
+                  const int ch = rank + k * CL;
+                  tma_load_2d_mc(dst + ch * kBoxBytes, &p.map_f1, n0 + ch * 32, row, &s.full[stage], kMask, keep);
+                }
+              }
+            }
           }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (new_item) ++items_done;
@@ -379,13 +447,14 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (whole warp converged, one elected lane issues) =====
+    {
       TileIter it;
-      it.init(p);
+      it.init(p, BN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t k = 0;
+      int probe_n = 0;
       while (it.valid()) {
         const bool last_of_item = it.last_of_item();
         const uint32_t acc = k & 1;
@@ -393,11 +462,15 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
         tc_fence_after();
         const uint32_t d_tmem = tmem + acc * BN;
         for (int kb = 0; kb < KB; ++kb) {
+          const bool probe = (p.debug & 16) && blockIdx.x == 0 && lane == 0 && probe_n + 4 <= 8192;
+          if (probe) g_probe[probe_n++] = clock64();
           mbar_wait(&s.full[stage], phase);
+          if (probe) g_probe[probe_n++] = clock64();
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(s.resident + kb * kTileKBytes);
-          const uint32_t b_addr = smem_u32(s.ring + stage * kTileKBytes);
-          if (!(p.debug & 1)) {
+          const uint32_t a_addr = smem_u32(s.resident + kb * kResKBytes);
+          const uint32_t b_addr = smem_u32(s.ring + stage * kStageBytes);
+          const bool leader = elect_one();
+          if (leader && !(p.debug & 1)) {
 #pragma unroll
             for (int ks = 0; ks < BK / UK; ++ks) {
               // 8 channels = 8 rows of 128 B = two 512-byte swizzle atoms per 32-position chunk
@@ -405,11 +478,17 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
                           make_desc(b_addr + ks * 1024, p.desc_lo, p.desc_hi), kIdesc, (kb | ks) != 0);
             }
           }
-          tc_commit(&s.empty[stage]);
-          if (last_of_item) tc_commit(&s.res_free[kb]);
+          if (probe) g_probe[probe_n++] = clock64();
+          if (leader) {
+            if constexpr (CL == 1) tc_commit(&s.empty[stage]); else tc_commit_mc(&s.empty[stage], kMask);
+            if (last_of_item) tc_commit(&s.res_free[kb]);
+          }
+          __syncwarp();
+          if (probe) g_probe[probe_n++] = clock64();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&s.acc_full[acc]);
+        if (elect_one()) tc_commit(&s.acc_full[acc]);
+        __syncwarp();
         it.next(p);
         ++k;
       }
@@ -423,7 +502,7 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
     const float scale = p.scale;
     const bool do_store = !(p.debug & 2);
     TileIter it;
-    it.init(p);
+    it.init(p, BN);
     uint32_t k = 0;
     while (it.valid()) {
       const uint32_t acc = k & 1;
@@ -437,6 +516,7 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
       const int n0 = it.n0();
 #pragma unroll 1
       for (int cc = half * (BN / 64); cc < (half + 1) * (BN / 64); ++cc) {
+        if (p.debug & 8) break;
         uint32_t v[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -470,6 +550,7 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while peers may still multicast into it
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
@@ -512,6 +593,21 @@ int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, 
   return EEM_OK;
 }
 
+// One function (hence one set of statics) per kernel instantiation: the > 48 KiB dynamic shared memory
+// opt-in is done once per instantiation, which also keeps it out of CUDA-graph capture.
+template <int BK, int BN, int CL>
+cudaError_t launch_tf32(cudaLaunchConfig_t cfg, const Tf32Params& p) {
+  constexpr size_t kSmem = sizeof(Tf32Smem<BK, BN>) + 1024;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(corr_tf32_kernel<BK, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  cfg.dynamicSmemBytes = kSmem;
+  return cudaLaunchKernelEx(&cfg, corr_tf32_kernel<BK, BN, CL>, p);
+}
+
 struct LevelDims {
   int h[kMaxLevels], w[kMaxLevels];
   int64_t pitch[kMaxLevels];   // element pitch of the pooled operand rows (level 0: P)
@@ -543,6 +639,12 @@ LevelDims level_dims(int B, int D, int H, int W, int L) {
 using namespace eem;
 
 extern "C" {
+
+// debug only (not part of the public header): copy the timeline probe to the host
+EEM_API int eem_debug_read_probe(long long* out, int n) {
+  if (n > 8192) n = 8192;
+  return cudaMemcpyFromSymbol(out, g_probe, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : -4;
+}
 
 size_t eem_corr_pyramid_workspace_bytes(int B, int D, int H, int W, int num_levels) {
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || num_levels <= 0 || num_levels > kMaxLevels) return 0;
@@ -605,10 +707,17 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
     return EEM_OK;
   }
 
-  int bk = (D % 64 == 0) ? 64 : 32;
-  if (const char* v = getenv("EEM_TF32_BK")) {   // timing experiments only
+  // Tile configuration (BK channels per stage, BN fmap1 positions per MMA).  Default BN = 256 / BK = 32:
+  // with both operands read MN-major from shared memory a 128x128x8 MMA needs 8 KiB per 64 cycles,
+  // i.e. the full 128 B/cycle of the SM's shared memory, and the tensor pipe runs at about half rate;
+  // N = 256 needs 96 B/cycle.  EEM_TF32_BN / EEM_TF32_BK override for timing experiments.
+  int bn = 256, bk = 32;
+  if (const char* v = getenv("EEM_TF32_BN")) {
+    if (atoi(v) == 128) { bn = 128; bk = (D % 64 == 0) ? 64 : 32; }
+  }
+  if (const char* v = getenv("EEM_TF32_BK")) {
     const int forced = atoi(v);
-    if ((forced == 32 || forced == 64) && D % forced == 0) bk = forced;
+    if (bn == 128 && (forced == 32 || forced == 64) && D % forced == 0) bk = forced;
   }
   const uint32_t box_bytes = 32u * (uint32_t)bk * 4u;
   Tf32Params p{};
@@ -642,28 +751,49 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
     nl = l + 1;
   }
   p.B = B; p.D = D; p.P = P; p.L = nl;
-  p.n_tiles = (int)ceil_div(P, BN);
-  p.n_items = (int64_t)B * p.mt_cum[nl];
+  p.n_tiles = (int)ceil_div(P, bn);
+  // CTAs of a cluster take consecutive 128-row tiles of the same sample and share one multicast fmap1
+  // stream.  Measured on B200 (MVSEC B=32): 2-CTA clusters 199 us vs 211 us without sharing; 4-CTA clusters
+  // were slower (lock-step stalls), so the choice is 1 or 2 (EEM_TF32_CLUSTER overrides for experiments).
+  int cl = 2;
+  if (const char* v = getenv("EEM_TF32_CLUSTER")) {
+    const int forced = atoi(v);
+    if (forced == 1 || forced == 2) cl = forced;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return fail(EEM_ERR_CUDA, "eem_corr_pyramid: cannot query SM count");
+  if (sms < cl) cl = 1;
+  p.cluster = cl;
+  p.gpb = (int)ceil_div(p.mt_cum[nl], cl);
+  p.n_items = (int64_t)B * p.gpb;
   p.scale = scale;
   if (p.n_items * p.n_tiles >= (int64_t)0x7fffffff)
     return fail(EEM_ERR_UNSUPPORTED, "eem_corr_pyramid(TF32): too many tiles in one call; split the batch");
-  int64_t grid = sm_count();
-  if (grid <= 0) return fail(EEM_ERR_CUDA, "eem_corr_pyramid: cannot query SM count");
-  if (grid > p.n_items * p.n_tiles) grid = p.n_items * p.n_tiles;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(corr_tf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(sizeof(Tf32Smem<32>) + 1024));
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(corr_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(Tf32Smem<64>) + 1024));
-  });
-  if (attr_err != cudaSuccess) return fail(EEM_ERR_CUDA, "corr_tf32_kernel attribute: %s", cudaGetErrorString(attr_err));
-  if (bk == 64)
-    corr_tf32_kernel<64><<<(unsigned)grid, kTf32Threads, sizeof(Tf32Smem<64>) + 1024, stream>>>(p);
-  else
-    corr_tf32_kernel<32><<<(unsigned)grid, kTf32Threads, sizeof(Tf32Smem<32>) + 1024, stream>>>(p);
+  int64_t clusters = sms / cl;
+  if (clusters > p.n_items * p.n_tiles) clusters = p.n_items * p.n_tiles;
+  const unsigned grid = (unsigned)(clusters * cl);
+
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTf32Threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+
+  cudaError_t err = cudaSuccess;
+  if (bn == 256) {
+    err = cl == 2 ? launch_tf32<32, 256, 2>(cfg, p) : launch_tf32<32, 256, 1>(cfg, p);
+  } else if (bk == 64) {
+    err = cl == 2 ? launch_tf32<64, 128, 2>(cfg, p) : launch_tf32<64, 128, 1>(cfg, p);
+  } else {
+    err = cl == 2 ? launch_tf32<32, 128, 2>(cfg, p) : launch_tf32<32, 128, 1>(cfg, p);
+  }
+  if (err != cudaSuccess) return fail(EEM_ERR_CUDA, "corr_tf32_kernel launch: %s", cudaGetErrorString(err));
   EEM_CHECK_LAUNCH("corr_tf32_kernel");
   return EEM_OK;
 }

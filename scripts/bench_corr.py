@@ -32,17 +32,10 @@ def run(B, D, H, W, L, label, iters=10, precision="tf32"):
 
 if __name__ == "__main__":
     shape = (32, 256, 36, 44, 4)
-    for bk in ("32", "64"):
-        os.environ["EEM_TF32_BK"] = bk
+    for bn, bk in (("256", "32"), ("128", "64"), ("128", "32")):
+        os.environ["EEM_TF32_BN"], os.environ["EEM_TF32_BK"] = bn, bk
+        for dbg, label in [(0, "full"), (12, "MMA only"), (7, "resident only"), (2, "no stores")]:
+            os.environ["EEM_TF32_DEBUG"] = str(dbg)
+            run(*shape, f"BN={bn} BK={bk} {label}")
         os.environ["EEM_TF32_DEBUG"] = "0"
-        run(*shape, f"BK={bk} full")
-        os.environ["EEM_TF32_DEBUG"] = "7"
-        run(*shape, f"BK={bk} resident loads only")
-    os.environ.pop("EEM_TF32_BK")
-    for dbg, label in [(0, "full"), (2, "no stores"), (1, "no MMA"), (3, "no MMA, no stores"), (4, "no streamed loads"),
-                       (6, "no streamed loads, no stores"), (7, "resident loads only")]:
-        os.environ["EEM_TF32_DEBUG"] = str(dbg)
-        run(*shape, label)
-    os.environ["EEM_TF32_DEBUG"] = "0"
-    run(8, 256, 92, 160, 4, "HREM B=8 full", iters=3)
-    run(32, 256, 36, 44, 4, "fp32 SIMT path", iters=3, precision="fp32")
+        run(4, 256, 92, 160, 4, f"BN={bn} BK={bk} HREM B=4", iters=3)

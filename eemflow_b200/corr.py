@@ -10,6 +10,7 @@ import os
 
 import torch
 
+from . import autograd as ag
 from . import ops
 
 
@@ -35,6 +36,10 @@ class CorrBlock:
         if precision is None:
             precision = _default_precision(dim, ht, wd)
         self.precision = precision
+        if ag.needs_grad(fmap1, fmap2):
+            raise NotImplementedError(
+                "eemflow_b200.CorrBlock has no backward kernels yet (inference / frozen-encoder use only); "
+                "wrap the call in torch.no_grad() or detach the feature maps")
         with torch.no_grad():
             self.corr_pyramid = ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision)
 
@@ -70,5 +75,4 @@ def upflow8(flow, mode='bilinear'):
     if mode != 'bilinear':
         raise NotImplementedError("eemflow_b200.upflow8 implements mode='bilinear' only")
     new_size = (8 * flow.shape[2], 8 * flow.shape[3])
-    with torch.no_grad():
-        return ops.bilinear_resize(flow, new_size, align_corners=True, scale0=8.0, scale1=8.0, scale_rest=8.0)
+    return ag.bilinear_resize(flow, new_size, align_corners=True, scale0=8.0, scale1=8.0, scale_rest=8.0)

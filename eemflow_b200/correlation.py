@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import autograd as ag
 
 
 class SpatialCorrelationSampler(nn.Module):
@@ -37,8 +37,7 @@ class SpatialCorrelationSampler(nn.Module):
     def forward(self, input1, input2):
         b, c, h, w = input1.shape
         md = (self.patch_size - 1) // 2
-        with torch.no_grad():
-            out = ops.local_corr(input1, input2, max_disp=md)
+        out = ag.local_corr(input1, input2, max_disp=md)
         return out.view(b, self.patch_size, self.patch_size, h, w)
 
 
@@ -51,9 +50,8 @@ class Correlation(nn.Module):
 
     def forward(self, x, y):
         b, c, h, w = x.shape
-        with torch.no_grad():
-            # "/ c" of the reference folded into the kernel's store
-            return ops.local_corr(x, y, max_disp=self.max_displacement, scale=1.0 / c)
+        # "/ c" of the reference folded into the kernel's store
+        return ag.local_corr(x, y, max_disp=self.max_displacement, scale=1.0 / c)
 
     def forward_select(self, x, y, index):
         return correlation_select(x, y, index, self.max_displacement)
@@ -63,8 +61,7 @@ def correlation_select(x, y, index, max_displacement=4):
     """index_select(Correlation(md)(x, y), dim=1, index) in one kernel: only the kept channels are written."""
     idx = index.tolist() if torch.is_tensor(index) else list(index)
     b, c, h, w = x.shape
-    with torch.no_grad():
-        return ops.local_corr(x, y, max_disp=max_displacement, index=[int(v) for v in idx], scale=1.0 / c)
+    return ag.local_corr(x, y, max_disp=max_displacement, index=[int(v) for v in idx], scale=1.0 / c)
 
 
 # The two fixed channel lists of the reference.

@@ -242,3 +242,40 @@ def replicate_pad(x: torch.Tensor, pad: Sequence[int]) -> torch.Tensor:
 
 def inv_sqrt_dim(d: int) -> float:
     return 1.0 / math.sqrt(float(d))
+
+
+# ------------------------------------------------------------------------------------------ backward (f1)
+def local_corr_backward(f1, f2, grad_out, max_disp=4, index=None, scale=1.0, need_f1=True, need_f2=True):
+    f1, f2, grad_out = L.require_cuda(f1, "f1"), L.require_cuda(f2, "f2"), L.require_cuda(grad_out, "grad_out")
+    B, Cc, H, W = f1.shape
+    n_out = grad_out.shape[1]
+    idx = None if index is None else (C.c_int * n_out)(*[int(v) for v in index])
+    g1 = torch.empty_like(f1) if need_f1 else None
+    g2 = torch.empty_like(f2) if need_f2 else None
+    with torch.cuda.device(f1.device):
+        L.check(L.lib().eem_local_corr_backward(f1.data_ptr(), f2.data_ptr(), grad_out.data_ptr(), B, Cc, H, W, max_disp,
+                                                idx, n_out, float(scale), L.ptr(g1), L.ptr(g2), L.stream_ptr(f1.device)))
+    return g1, g2
+
+
+def backwarp_backward(x, flow, grad_out, convention, mask_mode=L.MASK_NONE, need_x=True, need_flow=True):
+    x, flow, grad_out = L.require_cuda(x, "x"), L.require_cuda(flow, "flow"), L.require_cuda(grad_out, "grad_out")
+    B, Cc, H, W = x.shape
+    gx = torch.empty_like(x) if need_x else None
+    gf = torch.empty_like(flow) if need_flow else None
+    with torch.cuda.device(x.device):
+        L.check(L.lib().eem_backwarp_backward(x.data_ptr(), flow.data_ptr(), grad_out.data_ptr(), B, Cc, H, W, convention,
+                                              mask_mode, L.ptr(gx), L.ptr(gf), L.stream_ptr(x.device)))
+    return gx, gf
+
+
+def bilinear_resize_backward(grad_out, in_size, align_corners, scale0=1.0, scale1=1.0, scale_rest=1.0):
+    grad_out = L.require_cuda(grad_out, "grad_out")
+    B, Cc, H, W = grad_out.shape
+    h, w = int(in_size[0]), int(in_size[1])
+    gin = torch.empty((B, Cc, h, w), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        L.check(L.lib().eem_bilinear_resize_backward(grad_out.data_ptr(), B, Cc, h, w, H, W, int(bool(align_corners)),
+                                                     float(scale0), float(scale1), float(scale_rest), gin.data_ptr(),
+                                                     L.stream_ptr(grad_out.device)))
+    return gin

@@ -17,13 +17,13 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from . import autograd as ag
 from . import ops
 
 
 def warp(x, flo):
     """Bilinear sample of x at (px+u, py+v), zeros outside, exact pixel positions (align_corners=True)."""
-    with torch.no_grad():
-        return ops.backwarp(x, flo, L.WARP_EXACT)
+    return ag.backwarp(x, flo, L.WARP_EXACT)
 
 
 class tensor_tools:
@@ -36,13 +36,14 @@ class tensor_tools:
         Keeps the reference's convention: (W-1) normalisation + grid_sample's default
         align_corners=False, i.e. the sample lands at px'*W/(W-1) - 0.5.
         """
-        with torch.no_grad():
-            return ops.backwarp(x, flo, L.WARP_HALFPIX)
+        return ag.backwarp(x, flo, L.WARP_HALFPIX)
 
     @classmethod
     def torch_warp_mask(cls, x, flo):
         with torch.no_grad():
             out, mask = ops.backwarp(x, flo, L.WARP_HALFPIX, mask_mode=L.MASK_9999, return_mask=True)
+        if ag.needs_grad(x, flo):  # differentiable output; the 0/1 mask is a constant, as in the reference
+            out = ag.backwarp(x, flo, L.WARP_HALFPIX, L.MASK_9999)
         return out, mask.expand_as(out)
 
 
@@ -55,8 +56,7 @@ class WarpingLayer_no_div(nn.Module):
         super(WarpingLayer_no_div, self).__init__()
 
     def forward(self, x, flow):
-        with torch.no_grad():
-            return ops.backwarp(x, flow, L.WARP_HALFPIX, mask_mode=L.MASK_GE1)
+        return ag.backwarp(x, flow, L.WARP_HALFPIX, L.MASK_GE1)
 
 
 def upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate=False):
@@ -65,28 +65,29 @@ def upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate=False):
     if mode != "bilinear":
         raise NotImplementedError("eemflow_b200.upsample2d_flow_as implements mode='bilinear' only")
     _, _, h, w = target_as.shape
-    with torch.no_grad():
-        if if_rate:
-            _, _, h_, w_ = inputs.shape
-            u_scale, v_scale = (w / w_), (h / h_)
-            res = ops.bilinear_resize(inputs, (h, w), align_corners=True, scale0=u_scale, scale1=v_scale)
-            if inputs.is_contiguous() and inputs.dtype == torch.float32:
-                ops.scale_uv_(inputs, u_scale, v_scale)
-            else:  # keep the side effect for exotic views as well
-                inputs[:, 0, :, :] *= u_scale
-                inputs[:, 1, :, :] *= v_scale
-            return res
-        return ops.bilinear_resize(inputs, (h, w), align_corners=True)
+    if if_rate:
+        _, _, h_, w_ = inputs.shape
+        u_scale, v_scale = (w / w_), (h / h_)
+        res = ag.bilinear_resize(inputs, (h, w), align_corners=True, scale0=u_scale, scale1=v_scale)
+        if inputs.is_contiguous() and inputs.dtype == torch.float32 and not ag.needs_grad(inputs):
+            ops.scale_uv_(inputs, u_scale, v_scale)
+        else:  # autograd-tracked or exotic view: keep the side effect with (tiny) torch in-place ops
+            inputs[:, 0, :, :] *= u_scale
+            inputs[:, 1, :, :] *= v_scale
+        return res
+    return ag.bilinear_resize(inputs, (h, w), align_corners=True)
 
 
 def upsample_flow(flow, orig_size):
     """Meshflow -> dense flow: bilinear, align_corners=False, no magnitude rescale."""
-    with torch.no_grad():
-        return ops.bilinear_resize(flow, tuple(orig_size), align_corners=False)
+    return ag.bilinear_resize(flow, tuple(orig_size), align_corners=False)
 
 
 def cdc_blend(flow_init, inter_flow, inter_mask):
     """torch_warp(flow_init, inter_flow) * (1 - inter_mask) + flow_init * inter_mask, fused."""
+    if ag.needs_grad(flow_init, inter_flow, inter_mask):
+        # training: same expression as the reference, the warp itself runs (forward and backward) in the kernels
+        return ag.backwarp(flow_init, inter_flow, L.WARP_HALFPIX) * (1 - inter_mask) + flow_init * inter_mask
     with torch.no_grad():
         return ops.warp_blend(flow_init, inter_flow, inter_mask)
 

@@ -200,6 +200,26 @@ EEM_API int eem_scale_uv_inplace(float* flow, int B, int C, int h, int w, float 
 EEM_API int eem_replicate_pad(const float* in, int B, int C, int H, int W, int left, int right,
                               int top, int bottom, float* out, eem_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Backward (adjoint) kernels -- training drop-in.  In the reference these
+ * gradients come from autograd through spatial_correlation_sampler's backward (what the dead
+ * extension model/IRRPWC/correlation_package/correlation_cuda_kernel.cu:117-298 implemented),
+ * F.grid_sample and F.interpolate.  Either gradient output pointer may be NULL to skip it.
+ * ------------------------------------------------------------------------------------------ */
+/* grad_out [B,n_out,H,W] -> grad_f1, grad_f2 [B,C,H,W]; same index/scale meaning as eem_local_corr. */
+EEM_API int eem_local_corr_backward(const float* f1, const float* f2, const float* grad_out, int B,
+                                    int C, int H, int W, int max_disp, const int* index, int n_out,
+                                    float scale, float* grad_f1, float* grad_f2, eem_stream_t stream);
+/* grad_out [B,C,H,W] -> grad_x [B,C,H,W] (zero-filled by the call, accumulated with RED.ADD) and
+ * grad_flow [B,2,H,W]; the 0/1 validity mask of mask_mode is treated as a constant. */
+EEM_API int eem_backwarp_backward(const float* x, const float* flow, const float* grad_out, int B,
+                                  int C, int H, int W, int convention, int mask_mode, float* grad_x,
+                                  float* grad_flow, eem_stream_t stream);
+/* grad_out [B,C,H,W] -> grad_in [B,C,h,w]; adjoint of eem_bilinear_resize with the same scales. */
+EEM_API int eem_bilinear_resize_backward(const float* grad_out, int B, int C, int h, int w, int H,
+                                         int W, int align_corners, float scale0, float scale1,
+                                         float scale_rest, float* grad_in, eem_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

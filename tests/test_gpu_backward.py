@@ -1,0 +1,139 @@
+"""GPU parity of the backward kernels (csrc/backward.cu) and the autograd wrappers against torch autograd
+through the CPU oracle (the reference's own differentiable ATen calls).  Gate: <= 2e-4 relative to the
+largest gradient magnitude (fp32, differently ordered sums; the warp gradients multiply values ~N(0,1)).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    import eemflow_b200
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device is visible"
+    return eemflow_b200
+
+
+def close(a, b, tol=2e-4):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    scale = max(b.abs().max().item(), 1e-6)
+    return (a - b).abs().max().item() <= tol * scale, (a - b).abs().max().item() / scale
+
+
+@pytest.mark.parametrize("B,C,H,W,select", [(2, 8, 7, 9, False), (1, 16, 12, 20, True), (2, 64, 20, 24, True), (1, 19, 33, 37, False)])
+def test_local_corr_backward(E, B, C, H, W, select):
+    from eemflow_b200.correlation import EEMFLOW_CDC_INDEX
+    gen = torch.Generator().manual_seed(C * H)
+    f1 = torch.randn(B, C, H, W, generator=gen, requires_grad=True)
+    f2 = torch.randn(B, C, H, W, generator=gen, requires_grad=True)
+    idx = EEMFLOW_CDC_INDEX if select else None
+    ref = ref_ops.correlation(f1, f2, 4, index=idx)
+    g = torch.randn(ref.shape, generator=gen)
+    ref.backward(g)
+    a = f1.detach().cuda().requires_grad_(True)
+    b = f2.detach().cuda().requires_grad_(True)
+    out = E.correlation_select(a, b, idx) if select else E.Correlation(4)(a, b)
+    assert out.requires_grad
+    assert close(out, ref, 1e-5)[0]
+    out.backward(g.cuda())
+    ok1, e1 = close(a.grad, f1.grad)
+    ok2, e2 = close(b.grad, f2.grad)
+    assert ok1 and ok2, (e1, e2)
+    # only one input needs a gradient
+    a2 = f1.detach().cuda().requires_grad_(True)
+    out2 = E.Correlation(4)(a2, f2.detach().cuda()) if not select else E.correlation_select(a2, f2.detach().cuda(), idx)
+    out2.backward(g.cuda())
+    assert close(a2.grad, f1.grad)[0]
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 3, 7, 9), (1, 32, 20, 24), (2, 2, 45, 80)])
+@pytest.mark.parametrize("variant", ["exact", "halfpix", "no_div"])
+def test_backwarp_backward(E, B, C, H, W, variant):
+    gen = torch.Generator().manual_seed(H * W + C)
+    x = torch.randn(B, C, H, W, generator=gen, requires_grad=True)
+    flo = (2.0 * torch.randn(B, 2, H, W, generator=gen)).requires_grad_(True)
+    ref_fn = {"exact": ref_ops.warp_exact, "halfpix": ref_ops.torch_warp, "no_div": ref_ops.warping_layer_no_div}[variant]
+    ref = ref_fn(x, flo)
+    g = torch.randn(ref.shape, generator=gen)
+    ref.backward(g)
+    xc = x.detach().cuda().requires_grad_(True)
+    fc = flo.detach().cuda().requires_grad_(True)
+    fn = {"exact": E.warp, "halfpix": E.torch_warp, "no_div": E.WarpingLayer_no_div()}[variant]
+    out = fn(xc, fc)
+    assert out.requires_grad and close(out, ref, 1e-5)[0]
+    out.backward(g.cuda())
+    okx, ex = close(xc.grad, x.grad)
+    okf, ef = close(fc.grad, flo.grad)
+    assert okx and okf, (variant, ex, ef)
+
+
+@pytest.mark.parametrize("h,w,H,W,align,rate", [(3, 5, 7, 9, True, True), (12, 20, 24, 40, True, True), (10, 12, 260, 346, True, True),
+                                                 (16, 16, 45, 80, False, False), (24, 40, 5, 7, False, False), (7, 9, 7, 9, True, False)])
+def test_resize_backward(E, h, w, H, W, align, rate):
+    gen = torch.Generator().manual_seed(h * W)
+    fl = torch.randn(2, 2, h, w, generator=gen, requires_grad=True)
+    tgt = torch.zeros(2, 1, H, W)
+    if align:
+        ref = ref_ops.upsample2d_flow_as(fl.clone(), tgt, if_rate=rate)
+    else:
+        ref = ref_ops.upsample_flow(fl, (H, W))
+    g = torch.randn(ref.shape, generator=gen)
+    ref.backward(g)
+    fc = fl.detach().cuda().requires_grad_(True)
+    if align:
+        out = E.upsample2d_flow_as(fc.clone(), tgt.cuda(), if_rate=rate)
+    else:
+        out = E.upsample_flow(fc, (H, W))
+    assert out.requires_grad
+    out.backward(g.cuda())
+    ok, e = close(fc.grad, fl.grad)
+    assert ok, e
+
+
+def test_cdc_blend_and_chain_backward(E):
+    """A small differentiable chain as in cdc_model.forward + EEMFlow_cdc.forward:
+    upsample (rate) -> WarpingLayer_no_div -> blend -> warp -> correlation."""
+    from eemflow_b200.correlation import EEMFLOW_CDC_INDEX
+    gen = torch.Generator().manual_seed(5)
+    flow = torch.randn(1, 2, 6, 8, generator=gen, requires_grad=True)
+    f1 = torch.randn(1, 16, 12, 16, generator=gen, requires_grad=True)
+    f2 = torch.randn(1, 16, 12, 16, generator=gen, requires_grad=True)
+    inter = (0.7 * torch.randn(1, 2, 12, 16, generator=gen)).requires_grad_(True)
+    mask = torch.sigmoid(torch.randn(1, 1, 12, 16, generator=gen)).requires_grad_(True)
+
+    def chain(mod, flow, f1, f2, inter, mask, on_gpu):
+        if on_gpu:
+            up = mod.upsample2d_flow_as(flow.clone(), f1, if_rate=True)
+            w2 = mod.WarpingLayer_no_div()(f2, up)
+            blended = mod.cdc_blend(up, inter, mask)
+            f2w = mod.warp(f2, blended)
+            cv = mod.correlation_select(f1, f2w, EEMFLOW_CDC_INDEX)
+        else:
+            up = ref_ops.upsample2d_flow_as(flow.clone(), f1, if_rate=True)
+            w2 = ref_ops.warping_layer_no_div(f2, up)
+            blended = ref_ops.cdc_blend(up, inter, mask)
+            f2w = ref_ops.warp_exact(f2, blended)
+            cv = ref_ops.correlation(f1, f2w, 4, index=EEMFLOW_CDC_INDEX)
+        return (cv * cv).sum() + w2.sum()
+
+    loss_ref = chain(None, flow, f1, f2, inter, mask, False)
+    loss_ref.backward()
+    leaves = [t.detach().cuda().requires_grad_(True) for t in (flow, f1, f2, inter, mask)]
+    loss = chain(E, *leaves, True)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+    loss.backward()
+    for name, a, b in zip(("flow", "f1", "f2", "inter", "mask"), leaves, (flow, f1, f2, inter, mask)):
+        ok, e = close(a.grad, b.grad, 1e-3)
+        assert ok, (name, e)
+
+
+def test_corrblock_requires_no_grad(E):
+    f = torch.randn(1, 32, 8, 12, device="cuda", requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        E.CorrBlock(f, f)
+    with torch.no_grad():
+        E.CorrBlock(f, f)

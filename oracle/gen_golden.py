@@ -252,6 +252,41 @@ def gen_warp(R):
     np.savez_compressed(OUT / "warp.npz", **cases)
 
 
+def gen_e2e(R):
+    """BASELINE config 0: EEMFlow(_cdc) forward from synthetic events (5-bin voxel grids), reference CPU path.
+    The local cost volume of the model runs through the oracle's stand-in for the un-vendored
+    spatial_correlation_sampler (oracle/ref_ops.py::local_corr_sampler); everything else is the
+    reference's own code: voxelizer, InputPadder, convs, cdc_model, warps, upsampling."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import ref_ops
+    from oracle.det_weights import set_deterministic_weights
+
+    class Sampler(nn.Module):
+        def __init__(self, kernel_size=1, patch_size=9, stride=1, padding=0, dilation=1):
+            super().__init__()
+            self.md = (patch_size - 1) // 2
+
+        def forward(self, a, b):
+            return ref_ops.local_corr_sampler(a, b, self.md)
+
+    plus = R["plus"]
+    plus.SpatialCorrelationSampler = Sampler
+    net = plus.EEMFlow_cdc(None, groups=3, n_first_channels=5).eval()
+    set_deterministic_weights(net)
+    rng = np.random.default_rng(7)
+    h, w, nb = 128, 160, 5
+    ev1, ev2 = make_events(rng, 5000, h, w), make_events(rng, 5000, h, w)
+    enc = R["Voxel"](num_bins=nb, gpu=False, normalize=True, forkserver=False)
+    v1 = enc(_Seq(ev1.copy(), h, w))[None]
+    v2 = enc(_Seq(ev2.copy(), h, w))[None]
+    net.change_imagesize((h, w))
+    _, flows = net(events1=v1, events2=v2)
+    out = {"events1": ev1, "events2": ev2, "shape": np.array([nb, h, w]), "voxel1": v1.numpy(), "voxel2": v2.numpy()}
+    for k, f in enumerate(flows):
+        out[f"flow{k}"] = f.numpy()
+    np.savez_compressed(OUT / "e2e_eemflow_cdc.npz", **out)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(1)  # fixed summation order in the reference's ATen reductions
@@ -261,6 +296,7 @@ def main():
         gen_corr(R)
         gen_local_corr(R)
         gen_warp(R)
+        gen_e2e(R)
     for f in sorted(OUT.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size / 1024:.1f} KiB")
 

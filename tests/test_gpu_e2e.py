@@ -1,0 +1,71 @@
+"""GPU end-to-end parity (BASELINE config 0): synthetic events -> 5-bin voxel grids -> EEMFlow_cdc forward,
+against the REAL reference model run on the CPU (tests/golden/e2e_eemflow_cdc.npz, oracle/gen_golden.py).
+The drop-in model shares parameter names/shapes/order with the reference; both sides use the RNG-free
+parameter values of oracle/det_weights.py.  Gate: EPE-relative (mean |dflow| / mean |flow|) <= 1e-3 per
+prediction with cuDNN TF32 disabled, as the north star states for correlation and flow outputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.det_weights import set_deterministic_weights
+
+pytestmark = pytest.mark.gpu
+
+
+class Seq:
+    def __init__(self, features, h, w):
+        self.features, self.image_height, self.image_width = features, h, w
+
+
+def test_eemflow_cdc_forward_from_events(golden):
+    import eemflow_b200 as E
+    from eemflow_b200.models import EEMFlow_cdc
+    assert torch.cuda.is_available(), "GPU tests selected but no CUDA device is visible"
+    g = golden("e2e_eemflow_cdc")
+    nb, h, w = (int(v) for v in g["shape"])
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        enc = E.EventSequenceToVoxelGrid_Pytorch(nb, gpu=True, normalize=True, forkserver=False)
+        v1 = enc(Seq(g["events1"].copy(), h, w))[None]
+        v2 = enc(Seq(g["events2"].copy(), h, w))[None]
+        assert np.abs(v1.cpu().numpy() - g["voxel1"]).max() <= 1e-5 * max(1.0, np.abs(g["voxel1"]).max())
+        net = EEMFlow_cdc(None, groups=3, n_first_channels=nb)
+        set_deterministic_weights(net)
+        net = net.cuda().eval()
+        net.change_imagesize((h, w))
+        with torch.no_grad():
+            (e1, e2), flows = net(events1=v1, events2=v2)
+        assert e1 is v1 and e2 is v2 and len(flows) == 5
+        for k, f in enumerate(flows):
+            ref = g[f"flow{k}"]
+            assert tuple(f.shape) == ref.shape == (1, 2, h, w)
+            d = np.abs(f.cpu().numpy() - ref)
+            rel = d.mean() / np.abs(ref).mean()
+            assert rel <= 1e-3, (k, rel, d.max())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_eemflow_cdc_trains_through_the_kernels():
+    """One optimisation step through the drop-in model: gradients flow through the CUDA backward kernels."""
+    from eemflow_b200.models import EEMFlow_cdc
+    torch.manual_seed(0)
+    net = EEMFlow_cdc(None, groups=3, n_first_channels=5).cuda().train()
+    net.change_imagesize((64, 96))
+    v1 = torch.randn(2, 5, 64, 96, device="cuda")
+    v2 = torch.randn(2, 5, 64, 96, device="cuda")
+    target = torch.zeros(2, 2, 64, 96, device="cuda")
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
+    losses = []
+    for _ in range(3):
+        _, flows = net(events1=v1, events2=v2)
+        loss = sum((f - target).abs().mean() for f in flows)   # L1 sequence loss, train_mvsec.py:201-227
+        opt.zero_grad()
+        loss.backward()
+        grads = [p.grad for p in net.parameters() if p.grad is not None]
+        assert len(grads) > 100 and all(torch.isfinite(g_).all() for g_ in grads)
+        opt.step()
+        losses.append(loss.item())
+    assert np.isfinite(losses).all()

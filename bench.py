@@ -49,15 +49,30 @@ EEMFLOW_CDC_INDEX = [0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 21, 22, 23, 24, 26, 
                      41, 42, 44, 46, 47, 48, 49, 50, 51, 52, 54, 56, 57, 58, 59, 60, 62, 64, 66, 68, 70, 72, 74, 76, 78, 80]
 
 
+# Alternative workloads (parity-test shapes of BASELINE.json, not the driver's bench line): selected
+# with --workload; the constants above are the default, BASELINE configs[1].
+WORKLOADS = {
+    "mvsec_dt1": {},
+    # configs[2]: HREM dt1 shape -- 720p-class stream, ~10M events/window, 15-bin grids, 92x160 ERAFT
+    # feature maps (736x1280 padded / 8), EEMFlow_cdc pyramid of the 768x1280 padded input
+    "hrem_dt1": dict(H=720, W=1280, NB=15, EVENTS_PER_WINDOW=10_000_000, FH=92, FW=160,
+                     EEM_LEVELS=[(64, 12, 20), (64, 24, 40), (64, 48, 80), (64, 96, 160), (32, 192, 320)], batch=2, cpu_batch=1),
+    # configs[3]: HREM dt4 -- 4x longer windows
+    "hrem_dt4": dict(H=720, W=1280, NB=15, EVENTS_PER_WINDOW=40_000_000, FH=92, FW=160,
+                     EEM_LEVELS=[(64, 12, 20), (64, 24, 40), (64, 48, 80), (64, 96, 160), (32, 192, 320)], batch=1, cpu_batch=1),
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="mvsec_dt1", choices=sorted(WORKLOADS))
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frame pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="frame pairs per GPU per step (default 32; 2 / 1 for the HREM workloads)")
     ap.add_argument("--lookups", type=int, default=12, help="CorrBlock lookups per pair (ERAFT iterations)")
-    ap.add_argument("--cpu-batch", type=int, default=2, help="frame pairs per CPU-baseline sample step")
+    ap.add_argument("--cpu-batch", type=int, default=None, help="frame pairs per CPU-baseline sample step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -310,14 +325,21 @@ def peaks():
 
 def main():
     args = parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch is None:
+        args.batch = wl.pop("batch", 32)
+    if args.cpu_batch is None:
+        args.cpu_batch = wl.pop("cpu_batch", 2)
+    wl.pop("batch", None), wl.pop("cpu_batch", None)
+    globals().update(wl)          # H, W, NB, EVENTS_PER_WINDOW, FH, FW, EEM_LEVELS of the chosen workload
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "mvsec_dt1_260x346_batch32_voxelize+corrblock4x4+eemflow_cdc_ops",
+    config = {"workload": f"{args.workload}_{H}x{W}_batch{args.batch}_voxelize+corrblock4x4+eemflow_cdc_ops",
               "pairs_per_gpu": args.batch, "windows_per_pair": 2, "events_per_window": EVENTS_PER_WINDOW,
               "voxel": f"{NB}x{H}x{W}", "fmap": f"{FD}x{FH}x{FW}", "corr_levels": LEVELS, "radius": RADIUS,
               "lookups_per_pair": args.lookups, "eemflow_levels": EEM_LEVELS,
               "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
-              "l2": "no explicit flush: a step streams ~1.3 GB (425 MB volume written then gathered 12x) >> 126 MB L2"}
+              "l2": "no explicit flush: a step streams > 1 GB (the correlation volume alone is written then gathered 12x) >> 126 MB L2"}
 
     if args.impl == "reference":
         if rank != 0:

@@ -27,14 +27,43 @@ struct EventRow {
   double t, x, y, p;
 };
 
-// One 32-byte event row per load (LDG.E.256 on sm_100a), streaming: rows are read exactly once.
-__device__ __forceinline__ EventRow load_event(const double* ev, int64_t i) {
-  EventRow r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(r.t), "=d"(r.x), "=d"(r.y), "=d"(r.p)
-               : "l"(ev + 4 * i));
-  return r;
-}
+// Event sources.  Rows: the reference's [N,4] float64 layout, one 32-byte row per load (LDG.E.256 on
+// sm_100a), streaming -- rows are read exactly once.  SoA: packed columns (t float64 or raw int64
+// nanoseconds, x/y int16, p int8; 13 B/event), the layout of the HREM .npz files before
+// get_compressed_events / EventSequence expand them (loader/loader_utils.py:26-37, 352-397).
+struct RowSource {
+  const double* ev;
+  __device__ __forceinline__ EventRow load(int64_t i) const {
+    EventRow r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.t), "=d"(r.x), "=d"(r.y), "=d"(r.p)
+                 : "l"(ev + 4 * i));
+    return r;
+  }
+  __device__ __forceinline__ double time(int64_t i) const { return __ldg(ev + 4 * i); }
+};
+
+struct SoaSource {
+  const void* t;
+  const int16_t* x;
+  const int16_t* y;
+  const int8_t* p;
+  int t_is_ns;
+  // raw nanoseconds follow the reference's chain in float64: t*1e-9 (get_compressed_events), then
+  // *1e6 (EventSequence timestamp_multiplier); the subtraction of the first stamp happens in the vote
+  __device__ __forceinline__ double time(int64_t i) const {
+    if (t_is_ns) return __dmul_rn(__dmul_rn((double)__ldg(static_cast<const long long*>(t) + i), 1e-9), 1e6);
+    return __ldg(static_cast<const double*>(t) + i);
+  }
+  __device__ __forceinline__ EventRow load(int64_t i) const {
+    EventRow r;
+    r.t = time(i);
+    r.x = (double)__ldg(x + i);
+    r.y = (double)__ldg(y + i);
+    r.p = (double)__ldg(p + i);
+    return r;
+  }
+};
 
 struct Vote {
   int64_t idx_left, idx_right;  // flat index inside the window's grid, or -1 when the vote is skipped
@@ -77,10 +106,11 @@ struct WindowTimes {
   double t_first, dT;
 };
 
-__device__ __forceinline__ WindowTimes window_times(const double* ev, int64_t begin, int64_t end) {
+template <class Src>
+__device__ __forceinline__ WindowTimes window_times(const Src& ev, int64_t begin, int64_t end) {
   WindowTimes w;
-  w.t_first = __ldg(ev + 4 * begin);
-  const double t_last = __ldg(ev + 4 * (end - 1));
+  w.t_first = ev.time(begin);
+  const double t_last = ev.time(end - 1);
   w.dT = __dsub_rn(t_last, w.t_first);
   if (w.dT == 0.0) w.dT = 1.0;
   return w;
@@ -103,8 +133,9 @@ __device__ __forceinline__ int64_t interleaved_chunk(int64_t b, int64_t n_chunks
 // ---- atomic mode ------------------------------------------------------------------------------
 // grid = (ceil(max_events / (threads*EPT)), n_windows).  Loads of a thread's EPT rows are issued
 // back to back before any vote so each thread keeps EPT 32-byte requests in flight.
+template <class Src>
 __global__ void __launch_bounds__(kVoteThreads)
-voxel_vote_atomic_kernel(const double* __restrict__ ev, const int64_t* __restrict__ offsets, int nb,
+voxel_vote_atomic_kernel(const Src ev, const int64_t* __restrict__ offsets, int nb,
                          int H, int W, int lanes, float* __restrict__ grid, int64_t* __restrict__ dropped) {
   const int w = blockIdx.y;
   const int64_t begin = offsets[w], end = offsets[w + 1];
@@ -121,7 +152,7 @@ voxel_vote_atomic_kernel(const double* __restrict__ ev, const int64_t* __restric
 #pragma unroll
   for (int k = 0; k < kVoteEventsPerThread; ++k) {
     const int64_t i = first + (int64_t)k * kVoteThreads;
-    if (i < n) rows[k] = load_event(ev, begin + i);
+    if (i < n) rows[k] = ev.load(begin + i);
   }
   int ndrop = 0;
 #pragma unroll
@@ -150,8 +181,9 @@ __device__ __forceinline__ void red_add_f32x2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
+template <class Src>
 __global__ void __launch_bounds__(kVoteThreads)
-voxel_vote_pair_kernel(const double* __restrict__ ev, const int64_t* __restrict__ offsets, int nb,
+voxel_vote_pair_kernel(const Src ev, const int64_t* __restrict__ offsets, int nb,
                        int H, int W, int lanes, float* __restrict__ scratch, int64_t* __restrict__ dropped) {
   const int w = blockIdx.y;
   const int64_t begin = offsets[w], end = offsets[w + 1];
@@ -168,7 +200,7 @@ voxel_vote_pair_kernel(const double* __restrict__ ev, const int64_t* __restrict_
 #pragma unroll
   for (int k = 0; k < kVoteEventsPerThread; ++k) {
     const int64_t i = first + (int64_t)k * kVoteThreads;
-    if (i < n) rows[k] = load_event(ev, begin + i);
+    if (i < n) rows[k] = ev.load(begin + i);
   }
   int ndrop = 0;
 #pragma unroll
@@ -201,8 +233,9 @@ constexpr int kSortWarpsPerBlock = 8;
 constexpr int kSortSegment = 2048;  // keys owned by one warp per pass (kept in order)
 constexpr int kRadix = 256;
 
+template <class Src>
 __global__ void __launch_bounds__(kVoteThreads)
-voxel_vote_pairs_kernel(const double* __restrict__ ev, const int64_t* __restrict__ offsets, int nb,
+voxel_vote_pairs_kernel(const Src ev, const int64_t* __restrict__ offsets, int nb,
                         int H, int W, int64_t n_total, uint32_t invalid_key,
                         uint32_t* __restrict__ keys, float* __restrict__ vals,
                         int64_t* __restrict__ dropped) {
@@ -213,7 +246,7 @@ voxel_vote_pairs_kernel(const double* __restrict__ ev, const int64_t* __restrict
   if (i >= n) return;
   const WindowTimes wt = window_times(ev, begin, end);
   const int64_t HW = (int64_t)H * W, total = HW * nb;
-  const EventRow e = load_event(ev, begin + i);
+  const EventRow e = ev.load(begin + i);
   const Vote v = make_vote(e, wt.t_first, wt.dT, nb, W, HW, total);
   const int64_t g = begin + i;  // global event rank: concatenation order == per-window event order
   const int64_t wbase = (int64_t)w * total;
@@ -674,22 +707,14 @@ int launch_normalize(float* grid, int n_windows, int64_t vox, double* stats_out,
 }  // namespace
 }  // namespace eem
 
-extern "C" {
+extern "C" size_t eem_voxelize_workspace_bytes(int64_t n_total, int n_windows, int num_bins, int height, int width,
+                                               int mode, int normalize);
 
-size_t eem_voxelize_workspace_bytes(int64_t n_total, int n_windows, int num_bins, int height,
-                                    int width, int mode, int normalize) {
-  if (n_total < 0 || n_windows <= 0 || num_bins <= 0 || height <= 0 || width <= 0) return 0;
-  const int64_t total_vox = (int64_t)n_windows * num_bins * height * width;
-  size_t bytes = normalize ? stat_layout(n_windows).total : 0;
-  if (mode == EEM_VOXEL_DETERMINISTIC) bytes += det_layout(n_total).total;
-  else if (use_pair_path(n_total, total_vox)) bytes += align_up((size_t)total_vox * 2 * sizeof(float), 256);
-  return bytes;
-}
-
-int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, int64_t n_total,
-                 int64_t max_events_per_window, int num_bins, int height, int width, int mode,
-                 int normalize, float* grid, int64_t* dropped, double* stats_out, void* workspace,
-                 size_t workspace_bytes, eem_stream_t stream_) {
+template <class Src>
+int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64_t n_total,
+                  int64_t max_events_per_window, int num_bins, int height, int width, int mode,
+                  int normalize, float* grid, int64_t* dropped, double* stats_out, void* workspace,
+                  size_t workspace_bytes, eem_stream_t stream_) {
   EEM_CHECK_ARG(n_windows > 0, "eem_voxelize: n_windows must be > 0 (got %d)", n_windows);
   EEM_CHECK_ARG(num_bins > 0, "eem_voxelize: num_bins must be > 0 (got %d)", num_bins);
   EEM_CHECK_ARG(height > 0 && width > 0, "eem_voxelize: height/width must be > 0 (got %dx%d)", height, width);
@@ -697,11 +722,9 @@ int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, in
                 "eem_voxelize: bad event counts (n_total=%lld, max_per_window=%lld)",
                 (long long)n_total, (long long)max_events_per_window);
   EEM_CHECK_ARG(grid != nullptr && offsets != nullptr, "eem_voxelize: NULL grid/offsets");
-  EEM_CHECK_ARG(n_total == 0 || events != nullptr, "eem_voxelize: NULL events");
   EEM_CHECK_ARG(mode == EEM_VOXEL_ATOMIC || mode == EEM_VOXEL_DETERMINISTIC,
                 "eem_voxelize: unknown mode %d", mode);
   EEM_CHECK_ARG(n_windows <= 65535, "eem_voxelize: more than 65535 windows in one call");
-  EEM_CHECK_ALIGNED(events, 32);
   EEM_CHECK_ALIGNED(grid, 4);
   cudaStream_t stream = as_stream(stream_);
   const int64_t vox = (int64_t)num_bins * height * width;
@@ -727,7 +750,7 @@ int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, in
     const int64_t chunks = ceil_div(max_events_per_window, per_block);
     const int lanes = time_lanes(64);
     dim3 g((unsigned)(ceil_div(chunks, lanes) * lanes), (unsigned)n_windows);
-    voxel_vote_atomic_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height,
+    voxel_vote_atomic_kernel<Src><<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height,
                                                              width, lanes, grid, dropped);
     EEM_CHECK_LAUNCH("voxel_vote_atomic_kernel");
   } else if (pair) {
@@ -738,7 +761,7 @@ int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, in
     // the scratch is 2x the grid: keep the set of concurrently active bin planes small enough for L2
     const int lanes = time_lanes(4);
     dim3 g((unsigned)(ceil_div(chunks, lanes) * lanes), (unsigned)n_windows);
-    voxel_vote_pair_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width, lanes, scratch, dropped);
+    voxel_vote_pair_kernel<Src><<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width, lanes, scratch, dropped);
     EEM_CHECK_LAUNCH("voxel_vote_pair_kernel");
     const int64_t HW = (int64_t)height * width;
     dim3 gc((unsigned)stat_blocks(HW * 4, n_windows), (unsigned)n_windows);
@@ -776,7 +799,7 @@ int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, in
     const uint32_t invalid_key = (uint32_t)total_vox;
     {
       dim3 g((unsigned)ceil_div(max_events_per_window, kVoteThreads), (unsigned)n_windows);
-      voxel_vote_pairs_kernel<<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width,
+      voxel_vote_pairs_kernel<Src><<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width,
                                                               n_total, invalid_key, keys[0], vals[0], dropped);
       EEM_CHECK_LAUNCH("voxel_vote_pairs_kernel");
     }
@@ -805,6 +828,41 @@ int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, in
   }
   if (normalize) return launch_normalize(grid, n_windows, vox, stats_out, ws_stats, stream);
   return EEM_OK;
+}
+
+
+extern "C" {
+
+size_t eem_voxelize_workspace_bytes(int64_t n_total, int n_windows, int num_bins, int height,
+                                    int width, int mode, int normalize) {
+  if (n_total < 0 || n_windows <= 0 || num_bins <= 0 || height <= 0 || width <= 0) return 0;
+  const int64_t total_vox = (int64_t)n_windows * num_bins * height * width;
+  size_t bytes = normalize ? stat_layout(n_windows).total : 0;
+  if (mode == EEM_VOXEL_DETERMINISTIC) bytes += det_layout(n_total).total;
+  else if (use_pair_path(n_total, total_vox)) bytes += align_up((size_t)total_vox * 2 * sizeof(float), 256);
+  return bytes;
+}
+
+int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, int64_t n_total,
+                 int64_t max_events_per_window, int num_bins, int height, int width, int mode,
+                 int normalize, float* grid, int64_t* dropped, double* stats_out, void* workspace,
+                 size_t workspace_bytes, eem_stream_t stream) {
+  EEM_CHECK_ARG(n_total <= 0 || events != nullptr, "eem_voxelize: NULL events");
+  EEM_CHECK_ALIGNED(events, 32);
+  return voxelize_impl(RowSource{events}, offsets, n_windows, n_total, max_events_per_window, num_bins, height, width,
+                       mode, normalize, grid, dropped, stats_out, workspace, workspace_bytes, stream);
+}
+
+int eem_voxelize_soa(const void* t, int t_is_ns, const int16_t* x, const int16_t* y, const int8_t* p,
+                     const int64_t* offsets, int n_windows, int64_t n_total, int64_t max_events_per_window,
+                     int num_bins, int height, int width, int mode, int normalize, float* grid, int64_t* dropped,
+                     double* stats_out, void* workspace, size_t workspace_bytes, eem_stream_t stream) {
+  EEM_CHECK_ARG(n_total <= 0 || (t && x && y && p), "eem_voxelize_soa: NULL event column");
+  EEM_CHECK_ALIGNED(t, 8);
+  EEM_CHECK_ALIGNED(x, 2);
+  EEM_CHECK_ALIGNED(y, 2);
+  return voxelize_impl(SoaSource{t, x, y, p, t_is_ns ? 1 : 0}, offsets, n_windows, n_total, max_events_per_window,
+                       num_bins, height, width, mode, normalize, grid, dropped, stats_out, workspace, workspace_bytes, stream);
 }
 
 size_t eem_voxel_normalize_workspace_bytes(int n_windows, int64_t voxels_per_window) {

@@ -58,6 +58,37 @@ def voxelize(events: torch.Tensor, offsets: torch.Tensor, max_events: int, num_b
     return out
 
 
+def voxelize_soa(t: torch.Tensor, x: torch.Tensor, y: torch.Tensor, p: torch.Tensor, offsets: torch.Tensor,
+                 max_events: int, num_bins: int, height: int, width: int, *, normalize: bool = True,
+                 deterministic: bool = False, dropped: torch.Tensor | None = None,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
+    """Voxelize packed event columns (13 B/event): t float64 [N] (values of features[:,0]) or int64 [N]
+    raw nanoseconds (HREM .npz; the kernel applies *1e-9, *1e6 and the first-stamp subtraction of
+    loader/loader_utils.py:34,367-397 in float64), x/y int16 [N], p int8 [N]."""
+    assert t.dtype in (torch.float64, torch.int64), "t must be float64 or int64 (ns)"
+    assert num_bins > 0 and width > 0 and height > 0
+    t = L.require_cuda(t, "t", t.dtype)
+    x = L.require_cuda(x, "x", torch.int16)
+    y = L.require_cuda(y, "y", torch.int16)
+    p = L.require_cuda(p, "p", torch.int8)
+    offsets = L.require_cuda(offsets, "offsets", torch.int64)
+    dev = t.device
+    n_windows, n_total = offsets.numel() - 1, t.numel()
+    assert x.numel() == n_total and y.numel() == n_total and p.numel() == n_total
+    if out is None:
+        out = torch.empty((n_windows, num_bins, height, width), dtype=torch.float32, device=dev)
+    lib = L.lib()
+    mode = L.VOXEL_DETERMINISTIC if deterministic else L.VOXEL_ATOMIC
+    with torch.cuda.device(dev):
+        ws_bytes = lib.eem_voxelize_workspace_bytes(n_total, n_windows, num_bins, height, width, mode, int(normalize))
+        ws = L.workspace.get(dev, ws_bytes, "voxel")
+        L.check(lib.eem_voxelize_soa(t.data_ptr(), int(t.dtype == torch.int64), x.data_ptr(), y.data_ptr(), p.data_ptr(),
+                                     offsets.data_ptr(), n_windows, n_total, int(max_events), num_bins, height, width,
+                                     mode, int(normalize), out.data_ptr(), L.ptr(dropped), None, L.ptr(ws), ws_bytes,
+                                     L.stream_ptr(dev)))
+    return out
+
+
 def voxel_normalize_(grid: torch.Tensor, stats_out: torch.Tensor | None = None) -> torch.Tensor:
     """In-place non-zero mean/std normalisation of [n_windows, ...] grids (utils/transformers.py:114-122)."""
     grid = L.require_cuda(grid, "grid")

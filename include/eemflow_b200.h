@@ -85,6 +85,20 @@ EEM_API int eem_voxelize(const double* events, const int64_t* offsets, int n_win
                          int64_t* dropped, double* stats_out, void* workspace,
                          size_t workspace_bytes, eem_stream_t stream);
 
+/* K1 (packed columns)  Same voting, events given as separate columns -- 13 B/event instead of 32:
+ *   t : float64 [N] with the values of EventSequence.features[:,0] (t_is_ns = 0), or the raw int64
+ *       nanosecond stamps of an HREM .npz (t_is_ns = 1); the kernel then applies the reference's
+ *       float64 chain t*1e-9 (loader/loader_utils.py:34), *1e6 (EventSequence timestamp_multiplier,
+ *       :367-368) and "- first stamp" (:393-397) itself, bit for bit.
+ *   x, y : int16 [N];  p : int8 [N] (0/1 or -1/+1; 0 votes as -1, utils/transformers.py:82).
+ * Everything else as eem_voxelize (same workspace size). */
+EEM_API int eem_voxelize_soa(const void* t, int t_is_ns, const int16_t* x, const int16_t* y,
+                             const int8_t* p, const int64_t* offsets, int n_windows,
+                             int64_t n_total, int64_t max_events_per_window, int num_bins,
+                             int height, int width, int mode, int normalize, float* grid,
+                             int64_t* dropped, double* stats_out, void* workspace,
+                             size_t workspace_bytes, eem_stream_t stream);
+
 /* K2  voxel-grid normalisation: per window, mean / unbiased std over the NON-ZERO voxels, then
  *     v = (v - mean) / std on the non-zero voxels (v - mean when !(std > 0), which includes the
  *     NaN std of a single non-zero voxel).  In place.

@@ -191,3 +191,32 @@ def test_pair_layout_path_parity(golden, V, monkeypatch):
     with pytest.raises(IndexError):
         V(5, gpu=True, forkserver=False, strict=True)(Seq(bad, 32, 48))
     V(5, gpu=True, forkserver=False)(Seq(bad, 32, 48))
+
+
+def test_packed_columns_match_reference_loader_chain(V):
+    """HREM .npz style columns (x, y, t [int64 ns], p in {0,1}) through eem_voxelize_soa vs the reference chain
+    get_compressed_events -> EventSequence(x1e6, relative) -> voxelizer restated on the CPU: bit-exact in
+    deterministic mode, <= 1e-5 relative in atomic mode."""
+    from eemflow_b200 import EventSequence
+    rng = np.random.default_rng(11)
+    h, w, nb = 72, 128, 15
+    windows, seqs = [], []
+    for n in (5000, 1, 20000):
+        t_ns = np.sort(rng.integers(1_000_000_000, 1_050_000_000, size=n)).astype(np.int64)
+        cols = {"x": rng.integers(0, w, size=n).astype(np.uint16), "y": rng.integers(0, h, size=n).astype(np.uint16),
+                "t": t_ns, "p": rng.integers(0, 2, size=n).astype(np.uint8)}
+        windows.append(cols)
+        # loader/loader_utils.py:26-37 + EventSequence(timestamp_multiplier=1e6, convert_to_relative=True)
+        feats = np.stack([cols["t"] * 1e-9, cols["x"], cols["y"], 2 * cols["p"].astype(np.int64) - 1], axis=1).astype(np.float64)
+        seqs.append(EventSequence(None, {"height": h, "width": w}, features=feats, timestamp_multiplier=1e6, convert_to_relative=True))
+    det = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_columns(windows, h, w).cpu().numpy()
+    atom = V(nb, gpu=True, normalize=True, forkserver=False).voxelize_columns(windows, h, w).cpu().numpy()
+    for k, s in enumerate(seqs):
+        ref_raw, _, _ = c_oracle.voxelize(s.features, nb, h, w, normalize=False)
+        assert np.array_equal(det[k], ref_raw), k
+        ref_norm = ref_ops.voxelize(s.features, nb, h, w, normalize=True).numpy()
+        assert rel_close(atom[k], ref_norm).all(), k
+    # float64 columns = the values of features[:,0]
+    wf = [{"x": s.features[:, 1], "y": s.features[:, 2], "t": s.features[:, 0], "p": s.features[:, 3]} for s in seqs]
+    det2 = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_columns(wf, h, w).cpu().numpy()
+    assert np.array_equal(det2, det)

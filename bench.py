@@ -189,25 +189,52 @@ class B200Step:
         self.fam_eemflow_ops()
         return self.out, self.flow
 
+    def _e2e_buffers(self):
+        dev = self.dev
+        self.e2e_d = {"f1": torch.empty_like(self.d["f1"]), "f2": torch.empty_like(self.d["f2"]),
+                      "coords": [torch.empty_like(c) for c in self.d["coords"]],
+                      "eem": [{k: torch.empty_like(v) for k, v in lv.items()} for lv in self.d["eem"]]}
+        self.h2d_stream, self.d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        out_shape = (self.B, LEVELS * (2 * RADIUS + 1) ** 2, FH, FW)
+        self.out_host = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
+        self.flow_host = torch.empty((self.B, 2, H, W), dtype=torch.float32, pin_memory=True)
+
     def end_to_end(self):
         """Same step through the public API from HOST buffers: numpy events, pinned feature maps in,
-        last correlation features + final flow out to pinned host memory."""
-        dev = self.dev
-        self.enc.voxelize_batch(self.seqs)
-        hi = self.host
-        d = {"f1": hi["f1"].to(dev, non_blocking=True), "f2": hi["f2"].to(dev, non_blocking=True),
-             "coords": [c.to(dev, non_blocking=True) for c in hi["coords"]],
-             "eem": [{k: v.to(dev, non_blocking=True) for k, v in lv.items()} for lv in hi["eem"]]}
+        last correlation features + final flow out to pinned host memory.  The pinned tensors go up on a
+        copy stream while the host stages the event rows; results come back on a third stream."""
+        if self.out_host is None:
+            self._e2e_buffers()
+        cur = torch.cuda.current_stream(self.dev)
+        hi, d = self.host, self.e2e_d
+        self.h2d_stream.wait_stream(cur)          # last step's kernels are done with the device buffers
+        with torch.cuda.stream(self.h2d_stream):
+            d["f1"].copy_(hi["f1"], non_blocking=True)
+            d["f2"].copy_(hi["f2"], non_blocking=True)
+            for dc, hc in zip(d["coords"], hi["coords"]):
+                dc.copy_(hc, non_blocking=True)
+            corr_in = torch.cuda.Event()
+            corr_in.record()
+        self.enc.voxelize_batch(self.seqs)        # stages the event rows while the copies above are on the link
+        with torch.cuda.stream(self.h2d_stream):  # queued behind the event rows: arrives under voxelize/corr/lookup
+            for dl, hl in zip(d["eem"], hi["eem"]):
+                for k in dl:
+                    dl[k].copy_(hl[k], non_blocking=True)
+            eem_in = torch.cuda.Event()
+            eem_in.record()
+        cur.wait_event(corr_in)
         self.fam_corr_pyramid(d)
         self.fam_corr_lookup(d)
+        out = self.out
+        self.d2h_stream.wait_stream(cur)
+        with torch.cuda.stream(self.d2h_stream):
+            self.out_host.copy_(out, non_blocking=True)
+            out.record_stream(self.d2h_stream)
+        cur.wait_event(eem_in)
         self.fam_eemflow_ops(d)
-        out, flow = self.out, self.flow
-        if self.out_host is None:
-            self.out_host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
-            self.flow_host = torch.empty(flow.shape, dtype=flow.dtype, pin_memory=True)
-        self.out_host.copy_(out, non_blocking=True)
-        self.flow_host.copy_(flow, non_blocking=True)
-        return flow
+        self.flow_host.copy_(self.flow, non_blocking=True)
+        cur.wait_stream(self.d2h_stream)
+        return self.flow
 
     def d2h_bytes(self):
         return (self.out_host.numel() + self.flow_host.numel()) * 4 if self.out_host is not None else 0
@@ -462,8 +489,8 @@ def main():
     # end to end through the public API from host buffers
     e2e = None
     if not args.no_e2e:
-        k = max(3, args.steps // 4)
-        for _ in range(2):
+        k = max(5, args.steps // 2)
+        for _ in range(max(5, args.warmup)):
             step.end_to_end()
         torch.cuda.synchronize()
         if world > 1:

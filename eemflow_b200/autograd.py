@@ -3,8 +3,7 @@
 Used by the reference-shaped classes whenever an input requires grad, so the drop-in is valid inside
 the reference's training loop (train_mvsec.py:251-258: loss.backward() through the model).  Covered
 ops: local correlation (+ fused channel select), the three backward-warp variants, bilinear flow
-resize.  The all-pairs CorrBlock has no backward yet (its callers, the RAFT-family baselines, are
-outside the EEMFlow training path); it raises if a gradient is requested.
+resize, and the all-pairs CorrBlock (pyramid + lookup).
 """
 from __future__ import annotations
 
@@ -56,6 +55,79 @@ class ResizeFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         in_size, align, s0, s1, sr = ctx.cfg
         return ops.bilinear_resize_backward(grad_out.contiguous(), in_size, align, s0, s1, sr), None, None, None, None, None
+
+
+class CorrPyramidFn(torch.autograd.Function):
+    """CorrBlock.__init__ under autograd (model/corr.py:13-27, 52-60): fmaps -> pyramid levels.
+
+    Forward is the one fused kernel (level_l = fmap1^T pool^l(fmap2) / sqrt(D)).  Backward uses the same
+    linearity: d fmap1 = sum_l dV_l . pool^l(fmap2)^T, d pool^l(fmap2) = fmap1 . dV_l, folded back through
+    the pooling by the avg-pool backward kernel.  The four products are plain batched fp32 GEMMs and go to
+    cuBLAS (torch.bmm); everything else runs in this library's kernels.
+    """
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, num_levels, precision):
+        ctx.save_for_backward(fmap1, fmap2)
+        ctx.num_levels = num_levels
+        return tuple(ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision))
+
+    @staticmethod
+    def backward(ctx, *grad_levels):
+        f1, f2 = ctx.saved_tensors
+        B, D, H, W = f1.shape
+        P = H * W
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        scale = ops.inv_sqrt_dim(D)
+        f1m = f1.reshape(B, D, P)
+        d1 = None
+        d2_levels = []
+        f2l = f2.contiguous()
+        for l, g in enumerate(grad_levels):
+            hl, wl = f2l.shape[-2:]
+            d2 = None
+            if g is not None and hl * wl > 0:
+                G = g.reshape(B, P, hl * wl)
+                if need1:
+                    t = torch.bmm(f2l.reshape(B, D, hl * wl), G.transpose(1, 2))
+                    d1 = t if d1 is None else d1.add_(t)
+                if need2:
+                    d2 = torch.bmm(f1m, G).view(B, D, hl, wl)
+            d2_levels.append((d2, (hl, wl)))
+            if l + 1 < len(grad_levels):
+                f2l = ops.avg_pool2x2(f2l)
+        g2 = None
+        if need2:
+            for d2, (hl, wl) in reversed(d2_levels):         # fold the coarse gradients down to level 0
+                if g2 is not None:
+                    if d2 is None:
+                        d2 = torch.empty((B, D, hl, wl), dtype=torch.float32, device=f1.device)
+                        ops.avg_pool2x2_backward_(d2, g2, accumulate=False)
+                    else:
+                        ops.avg_pool2x2_backward_(d2, g2, accumulate=True)
+                g2 = d2
+            g2 = torch.zeros_like(f2) if g2 is None else g2.mul_(scale)
+        g1 = None
+        if need1:
+            g1 = torch.zeros_like(f1) if d1 is None else d1.mul_(scale).view(B, D, H, W)
+        return g1, g2, None, None
+
+
+class CorrLookupFn(torch.autograd.Function):
+    """CorrBlock.__call__ under autograd: gradient to the pyramid levels (the coordinates are detached by
+    every caller, model/eraft.py:141, and get none here)."""
+
+    @staticmethod
+    def forward(ctx, coords, radius, *levels):
+        ctx.save_for_backward(coords)
+        ctx.cfg = (radius, len(levels))
+        return ops.corr_lookup(levels, coords, radius)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (coords,) = ctx.saved_tensors
+        radius, n = ctx.cfg
+        return (None, None, *ops.corr_lookup_backward(grad_out.contiguous(), coords, radius, n))
 
 
 def needs_grad(*tensors) -> bool:

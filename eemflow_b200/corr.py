@@ -37,13 +37,18 @@ class CorrBlock:
             precision = _default_precision(dim, ht, wd)
         self.precision = precision
         if ag.needs_grad(fmap1, fmap2):
-            raise NotImplementedError(
-                "eemflow_b200.CorrBlock has no backward kernels yet (inference / frozen-encoder use only); "
-                "wrap the call in torch.no_grad() or detach the feature maps")
-        with torch.no_grad():
-            self.corr_pyramid = ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision)
+            self.corr_pyramid = list(ag.CorrPyramidFn.apply(fmap1, fmap2, num_levels, precision))
+        else:
+            with torch.no_grad():
+                self.corr_pyramid = ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision)
 
     def __call__(self, coords):
+        if ag.needs_grad(*self.corr_pyramid):
+            if torch.is_grad_enabled() and coords.requires_grad:
+                raise NotImplementedError(
+                    "eemflow_b200.CorrBlock gives no gradient to the lookup coordinates; detach them as the "
+                    "reference's callers do (model/eraft.py:141)")
+            return ag.CorrLookupFn.apply(coords, self.radius, *self.corr_pyramid)
         with torch.no_grad():
             return ops.corr_lookup(self.corr_pyramid, coords, self.radius)
 
@@ -52,8 +57,11 @@ class CorrBlock:
         batch, dim, ht, wd = fmap1.shape
         if precision is None:
             precision = _default_precision(dim, ht, wd)
-        with torch.no_grad():
-            (vol,) = ops.corr_pyramid(fmap1, fmap2, 1, precision=precision)
+        if ag.needs_grad(fmap1, fmap2):
+            (vol,) = ag.CorrPyramidFn.apply(fmap1, fmap2, 1, precision)
+        else:
+            with torch.no_grad():
+                (vol,) = ops.corr_pyramid(fmap1, fmap2, 1, precision=precision)
         return vol.view(batch, ht, wd, 1, ht, wd)
 
 

@@ -218,6 +218,135 @@ avg_pool2x2_kernel(const float* __restrict__ in, int64_t n_planes, int h, int w,
   }
 }
 
+
+// ---- backward of the lookup: d(level_l) from d(out) -------------------------------------------------
+// out[b, l*K*K + a*K + c, i] = bilinear(level_l[b*P+i], window tap (a, c)), so the gradient of row
+// (b, i) of level l is non-zero only inside that position's (K+1)^2 footprint.  A CTA owns 32
+// consecutive positions: it stages their L*K*K output gradients in shared memory (coalesced, 128 B per
+// channel), then writes every row of every level in full -- zeros outside the footprint, and inside it
+// the <= 4 contributions per cell gathered in a fixed order.  No atomics, no separate memset, and the
+// result is deterministic.  Coordinates carry no gradient (the callers detach them, model/eraft.py:141).
+struct LookupBwdParams {
+  float* dlevel[kMaxLevels];
+  int h[kMaxLevels], w[kMaxLevels];
+  int B, H, W, L;
+  const float* coords;
+  const float* gout;
+};
+
+template <int R>
+__global__ void __launch_bounds__(256)
+corr_lookup_backward_kernel(const __grid_constant__ LookupBwdParams p) {
+  constexpr int K = 2 * R + 1, T = K + 1, KK = K * K;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int P = p.H * p.W, L = p.L;
+  const int b = blockIdx.y, i0 = blockIdx.x * kPosPerBlock;
+  const int npos = min(kPosPerBlock, P - i0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  float* gs = reinterpret_cast<float*>(smem_raw);                 // [L*KK][33]
+  float* fxs = gs + (size_t)L * KK * 33;                           // [L][32][K]
+  float* fys = fxs + (size_t)L * kPosPerBlock * K;                 // [L][32][K]
+  int* org = reinterpret_cast<int*>(fys + (size_t)L * kPosPerBlock * K);   // [L][32][2]
+
+  for (int ch = warp; ch < L * KK; ch += 8)
+    gs[ch * 33 + lane] = lane < npos ? __ldg(p.gout + ((int64_t)b * L * KK + ch) * P + i0 + lane) : 0.f;
+  for (int t = threadIdx.x; t < kPosPerBlock * L; t += blockDim.x) {   // same geometry as the forward kernel
+    const int l = t / kPosPerBlock, pos = t % kPosPerBlock;
+    const int hl = p.h[l], wl = p.w[l];
+    float cx = 0.f, cy = 0.f;
+    if (pos < npos) {
+      cx = __ldg(p.coords + ((int64_t)b * 2 + 0) * P + i0 + pos);
+      cy = __ldg(p.coords + ((int64_t)b * 2 + 1) * P + i0 + pos);
+    }
+    const float inv = 1.0f / (float)(1 << l);
+    const float lx = cx * inv, ly = cy * inv;
+    const float ox = floorf(fminf(fmaxf(roundtrip(lx - (float)R, wl), -1.0e6f), 1.0e6f));
+    const float oy = floorf(fminf(fmaxf(roundtrip(ly - (float)R, hl), -1.0e6f), 1.0e6f));
+    org[(l * kPosPerBlock + pos) * 2 + 0] = (int)ox;
+    org[(l * kPosPerBlock + pos) * 2 + 1] = (int)oy;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      fxs[(l * kPosPerBlock + pos) * K + a] = roundtrip(lx + (float)(a - R), wl) - (ox + (float)a);
+      fys[(l * kPosPerBlock + pos) * K + a] = roundtrip(ly + (float)(a - R), hl) - (oy + (float)a);
+    }
+  }
+  __syncthreads();
+
+  for (int l = 0; l < L; ++l) {
+    const int hl = p.h[l], wl = p.w[l];
+    const int plane = hl * wl;
+    if (plane == 0) continue;
+    const int step_y = 256 / wl, step_x = 256 - step_y * wl;
+    for (int pos = 0; pos < npos; ++pos) {
+      float* row = p.dlevel[l] + ((int64_t)b * P + i0 + pos) * plane;
+      const int ox = org[(l * kPosPerBlock + pos) * 2 + 0], oy = org[(l * kPosPerBlock + pos) * 2 + 1];
+      const float* fx = fxs + (l * kPosPerBlock + pos) * K;
+      const float* fy = fys + (l * kPosPerBlock + pos) * K;
+      const float* g = gs + (size_t)l * KK * 33 + pos;
+      int y = (int)threadIdx.x / wl, x = (int)threadIdx.x - y * wl;
+      for (int j = threadIdx.x; j < plane; j += 256) {
+        const int u = x - ox, v = y - oy;
+        float val = 0.f;
+        if ((unsigned)u < (unsigned)T && (unsigned)v < (unsigned)T) {
+#pragma unroll
+          for (int da = 1; da >= 0; --da) {       // tap column a = u - da gives weight fx[a] (da=1) or 1-fx[a] (da=0)
+            const int a = u - da;
+            if ((unsigned)a >= (unsigned)K) continue;
+            const float wx = da ? fx[a] : 1.0f - fx[a];
+#pragma unroll
+            for (int dc = 1; dc >= 0; --dc) {
+              const int c = v - dc;
+              if ((unsigned)c >= (unsigned)K) continue;
+              const float wy = dc ? fy[c] : 1.0f - fy[c];
+              val = fmaf(g[(a * K + c) * 33], wx * wy, val);
+            }
+          }
+        }
+        st_stream(row + j, val);
+        x += step_x;
+        y += step_y;
+        if (x >= wl) { x -= wl; ++y; }
+      }
+    }
+  }
+}
+
+template <int R>
+int launch_lookup_backward(const LookupBwdParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int K = 2 * R + 1;
+  const size_t smem = ((size_t)p.L * K * K * 33 + 2 * (size_t)p.L * kPosPerBlock * K) * 4 + (size_t)p.L * kPosPerBlock * 2 * 4;
+  static std::mutex mu;
+  static size_t configured = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (smem > configured) {
+      EEM_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_backward_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+  }
+  corr_lookup_backward_kernel<R><<<grid, 256, smem, stream>>>(p);
+  return EEM_OK;
+}
+
+// gradient of avg_pool2d(2,2,floor): every fine cell under a coarse cell receives a quarter of it; the
+// odd last row / column (cropped by the floor) receives nothing.
+__global__ void __launch_bounds__(256)
+avg_pool2x2_backward_kernel(const float* __restrict__ gout, int64_t n_planes, int h, int w, float* __restrict__ gin,
+                            int accumulate) {
+  const int ho = h / 2, wo = w / 2;
+  const int64_t total = n_planes * h * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int64_t r = i / w;
+    const int y = (int)(r % h);
+    const int64_t pl = r / h;
+    float v = 0.f;
+    if ((y >> 1) < ho && (x >> 1) < wo) v = 0.25f * __ldg(gout + (pl * ho + (y >> 1)) * wo + (x >> 1));
+    gin[i] = accumulate ? gin[i] + v : v;
+  }
+}
+
 }  // namespace
 }  // namespace eem
 
@@ -271,6 +400,54 @@ int eem_avg_pool2x2(const float* in, int64_t n_planes, int h, int w, float* out,
   if (cap > 0 && blocks > cap) blocks = cap;
   avg_pool2x2_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(in, n_planes, h, w, out);
   EEM_CHECK_LAUNCH("avg_pool2x2_kernel");
+  return EEM_OK;
+}
+
+int eem_corr_lookup_backward(const float* grad_out, const float* coords, int B, int H, int W, int num_levels, int radius,
+                             float* const* grad_levels, eem_stream_t stream_) {
+  EEM_CHECK_ARG(grad_out && coords && grad_levels, "eem_corr_lookup_backward: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && H > 0 && W > 0, "eem_corr_lookup_backward: sizes must be > 0");
+  EEM_CHECK_ARG(num_levels > 0 && num_levels <= kMaxLevels, "eem_corr_lookup_backward: num_levels must be in [1,%d]", kMaxLevels);
+  EEM_CHECK_ARG(B <= 65535, "eem_corr_lookup_backward: batch > 65535 not supported in one call");
+  LookupBwdParams p{};
+  int h = H, w = W;
+  for (int l = 0; l < num_levels; ++l) {
+    p.dlevel[l] = grad_levels[l];
+    p.h[l] = h;
+    p.w[l] = w;
+    EEM_CHECK_ARG((int64_t)h * w == 0 || grad_levels[l] != nullptr, "eem_corr_lookup_backward: grad_levels[%d] is NULL", l);
+    h /= 2;
+    w /= 2;
+  }
+  p.B = B; p.H = H; p.W = W; p.L = num_levels;
+  p.coords = coords;
+  p.gout = grad_out;
+  dim3 grid((unsigned)ceil_div(H * W, kPosPerBlock), (unsigned)B);
+  cudaStream_t stream = as_stream(stream_);
+  int rc = EEM_OK;
+  switch (radius) {
+    case 4: rc = launch_lookup_backward<4>(p, grid, stream); break;
+    case 3: rc = launch_lookup_backward<3>(p, grid, stream); break;
+    case 2: rc = launch_lookup_backward<2>(p, grid, stream); break;
+    case 1: rc = launch_lookup_backward<1>(p, grid, stream); break;
+    default:
+      return fail(EEM_ERR_UNSUPPORTED, "eem_corr_lookup_backward: radius %d not in {1,2,3,4}", radius);
+  }
+  if (rc != EEM_OK) return rc;
+  EEM_CHECK_LAUNCH("corr_lookup_backward_kernel");
+  return EEM_OK;
+}
+
+int eem_avg_pool2x2_backward(const float* grad_out, int64_t n_planes, int h, int w, float* grad_in, int accumulate,
+                             eem_stream_t stream_) {
+  EEM_CHECK_ARG(grad_in && (grad_out || (h / 2) * (w / 2) == 0), "eem_avg_pool2x2_backward: NULL pointer");
+  EEM_CHECK_ARG(n_planes > 0 && h > 0 && w > 0, "eem_avg_pool2x2_backward: sizes must be > 0");
+  const int64_t total = n_planes * h * w;
+  int64_t blocks = ceil_div(total, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (cap > 0 && blocks > cap) blocks = cap;
+  avg_pool2x2_backward_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(grad_out, n_planes, h, w, grad_in, accumulate);
+  EEM_CHECK_LAUNCH("avg_pool2x2_backward_kernel");
   return EEM_OK;
 }
 

@@ -75,17 +75,35 @@ def _is_dataframe(obj) -> bool:
     return isinstance(obj, pandas.DataFrame)
 
 
+_STAGE_CHUNK_ROWS = 1 << 17      # 4 MiB of [*,4] float64 rows per staging task
+_STAGE_FLUSH_ROWS = 1 << 18      # issue the host->device copy every 8 MiB staged
+_stage_pool = None
+
+
+def _staging_pool():
+    """Worker threads for the pageable->pinned staging copy (numpy releases the GIL while it copies)."""
+    global _stage_pool
+    if _stage_pool is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _stage_pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1)), thread_name_prefix="eem-stage")
+    return _stage_pool
+
+
 class _PinnedStage:
     """Grow-only pinned staging buffer for the host->device copy of event rows.
 
     cudaHostAlloc costs milliseconds, so the buffer is kept between calls; an event recorded after
     each async copy guards it against being refilled while the previous copy is still in flight.
+    Large uploads are staged by a few threads in 4 MiB chunks and the DMA of finished chunks is issued
+    while later ones are still being staged, so the link is busy during the host memcpy instead of after it.
     """
 
     def __init__(self):
         self.buf = None
         self.off = None
         self.done = None
+        self.dev_buf = None       # grow-only device copy; reuse is ordered by the stream the caller runs on
 
     def upload(self, arrays: Sequence[numpy.ndarray], device: torch.device):
         counts = [int(a.shape[0]) for a in arrays]
@@ -97,16 +115,38 @@ class _PinnedStage:
         if self.off is None or self.off.numel() < len(arrays) + 1:
             self.off = torch.empty(max(len(arrays) + 1, 64), dtype=torch.int64, pin_memory=True)
         host = self.buf.numpy()
-        pos = 0
-        for a, n in zip(arrays, counts):
-            host[pos:pos + n] = a  # astype('float') + from_numpy of the reference, in one copy
-            pos += n
         off_host = self.off.numpy()
         off_host[0] = 0
         numpy.cumsum(counts, out=off_host[1:len(arrays) + 1])
         with torch.cuda.device(device):
-            ev = self.buf[:total].to(device, non_blocking=True)
             off = self.off[:len(arrays) + 1].to(device, non_blocking=True)
+            if total <= _STAGE_CHUNK_ROWS:
+                pos = 0
+                for a, n in zip(arrays, counts):
+                    host[pos:pos + n] = a  # astype('float') + from_numpy of the reference, in one copy
+                    pos += n
+                ev = self.buf[:total].to(device, non_blocking=True)
+            else:
+                if self.dev_buf is None or self.dev_buf.shape[0] < total or self.dev_buf.device != torch.device(device):
+                    self.dev_buf = torch.empty((total, 4), dtype=torch.float64, device=device)
+                ev = self.dev_buf[:total]
+                tasks, pos = [], 0
+                for a, n in zip(arrays, counts):
+                    for lo in range(0, n, _STAGE_CHUNK_ROWS):
+                        hi = min(n, lo + _STAGE_CHUNK_ROWS)
+                        tasks.append((pos + lo, pos + hi, a, lo, hi))
+                    pos += n
+
+                def stage(task):
+                    d0, d1, a, lo, hi = task
+                    host[d0:d1] = a[lo:hi]
+                    return d1
+
+                sent = 0
+                for staged in _staging_pool().map(stage, tasks):      # results arrive in submission order
+                    if staged - sent >= _STAGE_FLUSH_ROWS or staged == total:
+                        ev[sent:staged].copy_(self.buf[sent:staged], non_blocking=True)
+                        sent = staged
             self.done = torch.cuda.Event()
             self.done.record()
         return ev, off, max(counts) if counts else 0

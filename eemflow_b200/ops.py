@@ -310,3 +310,29 @@ def bilinear_resize_backward(grad_out, in_size, align_corners, scale0=1.0, scale
                                                      float(scale0), float(scale1), float(scale_rest), gin.data_ptr(),
                                                      L.stream_ptr(grad_out.device)))
     return gin
+
+
+def corr_lookup_backward(grad_out: torch.Tensor, coords: torch.Tensor, radius: int, num_levels: int) -> list[torch.Tensor]:
+    """d(levels) of CorrBlock.__call__ given d(out) [B, L*(2r+1)^2, H, W]: list of [B*H*W, 1, H_l, W_l]."""
+    grad_out = L.require_cuda(grad_out, "grad_out")
+    coords = L.require_cuda(coords, "coords")
+    B, _, H, W = coords.shape
+    dev = coords.device
+    grads = [torch.empty((B * H * W, 1, h, w), dtype=torch.float32, device=dev) for (h, w) in pyramid_level_shapes(H, W, num_levels)]
+    with torch.cuda.device(dev):
+        L.check(L.lib().eem_corr_lookup_backward(grad_out.data_ptr(), coords.data_ptr(), B, H, W, num_levels, radius,
+                                                 L.ptr_array(grads), L.stream_ptr(dev)))
+    return grads
+
+
+def avg_pool2x2_backward_(grad_fine: torch.Tensor, grad_coarse: torch.Tensor, accumulate: bool = True) -> torch.Tensor:
+    """grad_fine [N,C,h,w] (+)= unpool(grad_coarse [N,C,h//2,w//2]) / 4, in place."""
+    grad_fine = L.require_cuda(grad_fine, "grad_fine")
+    n, c, h, w = grad_fine.shape
+    assert tuple(grad_coarse.shape) == (n, c, h // 2, w // 2)
+    if grad_coarse.numel():
+        grad_coarse = L.require_cuda(grad_coarse, "grad_coarse")
+    with torch.cuda.device(grad_fine.device):
+        L.check(L.lib().eem_avg_pool2x2_backward(L.ptr(grad_coarse) if grad_coarse.numel() else None, n * c, h, w,
+                                                 grad_fine.data_ptr(), int(accumulate), L.stream_ptr(grad_fine.device)))
+    return grad_fine

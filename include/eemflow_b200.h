@@ -220,6 +220,20 @@ EEM_API int eem_replicate_pad(const float* in, int B, int C, int H, int W, int l
  * extension model/IRRPWC/correlation_package/correlation_cuda_kernel.cu:117-298 implemented),
  * F.grid_sample and F.interpolate.  Either gradient output pointer may be NULL to skip it.
  * ------------------------------------------------------------------------------------------ */
+/* Backward of K5 (training path of CorrBlock.__call__, model/corr.py:29-50 under autograd): the gradient of
+ * every pyramid level given the gradient of the lookup output.  grad_levels[l] ([B*H*W, H_l*W_l], HOST array
+ * of DEVICE pointers, same layout as K3's levels) is written IN FULL -- zeros outside each position's
+ * (2r+2)^2 footprint -- so no memset is needed.  Deterministic (gather, no atomics).  coords get no
+ * gradient: the callers detach them (model/eraft.py:141). */
+EEM_API int eem_corr_lookup_backward(const float* grad_out, const float* coords, int B, int H, int W,
+                                     int num_levels, int radius, float* const* grad_levels,
+                                     eem_stream_t stream);
+
+/* Backward of K4: grad_in [n_planes, h, w] (+)= 0.25 * grad_out [n_planes, h/2, w/2] under each coarse cell,
+ * 0 in the odd last row/column the floor crops.  accumulate != 0 adds into grad_in. */
+EEM_API int eem_avg_pool2x2_backward(const float* grad_out, int64_t n_planes, int h, int w, float* grad_in,
+                                     int accumulate, eem_stream_t stream);
+
 /* grad_out [B,n_out,H,W] -> grad_f1, grad_f2 [B,C,H,W]; same index/scale meaning as eem_local_corr. */
 EEM_API int eem_local_corr_backward(const float* f1, const float* f2, const float* grad_out, int B,
                                     int C, int H, int W, int max_disp, const int* index, int n_out,

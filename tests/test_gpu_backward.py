@@ -131,9 +131,56 @@ def test_cdc_blend_and_chain_backward(E):
         assert ok, (name, e)
 
 
-def test_corrblock_requires_no_grad(E):
-    f = torch.randn(1, 32, 8, 12, device="cuda", requires_grad=True)
+@pytest.mark.parametrize("B,D,H,W,levels,radius", [(2, 32, 8, 12, 3, 4), (1, 64, 9, 11, 3, 3), (2, 256, 16, 16, 4, 4), (1, 16, 5, 5, 2, 1)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_corrblock_backward(E, B, D, H, W, levels, radius, precision):
+    """(Level sizes stay >= 2: a 1-wide level divides by W-1 = 0 in the reference's normalisation.)
+    Gradient of two lookups (as ERAFT's iterations do) w.r.t. both feature maps vs torch autograd through
+    the oracle's CorrBlock (matmul + avg_pool2d + grid_sample).  The backward itself is fp32; with the TF32
+    forward only the saved operands are identical, so the same tolerance holds."""
+    from eemflow_b200 import ops as O
+    if precision == "tf32" and not O.tf32_supported(D, H, W):
+        pytest.skip("shape not on the tcgen05 path")
+    gen = torch.Generator().manual_seed(D + H)
+    f1 = torch.randn(B, D, H, W, generator=gen, requires_grad=True)
+    f2 = torch.randn(B, D, H, W, generator=gen, requires_grad=True)
+    base = torch.stack(torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")[::-1], 0).float()[None]
+    coords = [base + 2.0 * torch.randn(B, 2, H, W, generator=gen) for _ in range(2)]
+    ref_pyr = ref_ops.corr_pyramid(f1, f2, levels)
+    outs = [ref_ops.corr_lookup(ref_pyr, c, radius) for c in coords]
+    gs = [torch.randn(o.shape, generator=gen) for o in outs]
+    sum((o * g).sum() for o, g in zip(outs, gs)).backward()
+    a = f1.detach().cuda().requires_grad_(True)
+    b = f2.detach().cuda().requires_grad_(True)
+    blk = E.CorrBlock(a, b, num_levels=levels, radius=radius, precision=precision)
+    assert all(lv.requires_grad for lv in blk.corr_pyramid if lv.numel())
+    mine = [blk(c.cuda()) for c in coords]
+    tol_fwd = 1e-5 if precision == "fp32" else 2e-3
+    assert close(mine[0], outs[0], tol_fwd)[0]
+    sum((o * g.cuda()).sum() for o, g in zip(mine, gs)).backward()
+    ok1, e1 = close(a.grad, f1.grad)
+    ok2, e2 = close(b.grad, f2.grad)
+    assert ok1 and ok2, (e1, e2)
+
+
+def test_corrblock_backward_partial_and_guards(E):
+    gen = torch.Generator().manual_seed(3)
+    f1 = torch.randn(1, 32, 16, 24, generator=gen)
+    f2 = torch.randn(1, 32, 16, 24, generator=gen, requires_grad=True)
+    coords = torch.stack(torch.meshgrid(torch.arange(16), torch.arange(24), indexing="ij")[::-1], 0).float()[None] + 0.3
+    ref = ref_ops.corr_lookup(ref_ops.corr_pyramid(f1, f2, 4), coords, 4)
+    g = torch.randn(ref.shape, generator=gen)
+    ref.backward(g)
+    b = f2.detach().cuda().requires_grad_(True)
+    blk = E.CorrBlock(f1.cuda(), b, precision="fp32")
+    blk(coords.cuda()).backward(g.cuda())
+    assert close(b.grad, f2.grad)[0]
+    # CorrBlock.corr static method is differentiable too
+    v = E.CorrBlock.corr(f1.cuda(), b, precision="fp32")
+    assert v.requires_grad and v.shape == (1, 16, 24, 1, 16, 24)
+    # coordinates must be detached
     with pytest.raises(NotImplementedError):
-        E.CorrBlock(f, f)
+        blk(coords.cuda().requires_grad_(True))
+    # no gradient requested: plain inference path
     with torch.no_grad():
-        E.CorrBlock(f, f)
+        assert not E.CorrBlock(f1.cuda(), b)(coords.cuda()).requires_grad

@@ -56,6 +56,10 @@ SIGNATURES = {
     "eem_local_corr_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, _vp, _vp, _vp]),
     "eem_backwarp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eem_bilinear_resize_backward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp]),
+    "eem_event_mask": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp]),
+    "eem_voxel_bin_sum": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
+    "eem_flow_error": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "eem_motion_propagate": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "eem_replicate_pad": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

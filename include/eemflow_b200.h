@@ -248,6 +248,38 @@ EEM_API int eem_bilinear_resize_backward(const float* grad_out, int B, int C, in
                                          int W, int align_corners, float scale0, float scale1,
                                          float scale_rest, float* grad_in, eem_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Loader / evaluation helpers next to the hot path
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Per-pixel event mask of each window: mask[win][y][x] = 1 iff an event falls into pixel bin (x, y).
+ * replaces: loader/MVSEC.py:133-142 (np.histogram2d(x, y, bins=(W,H), range=[[0,W],[0,H]]).T > 0):
+ * bin = floor(v) for 0 <= v < S, v == S joins the last bin, anything else is ignored.
+ * events/offsets as for eem_voxelize (16-byte aligned rows); mask: [n_windows, height, width] uint8. */
+EEM_API int eem_event_mask(const double* events, const int64_t* offsets, int n_windows,
+                           int64_t max_events_per_window, int height, int width, uint8_t* mask,
+                           eem_stream_t stream);
+
+/* Sum of a voxel grid over its bins, accumulated bin by bin in fp32 (bit-exact with numpy):
+ * replaces: loader/HREM.py:238-239 (np.sum(event_volume_old, axis=0)).
+ * grid [n_windows, num_bins, height, width] -> out [n_windows, height, width]. */
+EEM_API int eem_voxel_bin_sum(const float* grid, int64_t n_windows, int num_bins, int height, int width,
+                              float* out, eem_stream_t stream);
+
+/* Masked end-point-error statistics of a batch, replaces: test_mvsec.py:291-346 (Test.flow_error).
+ * flow_gt, flow_pred: [B, 2, H, W]; event_img: [B, H, W] or NULL ("dense" evaluation); only rows
+ * < max_row count (190 for the MVSEC car sequences, H otherwise).  A pixel counts when gt is finite,
+ * |gt| > 0 and (event_img > 0 when given).  stats[b] = { n_points, #(EE < 1), #(EE < 3 or EE < 0.1*|gt|),
+ * sum EE, sum |gt| } as doubles; EE and |gt| are formed in fp32 exactly as numpy does. */
+EEM_API int eem_flow_error(const float* flow_gt, const float* flow_pred, const float* event_img, int B,
+                           int height, int width, int max_row, double* stats, eem_stream_t stream);
+
+/* Dense flow -> mesh flow, replaces: loader/HREM.py:41-101 (motion_propagate): per vertex the median
+ * (element n/2) of 4*radius clamped samples, then a 5x5 median over the mesh with replicated borders.
+ * fflow: [B, H, W, 2] float32 (u, v interleaved, 8-byte aligned); mesh: [B, 2, mesh_size, mesh_size]. */
+EEM_API int eem_motion_propagate(const float* fflow, int B, int height, int width, int mesh_size, int radius,
+                                 float* mesh, eem_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

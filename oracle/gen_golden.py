@@ -27,6 +27,7 @@ from __future__ import annotations
 import ast
 import importlib.util
 import sys
+import textwrap
 import types
 import warnings
 from pathlib import Path
@@ -287,8 +288,75 @@ def gen_e2e(R):
     np.savez_compressed(OUT / "e2e_eemflow_cdc.npz", **out)
 
 
+def _extract_functions(path, names):
+    """Source text of the named (possibly nested-in-class) functions of a reference file that cannot be imported."""
+    src = path.read_text()
+    found = {}
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            found[node.name] = textwrap.dedent(ast.get_source_segment(src, node, padded=True))
+    assert set(found) == set(names), (path, set(names) - set(found))
+    return found
+
+
+def hashed_flow(h, w):
+    """Deterministic pseudo-random [h, w, 2] float32 field, exact on every machine (integer hash / 64)."""
+    y, x, c = np.meshgrid(np.arange(h, dtype=np.int64), np.arange(w, dtype=np.int64), np.arange(2, dtype=np.int64), indexing="ij")
+    v = (y * 7919 + x * 104729 + c * 1299709 + (x * y) % 8191 * 31) % 2001 - 1000
+    return (v.astype(np.float32) / np.float32(64.0)) + (x.astype(np.float32) / np.float32(w) - np.float32(0.5)) * np.float32(8.0)
+
+
+def gen_eval(R):
+    """Loader / evaluation helpers: the reference's own source text, executed here.
+    flow_error: test_mvsec.py:291-346; motion_propagate: loader/HREM.py:30-101; event mask: the
+    np.histogram2d call of loader/MVSEC.py:133-142 (inline in get_sample, restated verbatim as a call)."""
+    import cv2
+    rng = np.random.default_rng(77)
+    cases = {}
+    # --- flow_error
+    fe_src = _extract_functions(REF / "test_mvsec.py", {"flow_error"})["flow_error"]
+    ns = {"np": np, "torch": torch}
+    exec(fe_src, ns)
+    for name, (h, w), kind, is_car in (("sparse", (64, 80), "sparse", False), ("dense", (48, 56), "dense", False),
+                                        ("car", (260, 346), "sparse", True)):
+        gt = rng.normal(0, 3, size=(1, 2, h, w)).astype(np.float32)
+        gt[0, :, rng.integers(0, h, 40), rng.integers(0, w, 40)] = np.inf
+        zero = rng.random((h, w)) < 0.1
+        gt[0, :, zero] = 0.0
+        pred = (gt + rng.normal(0, 1.2, size=gt.shape)).astype(np.float32)
+        pred[~np.isfinite(pred)] = 0.0
+        ev = (rng.random((1, 1, h, w)) < 0.4).astype(np.float32) * rng.integers(1, 5, size=(1, 1, h, w))
+        fake_self = types.SimpleNamespace(data_loader=types.SimpleNamespace(dataset=types.SimpleNamespace(evaluation_type=kind)))
+        res = ns["flow_error"](fake_self, torch.from_numpy(gt), torch.from_numpy(pred), torch.from_numpy(ev.astype(np.float32)), is_car)
+        cases[f"fe_{name}_gt"], cases[f"fe_{name}_pred"], cases[f"fe_{name}_ev"] = gt, pred, ev.astype(np.float32)
+        cases[f"fe_{name}_res"] = np.array([float(v) for v in res], dtype=np.float64)
+    # --- motion_propagate
+    mp = _extract_functions(REF / "loader" / "HREM.py", {"check_out_bounds", "motion_propagate"})
+    ns = {"np": np, "cv2": cv2}
+    exec(mp["check_out_bounds"] + "\n\n" + mp["motion_propagate"], ns)
+    for name, (h, w) in (("hrem", (720, 1280)), ("small", (100, 132))):
+        ff = hashed_flow(h, w)      # regenerated by the tests from the same formula: only the meshes are stored
+        xm, ym = ns["motion_propagate"](ff.copy(), h, w)
+        cases[f"mp_{name}_hw"] = np.array([h, w])
+        cases[f"mp_{name}_x"], cases[f"mp_{name}_y"] = xm, ym
+    # --- event mask (MVSEC val) and HREM event_valid
+    h, w = 60, 90
+    ev = make_events(rng, 3000, h, w)
+    ev[:5, 1] = w          # right edge joins the last bin
+    ev[5:8, 2] = -1.0      # outside: ignored
+    hist, _, _ = np.histogram2d(x=ev[:, 1], y=ev[:, 2], bins=(w, h), range=[[0, w], [0, h]])
+    cases["mask_events"], cases["mask_hw"], cases["mask_out"] = ev, np.array([h, w]), (hist.transpose() > 0)
+    vol = R["Voxel"](5, normalize=True, gpu=False)(_Seq(make_events(rng, 4000, h, w), h, w))
+    cases["binsum_in"], cases["binsum_out"] = vol.numpy(), np.sum(vol.data.numpy(), axis=0)
+    np.savez_compressed(OUT / "eval.npz", **cases)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "--only-eval" in sys.argv:
+        torch.set_num_threads(1)
+        gen_eval(load_reference())
+        return
     torch.set_num_threads(1)  # fixed summation order in the reference's ATen reductions
     R = load_reference()
     with torch.no_grad():
@@ -297,6 +365,7 @@ def main():
         gen_local_corr(R)
         gen_warp(R)
         gen_e2e(R)
+        gen_eval(R)
     for f in sorted(OUT.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size / 1024:.1f} KiB")
 

@@ -264,3 +264,68 @@ def input_pad(x: torch.Tensor, dims, mode: str = 'chairs', eval_pad_rate: int = 
     else:
         pad = [pad_wd // 2, pad_wd - pad_wd // 2, 0, pad_ht]
     return F.pad(x, pad, mode='replicate'), pad
+
+
+# ------------------------------------------------------------------------------------------------
+# loader / evaluation helpers
+# ------------------------------------------------------------------------------------------------
+def event_mask(features: np.ndarray, height: int, width: int) -> np.ndarray:
+    """loader/MVSEC.py:133-142: pixels that received at least one event (bool [H, W])."""
+    hist, _, _ = np.histogram2d(x=features[:, 1], y=features[:, 2], bins=(width, height), range=[[0, width], [0, height]])
+    return hist.transpose() > 0
+
+
+def voxel_bin_sum(volume: np.ndarray) -> np.ndarray:
+    """loader/HREM.py:238-239: event_valid = np.sum(event_volume_old, axis=0)."""
+    return np.sum(volume, axis=0)
+
+
+def flow_error(flow_gt: torch.Tensor, flow_pred: torch.Tensor, event_img: torch.Tensor, is_car: bool = False,
+               evaluation_type: str = "sparse"):
+    """test_mvsec.py:291-346 (Test.flow_error), evaluation_type = self.data_loader.dataset.evaluation_type."""
+    gt = flow_gt[0].numpy().transpose(1, 2, 0)
+    pred = flow_pred[0].numpy().transpose(1, 2, 0)
+    max_row = 190 if is_car else gt.shape[1]          # sic: the reference takes shape[1] of the [H, W, 2] array
+    gt, pred = gt[:max_row, :], pred[:max_row, :]
+    flow_mask = np.logical_and(np.logical_and(~np.isinf(gt[:, :, 0]), ~np.isinf(gt[:, :, 1])), np.linalg.norm(gt, axis=2) > 0)
+    if evaluation_type == "sparse":
+        event_mask_ = np.squeeze(event_img.numpy())[:max_row, :] > 0
+        total = np.squeeze(np.logical_and(event_mask_, flow_mask))
+    else:
+        total = flow_mask
+    gt_m, pred_m = gt[total, :], pred[total, :]
+    EE = np.linalg.norm(gt_m - pred_m, axis=-1)
+    EE_gt = np.linalg.norm(gt_m, axis=-1)
+    n_points = EE.shape[0]
+    percent_1 = float((EE < 1.).sum() / float(EE.shape[0] + 1e-5))
+    percent_3 = float(((EE < 3.) | (EE < 0.1 * EE_gt)).sum()) / float(EE.shape[0] + 1e-5)
+    EE, EE_gt = torch.from_numpy(EE), torch.from_numpy(EE_gt)
+    if torch.sum(EE) == 0:
+        return 0, percent_1, percent_3, n_points, 0, 0, 0
+    return torch.mean(EE), percent_1, percent_3, n_points, torch.sum(EE), torch.mean(EE_gt), torch.sum(EE_gt)
+
+
+def motion_propagate(fflow: np.ndarray, height: int, width: int, mesh_size: int = 16, radius: int = 3):
+    """loader/HREM.py:30-101: [H, W, 2] dense flow -> two [mesh, mesh] float64 meshes (x, y)."""
+    from scipy.signal import medfilt2d
+    u, v = fflow[..., 0], fflow[..., 1]
+    mesh_cols, mesh_rows = width // mesh_size, height // mesh_size
+    clamp = lambda p, hi: min(max(p, 0), hi - 1)
+    xm = np.zeros((mesh_size, mesh_size), dtype=float)
+    ym = np.zeros((mesh_size, mesh_size), dtype=float)
+    for i in range(mesh_size):
+        for j in range(mesh_size):
+            us, vs = [], []
+            for r in range(radius):
+                ox, oy = r * mesh_rows // 2, r * mesh_cols // 2
+                for si, sj in ((1, 1), (1, -1), (-1, 1), (-1, -1)):
+                    pi, pj = clamp(mesh_rows * i + si * ox, height), clamp(mesh_cols * j + sj * oy, width)
+                    us.append(u[pi, pj])
+                    vs.append(v[pi, pj])
+            if us:
+                xm[i, j] = sorted(us)[len(us) // 2]
+                ym[i, j] = sorted(vs)[len(vs) // 2]
+    pad = 2
+    xp, yp = np.pad(xm, pad, mode="edge"), np.pad(ym, pad, mode="edge")      # cv2.BORDER_REPLICATE
+    xp, yp = medfilt2d(xp, [5, 5]), medfilt2d(yp, [5, 5])
+    return xp[pad:pad + mesh_size, pad:pad + mesh_size], yp[pad:pad + mesh_size, pad:pad + mesh_size]

@@ -146,6 +146,7 @@ class B200Step:
                   "eem": [{k: v.to(dev) for k, v in lv.items()} for lv in inp["eem"]]}
         self.out_host = None
         self.flow_host = None
+        self.lanes = None
 
     # ---- the four kernel families of a step; each is also captured as its own CUDA graph ----------
     def fam_voxelize(self):
@@ -189,52 +190,69 @@ class B200Step:
         self.fam_eemflow_ops()
         return self.out, self.flow
 
-    def _e2e_buffers(self):
-        dev = self.dev
-        self.e2e_d = {"f1": torch.empty_like(self.d["f1"]), "f2": torch.empty_like(self.d["f2"]),
-                      "coords": [torch.empty_like(c) for c in self.d["coords"]],
-                      "eem": [{k: torch.empty_like(v) for k, v in lv.items()} for lv in self.d["eem"]]}
-        self.h2d_stream, self.d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        out_shape = (self.B, LEVELS * (2 * RADIUS + 1) ** 2, FH, FW)
-        self.out_host = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
-        self.flow_host = torch.empty((self.B, 2, H, W), dtype=torch.float32, pin_memory=True)
+    class _Lane:
+        """Streams, device input buffers, pinned result buffers and a voxel encoder of one in-flight step."""
 
-    def end_to_end(self):
+    def _make_lane(self):
+        dev, ln = self.dev, B200Step._Lane()
+        ln.d = {"f1": torch.empty_like(self.d["f1"]), "f2": torch.empty_like(self.d["f2"]),
+                "coords": [torch.empty_like(c) for c in self.d["coords"]],
+                "eem": [{k: torch.empty_like(v) for k, v in lv.items()} for lv in self.d["eem"]]}
+        ln.main, ln.h2d, ln.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ln.enc = self.E.EventSequenceToVoxelGrid_Pytorch(NB, gpu=True, gpu_nr=dev.index or 0, normalize=True, forkserver=False)
+        out_shape = (self.B, LEVELS * (2 * RADIUS + 1) ** 2, FH, FW)
+        ln.out_host = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
+        ln.flow_host = torch.empty((self.B, 2, H, W), dtype=torch.float32, pin_memory=True)
+        return ln
+
+    def end_to_end(self, i=0):
         """Same step through the public API from HOST buffers: numpy events, pinned feature maps in,
-        last correlation features + final flow out to pinned host memory.  The pinned tensors go up on a
-        copy stream while the host stages the event rows; results come back on a third stream."""
-        if self.out_host is None:
-            self._e2e_buffers()
-        cur = torch.cuda.current_stream(self.dev)
-        hi, d = self.host, self.e2e_d
-        self.h2d_stream.wait_stream(cur)          # last step's kernels are done with the device buffers
-        with torch.cuda.stream(self.h2d_stream):
-            d["f1"].copy_(hi["f1"], non_blocking=True)
-            d["f2"].copy_(hi["f2"], non_blocking=True)
-            for dc, hc in zip(d["coords"], hi["coords"]):
-                dc.copy_(hc, non_blocking=True)
-            corr_in = torch.cuda.Event()
-            corr_in.record()
-        self.enc.voxelize_batch(self.seqs)        # stages the event rows while the copies above are on the link
-        with torch.cuda.stream(self.h2d_stream):  # queued behind the event rows: arrives under voxelize/corr/lookup
-            for dl, hl in zip(d["eem"], hi["eem"]):
-                for k in dl:
-                    dl[k].copy_(hl[k], non_blocking=True)
-            eem_in = torch.cuda.Event()
-            eem_in.record()
-        cur.wait_event(corr_in)
-        self.fam_corr_pyramid(d)
-        self.fam_corr_lookup(d)
-        out = self.out
-        self.d2h_stream.wait_stream(cur)
-        with torch.cuda.stream(self.d2h_stream):
-            self.out_host.copy_(out, non_blocking=True)
-            out.record_stream(self.d2h_stream)
-        cur.wait_event(eem_in)
-        self.fam_eemflow_ops(d)
-        self.flow_host.copy_(self.flow, non_blocking=True)
-        cur.wait_stream(self.d2h_stream)
+        last correlation features + final flow out to pinned host memory.
+
+        Two steps are in flight (lane = i % 2), each on its own streams and buffers, so the copies of one step
+        overlap the kernels of the other as in any double-buffered serving loop; every step still uploads all of
+        its inputs and reads back its results.  Within a lane the pinned tensors go up on a copy stream while the
+        host stages the event rows, and the results come back on a third stream."""
+        if self.lanes is None:
+            self.lanes = [self._make_lane(), self._make_lane()]
+        ln = self.lanes[i % 2]
+        hi, d = self.host, ln.d
+        with torch.cuda.stream(ln.main):
+            cur = ln.main
+            ln.h2d.wait_stream(cur)               # the lane's previous step is done with these device buffers
+            with torch.cuda.stream(ln.h2d):
+                d["f1"].copy_(hi["f1"], non_blocking=True)
+                d["f2"].copy_(hi["f2"], non_blocking=True)
+                for dc, hc in zip(d["coords"], hi["coords"]):
+                    dc.copy_(hc, non_blocking=True)
+                corr_in = torch.cuda.Event()
+                corr_in.record()
+            ln.enc.voxelize_batch(self.seqs)      # stages the event rows while the copies above are on the link
+            with torch.cuda.stream(ln.h2d):       # queued behind the event rows: arrives under voxelize/corr/lookup
+                for dl, hl in zip(d["eem"], hi["eem"]):
+                    for k in dl:
+                        dl[k].copy_(hl[k], non_blocking=True)
+                eem_in = torch.cuda.Event()
+                eem_in.record()
+            cur.wait_event(corr_in)
+            self.fam_corr_pyramid(d)
+            self.fam_corr_lookup(d)
+            out = self.out
+            ln.d2h.wait_stream(cur)
+            with torch.cuda.stream(ln.d2h):
+                ln.out_host.copy_(out, non_blocking=True)
+                out.record_stream(ln.d2h)
+            cur.wait_event(eem_in)
+            self.fam_eemflow_ops(d)
+            ln.flow_host.copy_(self.flow, non_blocking=True)
+            cur.wait_stream(ln.d2h)
+            self.flow.record_stream(cur)
+        self.out_host, self.flow_host = ln.out_host, ln.flow_host
         return self.flow
+
+    def e2e_sync(self):
+        for ln in self.lanes or ():
+            ln.main.synchronize()
 
     def d2h_bytes(self):
         return (self.out_host.numel() + self.flow_host.numel()) * 4 if self.out_host is not None else 0
@@ -490,15 +508,16 @@ def main():
     e2e = None
     if not args.no_e2e:
         k = max(5, args.steps // 2)
-        for _ in range(max(5, args.warmup)):
-            step.end_to_end()
+        for i in range(max(6, args.warmup)):
+            step.end_to_end(i)
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
         t0 = time.perf_counter()
-        for _ in range(k):
-            flow = step.end_to_end()
+        for i in range(k):
+            flow = step.end_to_end(i)
             if world > 1:
+                torch.cuda.current_stream().wait_stream(step.lanes[i % 2].main)
                 edist.gather_batch(flow)
         torch.cuda.synchronize()
         dt = edist.max_over_ranks(time.perf_counter() - t0, dev)

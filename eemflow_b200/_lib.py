@@ -135,7 +135,8 @@ def ptr_array(tensors) -> "C.Array":
 
 
 class Workspace:
-    """Grow-only per-device scratch buffer handed to the C ABI (no hidden cudaMalloc in the library)."""
+    """Grow-only scratch buffer per (device, stream, op family) handed to the C ABI (no hidden cudaMalloc in the
+    library).  Keyed by the stream as well so that callers running the ops on several streams never share scratch."""
 
     def __init__(self):
         self._buf: dict[tuple, torch.Tensor] = {}
@@ -143,7 +144,8 @@ class Workspace:
     def get(self, device: torch.device, nbytes: int, tag: str = "") -> torch.Tensor | None:
         if nbytes <= 0:
             return None
-        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (index, torch.cuda.current_stream(index).cuda_stream, tag)
         buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

@@ -32,17 +32,19 @@ t0 = time.perf_counter()
 for _ in range(5):
     step.enc._stage.upload([s.features for s in step.seqs], dev)
 print(f"  upload() host-side return: {(time.perf_counter()-t0)/5*1e3:.2f} ms"); torch.cuda.synchronize()
-ms = tm(step.end_to_end); print(f"end_to_end: {ms:.2f} ms")
+it = [0]
+def e2e():
+    step.end_to_end(it[0]); it[0] += 1
+ms = tm(e2e, n=10); print(f"end_to_end (two lanes in flight): {ms:.2f} ms/step")
 ms = tm(step.resident); print(f"resident eager: {ms:.2f} ms")
-# copies only
-step._e2e_buffers() if step.out_host is None else None
+ln = step.lanes[0]
 def copies():
-    hi, d = step.host, step.e2e_d
+    hi, d = step.host, ln.d
     d["f1"].copy_(hi["f1"], non_blocking=True); d["f2"].copy_(hi["f2"], non_blocking=True)
     for dc, hc in zip(d["coords"], hi["coords"]): dc.copy_(hc, non_blocking=True)
     for dl, hl in zip(d["eem"], hi["eem"]):
         for k in dl: dl[k].copy_(hl[k], non_blocking=True)
 ms = tm(copies); print(f"pinned tensor copies only ({(bench.h2d_bytes(inp)-sum(e.nbytes for e in inp['events']))/1e6:.0f} MB): {ms:.2f} ms")
 def d2h():
-    step.out_host.copy_(step.out, non_blocking=True); step.flow_host.copy_(step.flow, non_blocking=True)
+    ln.out_host.copy_(step.out, non_blocking=True); ln.flow_host.copy_(step.flow, non_blocking=True)
 ms = tm(d2h); print(f"D2H results only: {ms:.2f} ms")

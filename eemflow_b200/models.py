@@ -145,3 +145,187 @@ class EEMFlow_cdc(nn.Module):
             flows[lvl] = getattr(self, f"decoder{lvl}")(torch.cat([cv, feat, flow_up], 1)) + flow_up
         predictions = [upsample2d_flow_as(flows[lvl], events1, mode="bilinear", if_rate=True) for lvl in (6, 5, 4, 3, 2)]
         return (events1, events2), predictions
+
+
+# ====================================================================================================
+# ERAFT: the caller of CorrBlock (model/eraft.py:39-175) with its encoders (model/extractor.py) and
+# update block (model/update.py).  State-dict compatible with the reference (same parameter and buffer
+# names), so ERAFT checkpoints load unchanged.  The all-pairs volume, its pyramid, the 12 window
+# lookups and the padding run in this library's kernels; convolutions, norms and the GRU stay on cuDNN.
+# ====================================================================================================
+def _norm(kind, planes):
+    if kind == "batch":
+        return nn.BatchNorm2d(planes)
+    if kind == "instance":
+        return nn.InstanceNorm2d(planes)
+    if kind == "group":
+        return nn.GroupNorm(num_groups=planes // 8, num_channels=planes)
+    return nn.Sequential()
+
+
+class _ResBlock(nn.Module):
+    def __init__(self, cin, planes, kind, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, planes, 3, stride, 1)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1)
+        self.relu = nn.ReLU(inplace=True)
+        self.norm1, self.norm2 = _norm(kind, planes), _norm(kind, planes)
+        self.downsample = None
+        if stride != 1:
+            self.norm3 = _norm(kind, planes)      # registered twice (norm3 and downsample.1), as in the reference
+            self.downsample = nn.Sequential(nn.Conv2d(cin, planes, 1, stride), self.norm3)
+
+    def forward(self, x):
+        y = self.relu(self.norm1(self.conv1(x)))
+        y = self.relu(self.norm2(self.conv2(y)))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return self.relu(x + y)
+
+
+class BasicEncoder(nn.Module):
+    """1/8-resolution feature encoder (model/extractor.py:114-190); a list input is batched through once."""
+
+    def __init__(self, output_dim=128, norm_fn='batch', dropout=0.0, n_first_channels=1):
+        super().__init__()
+        self.norm_fn = norm_fn
+        self.norm1 = nn.GroupNorm(8, 64) if norm_fn == "group" else _norm(norm_fn, 64)
+        self.conv1 = nn.Conv2d(n_first_channels, 64, 7, 2, 3)
+        self.relu1 = nn.ReLU(inplace=True)
+        widths, cin = ((64, 1), (96, 2), (128, 2)), 64
+        for k, (planes, stride) in enumerate(widths, start=1):
+            setattr(self, f"layer{k}", nn.Sequential(_ResBlock(cin, planes, norm_fn, stride), _ResBlock(planes, planes, norm_fn, 1)))
+            cin = planes
+        self.conv2 = nn.Conv2d(128, output_dim, 1)
+        self.dropout = nn.Dropout2d(p=dropout) if dropout > 0 else None
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+            elif isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d, nn.GroupNorm)):
+                if m.weight is not None:
+                    nn.init.constant_(m.weight, 1)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        parts = None
+        if isinstance(x, (tuple, list)):
+            parts = [t.shape[0] for t in x]
+            x = torch.cat(x, dim=0)
+        x = self.relu1(self.norm1(self.conv1(x)))
+        x = self.conv2(self.layer3(self.layer2(self.layer1(x))))
+        if self.training and self.dropout is not None:
+            x = self.dropout(x)
+        return torch.split(x, parts, dim=0) if parts is not None else x
+
+
+class _FlowHead(nn.Module):
+    def __init__(self, cin=128, hidden=256):
+        super().__init__()
+        self.conv1, self.conv2 = nn.Conv2d(cin, hidden, 3, padding=1), nn.Conv2d(hidden, 2, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.conv1(x)))
+
+
+class _SepConvGRU(nn.Module):
+    """Horizontal (1x5) then vertical (5x1) GRU update (model/update.py:35-62)."""
+
+    def __init__(self, hidden=128, cin=192 + 128):
+        super().__init__()
+        for tag, k, p in (("1", (1, 5), (0, 2)), ("2", (5, 1), (2, 0))):
+            for gate in "zrq":
+                setattr(self, f"conv{gate}{tag}", nn.Conv2d(hidden + cin, hidden, k, padding=p))
+
+    def forward(self, h, x):
+        for tag in "12":
+            hx = torch.cat([h, x], dim=1)
+            z = torch.sigmoid(getattr(self, "convz" + tag)(hx))
+            r = torch.sigmoid(getattr(self, "convr" + tag)(hx))
+            q = torch.tanh(getattr(self, "convq" + tag)(torch.cat([r * h, x], dim=1)))
+            h = (1 - z) * h + z * q
+        return h
+
+
+class _MotionEncoder(nn.Module):
+    def __init__(self, cor_planes):
+        super().__init__()
+        self.convc1, self.convc2 = nn.Conv2d(cor_planes, 256, 1), nn.Conv2d(256, 192, 3, padding=1)
+        self.convf1, self.convf2 = nn.Conv2d(2, 128, 7, padding=3), nn.Conv2d(128, 64, 3, padding=1)
+        self.conv = nn.Conv2d(64 + 192, 128 - 2, 3, padding=1)
+
+    def forward(self, flow, corr):
+        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
+        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
+        return torch.cat([F.relu(self.conv(torch.cat([cor, flo], dim=1))), flow], dim=1)
+
+
+class BasicUpdateBlock(nn.Module):
+    def __init__(self, args, hidden_dim=128, input_dim=128):
+        super().__init__()
+        self.args = args
+        self.encoder = _MotionEncoder(args.corr_levels * (2 * args.corr_radius + 1) ** 2)
+        self.gru = _SepConvGRU(hidden_dim, 128 + hidden_dim)
+        self.flow_head = _FlowHead(hidden_dim, 256)
+        self.mask = nn.Sequential(nn.Conv2d(hidden_dim, hidden_dim * 2, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(hidden_dim * 2, 64 * 9, 1))
+
+    def forward(self, net, inp, corr, flow, upsample=True):
+        net = self.gru(net, torch.cat([inp, self.encoder(flow, corr)], dim=1))
+        return net, .25 * self.mask(net), self.flow_head(net)
+
+
+class ERAFT(nn.Module):
+    """model/eraft.py:39-175.  `corr_precision` ("tf32" | "fp32" | None = library default) is the one extra knob."""
+
+    def __init__(self, config=None, n_first_channels=5, corr_precision=None):
+        super().__init__()
+        from argparse import Namespace
+        self.args = Namespace(small=False, dropout=False, mixed_precision=False, clip=1.0, corr_levels=4, corr_radius=4)
+        self.hidden_dim = self.context_dim = 128
+        self.corr_precision = corr_precision
+        self.fnet = BasicEncoder(256, 'instance', 0, n_first_channels)
+        self.cnet = BasicEncoder(self.hidden_dim + self.context_dim, 'batch', 0, n_first_channels)
+        self.update_block = BasicUpdateBlock(self.args, hidden_dim=self.hidden_dim)
+
+    def change_imagesize(self, img_size):
+        self.image_size = img_size
+        self.image_padder = InputPadder(img_size, mode='chairs')
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def initialize_flow(self, img):
+        from .corr import coords_grid
+        n, _, h, w = img.shape
+        return coords_grid(n, h // 8, w // 8).to(img.device), coords_grid(n, h // 8, w // 8).to(img.device)
+
+    def upsample_flow(self, flow, mask):
+        """[N,2,H/8,W/8] -> [N,2,H,W] by the learned convex combination of the 3x3 coarse neighbours."""
+        n, _, h, w = flow.shape
+        mask = torch.softmax(mask.view(n, 1, 9, 8, 8, h, w), dim=2)
+        nb = F.unfold(8 * flow, [3, 3], padding=1).view(n, 2, 9, 1, 1, h, w)
+        return torch.sum(mask * nb, dim=2).permute(0, 1, 4, 2, 5, 3).reshape(n, 2, 8 * h, 8 * w)
+
+    def forward(self, events1, events2, iters=12, flow_init=None, upsample=True, normal=False):
+        from .corr import CorrBlock, upflow8
+        image1, image2 = self.image_padder.pad(events1, events2)
+        fmap1, fmap2 = self.fnet([image1.contiguous(), image2.contiguous()])
+        corr_fn = CorrBlock(fmap1.float(), fmap2.float(), radius=self.args.corr_radius, precision=self.corr_precision)
+        net, inp = torch.split(self.cnet(image1), [self.hidden_dim, self.context_dim], dim=1)
+        net, inp = torch.tanh(net), torch.relu(inp)
+        coords0, coords1 = self.initialize_flow(image1)
+        if flow_init is not None:
+            coords1 = coords1 + flow_init
+        flow_predictions = []
+        for _ in range(iters):
+            coords1 = coords1.detach()
+            corr = corr_fn(coords1)
+            net, up_mask, delta_flow = self.update_block(net, inp, corr, coords1 - coords0)
+            coords1 = coords1 + delta_flow
+            flow_up = upflow8(coords1 - coords0) if up_mask is None else self.upsample_flow(coords1 - coords0, up_mask)
+            flow_predictions.append(self.image_padder.unpad(flow_up))
+        return (events1, events2), flow_predictions

@@ -288,6 +288,32 @@ def gen_e2e(R):
     np.savez_compressed(OUT / "e2e_eemflow_cdc.npz", **out)
 
 
+def gen_e2e_eraft(R):
+    """ERAFT (model/eraft.py) forward, 12 iterations, reference CPU path end to end: voxelizer, InputPadder,
+    encoders, CorrBlock (matmul + avg_pool2d + grid_sample lookups), GRU update block, convex upsampling.
+    This is the caller that amplifies any error of the correlation volume through 12 recurrent updates."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle.det_weights import set_hashed_weights
+    from model.eraft import ERAFT
+    net = ERAFT(None, n_first_channels=5).eval()
+    # gain 0.8: flows of 10-25 px that depend on the lookups (zeroing them changes the flow by 90 %,
+    # 1e-3 multiplicative noise on them by 1e-4), GRU gates not saturated
+    set_hashed_weights(net, weight_gain=0.8)
+    rng = np.random.default_rng(21)
+    h, w, nb = 128, 160, 5
+    ev1, ev2 = make_events(rng, 6000, h, w), make_events(rng, 6000, h, w)
+    enc = R["Voxel"](num_bins=nb, gpu=False, normalize=True, forkserver=False)
+    v1 = enc(_Seq(ev1.copy(), h, w))[None]
+    v2 = enc(_Seq(ev2.copy(), h, w))[None]
+    net.change_imagesize((h, w))
+    _, flows = net(events1=v1, events2=v2, iters=12)
+    out = {"events1": ev1, "events2": ev2, "shape": np.array([nb, h, w])}
+    for k in (0, 5, 11):
+        out[f"flow{k}"] = flows[k].numpy()
+        print("eraft iter", k, "mean |flow|", float(flows[k].abs().mean()), "max", float(flows[k].abs().max()))
+    np.savez_compressed(OUT / "e2e_eraft.npz", **out)
+
+
 def _extract_functions(path, names):
     """Source text of the named (possibly nested-in-class) functions of a reference file that cannot be imported."""
     src = path.read_text()
@@ -353,9 +379,11 @@ def gen_eval(R):
 
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
-    if "--only-eval" in sys.argv:
+    if "--only-eval" in sys.argv or "--only-eraft" in sys.argv:
         torch.set_num_threads(1)
-        gen_eval(load_reference())
+        R = load_reference()
+        with torch.no_grad():
+            gen_eval(R) if "--only-eval" in sys.argv else gen_e2e_eraft(R)
         return
     torch.set_num_threads(1)  # fixed summation order in the reference's ATen reductions
     R = load_reference()
@@ -365,6 +393,7 @@ def main():
         gen_local_corr(R)
         gen_warp(R)
         gen_e2e(R)
+        gen_e2e_eraft(R)
         gen_eval(R)
     for f in sorted(OUT.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size / 1024:.1f} KiB")

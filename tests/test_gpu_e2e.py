@@ -69,3 +69,54 @@ def test_eemflow_cdc_trains_through_the_kernels():
         opt.step()
         losses.append(loss.item())
     assert np.isfinite(losses).all()
+
+
+@pytest.mark.parametrize("precision,gate", [("fp32", 2e-4), ("tf32", 1e-3)])
+def test_eraft_forward_from_events(golden, precision, gate):
+    """ERAFT, the caller of CorrBlock: events -> voxel grids -> encoders -> all-pairs pyramid -> 12 x (lookup + GRU
+    update) -> convex upsampling, against the REAL reference ERAFT on the CPU (tests/golden/e2e_eraft.npz).
+    Any error of the correlation volume is fed back through 12 recurrent updates, which is why the north star
+    states the TF32 tolerance end to end: EPE-relative <= 1e-3.  (The golden's weights make the flow depend
+    on the lookups: zeroing them changes it by 90 %, see oracle/gen_golden.py::gen_e2e_eraft.)"""
+    import eemflow_b200 as E
+    from eemflow_b200.models import ERAFT
+    from oracle.det_weights import set_hashed_weights
+    g = golden("e2e_eraft")
+    nb, h, w = (int(v) for v in g["shape"])
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        enc = E.EventSequenceToVoxelGrid_Pytorch(nb, gpu=True, normalize=True, forkserver=False)
+        v1 = enc(Seq(g["events1"].copy(), h, w))[None]
+        v2 = enc(Seq(g["events2"].copy(), h, w))[None]
+        net = ERAFT(None, n_first_channels=nb, corr_precision=precision)
+        set_hashed_weights(net, weight_gain=0.8)
+        net = net.cuda().eval()
+        net.change_imagesize((h, w))
+        with torch.no_grad():
+            _, flows = net(events1=v1, events2=v2, iters=12)
+        assert len(flows) == 12
+        for k in (0, 5, 11):
+            ref = g[f"flow{k}"]
+            f = flows[k].cpu().numpy()
+            assert f.shape == ref.shape == (1, 2, h, w)
+            rel = np.abs(f - ref).mean() / np.abs(ref).mean()
+            assert rel <= gate, (precision, k, rel)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_eraft_trains_through_the_kernels():
+    """Gradients reach the feature encoder through the CorrBlock backward (lookup gradient + pyramid GEMMs)."""
+    from eemflow_b200.models import ERAFT
+    torch.manual_seed(0)
+    net = ERAFT(None, n_first_channels=5).cuda().train()
+    net.change_imagesize((128, 192))      # 1/8 maps of 16x24: every pyramid level stays >= 2 wide (a 1-wide level
+    v1 = torch.randn(2, 5, 128, 192, device="cuda")   # is NaN in the reference too: division by W-1 = 0)
+    v2 = torch.randn(2, 5, 128, 192, device="cuda")
+    _, flows = net(events1=v1, events2=v2, iters=3)
+    loss = sum(f.abs().mean() for f in flows)
+    loss.backward()
+    for p in (net.fnet.conv1.weight, net.fnet.conv2.weight, net.update_block.encoder.convc1.weight, net.cnet.conv1.weight):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0

@@ -153,33 +153,47 @@ __device__ __forceinline__ void source_index(int dst, int in_size, int out_size,
   l0 = 1.f - l1;
 }
 
+// Thread = V horizontally adjacent output pixels of one row (V = 4/2/1 by the divisibility of W and the
+// alignment of `out`): the vertical taps/weights are shared, the V horizontal tap pairs are computed once, and
+// the plane loop issues 4V independent (L1-resident) loads and one V-wide streaming store per plane.
+template <int V>
 __global__ void __launch_bounds__(256)
 bilinear_resize_kernel(const float* __restrict__ in, int B, int C, int h, int w, float* __restrict__ out,
                        int H, int W, int align_corners, float scale0, float scale1, float scale_rest) {
-  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int X = (blockIdx.x * 32 + (threadIdx.x & 31)) * V;
   const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (X >= W || Y >= H) return;
-  int x0, x1, y0, y1;
-  float lx0, lx1, ly0, ly1;
-  source_index(X, w, W, align_corners, x0, x1, lx0, lx1);
+  int xa[V], xb[V], y0, y1;
+  float la[V], lb[V], ly0, ly1;
+#pragma unroll
+  for (int i = 0; i < V; ++i) source_index(X + i, w, W, align_corners, xa[i], xb[i], la[i], lb[i]);
   source_index(Y, h, H, align_corners, y0, y1, ly0, ly1);
   const int64_t ip = (int64_t)h * w, op = (int64_t)H * W;
-  // source taps and weights are computed once per output pixel and reused over the planes
-  const int o00 = y0 * w + x0, o01 = y0 * w + x1, o10 = y1 * w + x0, o11 = y1 * w + x1;
-  const int64_t opix = (int64_t)Y * W + X;
   // plane loop with running pointers and a running channel id (no div/mod, no 64-bit multiplies)
   const int gz = gridDim.z, BC = B * C;
-  const float* s = in + (int64_t)blockIdx.z * ip;
-  float* o = out + (int64_t)blockIdx.z * op + opix;
+  const float* r0 = in + (int64_t)blockIdx.z * ip + y0 * w;
+  const float* r1 = in + (int64_t)blockIdx.z * ip + y1 * w;
+  float* o = out + (int64_t)blockIdx.z * op + (int64_t)Y * W + X;
   const int64_t s_step = (int64_t)gz * ip, o_step = (int64_t)gz * op;
   int c = blockIdx.z % C;
   const int c_step = gz % C;
-#pragma unroll 4
+#pragma unroll 2
   for (int bc = blockIdx.z; bc < BC; bc += gz) {
-    const float v = ly0 * (lx0 * __ldg(s + o00) + lx1 * __ldg(s + o01)) + ly1 * (lx0 * __ldg(s + o10) + lx1 * __ldg(s + o11));
     const float sc = c == 0 ? scale0 : (c == 1 ? scale1 : scale_rest);
-    st_stream(o, v * sc);
-    s += s_step;
+    float v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      v[i] = (ly0 * (la[i] * __ldg(r0 + xa[i]) + lb[i] * __ldg(r0 + xb[i])) +
+              ly1 * (la[i] * __ldg(r1 + xa[i]) + lb[i] * __ldg(r1 + xb[i]))) * sc;
+    if constexpr (V == 4) {
+      st_stream4(o, make_float4(v[0], v[1], v[2], v[3]));
+    } else if constexpr (V == 2) {
+      asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(o), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+      st_stream(o, v[0]);
+    }
+    r0 += s_step;
+    r1 += s_step;
     o += o_step;
     c += c_step;
     if (c >= C) c -= C;
@@ -265,14 +279,20 @@ int eem_bilinear_resize(const float* in, int B, int C, int h, int w, float* out,
   EEM_CHECK_ARG(in && out, "eem_bilinear_resize: NULL pointer");
   EEM_CHECK_ARG(B > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "eem_bilinear_resize: sizes must be > 0");
   const int64_t bc = (int64_t)B * C;
+  const int V = (W % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) ? 4
+              : (W % 2 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0) ? 2 : 1;
   // enough CTAs to fill the chip (~8 per SM), the rest of the planes are looped inside the thread
-  const int64_t blocks_xy = ceil_div(W, 32) * ceil_div(H, 8);
+  const int64_t blocks_xy = ceil_div(W, 32 * V) * ceil_div(H, 8);
   int64_t gz = ceil_div((int64_t)sm_count() * 8, blocks_xy);
   if (gz < 1) gz = 1;
   if (gz > bc) gz = bc;
   if (gz > 65535) gz = 65535;
-  dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)gz);
-  bilinear_resize_kernel<<<grid, 256, 0, as_stream(stream_)>>>(in, B, C, h, w, out, H, W, align_corners ? 1 : 0, scale0, scale1, scale_rest);
+  dim3 grid((unsigned)ceil_div(W, 32 * V), (unsigned)ceil_div(H, 8), (unsigned)gz);
+  cudaStream_t stream = as_stream(stream_);
+  const int ac = align_corners ? 1 : 0;
+  if (V == 4) bilinear_resize_kernel<4><<<grid, 256, 0, stream>>>(in, B, C, h, w, out, H, W, ac, scale0, scale1, scale_rest);
+  else if (V == 2) bilinear_resize_kernel<2><<<grid, 256, 0, stream>>>(in, B, C, h, w, out, H, W, ac, scale0, scale1, scale_rest);
+  else bilinear_resize_kernel<1><<<grid, 256, 0, stream>>>(in, B, C, h, w, out, H, W, ac, scale0, scale1, scale_rest);
   EEM_CHECK_LAUNCH("bilinear_resize_kernel");
   return EEM_OK;
 }

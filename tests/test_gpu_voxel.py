@@ -220,3 +220,34 @@ def test_packed_columns_match_reference_loader_chain(V):
     wf = [{"x": s.features[:, 1], "y": s.features[:, 2], "t": s.features[:, 0], "p": s.features[:, 3]} for s in seqs]
     det2 = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_columns(wf, h, w).cpu().numpy()
     assert np.array_equal(det2, det)
+
+
+def test_direct_ctypes_binding_as_documented():
+    """The raw C-ABI call sequence INTEGRATION.md section 4 shows (no eemflow_b200 Python layer involved)."""
+    import ctypes as C
+    from pathlib import Path
+    lib = C.CDLL(str(Path(__file__).resolve().parent.parent / "eemflow_b200" / "libeemflow_b200.so"))
+    lib.eem_voxelize.restype = C.c_int
+    lib.eem_voxelize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.eem_voxelize_workspace_bytes.restype = C.c_size_t
+    lib.eem_voxelize_workspace_bytes.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.eem_last_error_string.restype = C.c_char_p
+    rng = np.random.default_rng(2)
+    nb, h, w = 5, 40, 60
+    feats = make_events(rng, 4000, h, w)
+    ev = torch.from_numpy(feats).cuda()
+    off = torch.tensor([0, ev.shape[0]], dtype=torch.int64, device="cuda")
+    grid = torch.empty(nb, h, w, device="cuda")
+    mode, normalize = 0, 1
+    nbytes = lib.eem_voxelize_workspace_bytes(ev.shape[0], 1, nb, h, w, mode, normalize)
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device="cuda")
+    rc = lib.eem_voxelize(ev.data_ptr(), off.data_ptr(), 1, ev.shape[0], ev.shape[0], nb, h, w, mode, normalize,
+                          grid.data_ptr(), None, None, ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.eem_last_error_string().decode()
+    ref = ref_ops.voxelize(feats, nb, h, w, normalize=True).numpy()
+    assert rel_close(grid.cpu().numpy(), ref).all()
+    # a NULL events pointer is reported through the status code and the error string, never thrown
+    rc = lib.eem_voxelize(None, off.data_ptr(), 1, 10, 10, nb, h, w, mode, normalize, grid.data_ptr(), None, None,
+                          ws.data_ptr(), nbytes, None)
+    assert rc == -1 and b"NULL" in lib.eem_last_error_string()

@@ -47,6 +47,49 @@ pool_fmap_kernel(const float* __restrict__ in, int64_t n_planes, int h, int w, i
   }
 }
 
+// All pooled levels of one plane in one pass: a CTA stages its [h, w] plane in shared memory, then forms
+// level 1 from it, level 2 from level 1, ... (same ((a+b)+c)+d order as the per-level kernel), writing each
+// level to its operand buffer.  The input is read from HBM once and the 2-3 tiny follow-up launches go away.
+struct PoolPyramidParams {
+  const float* in;
+  float* out[kMaxLevels];        // out[l] for l >= 1
+  int64_t pitch[kMaxLevels];
+  int h[kMaxLevels], w[kMaxLevels];
+  int num_levels;
+  int64_t n_planes;
+};
+
+__global__ void __launch_bounds__(256)
+pool_pyramid_kernel(const __grid_constant__ PoolPyramidParams p) {
+  extern __shared__ __align__(16) float pp_smem[];
+  const int P0 = p.h[0] * p.w[0];
+  for (int64_t pl = blockIdx.x; pl < p.n_planes; pl += gridDim.x) {
+    const float* src = p.in + pl * p.pitch[0];
+    if ((P0 & 3) == 0) {
+      for (int i = threadIdx.x * 4; i < P0; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(pp_smem + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+    } else {
+      for (int i = threadIdx.x; i < P0; i += blockDim.x) pp_smem[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    float* cur = pp_smem;
+    for (int l = 1; l < p.num_levels; ++l) {
+      const int hi = p.h[l - 1], wi = p.w[l - 1], ho = p.h[l], wo = p.w[l];
+      float* nxt = cur + hi * wi;
+      float* dst = p.out[l] + pl * p.pitch[l];
+      for (int r = threadIdx.x; r < ho * wo; r += blockDim.x) {
+        const int y = r / wo, x = r - y * wo;
+        const float* s4 = cur + (2 * y) * wi + 2 * x;
+        const float v = (((s4[0] + s4[1]) + s4[wi]) + s4[wi + 1]) * 0.25f;
+        nxt[r] = v;
+        dst[r] = v;
+      }
+      __syncthreads();
+      cur = nxt;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32 path: C[i,j] = scale * sum_d A[d,i] * Bm[d,j] per sample; A = fmap1[b] ([D,P], pitch P),
 // Bm = level operand ([D,P_l], pitch given).  64x64 tile, 256 threads, 4x4 outputs per thread.
@@ -675,7 +718,40 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   // pooled fmap2 operands (level l from level l-1)
   const float* op[kMaxLevels];
   op[0] = fmap2;
-  for (int l = 1; l < num_levels; ++l) {
+  size_t pyr_floats = 0;
+  for (int l = 0; l < num_levels; ++l) pyr_floats += (size_t)ld.h[l] * ld.w[l];
+  const bool fused_pool = num_levels > 1 && pyr_floats * sizeof(float) <= 96 * 1024 && (int64_t)ld.h[1] * ld.w[1] > 0;
+  if (fused_pool) {
+    PoolPyramidParams pp{};
+    pp.in = fmap2;
+    pp.num_levels = num_levels;
+    pp.n_planes = planes;
+    for (int l = 0; l < num_levels; ++l) {
+      pp.h[l] = ld.h[l];
+      pp.w[l] = ld.w[l];
+      pp.pitch[l] = ld.pitch[l];
+      if (l > 0) {
+        pp.out[l] = reinterpret_cast<float*>(static_cast<char*>(workspace) + ld.ws_off[l]);
+        op[l] = pp.out[l];
+      }
+    }
+    const size_t smem = pyr_floats * sizeof(float);
+    static std::mutex mu;
+    static size_t configured = 48 * 1024;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (smem > configured) {
+        EEM_CHECK_CUDA(cudaFuncSetAttribute(pool_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+      }
+    }
+    int64_t blocks = planes;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    pool_pyramid_kernel<<<(unsigned)blocks, 256, smem, stream>>>(pp);
+    EEM_CHECK_LAUNCH("pool_pyramid_kernel");
+  }
+  for (int l = 1; l < num_levels && !fused_pool; ++l) {
     float* dst = reinterpret_cast<float*>(static_cast<char*>(workspace) + ld.ws_off[l]);
     op[l] = dst;
     const int64_t total = planes * ld.h[l] * ld.w[l];

@@ -50,11 +50,14 @@ def shard(seq, rank: int | None = None, world: int | None = None):
     return seq[lo:hi]
 
 
-def gather_batch(local: torch.Tensor, total: int | None = None) -> torch.Tensor:
+def gather_batch(local: torch.Tensor, total: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """All-gather per-rank results `[B_r, ...]` into the rank-ordered global `[B, ...]` on every rank.
 
     Shards may be ragged (B not divisible by the world size): ranks pad to the largest shard for the
-    collective and the padding is cut after it.
+    collective and the padding is cut after it.  Pass `total` (the global batch size) to skip the size
+    exchange -- it costs a host synchronisation per call -- and `out` to reuse a result buffer (equal shards).
+    The collective is enqueued on the current stream, so it can be overlapped with the next batch by calling
+    it under a side stream.
     """
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
@@ -68,7 +71,8 @@ def gather_batch(local: torch.Tensor, total: int | None = None) -> torch.Tensor:
         sizes = [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)]
     m = max(sizes)
     if all(s == m for s in sizes):
-        out = torch.empty((world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        if out is None:
+            out = torch.empty((world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous())
         return out
     padded = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)

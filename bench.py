@@ -360,6 +360,20 @@ def lookup_algorithmic_bytes(B):
     return B * P * (4 * LEVELS * (2 * RADIUS + 1) ** 2 + 8 + 4 * taps)
 
 
+def ncu_traffic(kernel, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of
+    this very command (profiles/r01/ncu_full_summary_v4.json); only quoted for the workload it was captured on."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01", "ncu_full_summary_v4.json")
+    if args.workload != "mvsec_dt1" or args.batch != 32 or not os.path.exists(path):
+        return None, None
+    try:
+        with open(path) as fh:
+            d = json.load(fh)[kernel]
+        return int(d["dram_rd"] + d["dram_wr"]), "profiles/r01/prof_%s_v4_raw.csv (ncu --set full, one launch)" % kernel
+    except (KeyError, ValueError, TypeError):
+        return None, None
+
+
 def peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -523,8 +537,10 @@ def main():
     peak, peak_src = peaks()
     algo = lookup_algorithmic_bytes(args.batch)
     achieved = algo / (lookup_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic("corr_lookup_kernel", args)
     roofline = {"kernel": "corr_lookup_kernel<4>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo,
                 "avg_launch_ms": lookup_ms, "share_of_step": fam["corr_lookup"] / total_fam,
                 "timing": "CUDA events around a graph replay of the 12 lookups, K steps, same inputs as the timed region",
                 "family_ms_per_step": {k: v / args.steps for k, v in fam.items()}}

@@ -13,7 +13,9 @@
 // 256-bit LDG per event row, so a warp reads 1 KiB contiguous per instruction.  The grid is
 // zero-filled with a memset and updated with fire-and-forget RED.ADD.F32 resolved in L2 (the 55 MB
 // HREM grid is L2-resident on B200), so HBM sees 32*N bytes in and 4*nb*H*W bytes out.
+#include <cooperative_groups.h>
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -598,6 +600,166 @@ voxel_apply_kernel(float* __restrict__ grid, int64_t vox, const float* __restric
   for (int64_t i = nvec * 4 + tid; i < vox; i += stride) g[i] = normalize_one(g[i], mean, sd, divide);
 }
 
+
+// ---- cluster-resident path (windows whose grid fits the shared memory of one 8-CTA cluster) -------------------
+// (Experiment, off by default -- see cluster_plan() for the measurement.)
+// MVSEC-sized windows (5 x 260 x 346 fp32 = 1.8 MB) fit the distributed shared memory of a cluster of 8 CTAs
+// (8 x 225 KB).  One cluster then owns a window from the first vote to the normalised result: every CTA keeps
+// one eighth of the grid in its shared memory, votes are float atomics into the owning CTA's slice over DSMEM,
+// the non-zero statistics are reduced inside the cluster, and the finished grid goes to HBM exactly once.  HBM
+// traffic per window = 32 N bytes of events + one grid write, instead of memset + L2 atomics + a statistics read
+// + a read-modify-write for the normalisation; four launches (and the 2 us floor each has) become one.
+namespace cg = cooperative_groups;
+constexpr int kClusterSize = 8;
+constexpr int kClusterThreads = 1024;
+constexpr int kClusterScratchBytes = 1024;   // [3][32] warp partials + 3 doubles CTA partial + mean/std
+
+template <class Src>
+__global__ void __launch_bounds__(kClusterThreads, 1)
+voxel_cluster_kernel(const Src ev, const int64_t* __restrict__ offsets, int n_windows, int nb, int H, int W,
+                     int slice, int normalize, float* __restrict__ grid, int64_t* __restrict__ dropped,
+                     double* __restrict__ stats_out) {
+  extern __shared__ __align__(16) float cl_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / kClusterSize, n_clusters = gridDim.x / kClusterSize;
+  float* mine = cl_smem;
+  double* red = reinterpret_cast<double*>(cl_smem + slice);     // slice is a multiple of 4 floats
+  double* partial = red + 96;
+  float* ms = reinterpret_cast<float*>(partial + 3);
+  float* peer[kClusterSize];
+#pragma unroll
+  for (int r = 0; r < kClusterSize; ++r) peer[r] = cluster.map_shared_rank(mine, r);
+  const int64_t HW = (int64_t)H * W, vox = HW * nb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int w = cluster_id; w < n_windows; w += n_clusters) {
+    for (int i = threadIdx.x * 4; i < slice; i += kClusterThreads * 4)
+      *reinterpret_cast<float4*>(mine + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    cluster.sync();
+
+    const int64_t begin = offsets[w], end = offsets[w + 1];
+    const int64_t n = end - begin;
+    int ndrop = 0;
+    if (n > 0) {
+      const WindowTimes wt = window_times(ev, begin, end);
+      constexpr int kE = 4;
+      const int64_t stride = (int64_t)kClusterSize * kClusterThreads;
+      for (int64_t i0 = (int64_t)rank * kClusterThreads + threadIdx.x; i0 < n; i0 += stride * kE) {
+        EventRow rows[kE];
+#pragma unroll
+        for (int k = 0; k < kE; ++k)
+          if (i0 + k * stride < n) rows[k] = ev.load(begin + i0 + k * stride);
+#pragma unroll
+        for (int k = 0; k < kE; ++k) {
+          if (i0 + k * stride < n) {
+            const Vote v = make_vote(rows[k], wt.t_first, wt.dT, nb, W, HW, vox);
+            if (v.idx_left >= 0) {                    // vox < 2^31 on this path: 32-bit index arithmetic
+              const int il = (int)v.idx_left, r = il / slice;
+              atomicAdd(peer[r] + (il - r * slice), v.val_left);
+            }
+            if (v.idx_right >= 0) {
+              const int ir = (int)v.idx_right, r = ir / slice;
+              atomicAdd(peer[r] + (ir - r * slice), v.val_right);
+            }
+            ndrop += (int)v.oob_left + (int)v.oob_right;
+          }
+        }
+      }
+    }
+    if (dropped != nullptr && ndrop != 0)
+      atomicAdd(reinterpret_cast<unsigned long long*>(dropped), (unsigned long long)ndrop);
+    cluster.sync();
+
+    float mean = 0.f, sd = 0.f;
+    if (normalize) {
+      double c = 0, s = 0, q = 0;
+      for (int i = threadIdx.x * 4; i < slice; i += kClusterThreads * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(mine + i);   // cells past the window's end stay zero
+        accum_stat(v.x, c, s, q);
+        accum_stat(v.y, c, s, q);
+        accum_stat(v.z, c, s, q);
+        accum_stat(v.w, c, s, q);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) {
+        red[warp] = c;
+        red[32 + warp] = s;
+        red[64 + warp] = q;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double bc = 0, bs = 0, bq = 0;
+        for (int k = 0; k < kClusterThreads / 32; ++k) {
+          bc += red[k];
+          bs += red[32 + k];
+          bq += red[64 + k];
+        }
+        partial[0] = bc;
+        partial[1] = bs;
+        partial[2] = bq;
+      }
+      cluster.sync();
+      if (threadIdx.x == 0) {
+        double tc = 0, ts = 0, tq = 0;
+        for (int r = 0; r < kClusterSize; ++r) {       // rank order: every CTA derives identical statistics
+          const double* pr = cluster.map_shared_rank(partial, r);
+          tc += pr[0];
+          ts += pr[1];
+          tq += pr[2];
+        }
+        float m_ = 0.0f, sd_ = 0.0f;                    // same arithmetic as finish_stats
+        if (tc > 0) {
+          const double m = ts / tc;
+          m_ = (float)m;
+          if (tc > 1) {
+            double var = (tq - ts * m) / (tc - 1.0);
+            if (var < 0) var = 0;
+            sd_ = (float)sqrt(var);
+          } else {
+            sd_ = __int_as_float(0x7fc00000);
+          }
+        }
+        ms[0] = m_;
+        ms[1] = sd_;
+        if (stats_out != nullptr && rank == 0) {
+          stats_out[3 * w + 0] = tc;
+          stats_out[3 * w + 1] = (double)m_;
+          stats_out[3 * w + 2] = (double)sd_;
+        }
+      }
+      __syncthreads();
+      mean = ms[0];
+      sd = ms[1];
+    }
+    const bool divide = sd > 0.0f;
+    float* out = grid + (int64_t)w * vox + (int64_t)rank * slice;
+    const int64_t left = vox - (int64_t)rank * slice;             // cells of this slice inside the window
+    const int valid = (int)(left < 0 ? 0 : (left < slice ? left : slice));
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int nvec = vec_ok ? valid / 4 : 0;
+    for (int i = threadIdx.x; i < nvec; i += kClusterThreads) {
+      float4 v = *reinterpret_cast<const float4*>(mine + 4 * i);
+      if (normalize) {
+        v.x = normalize_one(v.x, mean, sd, divide);
+        v.y = normalize_one(v.y, mean, sd, divide);
+        v.z = normalize_one(v.z, mean, sd, divide);
+        v.w = normalize_one(v.w, mean, sd, divide);
+      }
+      st_stream4(out + 4 * i, v);
+    }
+    for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads)
+      out[i] = normalize ? normalize_one(mine[i], mean, sd, divide) : mine[i];
+    // no barrier needed here: the next window's first cluster.sync() orders this slice's reuse
+  }
+  cluster.sync();   // keep every CTA's shared memory alive until all peers are done with it
+}
+
 int bit_length(uint64_t v) {
   int b = 0;
   while (v) {
@@ -689,6 +851,68 @@ int time_lanes(int dflt) {
   return dflt;
 }
 
+// Cluster-resident path: possible when one window's grid fits the shared memory of an 8-CTA cluster.
+// MEASURED SLOWER than the L2-atomic path and therefore only taken when forced (EEM_VOXEL_PATH=cluster):
+// sm_100a has no native fp32 add on shared memory -- atomicAdd on (distributed) shared memory compiles to
+// ATOMS.CAST.SPIN / ATOM.E.CAST.SPIN compare-and-swap loops, and over the cluster network each one is a remote
+// round trip: MVSEC x64 windows take 277 us here against 156 us for memset + RED.ADD.F32 in L2 + stats + apply
+// (profiles/r01/README.md).  Kept as a tested experiment for parts that get a native shared-memory float RED.
+struct ClusterPlan {
+  bool ok;
+  int slice;          // floats of the window grid held by each CTA
+  size_t smem;
+  int max_clusters;   // co-resident clusters on this device
+};
+
+template <class Src>
+ClusterPlan cluster_plan(int64_t vox, int n_windows, int64_t n_total) {
+  ClusterPlan pl{false, 0, 0, 0};
+  if (const char* v = getenv("EEM_VOXEL_PATH")) {   // timing experiments only
+    if (v[0] == 'd' || v[0] == 'p') return pl;
+  }
+  if (vox >= (1ll << 31)) return pl;
+  pl.slice = (int)align_up((size_t)ceil_div(vox, kClusterSize), 4);
+  pl.smem = (size_t)pl.slice * sizeof(float) + kClusterScratchBytes;
+  int dev = 0, optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return pl;
+  if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return pl;
+  if (pl.smem > (size_t)optin) return pl;
+  static std::mutex mu;
+  static size_t configured = 0;
+  static int cached_clusters = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (pl.smem > configured || cached_clusters == 0) {
+    if (cudaFuncSetAttribute(voxel_cluster_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) {
+      cudaGetLastError();
+      return pl;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kClusterSize, 1, 1);
+    cfg.blockDim = dim3(kClusterThreads, 1, 1);
+    cfg.dynamicSmemBytes = pl.smem;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kClusterSize;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, voxel_cluster_kernel<Src>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return pl;
+    }
+    configured = pl.smem;
+    cached_clusters = n;
+  }
+  pl.max_clusters = cached_clusters;
+  const int active = n_windows < pl.max_clusters ? n_windows : pl.max_clusters;
+  (void)active;
+  (void)n_total;
+  pl.ok = getenv("EEM_VOXEL_PATH") != nullptr && getenv("EEM_VOXEL_PATH")[0] == 'c';
+  return pl;
+}
+
 int launch_normalize(float* grid, int n_windows, int64_t vox, double* stats_out, char* ws, cudaStream_t stream) {
   const StatLayout L = stat_layout(n_windows);
   StatPartial* partials = reinterpret_cast<StatPartial*>(ws + L.partials);
@@ -741,6 +965,28 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
 
   const bool no_events = (n_total == 0 || max_events_per_window == 0);
   const bool pair = !no_events && mode == EEM_VOXEL_ATOMIC && use_pair_path(n_total, total_vox);
+  if (!no_events && mode == EEM_VOXEL_ATOMIC && !pair && (reinterpret_cast<uintptr_t>(grid) & 15) == 0) {
+    const ClusterPlan pl = cluster_plan<Src>(vox, n_windows, n_total);
+    if (pl.ok) {
+      const int n_clusters = n_windows < pl.max_clusters ? n_windows : pl.max_clusters;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(n_clusters * kClusterSize), 1, 1);
+      cfg.blockDim = dim3(kClusterThreads, 1, 1);
+      cfg.dynamicSmemBytes = pl.smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = kClusterSize;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      EEM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, voxel_cluster_kernel<Src>, events, offsets, n_windows, num_bins, height, width,
+                                        pl.slice, normalize, grid, dropped, stats_out));
+      EEM_CHECK_LAUNCH("voxel_cluster_kernel");
+      return EEM_OK;
+    }
+  }
   if (!pair) EEM_CHECK_CUDA(cudaMemsetAsync(grid, 0, (size_t)total_vox * sizeof(float), stream));
 
   if (no_events) {

@@ -89,6 +89,12 @@ def bench_voxel():
         os.environ.pop("EEM_VOXEL_PATH")
         s = timeit(lambda: ops.voxelize(d_ev, d_off, n, nb, h, w, normalize=True, out=out))
         row("K1+K2 voxelize+normalize/auto", label, s, vox_bytes + 12 * nb * h * w * nwin)
+        # packed columns (eem_voxelize_soa): t f64, x/y int16, p int8 = 13 B/event
+        d_t = d_ev[:, 0].contiguous()
+        d_x, d_y, d_p = d_ev[:, 1].to(torch.int16), d_ev[:, 2].to(torch.int16), d_ev[:, 3].to(torch.int8)
+        s = timeit(lambda: ops.voxelize_soa(d_t, d_x, d_y, d_p, d_off, n, nb, h, w, normalize=True, out=out))
+        row("K1+K2 voxelize_soa+normalize/auto", label, s, 13 * n * nwin + 4 * nb * h * w * nwin + 12 * nb * h * w * nwin, note="13 B/event")
+        del d_t, d_x, d_y, d_p
         s2 = timeit(lambda: ops.voxel_normalize_(out))
         row("K2 voxel_normalize", label, s2, 12 * nb * h * w * nwin)
         if n * nwin <= 12_000_000:

@@ -156,11 +156,13 @@ def test_device_contract_and_errors(V):
     V(5, gpu=True, forkserver=False)(Seq(bad, 32, 48))            # non-strict: vote dropped, no error
 
 
-def test_pair_layout_path_parity(golden, V, monkeypatch):
-    """The event-dominated path (scratch pair layout, one vector RED per event, fused combine + stats) is
-    normally chosen only when a call has >= 2 events per voxel; force it and repeat the parity checks,
-    including the reference's row-wrap and dropped-vote corner cases."""
-    monkeypatch.setenv("EEM_VOXEL_PATH", "pair")
+@pytest.mark.parametrize("path", ["pair", "direct", "cluster"])
+def test_forced_vote_path_parity(golden, V, monkeypatch, path):
+    """The atomic mode has three implementations chosen by size: cluster-resident (a window's grid lives in the
+    shared memory of an 8-CTA cluster; MVSEC-sized windows), direct L2 atomics, and the pair layout (>= 2 events
+    per voxel).  Force each one and repeat the parity checks, including the reference's row-wrap and
+    dropped-vote corner cases (a forced cluster path falls back to direct for grids that do not fit)."""
+    monkeypatch.setenv("EEM_VOXEL_PATH", path)
     g = golden("voxel")
     for name in cases_of(g):
         nb, h, w = (int(v) for v in g[f"{name}__shape"])
@@ -178,11 +180,16 @@ def test_pair_layout_path_parity(golden, V, monkeypatch):
         ref_norm = ref_ops.voxelize(ev, nb, h, w, normalize=True).numpy()
         out_n = V(nb, gpu=True, normalize=True, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
         assert rel_close(out_n, ref_norm).all(), np.abs(out_n - ref_norm).max()
-    # ragged batch through the pair path
-    seqs = [Seq(make_events(rng, n, 64, 96), 64, 96) for n in (1, 2, 777, 5000, 31, 12345)]
+    # ragged batch through the forced path (more windows than co-resident clusters for the cluster path)
+    seqs = [Seq(make_events(rng, n, 64, 96), 64, 96) for n in (1, 2, 777, 5000, 31, 12345) * 7]
     batch = V(5, gpu=True, normalize=True, forkserver=False).voxelize_batch(seqs).cpu().numpy()
     for k, s in enumerate(seqs):
         assert rel_close(batch[k], ref_ops.voxelize(s.features, 5, 64, 96, normalize=True).numpy()).all(), k
+    # strict mode still sees dropped votes
+    bad = make_events(rng, 2000, 64, 96)
+    bad[7, 2] = 5000.0
+    with pytest.raises(IndexError):
+        V(5, gpu=True, forkserver=False, strict=True)(Seq(bad, 64, 96))
     # out-of-grid votes are dropped (and counted in strict mode) on this path too
     bad = make_events(rng, 1000, 32, 48)
     bad[10, 2] = 4000.0

@@ -103,7 +103,7 @@ class _PinnedStage:
         self.buf = None
         self.off = None
         self.done = None
-        self.dev_buf = None       # grow-only device copy; reuse is ordered by the stream the caller runs on
+        self.dev_buf = {}         # grow-only device copy per (device, stream): reuse is ordered by that stream
 
     def upload(self, arrays: Sequence[numpy.ndarray], device: torch.device):
         counts = [int(a.shape[0]) for a in arrays]
@@ -127,9 +127,11 @@ class _PinnedStage:
                     pos += n
                 ev = self.buf[:total].to(device, non_blocking=True)
             else:
-                if self.dev_buf is None or self.dev_buf.shape[0] < total or self.dev_buf.device != torch.device(device):
-                    self.dev_buf = torch.empty((total, 4), dtype=torch.float64, device=device)
-                ev = self.dev_buf[:total]
+                key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+                buf = self.dev_buf.get(key)
+                if buf is None or buf.shape[0] < total:
+                    buf = self.dev_buf[key] = torch.empty((total, 4), dtype=torch.float64, device=device)
+                ev = buf[:total]
                 tasks, pos = [], 0
                 for a, n in zip(arrays, counts):
                     for lo in range(0, n, _STAGE_CHUNK_ROWS):

@@ -480,7 +480,8 @@ def main():
             ready.record(cur)
             with torch.cuda.stream(comm):
                 comm.wait_event(ready)
-                edist.gather_batch(snap[k], total=world * args.batch, out=gathered[k])
+                if os.environ.get("EEM_BENCH_GATHER", "1") != "0":     # timing experiments only
+                    edist.gather_batch(snap[k], total=world * args.batch, out=gathered[k])
                 edist.reduce_metrics(flow_error_stats(flow_gt, snap[k]))   # EPE sums / counts of this rank's pairs
                 snap_free[k] = torch.cuda.Event()
                 snap_free[k].record(comm)

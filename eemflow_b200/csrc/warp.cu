@@ -211,15 +211,38 @@ scale_uv_kernel(float* __restrict__ flow, int B, int C, int64_t plane, float s0,
   }
 }
 
+// Thread = V horizontally adjacent output pixels (one V-wide streaming store), looping over a strided set of
+// planes so a few thousand fat CTAs cover the tensor instead of one tiny CTA per (tile, plane).
+template <int V>
 __global__ void __launch_bounds__(256)
 replicate_pad_kernel(const float* __restrict__ in, int64_t n_planes, int H, int W, int left, int top,
                      int Ho, int Wo, float* __restrict__ out) {
-  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int X = (blockIdx.x * 32 + (threadIdx.x & 31)) * V;
   const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (X >= Wo || Y >= Ho) return;
-  const int sx = min(max(X - left, 0), W - 1), sy = min(max(Y - top, 0), H - 1);
-  for (int64_t pl = blockIdx.z; pl < n_planes; pl += gridDim.z)
-    out[pl * Ho * Wo + (int64_t)Y * Wo + X] = __ldg(in + pl * H * W + (int64_t)sy * W + sx);
+  const int sy = min(max(Y - top, 0), H - 1);
+  int sx[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) sx[i] = min(max(X + i - left, 0), W - 1);
+  const int64_t ip = (int64_t)H * W, op = (int64_t)Ho * Wo;
+  const float* src = in + (int64_t)blockIdx.z * ip + (int64_t)sy * W;
+  float* dst = out + (int64_t)blockIdx.z * op + (int64_t)Y * Wo + X;
+  const int64_t s_step = (int64_t)gridDim.z * ip, d_step = (int64_t)gridDim.z * op;
+#pragma unroll 4
+  for (int64_t pl = blockIdx.z; pl < n_planes; pl += gridDim.z) {
+    float v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = ld_stream(src + sx[i]);
+    if constexpr (V == 4) {
+      st_stream4(dst, make_float4(v[0], v[1], v[2], v[3]));
+    } else if constexpr (V == 2) {
+      asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(dst), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+      st_stream(dst, v[0]);
+    }
+    src += s_step;
+    dst += d_step;
+  }
 }
 
 // bilinear_sampler (model/model_utils.py:7-15): img [N,C,H,W], coords [N,Ho,Wo,2] in pixels, sampled
@@ -316,8 +339,18 @@ int eem_replicate_pad(const float* in, int B, int C, int H, int W, int left, int
   EEM_CHECK_ARG(left >= 0 && right >= 0 && top >= 0 && bottom >= 0, "eem_replicate_pad: negative padding");
   const int Ho = H + top + bottom, Wo = W + left + right;
   const int64_t planes = (int64_t)B * C;
-  dim3 grid((unsigned)ceil_div(Wo, 32), (unsigned)ceil_div(Ho, 8), (unsigned)(planes < 65535 ? planes : 65535));
-  replicate_pad_kernel<<<grid, 256, 0, as_stream(stream_)>>>(in, planes, H, W, left, top, Ho, Wo, out);
+  const int V = (Wo % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) ? 4
+              : (Wo % 2 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0) ? 2 : 1;
+  const int64_t blocks_xy = ceil_div(Wo, 32 * V) * ceil_div(Ho, 8);
+  int64_t gz = ceil_div((int64_t)sm_count() * 16, blocks_xy);      // ~16 CTAs per SM, planes looped inside
+  if (gz < 1) gz = 1;
+  if (gz > planes) gz = planes;
+  if (gz > 65535) gz = 65535;
+  dim3 grid((unsigned)ceil_div(Wo, 32 * V), (unsigned)ceil_div(Ho, 8), (unsigned)gz);
+  cudaStream_t stream = as_stream(stream_);
+  if (V == 4) replicate_pad_kernel<4><<<grid, 256, 0, stream>>>(in, planes, H, W, left, top, Ho, Wo, out);
+  else if (V == 2) replicate_pad_kernel<2><<<grid, 256, 0, stream>>>(in, planes, H, W, left, top, Ho, Wo, out);
+  else replicate_pad_kernel<1><<<grid, 256, 0, stream>>>(in, planes, H, W, left, top, Ho, Wo, out);
   EEM_CHECK_LAUNCH("replicate_pad_kernel");
   return EEM_OK;
 }

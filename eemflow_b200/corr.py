@@ -73,8 +73,10 @@ def bilinear_sampler(img, coords, mode='bilinear', mask=False):
         return ops.bilinear_sample(img, coords, mask=mask)
 
 
-def coords_grid(batch, ht, wd):
-    coords = torch.meshgrid(torch.arange(ht), torch.arange(wd), indexing='ij')
+def coords_grid(batch, ht, wd, device=None):
+    """model/model_utils.py:24-27; `device` (extra, optional) builds the grid there directly, which keeps a model
+    forward free of host->device copies and therefore capturable in a CUDA graph."""
+    coords = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing='ij')
     coords = torch.stack(coords[::-1], dim=0).float()
     return coords[None].repeat(batch, 1, 1, 1)
 

@@ -301,7 +301,7 @@ class ERAFT(nn.Module):
     def initialize_flow(self, img):
         from .corr import coords_grid
         n, _, h, w = img.shape
-        return coords_grid(n, h // 8, w // 8).to(img.device), coords_grid(n, h // 8, w // 8).to(img.device)
+        return coords_grid(n, h // 8, w // 8, device=img.device), coords_grid(n, h // 8, w // 8, device=img.device)
 
     def upsample_flow(self, flow, mask):
         """[N,2,H/8,W/8] -> [N,2,H,W] by the learned convex combination of the 3x3 coarse neighbours."""
@@ -329,3 +329,43 @@ class ERAFT(nn.Module):
             flow_up = upflow8(coords1 - coords0) if up_mask is None else self.upsample_flow(coords1 - coords0, up_mask)
             flow_predictions.append(self.image_padder.unpad(flow_up))
         return (events1, events2), flow_predictions
+
+
+class GraphedInference:
+    """Replay a model's inference forward as ONE CUDA graph per input shape.
+
+    At small batch the reference-shaped forward is launch-bound (EEMFlow_cdc: ~150 kernels, 5 ms per MVSEC pair
+    eager on a B200 for ~1 ms of device work).  The first call with a new (shape, dtype, kwargs) runs the model a
+    few times on a side stream (cuDNN autotuning, scratch allocation), captures one forward, and later calls copy
+    the inputs into the captured buffers and replay.  Inference only (`torch.no_grad`); the returned flow tensors
+    are the graph's output buffers and stay valid until the next call with the same shape.
+    """
+
+    def __init__(self, model: nn.Module, warmup: int = 3):
+        self.model = model
+        self.warmup = warmup
+        self._captured = {}
+
+    def change_imagesize(self, img_size):
+        self.model.change_imagesize(img_size)
+
+    def __call__(self, events1, events2, **kwargs):
+        key = (tuple(events1.shape), events1.dtype, events1.device, tuple(sorted(kwargs.items())), getattr(self.model, "image_size", None))
+        entry = self._captured.get(key)
+        if entry is None:
+            static1, static2 = events1.clone(), events2.clone()
+            side = torch.cuda.Stream(events1.device)
+            side.wait_stream(torch.cuda.current_stream(events1.device))
+            with torch.no_grad(), torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self.model(events1=static1, events2=static2, **kwargs)
+            torch.cuda.current_stream(events1.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                _, flows = self.model(events1=static1, events2=static2, **kwargs)
+            entry = self._captured[key] = (graph, static1, static2, flows)
+        graph, static1, static2, flows = entry
+        static1.copy_(events1, non_blocking=True)
+        static2.copy_(events2, non_blocking=True)
+        graph.replay()
+        return (events1, events2), flows

@@ -6,15 +6,18 @@ build container are quoted in profiles/r01/README.md."""
 import sys, time, statistics
 sys.path.insert(0, ".")
 import torch
-from eemflow_b200.models import EEMFlow_cdc, ERAFT
+from eemflow_b200.models import EEMFlow_cdc, ERAFT, GraphedInference
 
 dev = torch.device("cuda:0")
 torch.backends.cudnn.benchmark = True
 
-def run(model, nb, h, w, batch, iters=5, **kw):
+def run(model, nb, h, w, batch, iters=5, graphed=False, **kw):
     v1 = torch.randn(batch, nb, h, w, device=dev)
     v2 = torch.randn(batch, nb, h, w, device=dev)
     model.change_imagesize((h, w))
+    if graphed:
+        g = GraphedInference(model)
+        model = lambda events1, events2, **k: g(events1, events2, **k)
     with torch.no_grad():
         for _ in range(2):
             model(events1=v1, events2=v2, **kw)
@@ -26,8 +29,8 @@ def run(model, nb, h, w, batch, iters=5, **kw):
             ts.append(a.elapsed_time(b))
     return statistics.median(ts)
 
-print("| model | resolution | batch | ms / forward | frame pairs / s | peak mem GB |")
-print("|---|---|---:|---:|---:|---:|")
+print("| model | resolution | batch | ms / forward | frame pairs / s | peak mem GB | one CUDA graph: ms | pairs / s |")
+print("|---|---|---:|---:|---:|---:|---:|---:|")
 for name, ctor, kw in (("EEMFlow_cdc", lambda nb: EEMFlow_cdc(None, groups=3, n_first_channels=nb), {}),
                        ("ERAFT (12 iters, tf32 volume)", lambda nb: ERAFT(None, n_first_channels=nb), {"iters": 12})):
     for res, nb, h, w, batches in (("MVSEC 260x346", 5, 260, 346, (1, 8, 32, 128)), ("HREM 720x1280", 15, 720, 1280, (1, 2, 4, 8, 16, 32))):
@@ -40,6 +43,8 @@ for name, ctor, kw in (("EEMFlow_cdc", lambda nb: EEMFlow_cdc(None, groups=3, n_
                 print(f"| {name} | {res} | {B} | OOM | | |", flush=True)
                 torch.cuda.empty_cache()
                 break
-            print(f"| {name} | {res} | {B} | {ms:.1f} | {B / ms * 1e3:.1f} | {torch.cuda.max_memory_allocated() / 1e9:.1f} |", flush=True)
+            mem = torch.cuda.max_memory_allocated() / 1e9
+            gms = run(model, nb, h, w, B, graphed=True, **kw) if B <= 8 else float("nan")
+            print(f"| {name} | {res} | {B} | {ms:.1f} | {B / ms * 1e3:.1f} | {mem:.1f} | {gms:.2f} | {B / gms * 1e3:.1f} |", flush=True)
         del model
         torch.cuda.empty_cache()

@@ -843,6 +843,15 @@ bool use_pair_path(int64_t n_total, int64_t total_vox) {
   return n_total >= 2 * total_vox;
 }
 
+int64_t l2_group_bytes() {
+  if (const char* v = getenv("EEM_VOXEL_GROUP_MB")) {   // timing experiments only; 0 disables the grouping
+    const long mb = atol(v);
+    if (mb == 0) return (int64_t)1 << 62;
+    if (mb > 0) return (int64_t)mb << 20;
+  }
+  return (int64_t)60 << 20;
+}
+
 int time_lanes(int dflt) {
   if (const char* v = getenv("EEM_VOXEL_LANES")) {   // timing experiments only
     const int n = atoi(v);
@@ -958,6 +967,25 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
     if (workspace == nullptr || workspace_bytes < need)
       return fail(EEM_ERR_WORKSPACE, "eem_voxelize: workspace of %zu bytes required, got %zu", need, workspace_bytes);
     EEM_CHECK_ALIGNED(workspace, 256);
+  }
+  // Many small windows whose grids together exceed the L2: run them in groups whose grids fit (~half of the
+  // 126 MB L2), so the memset, the L2-resolved votes, the statistics read and the normalisation read-modify-write
+  // of a group all hit L2 and HBM only sees the events and one write-back of each grid.
+  if (mode == EEM_VOXEL_ATOMIC && n_windows > 1 && total_vox * (int64_t)sizeof(float) > l2_group_bytes() &&
+      vox * (int64_t)sizeof(float) <= l2_group_bytes()) {
+    const int per_group = (int)(l2_group_bytes() / (vox * (int64_t)sizeof(float)));
+    const int n_groups = (int)ceil_div(n_windows, per_group);
+    const int even = (int)ceil_div(n_windows, n_groups);             // equal-sized groups
+    for (int w0 = 0; w0 < n_windows; w0 += even) {
+      const int nw = n_windows - w0 < even ? n_windows - w0 : even;
+      int64_t n_est = ceil_div(n_total * nw, n_windows);
+      if (n_est < max_events_per_window) n_est = max_events_per_window;
+      const int rc = voxelize_impl<Src>(events, offsets + w0, nw, n_est, max_events_per_window, num_bins, height, width, mode,
+                                        normalize, grid + (int64_t)w0 * vox, dropped, stats_out ? stats_out + 3 * w0 : nullptr,
+                                        workspace, workspace_bytes, stream_);
+      if (rc != EEM_OK) return rc;
+    }
+    return EEM_OK;
   }
   char* ws = static_cast<char*>(workspace);
   char* ws_stats = ws;                                             // [stats | mode-specific]

@@ -11,6 +11,7 @@
 // fetched once per position, all loads in flight together), then warp `a` / lane `position`
 // produces the 2r+1 outputs of window column `a`, so every store instruction writes 32
 // consecutive positions of one output channel (128 B).
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -46,23 +47,28 @@ __device__ __forceinline__ float roundtrip(float p, int size) {
 // down the rows, so consecutive lanes read consecutive addresses of a window row; (3) interpolation
 // with warp = window column, lane = position, so each store instruction writes 32 consecutive
 // positions of one output channel (128 B).  Two block barriers in total.
-template <int R>
+template <int R, int PB>
 struct LookupSmem {
   static constexpr int K = 2 * R + 1, T = K + 1, TT = T * T;
   // tap stride per position: == T+1 (mod 32) so the T lanes of consecutive positions written by one
   // cp.async instruction land in disjoint banks, and odd so lane = position reads are conflict-free
   static constexpr int kStride = TT + ((T + 1 - TT % 32 + 32) % 32);
   static constexpr int kColsPerTask = 3, kGroups = (K + kColsPerTask - 1) / kColsPerTask;
-  // threads: >= 32*T for the gather phase, and 4*kGroups warps so a 4-level pyramid is one task per warp
-  static constexpr int kThreads = 32 * (T > 4 * kGroups ? T : 4 * kGroups);
-  static constexpr int kPerLevelFloats = kPosPerBlock * kStride + 2 * kPosPerBlock * K;
-  static constexpr int kPerLevelBytes = kPerLevelFloats * 4 + kPosPerBlock * 2 * 4;
+  // threads: >= PB*T for the gather phase, and enough (32/PB)-position slots that a 4-level pyramid is one
+  // interpolation task per slot
+  static constexpr int kSlotsPerWarp = 32 / PB;
+  static constexpr int kGatherWarps = (PB * T + 31) / 32;
+  static constexpr int kTaskWarps = (4 * kGroups + kSlotsPerWarp - 1) / kSlotsPerWarp;
+  static constexpr int kThreads = 32 * (kGatherWarps > kTaskWarps ? kGatherWarps : kTaskWarps);
+  static constexpr int kPerLevelFloats = PB * kStride + 2 * PB * K;
+  static constexpr int kPerLevelBytes = kPerLevelFloats * 4 + PB * 2 * 4;
 };
 
-template <int R>
-__global__ void __launch_bounds__(LookupSmem<R>::kThreads)
+template <int R, int PB>
+__global__ void __launch_bounds__(LookupSmem<R, PB>::kThreads)
 corr_lookup_kernel(const __grid_constant__ LookupParams p) {
-  using S = LookupSmem<R>;
+  using S = LookupSmem<R, PB>;
+  constexpr int kPosPerBlock = PB;   // shadows the file-level default inside this kernel
   constexpr int K = S::K, T = S::T, kStride = S::kStride;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -143,11 +149,14 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
   //    (adjacent columns share a tap), then combines with the previous row: (G+1)*T tap loads per
   //    G*K outputs, and every store instruction writes 32 consecutive positions of one channel.
   constexpr int G = S::kColsPerTask, kGroups = S::kGroups;
-  const int n_warps = blockDim.x >> 5;
-  if (lane < npos) {
-    for (int task = warp; task < L * kGroups; task += n_warps) {
+  // slot = a group of PB lanes working on one task; with PB = 16 a warp runs two tasks side by side
+  const int n_slots = (blockDim.x >> 5) * S::kSlotsPerWarp;
+  const int slot = warp * S::kSlotsPerWarp + lane / PB;
+  const int lane_pos = lane % PB;
+  if (lane_pos < npos) {
+    for (int task = slot; task < L * kGroups; task += n_slots) {
       const int l = task / kGroups, a0 = (task - l * kGroups) * G;
-      float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a0 * K) * P + i0 + lane;
+      float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a0 * K) * P + i0 + lane_pos;
       if ((int64_t)p.h[l] * p.w[l] == 0) {  // level pooled away: an empty map contributes zeros
 #pragma unroll
         for (int g = 0; g < G; ++g)
@@ -156,11 +165,11 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
             for (int c = 0; c < K; ++c) st_stream(o + (int64_t)(g * K + c) * P, 0.f);
         continue;
       }
-      const float* tp = taps_of(l) + lane * kStride + a0;
-      const float* fyp = fy_of(l) + lane * K;
+      const float* tp = taps_of(l) + lane_pos * kStride + a0;
+      const float* fyp = fy_of(l) + lane_pos * K;
       float fx[G], prev[G];
 #pragma unroll
-      for (int g = 0; g < G; ++g) fx[g] = (a0 + g < K) ? fx_of(l)[lane * K + a0 + g] : 0.f;
+      for (int g = 0; g < G; ++g) fx[g] = (a0 + g < K) ? fx_of(l)[lane_pos * K + a0 + g] : 0.f;
       {
         float t[G + 1];
 #pragma unroll
@@ -186,21 +195,34 @@ corr_lookup_kernel(const __grid_constant__ LookupParams p) {
   }
 }
 
-template <int R>
-int launch_lookup(const LookupParams& p, dim3 grid, cudaStream_t stream) {
-  using S = LookupSmem<R>;
+template <int R, int PB>
+int launch_lookup(const LookupParams& p, cudaStream_t stream) {
+  using S = LookupSmem<R, PB>;
   const size_t smem = (size_t)p.L * S::kPerLevelBytes;
+  dim3 grid((unsigned)ceil_div(p.H * p.W, PB), (unsigned)p.B);
   static std::mutex mu;
   static size_t configured = 0;
   {
     std::lock_guard<std::mutex> lock(mu);
     if (smem > configured) {
-      EEM_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      EEM_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<R, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
   }
-  corr_lookup_kernel<R><<<grid, S::kThreads, smem, stream>>>(p);
+  corr_lookup_kernel<R, PB><<<grid, S::kThreads, smem, stream>>>(p);
   return EEM_OK;
+}
+
+// Positions per CTA: 32.  EEM_LOOKUP_PB=16 selects a CTA with half the shared memory (~7 instead of 3 CTAs per
+// SM, two interpolation tasks per warp) for timing comparisons: measured SLOWER on B200 (50.3 vs 40.0 us per
+// launch at MVSEC B=32), so more phase-staggered CTAs is not what the kernel lacks (profiles/r01/README.md).
+template <int R>
+int launch_lookup_any(const LookupParams& p, cudaStream_t stream) {
+  static const int pb = [] {
+    const char* v = getenv("EEM_LOOKUP_PB");
+    return (v != nullptr && atoi(v) == 16) ? 16 : 32;
+  }();
+  return pb == 32 ? launch_lookup<R, 32>(p, stream) : launch_lookup<R, 16>(p, stream);
 }
 
 __global__ void __launch_bounds__(256)
@@ -373,15 +395,13 @@ int eem_corr_lookup(const float* const* levels, int B, int H, int W, int num_lev
   p.B = B; p.H = H; p.W = W; p.L = num_levels;
   p.coords = coords;
   p.out = out;
-  const int P = H * W;
-  dim3 grid((unsigned)ceil_div(P, kPosPerBlock), (unsigned)B);
   cudaStream_t stream = as_stream(stream_);
   int rc = EEM_OK;
   switch (radius) {
-    case 4: rc = launch_lookup<4>(p, grid, stream); break;
-    case 3: rc = launch_lookup<3>(p, grid, stream); break;
-    case 2: rc = launch_lookup<2>(p, grid, stream); break;
-    case 1: rc = launch_lookup<1>(p, grid, stream); break;
+    case 4: rc = launch_lookup_any<4>(p, stream); break;
+    case 3: rc = launch_lookup_any<3>(p, stream); break;
+    case 2: rc = launch_lookup_any<2>(p, stream); break;
+    case 1: rc = launch_lookup_any<1>(p, stream); break;
     default:
       return fail(EEM_ERR_UNSUPPORTED, "eem_corr_lookup: radius %d not in {1,2,3,4}", radius);
   }

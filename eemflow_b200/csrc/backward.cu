@@ -185,51 +185,74 @@ __device__ __forceinline__ void source_index(int dst, int in_size, int out_size,
   l0 = 1.f - l1;
 }
 
-// thread = INPUT cell (gather form): it visits the output pixels whose interpolation footprint
-// contains the cell, so there are no atomics and the result is deterministic.  For up-sampling a
-// cell's footprint is the output range that maps into (cell-1, cell+1).
+// ATen's source index with the scale hoisted (same value: it is formed by the same fp32 division).
+__device__ __forceinline__ void source_index_s(int dst, int in_size, float scale, int align_corners, int& i0, int& i1,
+                                               float& l0, float& l1) {
+  float src;
+  if (align_corners) {
+    src = scale * (float)dst;
+  } else {
+    src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+// WARP = one input cell of one plane (gather form): its lanes stride over the output pixels whose interpolation
+// footprint contains the cell and combine with a fixed shuffle tree, so there are no atomics and the result is
+// deterministic.  (One thread per cell serialised the 100 x 100-pixel footprints of the model's final 4x5 ->
+// full-resolution upsamples: 2.9 ms of a 14 ms training step.)
 __global__ void __launch_bounds__(256)
 bilinear_resize_backward_kernel(const float* __restrict__ gout, int B, int C, int h, int w, int H, int W,
                                 int align_corners, float scale0, float scale1, float scale_rest,
                                 float* __restrict__ gin) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= w || y >= h) return;
-  // conservative output ranges that can touch input row y / column x
+  const int lane = threadIdx.x & 31;
+  const int64_t cells = (int64_t)B * C * h * w;
   const float sy = align_corners ? (H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f) : (float)h / (float)H;
   const float sx = align_corners ? (W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f) : (float)w / (float)W;
-  int Y0 = 0, Y1 = H - 1, X0 = 0, X1 = W - 1;
-  if (sy > 0.f) {
-    const float off = align_corners ? 0.f : 0.5f;
-    Y0 = max(0, (int)floorf(((float)(y - 1) + off) / sy - off) - 1);
-    Y1 = min(H - 1, (int)ceilf(((float)(y + 1) + off) / sy - off) + 1);
-  }
-  if (sx > 0.f) {
-    const float off = align_corners ? 0.f : 0.5f;
-    X0 = max(0, (int)floorf(((float)(x - 1) + off) / sx - off) - 1);
-    X1 = min(W - 1, (int)ceilf(((float)(x + 1) + off) / sx - off) + 1);
-  }
-  const int64_t ip = (int64_t)h * w, op = (int64_t)H * W;
-  for (int bc = blockIdx.z; bc < B * C; bc += gridDim.z) {
-    const int c = bc % C;
-    const float* g = gout + (int64_t)bc * op;
+  const float off = align_corners ? 0.f : 0.5f;
+  const int64_t op = (int64_t)H * W;
+  for (int64_t cell = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); cell < cells; cell += (int64_t)gridDim.x * 8) {
+    const int x = (int)(cell % w);
+    const int y = (int)((cell / w) % h);
+    const int64_t bc = cell / ((int64_t)w * h);
+    // conservative output ranges that can touch input row y / column x
+    int Y0 = 0, Y1 = H - 1, X0 = 0, X1 = W - 1;
+    if (sy > 0.f) {
+      Y0 = max(0, (int)floorf(((float)(y - 1) + off) / sy - off) - 1);
+      Y1 = min(H - 1, (int)ceilf(((float)(y + 1) + off) / sy - off) + 1);
+    }
+    if (sx > 0.f) {
+      X0 = max(0, (int)floorf(((float)(x - 1) + off) / sx - off) - 1);
+      X1 = min(W - 1, (int)ceilf(((float)(x + 1) + off) / sx - off) + 1);
+    }
+    const float* g = gout + bc * op;
     float acc = 0.f;
     for (int Y = Y0; Y <= Y1; ++Y) {
       int y0, y1;
       float ly0, ly1;
-      source_index(Y, h, H, align_corners, y0, y1, ly0, ly1);
+      source_index_s(Y, h, sy, align_corners, y0, y1, ly0, ly1);
       const float wy = (y0 == y ? ly0 : 0.f) + (y1 == y ? ly1 : 0.f);
-      if (wy == 0.f) continue;
-      for (int X = X0; X <= X1; ++X) {
+      if (wy == 0.f) continue;                               // warp-uniform
+      for (int X = X0 + lane; X <= X1; X += 32) {
         int x0, x1;
         float lx0, lx1;
-        source_index(X, w, W, align_corners, x0, x1, lx0, lx1);
+        source_index_s(X, w, sx, align_corners, x0, x1, lx0, lx1);
         const float wx = (x0 == x ? lx0 : 0.f) + (x1 == x ? lx1 : 0.f);
         if (wx != 0.f) acc = fmaf(wy * wx, __ldg(g + (int64_t)Y * W + X), acc);
       }
     }
-    const float sc = c == 0 ? scale0 : (c == 1 ? scale1 : scale_rest);
-    gin[(int64_t)bc * ip + (int64_t)y * w + x] = acc * sc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const int c = (int)(bc % C);
+      const float sc = c == 0 ? scale0 : (c == 1 ? scale1 : scale_rest);
+      gin[cell] = acc * sc;
+    }
   }
 }
 
@@ -291,10 +314,12 @@ int eem_bilinear_resize_backward(const float* grad_out, int B, int C, int h, int
                                  float scale0, float scale1, float scale_rest, float* grad_in, eem_stream_t stream_) {
   EEM_CHECK_ARG(grad_out && grad_in, "eem_bilinear_resize_backward: NULL pointer");
   EEM_CHECK_ARG(B > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "eem_bilinear_resize_backward: sizes must be > 0");
-  const int64_t bc = (int64_t)B * C;
-  dim3 grid((unsigned)ceil_div(w, 32), (unsigned)ceil_div(h, 8), (unsigned)(bc < 65535 ? bc : 65535));
-  bilinear_resize_backward_kernel<<<grid, 256, 0, as_stream(stream_)>>>(grad_out, B, C, h, w, H, W, align_corners ? 1 : 0,
-                                                                        scale0, scale1, scale_rest, grad_in);
+  const int64_t cells = (int64_t)B * C * h * w;
+  int64_t blocks = ceil_div(cells, 8);
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  bilinear_resize_backward_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(grad_out, B, C, h, w, H, W, align_corners ? 1 : 0,
+                                                                                    scale0, scale1, scale_rest, grad_in);
   EEM_CHECK_LAUNCH("bilinear_resize_backward_kernel");
   return EEM_OK;
 }

@@ -75,6 +75,29 @@ def test_no_cpu_fallback():
         eemflow_b200.warp(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
     with pytest.raises(NotImplementedError):
         eemflow_b200.SpatialCorrelationSampler(3, 9, 1, 0, 1)
+    if not torch.cuda.is_available():
+        # the evaluation helpers accept host arrays (they upload them) but have no CPU implementation either
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            eemflow_b200.flow_error(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4), torch.ones(1, 1, 4, 4))
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            eemflow_b200.motion_propagate(np.zeros((32, 32, 2), np.float32), 32, 32)
+        from eemflow_b200.models import ERAFT
+        net = ERAFT(None, n_first_channels=5).eval()       # builds on the CPU (state-dict work), cannot run there
+        net.change_imagesize((64, 64))
+        with pytest.raises(RuntimeError, match="no CPU path"), torch.no_grad():
+            net(events1=torch.zeros(1, 5, 64, 64), events2=torch.zeros(1, 5, 64, 64))
+
+
+def test_new_entry_points_validate_arguments():
+    from eemflow_b200 import _lib
+    lib = _lib.lib()
+    assert lib.eem_flow_error(None, None, None, 1, 4, 4, 4, None, None) == _lib.EEM_ERR_BAD_ARG
+    assert lib.eem_flow_error(1, 1, None, 1, 4, 4, 9, 1, None) == _lib.EEM_ERR_BAD_ARG          # max_row > height
+    assert lib.eem_motion_propagate(1, 1, 64, 64, 64, 3, 1, None) == _lib.EEM_ERR_BAD_ARG       # mesh too large
+    assert lib.eem_corr_lookup_backward(1, 1, 1, 4, 4, 4, 7, None, None) == _lib.EEM_ERR_BAD_ARG
+    arr = (_lib._vp * 4)(1, 1, 1, 1)
+    assert lib.eem_corr_lookup_backward(1, 1, 1, 8, 8, 4, 7, arr, None) == _lib.EEM_ERR_UNSUPPORTED   # radius 7
+    assert lib.eem_voxelize_soa(None, 0, None, None, None, None, 1, 0, 0, 5, 4, 4, 0, 0, None, None, None, None, 0, None) == _lib.EEM_ERR_BAD_ARG
 
 
 def test_product_code_never_imports_the_oracle():

@@ -600,6 +600,222 @@ corr_tf32_kernel(const __grid_constant__ Tf32Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2-SM variant (tcgen05 cta_group::2).  The CTA pair of a cluster issues ONE stream of 256 x 256 x 8 MMAs from
+// the leader CTA: each CTA contributes its own 128-row level panel (A, resident) and HALF of every fmap1 stage
+// (B: 128 of the 256 positions), so the streamed operand costs each SM half the shared memory -- the 96 KiB
+// ring holds 6 stages instead of 3 -- and half the shared-memory read bandwidth, and there is no skew between
+// the two CTAs to stall the ring.  Both CTAs' TMA loads complete on the LEADER's `full` barrier
+// (cp.async.bulk.tensor .cta_group::2), the MMA completion is multicast to both CTAs' `empty` / `res_free` /
+// `acc_full` barriers, and both CTAs' epilogue warps release the accumulator on the leader's `acc_empty`.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA
+
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(x), "r"(y), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+
+template <int BK, int BN>
+struct PairCfg {
+  static constexpr int kBoxBytes = 32 * BK * 4;
+  static constexpr int kResKBytes = (BM / 32) * kBoxBytes;          // own 128-row panel, one k-block
+  static constexpr int kHalfStageBytes = (BN / 64) * kBoxBytes;     // this CTA's half of a fmap1 stage
+  static constexpr int kStages = kRingBytes / kHalfStageBytes;      // 6 at BK = 32, BN = 256
+  static constexpr int kMaxKB = kMaxD / BK;
+  static constexpr int kTmemCols = 2 * BN;
+  // M = 256 across the pair, N = BN
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                     ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+};
+
+template <int BK, int BN>
+struct __align__(1024) Tf32PairSmem {
+  uint8_t resident[kMaxD * 128 * 4];
+  uint8_t ring[kRingBytes];
+  uint64_t full[PairCfg<BK, BN>::kStages], empty[PairCfg<BK, BN>::kStages];
+  uint64_t res_free[PairCfg<BK, BN>::kMaxKB];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int BK, int BN>
+__global__ void __launch_bounds__(kTf32Threads, 1)
+corr_tf32_pair_kernel(const __grid_constant__ Tf32Params p) {
+  using C = PairCfg<BK, BN>;
+  constexpr int kStages = C::kStages, kMaxKB = C::kMaxKB, kTmemCols = C::kTmemCols;
+  constexpr int kBoxBytes = C::kBoxBytes, kResKBytes = C::kResKBytes, kHalfStageBytes = C::kHalfStageBytes;
+  constexpr uint32_t kIdesc = C::kIdesc;
+  extern __shared__ uint8_t smem_raw[];
+  Tf32PairSmem<BK, BN>& s = *reinterpret_cast<Tf32PairSmem<BK, BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.D / BK;
+  const int rank = (int)(blockIdx.x & 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < kMaxKB; ++i) mbar_init(&s.res_free[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {   // the same warp of both CTAs allocates the pair's tensor memory
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == kProducerWarp) {
+    const uint64_t keep = policy_evict_last();
+    TileIter it;
+    it.init(p, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool new_item = true;
+    uint32_t items_done = 0;
+    while (it.valid()) {
+      const int n0 = it.n0();
+      for (int kb = 0; kb < KB; ++kb) {
+        if (new_item && items_done > 0) mbar_wait(&s.res_free[kb], (items_done - 1) & 1);
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        const int row = it.b * p.D + kb * BK;
+        if (elect_one()) {
+          // the leader's barrier counts the bytes of BOTH CTAs (the peer's loads complete on it as well)
+          if (rank == 0) mbar_expect_tx(&s.full[stage], 2 * ((new_item ? kResKBytes : 0) + kHalfStageBytes));
+          if (new_item) {
+            uint8_t* dst = s.resident + kb * kResKBytes;
+#pragma unroll
+            for (int ch = 0; ch < BM / 32; ++ch)
+              tma_load_2d_pair(dst + ch * kBoxBytes, &p.map_lvl[it.l], it.m0 + ch * 32, row, &s.full[stage], keep);
+          }
+          uint8_t* dst = s.ring + stage * kHalfStageBytes;
+#pragma unroll
+          for (int k = 0; k < BN / 64; ++k)
+            tma_load_2d_pair(dst + k * kBoxBytes, &p.map_f1, n0 + (rank * (BN / 64) + k) * 32, row, &s.full[stage], keep);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (new_item) ++items_done;
+      new_item = it.next(p);
+    }
+  } else if (warp == kMmaWarp) {
+    if (rank == 0) {   // the leader issues the pair's MMAs
+      TileIter it;
+      it.init(p, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t k = 0;
+      while (it.valid()) {
+        const bool last_of_item = it.last_of_item();
+        const uint32_t acc = k & 1;
+        mbar_wait(&s.acc_empty[acc], ((k >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + acc * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s.resident + kb * kResKBytes);
+          const uint32_t b_addr = smem_u32(s.ring + stage * kHalfStageBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < BK / UK; ++ks)
+              tc_mma_tf32_pair(d_tmem, make_desc(a_addr + ks * 1024, p.desc_lo, p.desc_hi),
+                               make_desc(b_addr + ks * 1024, p.desc_lo, p.desc_hi), kIdesc, (kb | ks) != 0);
+            tc_commit_pair(&s.empty[stage]);
+            if (last_of_item) tc_commit_pair(&s.res_free[kb]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) tc_commit_pair(&s.acc_full[acc]);
+        __syncwarp();
+        it.next(p);
+        ++k;
+      }
+    }
+  } else {
+    // epilogue warps of BOTH CTAs: each CTA drains its own 128 TMEM lanes (its 128 rows of the 256-row tile)
+    const uint64_t stream_out = policy_evict_first();
+    const int quarter = warp & 3, half = warp >> 2;
+    const float scale = p.scale;
+    TileIter it;
+    it.init(p, BN);
+    uint32_t k = 0;
+    while (it.valid()) {
+      const uint32_t acc = k & 1;
+      mbar_wait(&s.acc_full[acc], (k >> 1) & 1);
+      tc_fence_after();
+      const int Pl = p.Pl[it.l];
+      const int j = it.m0 + quarter * 32 + lane;
+      const bool j_ok = j < Pl;
+      float* obase = p.out[it.l] + ((int64_t)it.b * p.P) * Pl + j;
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      const int n0 = it.n0();
+#pragma unroll 1
+      for (int cc = half * (BN / 64); cc < (half + 1) * (BN / 64); ++cc) {
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + cc * 32));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int i_base = n0 + cc * 32;
+        if (j_ok) {
+          float* o = obase + (int64_t)i_base * Pl;
+          const int n_valid = p.P - i_base;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            st_evict_first_if(o, __uint_as_float(v[r]) * scale, stream_out, r < n_valid);
+            o += Pl;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&s.acc_empty[acc]);
+      it.next(p);
+      ++k;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -649,6 +865,19 @@ cudaError_t launch_tf32(cudaLaunchConfig_t cfg, const Tf32Params& p) {
   if (attr_err != cudaSuccess) return attr_err;
   cfg.dynamicSmemBytes = kSmem;
   return cudaLaunchKernelEx(&cfg, corr_tf32_kernel<BK, BN, CL>, p);
+}
+
+template <int BK, int BN>
+cudaError_t launch_tf32_pair(cudaLaunchConfig_t cfg, const Tf32Params& p) {
+  constexpr size_t kSmem = sizeof(Tf32PairSmem<BK, BN>) + 1024;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(corr_tf32_pair_kernel<BK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  cfg.dynamicSmemBytes = kSmem;
+  return cudaLaunchKernelEx(&cfg, corr_tf32_pair_kernel<BK, BN>, p);
 }
 
 struct LevelDims {
@@ -862,7 +1091,12 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   cfg.numAttrs = 1;
 
   cudaError_t err = cudaSuccess;
-  if (bn == 256) {
+  // 2-SM MMAs (cta_group::2) are the default: MVSEC B=32 164 -> 142 us, HREM B=2 0.71 -> 0.58 ms, results
+  // bit-identical to the 1-SM kernel.  EEM_TF32_PAIR=0 selects the 1-SM multicast kernel for comparisons.
+  const bool pair = bn == 256 && cl == 2 && !(getenv("EEM_TF32_PAIR") != nullptr && atoi(getenv("EEM_TF32_PAIR")) == 0);
+  if (pair) {
+    err = launch_tf32_pair<32, 256>(cfg, p);
+  } else if (bn == 256) {
     err = cl == 2 ? launch_tf32<32, 256, 2>(cfg, p) : launch_tf32<32, 256, 1>(cfg, p);
   } else if (bk == 64) {
     err = cl == 2 ? launch_tf32<64, 128, 2>(cfg, p) : launch_tf32<64, 128, 1>(cfg, p);

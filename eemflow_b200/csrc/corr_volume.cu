@@ -758,7 +758,11 @@ corr_tf32_pair_kernel(const __grid_constant__ Tf32Params p) {
       }
     }
   } else {
-    // epilogue warps of BOTH CTAs: each CTA drains its own 128 TMEM lanes (its 128 rows of the 256-row tile)
+    // epilogue warps of BOTH CTAs: each CTA drains its own 128 TMEM lanes (its 128 rows of the 256-row tile).
+    // A warp pulls its whole 32-lane x 128-column share into registers with two back-to-back x64 loads and ONE
+    // wait, hands the accumulator back to the MMA warp immediately, and only then streams the 128 row segments
+    // out: the TMEM read latency (long while the tensor core is busy read-modify-writing the other
+    // accumulator) is paid once per tile instead of once per 32 columns, and the stores overlap the next MMAs.
     const uint64_t stream_out = policy_evict_first();
     const int quarter = warp & 3, half = warp >> 2;
     const float scale = p.scale;
@@ -772,36 +776,29 @@ corr_tf32_pair_kernel(const __grid_constant__ Tf32Params p) {
       const int Pl = p.Pl[it.l];
       const int j = it.m0 + quarter * 32 + lane;
       const bool j_ok = j < Pl;
-      float* obase = p.out[it.l] + ((int64_t)it.b * p.P) * Pl + j;
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-      const int n0 = it.n0();
-#pragma unroll 1
-      for (int cc = half * (BN / 64); cc < (half + 1) * (BN / 64); ++cc) {
-        uint32_t v[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr + cc * 32));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int i_base = n0 + cc * 32;
-        if (j_ok) {
-          float* o = obase + (int64_t)i_base * Pl;
-          const int n_valid = p.P - i_base;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            st_evict_first_if(o, __uint_as_float(v[r]) * scale, stream_out, r < n_valid);
-            o += Pl;
-          }
-        }
-      }
+      const int i_base = it.n0() + half * (BN / 2);
+      float* o = p.out[it.l] + ((int64_t)it.b * p.P + i_base) * Pl + j;
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+      uint32_t v[BN / 2];
+      static_assert(BN / 2 == 128, "epilogue register tile is written for BN = 256");
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                   : "=r"(v[0+0]), "=r"(v[0+1]), "=r"(v[0+2]), "=r"(v[0+3]), "=r"(v[0+4]), "=r"(v[0+5]), "=r"(v[0+6]), "=r"(v[0+7]), "=r"(v[0+8]), "=r"(v[0+9]), "=r"(v[0+10]), "=r"(v[0+11]), "=r"(v[0+12]), "=r"(v[0+13]), "=r"(v[0+14]), "=r"(v[0+15]), "=r"(v[0+16]), "=r"(v[0+17]), "=r"(v[0+18]), "=r"(v[0+19]), "=r"(v[0+20]), "=r"(v[0+21]), "=r"(v[0+22]), "=r"(v[0+23]), "=r"(v[0+24]), "=r"(v[0+25]), "=r"(v[0+26]), "=r"(v[0+27]), "=r"(v[0+28]), "=r"(v[0+29]), "=r"(v[0+30]), "=r"(v[0+31]), "=r"(v[0+32]), "=r"(v[0+33]), "=r"(v[0+34]), "=r"(v[0+35]), "=r"(v[0+36]), "=r"(v[0+37]), "=r"(v[0+38]), "=r"(v[0+39]), "=r"(v[0+40]), "=r"(v[0+41]), "=r"(v[0+42]), "=r"(v[0+43]), "=r"(v[0+44]), "=r"(v[0+45]), "=r"(v[0+46]), "=r"(v[0+47]), "=r"(v[0+48]), "=r"(v[0+49]), "=r"(v[0+50]), "=r"(v[0+51]), "=r"(v[0+52]), "=r"(v[0+53]), "=r"(v[0+54]), "=r"(v[0+55]), "=r"(v[0+56]), "=r"(v[0+57]), "=r"(v[0+58]), "=r"(v[0+59]), "=r"(v[0+60]), "=r"(v[0+61]), "=r"(v[0+62]), "=r"(v[0+63])
+                   : "r"(taddr));
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                   : "=r"(v[64+0]), "=r"(v[64+1]), "=r"(v[64+2]), "=r"(v[64+3]), "=r"(v[64+4]), "=r"(v[64+5]), "=r"(v[64+6]), "=r"(v[64+7]), "=r"(v[64+8]), "=r"(v[64+9]), "=r"(v[64+10]), "=r"(v[64+11]), "=r"(v[64+12]), "=r"(v[64+13]), "=r"(v[64+14]), "=r"(v[64+15]), "=r"(v[64+16]), "=r"(v[64+17]), "=r"(v[64+18]), "=r"(v[64+19]), "=r"(v[64+20]), "=r"(v[64+21]), "=r"(v[64+22]), "=r"(v[64+23]), "=r"(v[64+24]), "=r"(v[64+25]), "=r"(v[64+26]), "=r"(v[64+27]), "=r"(v[64+28]), "=r"(v[64+29]), "=r"(v[64+30]), "=r"(v[64+31]), "=r"(v[64+32]), "=r"(v[64+33]), "=r"(v[64+34]), "=r"(v[64+35]), "=r"(v[64+36]), "=r"(v[64+37]), "=r"(v[64+38]), "=r"(v[64+39]), "=r"(v[64+40]), "=r"(v[64+41]), "=r"(v[64+42]), "=r"(v[64+43]), "=r"(v[64+44]), "=r"(v[64+45]), "=r"(v[64+46]), "=r"(v[64+47]), "=r"(v[64+48]), "=r"(v[64+49]), "=r"(v[64+50]), "=r"(v[64+51]), "=r"(v[64+52]), "=r"(v[64+53]), "=r"(v[64+54]), "=r"(v[64+55]), "=r"(v[64+56]), "=r"(v[64+57]), "=r"(v[64+58]), "=r"(v[64+59]), "=r"(v[64+60]), "=r"(v[64+61]), "=r"(v[64+62]), "=r"(v[64+63])
+                   : "r"(taddr + 64));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&s.acc_empty[acc]);
+      if (j_ok) {
+        const int n_valid = p.P - i_base;    // >= 128 on interior tiles
+#pragma unroll
+        for (int r = 0; r < BN / 2; ++r) {
+          st_evict_first_if(o, __uint_as_float(v[r]) * scale, stream_out, r < n_valid);
+          o += Pl;
+        }
+      }
       it.next(p);
       ++k;
     }

@@ -362,14 +362,14 @@ def lookup_algorithmic_bytes(B):
 
 def ncu_traffic(kernel, args):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of
-    this very command (profiles/r01/ncu_full_summary_v4.json); only quoted for the workload it was captured on."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01", "ncu_full_summary_v4.json")
+    this very command (profiles/r01/ncu_full_summary_v5.json); only quoted for the workload it was captured on."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01", "ncu_full_summary_v5.json")
     if args.workload != "mvsec_dt1" or args.batch != 32 or not os.path.exists(path):
         return None, None
     try:
         with open(path) as fh:
             d = json.load(fh)[kernel]
-        return int(d["dram_rd"] + d["dram_wr"]), "profiles/r01/prof_%s_v4_raw.csv (ncu --set full, one launch)" % kernel
+        return int(d["dram_rd"] + d["dram_wr"]), "profiles/r01/prof_%s_v5_raw.csv (ncu --set full, one launch)" % kernel
     except (KeyError, ValueError, TypeError):
         return None, None
 

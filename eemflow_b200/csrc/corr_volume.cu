@@ -1020,6 +1020,8 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   if (const char* v = getenv("EEM_TF32_BK")) {
     const int forced = atoi(v);
     if (bn == 128 && (forced == 32 || forced == 64) && D % forced == 0) bk = forced;
+    const bool pair_off = getenv("EEM_TF32_PAIR") != nullptr && atoi(getenv("EEM_TF32_PAIR")) == 0;
+    if (bn == 256 && forced == 64 && D % 64 == 0 && !pair_off) bk = 64;     // 2-SM kernel only (half stages of 32 KiB)
   }
   const uint32_t box_bytes = 32u * (uint32_t)bk * 4u;
   Tf32Params p{};
@@ -1092,7 +1094,7 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   // bit-identical to the 1-SM kernel.  EEM_TF32_PAIR=0 selects the 1-SM multicast kernel for comparisons.
   const bool pair = bn == 256 && cl == 2 && !(getenv("EEM_TF32_PAIR") != nullptr && atoi(getenv("EEM_TF32_PAIR")) == 0);
   if (pair) {
-    err = launch_tf32_pair<32, 256>(cfg, p);
+    err = bk == 64 ? launch_tf32_pair<64, 256>(cfg, p) : launch_tf32_pair<32, 256>(cfg, p);
   } else if (bn == 256) {
     err = cl == 2 ? launch_tf32<32, 256, 2>(cfg, p) : launch_tf32<32, 256, 1>(cfg, p);
   } else if (bk == 64) {

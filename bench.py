@@ -75,6 +75,9 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=None, help="frame pairs per CPU-baseline sample step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--events-format", default="rows", choices=["rows", "columns"],
+                    help="host layout of the events in the end-to-end arm: the reference's [N,4] float64 rows (32 B/event) "
+                         "or packed columns as in the HREM .npz files (t f64, x/y int16, p int8 = 13 B/event)")
     return ap.parse_args()
 
 
@@ -114,8 +117,9 @@ def make_host_inputs(B: int, lookups: int, seed: int, pin: bool):
     return inp
 
 
-def h2d_bytes(inp) -> int:
-    n = sum(e.nbytes for e in inp["events"]) + inp["f1"].numel() * 4 * 2 + sum(c.numel() * 4 for c in inp["coords"])
+def h2d_bytes(inp, columns: bool = False) -> int:
+    ev_bytes = sum(13 * e.shape[0] for e in inp["events"]) if columns else sum(e.nbytes for e in inp["events"])
+    n = ev_bytes + inp["f1"].numel() * 4 * 2 + sum(c.numel() * 4 for c in inp["coords"])
     for lv in inp["eem"]:
         n += sum(v.numel() * 4 for v in lv.values())
     return n
@@ -136,6 +140,7 @@ class B200Step:
         self.target = torch.empty(self.B, 1, H, W, device=dev)
         self.enc = E.EventSequenceToVoxelGrid_Pytorch(NB, gpu=True, gpu_nr=dev.index or 0, normalize=True, forkserver=False)
         self.seqs = [E.EventSequence(None, {"height": H, "width": W}, features=e) for e in inp["events"]]
+        self.columns = None       # packed-column copy of the same events (--events-format columns)
         # device-resident copies for the kernel-only number
         ev = np.concatenate(inp["events"], 0)
         self.d_events = torch.from_numpy(ev).to(dev)
@@ -227,7 +232,10 @@ class B200Step:
                     dc.copy_(hc, non_blocking=True)
                 corr_in = torch.cuda.Event()
                 corr_in.record()
-            ln.enc.voxelize_batch(self.seqs)      # stages the event rows while the copies above are on the link
+            if self.columns is not None:          # stages the events while the copies above are on the link
+                ln.enc.voxelize_columns(self.columns, H, W)
+            else:
+                ln.enc.voxelize_batch(self.seqs)
             with torch.cuda.stream(ln.h2d):       # queued behind the event rows: arrives under voxelize/corr/lookup
                 for dl, hl in zip(d["eem"], hi["eem"]):
                     for k in dl:
@@ -427,6 +435,9 @@ def main():
 
     inp = make_host_inputs(args.batch, args.lookups, seed=100 + rank, pin=True)
     step = B200Step(inp, dev, args.lookups)
+    if args.events_format == "columns":
+        step.columns = [{"t": np.ascontiguousarray(e[:, 0]), "x": e[:, 1].astype(np.int16), "y": e[:, 2].astype(np.int16),
+                         "p": e[:, 3].astype(np.int8)} for e in inp["events"]]
 
     def eager_step():
         out, flow = step.resident()
@@ -565,7 +576,7 @@ def main():
                 edist.gather_batch(flow, total=world * args.batch)
         torch.cuda.synchronize()
         dt = edist.max_over_ranks(time.perf_counter() - t0, dev)
-        e2e = {"value": args.batch * world * k / dt, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d_bytes(inp),
+        e2e = {"value": args.batch * world * k / dt, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d_bytes(inp, args.events_format == "columns"), "events_format": args.events_format,
                "d2h_bytes_per_step": step.d2h_bytes(), "steps": k, "ms_per_step": 1e3 * dt / k,
                "timer": "host perf_counter around synchronize (host staging + H2D + kernels + D2H)"}
 

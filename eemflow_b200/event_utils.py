@@ -224,38 +224,100 @@ class EventSequenceToVoxelGrid_Pytorch(object):
         on the host->device link and in HBM.  `windows`: sequence of dicts (or npz files) with keys x, y, t, p;
         float64 `t` is taken as the already scaled, relative stamps of EventSequence.features[:,0].
         """
-        cols = {"t": [], "x": [], "y": [], "p": []}
+        cols = []
         counts = []
         t_dtype = None
         for wdw in windows:
             t = numpy.asarray(wdw["t"])
             if t.shape[0] == 0:
                 raise IndexError("index -1 is out of bounds for dimension 0 with size 0")
-            t = t.astype(numpy.int64) if numpy.issubdtype(t.dtype, numpy.integer) else t.astype(numpy.float64)
-            assert t_dtype in (None, t.dtype), "all windows must use the same time representation"
-            t_dtype = t.dtype
+            want = numpy.int64 if numpy.issubdtype(t.dtype, numpy.integer) else numpy.float64
+            assert t_dtype in (None, want), "all windows must use the same time representation"
+            t_dtype = want
             x, y, p = (numpy.asarray(wdw[k]) for k in ("x", "y", "p"))
             if not numpy.all(t[:-1] <= t[1:]):            # EventSequence.sort_by_timestamp
                 order = numpy.argsort(t)
                 t, x, y, p = t[order], x[order], y[order], p[order]
-            cols["t"].append(t)
-            cols["x"].append(x.astype(numpy.int16))       # .long() truncation of the reference == integer pixels here
-            cols["y"].append(y.astype(numpy.int16))
-            cols["p"].append(p.astype(numpy.int8))
+            cols.append((t, x, y, p))
             counts.append(t.shape[0])
         assert (self.num_bins > 0)
         assert (width > 0)
         assert (height > 0)
         dev = self.compute_device
         with torch.no_grad():
-            dcols = {k: torch.from_numpy(numpy.concatenate(v)).pin_memory().to(dev, non_blocking=True) for k, v in cols.items()}
-            off = torch.tensor([0] + list(numpy.cumsum(counts)), dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+            d_t, d_x, d_y, d_p, off = self._column_stage().upload(cols, counts, t_dtype, dev)
             dropped = torch.zeros(1, dtype=torch.int64, device=dev) if self.strict else None
-            grid = ops.voxelize_soa(dcols["t"], dcols["x"], dcols["y"], dcols["p"], off, max(counts), self.num_bins,
-                                    height, width, normalize=self.normalize, deterministic=self.deterministic,
-                                    dropped=dropped)
+            grid = ops.voxelize_soa(d_t, d_x, d_y, d_p, off, max(counts), self.num_bins, height, width,
+                                    normalize=self.normalize, deterministic=self.deterministic, dropped=dropped)
             if self.strict and int(dropped.item()) != 0:
                 raise IndexError(f"index out of range in self ({int(dropped.item())} votes fell outside the voxel grid)")
         if grid.device != self.device:
             grid = grid.to(self.device)
         return grid
+
+    def _column_stage(self):
+        if getattr(self, "_col_stage", None) is None:
+            self._col_stage = _ColumnStage()
+        return self._col_stage
+
+
+class _ColumnStage:
+    """Pinned staging of packed event columns (t 8 B, x/y int16, p int8), kept between calls like _PinnedStage;
+    the dtype conversions of the .npz columns (uint16 -> int16, uint8 -> int8; the reference's `.long()` of
+    integer pixel coordinates) happen in the same pass that fills the pinned buffers, on the staging threads."""
+
+    _DT = (None, numpy.int16, numpy.int16, numpy.int8)
+
+    def __init__(self):
+        self.host = None
+        self.off = None
+        self.done = None
+        self.t_dtype = None
+
+    def upload(self, cols, counts, t_dtype, device):
+        total = sum(counts)
+        if self.done is not None:
+            self.done.synchronize()
+        if self.host is None or self.host[1].shape[0] < total or self.t_dtype != t_dtype:
+            cap = max(total, 1024)
+            tt = torch.int64 if t_dtype == numpy.int64 else torch.float64
+            self.host = [torch.empty(cap, dtype=tt, pin_memory=True), torch.empty(cap, dtype=torch.int16, pin_memory=True),
+                         torch.empty(cap, dtype=torch.int16, pin_memory=True), torch.empty(cap, dtype=torch.int8, pin_memory=True)]
+            self.t_dtype = t_dtype
+        if self.off is None or self.off.numel() < len(counts) + 1:
+            self.off = torch.empty(max(len(counts) + 1, 64), dtype=torch.int64, pin_memory=True)
+        views = [h.numpy() for h in self.host]
+        tasks, pos = [], 0
+        for window, n in zip(cols, counts):
+            for lo in range(0, n, 4 * _STAGE_CHUNK_ROWS):
+                hi = min(n, lo + 4 * _STAGE_CHUNK_ROWS)
+                tasks.append((pos + lo, pos + hi, window, lo, hi))
+            pos += n
+
+        def stage(task):
+            d0, d1, window, lo, hi = task
+            for view, col in zip(views, window):
+                numpy.copyto(view[d0:d1], col[lo:hi], casting="unsafe")
+            return d1
+
+        off_host = self.off.numpy()
+        off_host[0] = 0
+        numpy.cumsum(counts, out=off_host[1:len(counts) + 1])
+        with torch.cuda.device(device):
+            off = self.off[:len(counts) + 1].to(device, non_blocking=True)
+            if total <= _STAGE_CHUNK_ROWS:
+                for task in tasks:
+                    stage(task)
+                out = [h[:total].to(device, non_blocking=True) for h in self.host]
+            else:
+                # the DMA of finished chunks is issued while later ones are still being staged
+                out = [torch.empty(total, dtype=h.dtype, device=device) for h in self.host]
+                sent = 0
+                for staged in _staging_pool().map(stage, tasks):      # results arrive in submission order
+                    if staged - sent >= 4 * _STAGE_FLUSH_ROWS or staged == total:
+                        for o, h in zip(out, self.host):
+                            o[sent:staged].copy_(h[sent:staged], non_blocking=True)
+                        sent = staged
+            self.done = torch.cuda.Event()
+            self.done.record()
+        return (*out, off)

@@ -1073,7 +1073,15 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   p.scale = scale;
   if (p.n_items * p.n_tiles >= (int64_t)0x7fffffff)
     return fail(EEM_ERR_UNSUPPORTED, "eem_corr_pyramid(TF32): too many tiles in one call; split the batch");
-  int64_t clusters = sms / cl;
+  // The grid is persistent and the items are dealt statically, so a CTA that cannot start because its SM is
+  // held by another stream's kernel (e.g. an overlapped NCCL collective) delays its whole share of the work.
+  // EEM_TF32_MAX_SMS leaves SMs free for such neighbours (callers that overlap communication set it).
+  int usable = sms;
+  if (const char* v = getenv("EEM_TF32_MAX_SMS")) {
+    const int cap = atoi(v);
+    if (cap >= cl && cap < usable) usable = cap;
+  }
+  int64_t clusters = usable / cl;
   if (clusters > p.n_items * p.n_tiles) clusters = p.n_items * p.n_tiles;
   const unsigned grid = (unsigned)(clusters * cl);
 

@@ -12,6 +12,7 @@
 // the loop is FMA-bound rather than LDS-bound.  Channels stream through shared memory in chunks
 // of 8 with the f2 halo (+-4) loaded once per chunk.
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -33,6 +34,7 @@ struct LocalCorrParams {
   int B, C, H, W, n_out;
   float scale;
   signed char slot[ND * ND];  // output channel of displacement channel ch, or -1 when not selected
+  signed char cls[ND];        // per dy row: which of the kernel's compile-time dx masks applies (5 = all nine)
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -149,6 +151,13 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
 }
 
+// MA..ME: the distinct per-row dx masks (bit d = displacement column d is kept) of a known channel-selection
+// pattern.  The kernel is FFMA-issue-bound (72 FMAs per channel per thread for all nine columns) and EEMFlow
+// keeps 53 or 49 of the 81 displacements, so every warp (= dy row) runs a copy of the WHOLE channel loop that
+// is specialised for its row's mask: the FMAs and accumulators of dropped displacements do not exist in that
+// copy (at most 56 FMAs per channel).  Rows whose mask is not among the five (p.cls == 5) compute all nine
+// columns, so any selection stays correct.  All copies execute the same number of block barriers.
+template <unsigned MA, unsigned MB, unsigned MC, unsigned MD_, unsigned ME>
 __global__ void __launch_bounds__(kThreads, 2)
 local_corr_vec_kernel(const __grid_constant__ LocalCorrParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -216,51 +225,79 @@ local_corr_vec_kernel(const __grid_constant__ LocalCorrParams p) {
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  float acc[8][ND];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int d = 0; d < ND; ++d) acc[i][d] = 0.f;
+  auto run = [&](auto mask_tag) {
+    constexpr unsigned M = decltype(mask_tag)::value;
+    float acc[8][ND];
+  #pragma unroll
+    for (int i = 0; i < 8; ++i)
+  #pragma unroll
+      for (int d = 0; d < ND; ++d) acc[i][d] = 0.f;
 
-  issue(0, 0);
-  for (int k = 0; k < n_chunks; ++k) {
-    if (k + 1 < n_chunks) {
-      issue(k + 1, (k + 1) & 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    issue(0, 0);
+    for (int k = 0; k < n_chunks; ++k) {
+      if (k + 1 < n_chunks) {
+        issue(k + 1, (k + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const float* s1 = smem + (k & 1) * kStageFloats;
+      const float* s2 = s1 + kS1Floats;
+  #pragma unroll 1
+      for (int c = 0; c < VC; ++c) {
+        const float4* a4 = reinterpret_cast<const float4*>(s1 + (c * VH + row) * S1P + oct);
+        const float4* w4 = reinterpret_cast<const float4*>(s2 + (c * S2H + row + MD + dy) * S2P + oct);
+        const float4 a0 = a4[0], a1 = a4[1];
+        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+  #pragma unroll
+        for (int i = 0; i < 8; ++i)
+  #pragma unroll
+          for (int d = 0; d < ND; ++d)
+            if ((M >> d) & 1u) acc[i][d] = fmaf(av[i], wv[i + d], acc[i][d]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    const float* s1 = smem + (k & 1) * kStageFloats;
-    const float* s2 = s1 + kS1Floats;
-#pragma unroll 1
-    for (int c = 0; c < VC; ++c) {
-      const float4* a4 = reinterpret_cast<const float4*>(s1 + (c * VH + row) * S1P + oct);
-      const float4* w4 = reinterpret_cast<const float4*>(s2 + (c * S2H + row + MD + dy) * S2P + oct);
-      const float4 a0 = a4[0], a1 = a4[1];
-      const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int d = 0; d < ND; ++d) acc[i][d] = fmaf(av[i], wv[i + d], acc[i][d]);
-    }
-    __syncthreads();
-  }
 
-  const int gy = y0 + row, gx = x0 + oct;
-  if (gy >= p.H || gx >= p.W) return;
-  const bool second = gx + 4 < p.W;
-#pragma unroll
-  for (int d = 0; d < ND; ++d) {
-    const int slot = p.slot[(dy + MD) * ND + d];
-    if (slot < 0) continue;
-    float* o = p.out + ((int64_t)b * p.n_out + slot) * plane + (int64_t)gy * p.W + gx;
-    st_stream4(o, make_float4(acc[0][d] * p.scale, acc[1][d] * p.scale, acc[2][d] * p.scale, acc[3][d] * p.scale));
-    if (second)
-      st_stream4(o + 4, make_float4(acc[4][d] * p.scale, acc[5][d] * p.scale, acc[6][d] * p.scale, acc[7][d] * p.scale));
+    const int gy = y0 + row, gx = x0 + oct;
+    if (gy >= p.H || gx >= p.W) return;
+    const bool second = gx + 4 < p.W;
+  #pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      if (!((M >> d) & 1u)) continue;
+      const int slot = p.slot[(dy + MD) * ND + d];
+      if (slot < 0) continue;
+      float* o = p.out + ((int64_t)b * p.n_out + slot) * plane + (int64_t)gy * p.W + gx;
+      st_stream4(o, make_float4(acc[0][d] * p.scale, acc[1][d] * p.scale, acc[2][d] * p.scale, acc[3][d] * p.scale));
+      if (second)
+        st_stream4(o + 4, make_float4(acc[4][d] * p.scale, acc[5][d] * p.scale, acc[6][d] * p.scale, acc[7][d] * p.scale));
+    }
+  };
+  switch (p.cls[warp]) {      // warp-uniform: one specialised copy of the loop per row class
+    case 0: run(std::integral_constant<unsigned, MA>{}); break;
+    case 1: run(std::integral_constant<unsigned, MB>{}); break;
+    case 2: run(std::integral_constant<unsigned, MC>{}); break;
+    case 3: run(std::integral_constant<unsigned, MD_>{}); break;
+    case 4: run(std::integral_constant<unsigned, ME>{}); break;
+    default: run(std::integral_constant<unsigned, 0x1FFu>{}); break;
   }
+}
+
+template <unsigned MA, unsigned MB, unsigned MC, unsigned MD_, unsigned ME>
+int launch_vec(const LocalCorrParams& p, int B, int H, int W, cudaStream_t stream) {
+  const size_t smem = 2 * (size_t)kStageFloats * sizeof(float);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(local_corr_vec_kernel<MA, MB, MC, MD_, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  if (attr_err != cudaSuccess) return fail(EEM_ERR_CUDA, "local_corr_vec_kernel attribute: %s", cudaGetErrorString(attr_err));
+  dim3 grid((unsigned)ceil_div(W, VW), (unsigned)ceil_div(H, VH), (unsigned)B);
+  local_corr_vec_kernel<MA, MB, MC, MD_, ME><<<grid, kThreads, smem, stream>>>(p);
+  EEM_CHECK_LAUNCH("local_corr_vec_kernel");
+  return EEM_OK;
 }
 
 }  // namespace
@@ -296,17 +333,30 @@ extern "C" int eem_local_corr(const float* f1, const float* f2, int B, int C, in
   const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) |
                                         reinterpret_cast<uintptr_t>(out)) % 16 == 0);
   if (vec_ok) {
-    const size_t smem = 2 * (size_t)kStageFloats * sizeof(float);
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-      attr_err = cudaFuncSetAttribute(local_corr_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    });
-    if (attr_err != cudaSuccess) return fail(EEM_ERR_CUDA, "local_corr_vec_kernel attribute: %s", cudaGetErrorString(attr_err));
-    dim3 grid((unsigned)ceil_div(W, VW), (unsigned)ceil_div(H, VH), (unsigned)B);
-    local_corr_vec_kernel<<<grid, kThreads, smem, as_stream(stream_)>>>(p);
-    EEM_CHECK_LAUNCH("local_corr_vec_kernel");
-    return EEM_OK;
+    // per-row dx masks of this selection, matched against the two precompiled patterns (EEMFlow_cdc's 53 and
+    // EEMFlow's 49 channels); rows that match no compile-time mask fall back to all nine columns
+    unsigned row_mask[ND];
+    for (int r = 0; r < ND; ++r) {
+      row_mask[r] = 0;
+      for (int d = 0; d < ND; ++d)
+        if (p.slot[r * ND + d] >= 0) row_mask[r] |= 1u << d;
+    }
+    auto classify = [&](const unsigned (&set)[5]) {
+      int hits = 0;
+      for (int r = 0; r < ND; ++r) {
+        p.cls[r] = 5;
+        for (int k = 0; k < 5; ++k)
+          if (row_mask[r] == set[k]) { p.cls[r] = (signed char)k; ++hits; break; }
+      }
+      return hits;
+    };
+    static const unsigned kCdc[5] = {0x155u, 0x0AAu, 0x17Du, 0x0FEu, 0x1FFu};
+    static const unsigned kEem[5] = {0x0AAu, 0x155u, 0x0BAu, 0x17Du, 0x0FEu};
+    const int hits_cdc = classify(kCdc);
+    const bool use_cdc = hits_cdc >= classify(kEem);
+    if (use_cdc) classify(kCdc);
+    return use_cdc ? launch_vec<0x155u, 0x0AAu, 0x17Du, 0x0FEu, 0x1FFu>(p, B, H, W, as_stream(stream_))
+                   : launch_vec<0x0AAu, 0x155u, 0x0BAu, 0x17Du, 0x0FEu>(p, B, H, W, as_stream(stream_));
   }
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)ceil_div(H, TH), (unsigned)B);
   local_corr_generic_kernel<<<grid, kThreads, 0, as_stream(stream_)>>>(p);

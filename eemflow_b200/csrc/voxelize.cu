@@ -415,6 +415,59 @@ segmented_sum_kernel(const uint32_t* __restrict__ keys, const float* __restrict_
   grid[k] = acc;
 }
 
+
+// ---- atomic mode, bin-interleaved layout (many bins per pixel) -----------------------------------------
+// The two votes of an event go to bins k and k+1 of the SAME pixel.  In a scratch array T[window][pixel][bin]
+// (bins innermost, padded to an even count) they are neighbours, so whenever k is even ONE 8-byte vector RED
+// (REDG.ADD.F32x2) carries both: 1.5 instead of 2 L2 sector operations per event on average, and L2 atomic
+// throughput is what binds the vote pass.  The statistics pass reads T as it is (padding stays zero) and the
+// normalisation pass transposes T into the reference's [bin][y][x] layout on its way out, so compared with the
+// direct path no pass is added; T costs nbp/nb more bytes (HREM: 15 -> 16 bins).  (Experiment, off by default.)
+template <class Src>
+__global__ void __launch_bounds__(kVoteThreads)
+voxel_vote_interleaved_kernel(const Src ev, const int64_t* __restrict__ offsets, int nb, int nbp, int H, int W, int lanes,
+                              float* __restrict__ T, int64_t* __restrict__ dropped) {
+  const int w = blockIdx.y;
+  const int64_t begin = offsets[w], end = offsets[w + 1];
+  const int64_t n = end - begin;
+  const int64_t per_block = kVoteThreads * kVoteEventsPerThread;
+  const int64_t chunk = interleaved_chunk(blockIdx.x, (n + per_block - 1) / per_block, lanes);
+  if (chunk < 0) return;
+  const int64_t first = chunk * per_block + threadIdx.x;
+  const WindowTimes wt = window_times(ev, begin, end);
+  const int64_t HW = (int64_t)H * W, total = HW * nb;
+  const unsigned hw = (unsigned)HW;                      // total < 2^31 on this path (checked by the host)
+  float* t = T + (int64_t)w * HW * nbp;
+
+  EventRow rows[kVoteEventsPerThread];
+#pragma unroll
+  for (int k = 0; k < kVoteEventsPerThread; ++k) {
+    const int64_t i = first + (int64_t)k * kVoteThreads;
+    if (i < n) rows[k] = ev.load(begin + i);
+  }
+  int ndrop = 0;
+#pragma unroll
+  for (int k = 0; k < kVoteEventsPerThread; ++k) {
+    const int64_t i = first + (int64_t)k * kVoteThreads;
+    if (i < n) {
+      const Vote v = make_vote(rows[k], wt.t_first, wt.dT, nb, W, HW, total);
+      // flat reference index -> (bin, pixel); the reference's silent wrap of x >= W into the next row / bin is kept
+      unsigned bl = 0, pl = 0, br = 0, pr = 0;
+      if (v.idx_left >= 0) { bl = (unsigned)v.idx_left / hw; pl = (unsigned)v.idx_left - bl * hw; }
+      if (v.idx_right >= 0) { br = (unsigned)v.idx_right / hw; pr = (unsigned)v.idx_right - br * hw; }
+      if (v.idx_left >= 0 && v.idx_right >= 0 && pl == pr && br == bl + 1 && (bl & 1u) == 0) {
+        red_add_f32x2(t + (int64_t)pl * nbp + bl, v.val_left, v.val_right);
+      } else {
+        if (v.idx_left >= 0) red_add_f32(t + (int64_t)pl * nbp + bl, v.val_left);
+        if (v.idx_right >= 0) red_add_f32(t + (int64_t)pr * nbp + br, v.val_right);
+      }
+      ndrop += (int)v.oob_left + (int)v.oob_right;
+    }
+  }
+  if (dropped != nullptr && ndrop != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(dropped), (unsigned long long)ndrop);
+}
+
 // ---- K2 normalisation -----------------------------------------------------------------------
 constexpr int kStatThreads = 256;
 constexpr int kStatBlocksPerWindowMax = 2048;
@@ -600,6 +653,33 @@ voxel_apply_kernel(float* __restrict__ grid, int64_t vox, const float* __restric
   for (int64_t i = nvec * 4 + tid; i < vox; i += stride) g[i] = normalize_one(g[i], mean, sd, divide);
 }
 
+
+// T[window][pixel][nbp] -> grid[window][bin][pixel], normalising on the way when kNorm.  A thread owns one pixel:
+// it reads the pixel's nbp contiguous bins and writes one value per bin plane, so a warp reads 32*nbp*4 contiguous
+// bytes and every store instruction writes 128 contiguous bytes of one plane.  grid = (blocks, n_windows).
+template <bool kNorm>
+__global__ void __launch_bounds__(256)
+voxel_deinterleave_kernel(const float* __restrict__ T, int nb, int nbp, int64_t HW, float* __restrict__ grid,
+                          const float* __restrict__ mean_std) {
+  const int w = blockIdx.y;
+  const float* t = T + (int64_t)w * HW * nbp;
+  float* g = grid + (int64_t)w * HW * nb;
+  float mean = 0.f, sd = 0.f;
+  if (kNorm) {
+    mean = mean_std[2 * w + 0];
+    sd = mean_std[2 * w + 1];
+  }
+  const bool divide = sd > 0.0f;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += (int64_t)gridDim.x * blockDim.x) {
+    const float2* src = reinterpret_cast<const float2*>(t + pix * nbp);      // nbp is even: 8-byte aligned
+    for (int b = 0; b < nbp; b += 2) {
+      float2 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(src + (b >> 1)));
+      st_stream(g + (int64_t)b * HW + pix, kNorm ? normalize_one(v.x, mean, sd, divide) : v.x);
+      if (b + 1 < nb) st_stream(g + (int64_t)(b + 1) * HW + pix, kNorm ? normalize_one(v.y, mean, sd, divide) : v.y);
+    }
+  }
+}
 
 // ---- cluster-resident path (windows whose grid fits the shared memory of one 8-CTA cluster) -------------------
 // (Experiment, off by default -- see cluster_plan() for the measurement.)
@@ -843,6 +923,18 @@ bool use_pair_path(int64_t n_total, int64_t total_vox) {
   return n_total >= 2 * total_vox;
 }
 
+// Bin-interleaved scratch layout.  MEASURED SLOWER than the direct path (HREM dt1, 15 bins, 4 x 10 M events: voxel
+// family 0.735 vs 0.697 ms) although it issues 25 % fewer L2 atomic operations, so it is only taken when forced
+// (EEM_VOXEL_PATH=interleaved); kept, with its parity test, as a measured experiment.
+bool use_interleaved_path(int num_bins) {
+  if (const char* v = getenv("EEM_VOXEL_PATH")) {   // timing experiments only
+    if (v[0] == 'i') return true;
+    if (v[0] == 'd' || v[0] == 'p' || v[0] == 'c') return false;
+  }
+  (void)num_bins;
+  return false;
+}
+
 int64_t l2_group_bytes() {
   if (const char* v = getenv("EEM_VOXEL_GROUP_MB")) {   // timing experiments only; 0 disables the grouping
     const long mb = atol(v);
@@ -1015,6 +1107,34 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
       return EEM_OK;
     }
   }
+  if (!no_events && mode == EEM_VOXEL_ATOMIC && !pair && use_interleaved_path(num_bins) && vox < (1ll << 31)) {
+    const int nbp = (num_bins + 1) & ~1;
+    const int64_t HW = (int64_t)height * width, vox_p = HW * nbp;
+    float* T = reinterpret_cast<float*>(ws_mode);
+    EEM_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)n_windows * vox_p * sizeof(float), stream));
+    const int64_t per_block = (int64_t)kVoteThreads * kVoteEventsPerThread;
+    const int64_t chunks = ceil_div(max_events_per_window, per_block);
+    const int lanes = time_lanes(64);
+    dim3 g((unsigned)(ceil_div(chunks, lanes) * lanes), (unsigned)n_windows);
+    voxel_vote_interleaved_kernel<Src><<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, nbp, height, width, lanes, T, dropped);
+    EEM_CHECK_LAUNCH("voxel_vote_interleaved_kernel");
+    dim3 gd((unsigned)stat_blocks(HW * 4, n_windows), (unsigned)n_windows);
+    if (normalize) {
+      const StatLayout L = stat_layout(n_windows);
+      StatPartial* partials = reinterpret_cast<StatPartial*>(ws_stats + L.partials);
+      unsigned int* tickets = reinterpret_cast<unsigned int*>(ws_stats + L.tickets);
+      float* mean_std = reinterpret_cast<float*>(ws_stats + L.mean_std);
+      EEM_CHECK_CUDA(cudaMemsetAsync(tickets, 0, (size_t)n_windows * sizeof(unsigned int), stream));
+      dim3 gs((unsigned)stat_blocks(vox_p, n_windows), (unsigned)n_windows);
+      voxel_stats_kernel<<<gs, kStatThreads, 0, stream>>>(T, vox_p, partials, tickets, mean_std, stats_out);
+      EEM_CHECK_LAUNCH("voxel_stats_kernel");
+      voxel_deinterleave_kernel<true><<<gd, 256, 0, stream>>>(T, num_bins, nbp, HW, grid, mean_std);
+    } else {
+      voxel_deinterleave_kernel<false><<<gd, 256, 0, stream>>>(T, num_bins, nbp, HW, grid, nullptr);
+    }
+    EEM_CHECK_LAUNCH("voxel_deinterleave_kernel");
+    return EEM_OK;
+  }
   if (!pair) EEM_CHECK_CUDA(cudaMemsetAsync(grid, 0, (size_t)total_vox * sizeof(float), stream));
 
   if (no_events) {
@@ -1114,6 +1234,8 @@ size_t eem_voxelize_workspace_bytes(int64_t n_total, int n_windows, int num_bins
   size_t bytes = normalize ? stat_layout(n_windows).total : 0;
   if (mode == EEM_VOXEL_DETERMINISTIC) bytes += det_layout(n_total).total;
   else if (use_pair_path(n_total, total_vox)) bytes += align_up((size_t)total_vox * 2 * sizeof(float), 256);
+  else if (use_interleaved_path(num_bins))
+    bytes += align_up((size_t)n_windows * height * width * ((num_bins + 1) & ~1) * sizeof(float), 256);
   return bytes;
 }
 

@@ -156,7 +156,7 @@ def test_device_contract_and_errors(V):
     V(5, gpu=True, forkserver=False)(Seq(bad, 32, 48))            # non-strict: vote dropped, no error
 
 
-@pytest.mark.parametrize("path", ["pair", "direct", "cluster"])
+@pytest.mark.parametrize("path", ["pair", "direct", "cluster", "interleaved"])
 def test_forced_vote_path_parity(golden, V, monkeypatch, path):
     """The atomic mode has three implementations chosen by size: cluster-resident (a window's grid lives in the
     shared memory of an 8-CTA cluster; MVSEC-sized windows), direct L2 atomics, and the pair layout (>= 2 events

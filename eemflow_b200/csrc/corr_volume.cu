@@ -972,9 +972,16 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
       }
     }
     int64_t blocks = planes;
-    const int64_t cap = (int64_t)sm_count() * 16;
+    const int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    pool_pyramid_kernel<<<(unsigned)blocks, 256, smem, stream>>>(pp);
+    // small CTAs (EEM_POOL_THREADS, default 128): a plane is a few KB, so the pass is latency-bound and wants many
+    // planes in flight per SM rather than many threads per plane
+    int threads = 128;
+    if (const char* v = getenv("EEM_POOL_THREADS")) {
+      const int t = atoi(v);
+      if (t == 64 || t == 128 || t == 256) threads = t;
+    }
+    pool_pyramid_kernel<<<(unsigned)blocks, threads, smem, stream>>>(pp);
     EEM_CHECK_LAUNCH("pool_pyramid_kernel");
   }
   for (int l = 1; l < num_levels && !fused_pool; ++l) {

@@ -369,6 +369,19 @@ class ClockSampler:
                 break
             time.sleep(0.002)
 
+    def poke(self):
+        """One sample taken synchronously by the caller (the main thread calls this right after enqueueing the timed
+        steps and the stop event, while the GPU is still executing them, so there are under-load samples even if the polling thread
+        did not get the GIL during the few milliseconds of the timed region)."""
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
@@ -587,6 +600,9 @@ def main():
         timed_step()
     drain()
     t_stop.record()
+    if rank == 0:                       # the steps are only enqueued so far: the device is executing them right now
+        for _ in range(4):
+            sampler.poke()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()

@@ -235,9 +235,6 @@ class EventSequenceToVoxelGrid_Pytorch(object):
             assert t_dtype in (None, want), "all windows must use the same time representation"
             t_dtype = want
             x, y, p = (numpy.asarray(wdw[k]) for k in ("x", "y", "p"))
-            if not numpy.all(t[:-1] <= t[1:]):            # EventSequence.sort_by_timestamp
-                order = numpy.argsort(t)
-                t, x, y, p = t[order], x[order], y[order], p[order]
             cols.append((t, x, y, p))
             counts.append(t.shape[0])
         assert (self.num_bins > 0)
@@ -245,7 +242,13 @@ class EventSequenceToVoxelGrid_Pytorch(object):
         assert (height > 0)
         dev = self.compute_device
         with torch.no_grad():
-            d_t, d_x, d_y, d_p, off = self._column_stage().upload(cols, counts, t_dtype, dev)
+            d_t, d_x, d_y, d_p, off, unsorted = self._column_stage().upload(cols, counts, t_dtype, dev)
+            if unsorted:                                  # EventSequence.sort_by_timestamp, then stage again (rare)
+                for k in unsorted:
+                    t, x, y, p = cols[k]
+                    order = numpy.argsort(t)
+                    cols[k] = (t[order], x[order], y[order], p[order])
+                d_t, d_x, d_y, d_p, off, _ = self._column_stage().upload(cols, counts, t_dtype, dev)
             dropped = torch.zeros(1, dtype=torch.int64, device=dev) if self.strict else None
             grid = ops.voxelize_soa(d_t, d_x, d_y, d_p, off, max(counts), self.num_bins, height, width,
                                     normalize=self.normalize, deterministic=self.deterministic, dropped=dropped)
@@ -288,14 +291,20 @@ class _ColumnStage:
             self.off = torch.empty(max(len(counts) + 1, 64), dtype=torch.int64, pin_memory=True)
         views = [h.numpy() for h in self.host]
         tasks, pos = [], 0
-        for window, n in zip(cols, counts):
+        for k, (window, n) in enumerate(zip(cols, counts)):
             for lo in range(0, n, 4 * _STAGE_CHUNK_ROWS):
                 hi = min(n, lo + 4 * _STAGE_CHUNK_ROWS)
-                tasks.append((pos + lo, pos + hi, window, lo, hi))
+                tasks.append((pos + lo, pos + hi, window, lo, hi, k))
             pos += n
+        unsorted = set()
 
         def stage(task):
-            d0, d1, window, lo, hi = task
+            # the sortedness scan of EventSequence.is_sorted runs here, chunk by chunk on the staging threads,
+            # while the chunk is in cache anyway (one single-threaded pass over 10 M stamps costs more than staging)
+            d0, d1, window, lo, hi, k = task
+            t = window[0]
+            if not numpy.all(t[max(lo - 1, 0):hi - 1] <= t[max(lo, 1):hi]):
+                unsorted.add(k)
             for view, col in zip(views, window):
                 numpy.copyto(view[d0:d1], col[lo:hi], casting="unsafe")
             return d1
@@ -320,4 +329,4 @@ class _ColumnStage:
                         sent = staged
             self.done = torch.cuda.Event()
             self.done.record()
-        return (*out, off)
+        return (*out, off, sorted(unsorted))

@@ -223,6 +223,14 @@ def test_packed_columns_match_reference_loader_chain(V):
         assert np.array_equal(det[k], ref_raw), k
         ref_norm = ref_ops.voxelize(s.features, nb, h, w, normalize=True).numpy()
         assert rel_close(atom[k], ref_norm).all(), k
+    # unsorted columns are sorted by time stamp first, as EventSequence does (loader/loader_utils.py:365-366)
+    perm = rng.permutation(windows[2]["t"].shape[0])
+    shuffled = [windows[0], windows[1], {k: v[perm] for k, v in windows[2].items()}]
+    if len(np.unique(windows[2]["t"])) == windows[2]["t"].shape[0]:       # argsort is then a unique permutation
+        det_s = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_columns(shuffled, h, w).cpu().numpy()
+        assert np.array_equal(det_s, det)
+    atom_s = V(nb, gpu=True, normalize=True, forkserver=False).voxelize_columns(shuffled, h, w).cpu().numpy()
+    assert rel_close(atom_s[2], ref_ops.voxelize(seqs[2].features, nb, h, w, normalize=True).numpy()).all()
     # float64 columns = the values of features[:,0]
     wf = [{"x": s.features[:, 1], "y": s.features[:, 2], "t": s.features[:, 0], "p": s.features[:, 3]} for s in seqs]
     det2 = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_columns(wf, h, w).cpu().numpy()

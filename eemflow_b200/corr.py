@@ -69,6 +69,8 @@ def bilinear_sampler(img, coords, mode='bilinear', mask=False):
     """ Wrapper for grid_sample, uses pixel coordinates """
     if mode != 'bilinear':
         raise NotImplementedError("eemflow_b200.bilinear_sampler implements mode='bilinear' only")
+    if ag.needs_grad(img, coords):      # never a silent zero gradient: CorrBlock is the differentiable user of this op
+        raise NotImplementedError("eemflow_b200.bilinear_sampler has no backward; use CorrBlock (differentiable) or detach the inputs")
     with torch.no_grad():
         return ops.bilinear_sample(img, coords, mask=mask)
 

@@ -106,6 +106,8 @@ class InputPadder:
             self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, 0, pad_ht]
 
     def pad(self, *inputs):
+        if ag.needs_grad(*inputs):      # the models pad event grids (no gradient); never return a silently detached result
+            raise NotImplementedError("eemflow_b200.InputPadder.pad has no backward; pad tensors that do not require grad")
         with torch.no_grad():
             return [ops.replicate_pad(x, self._pad) for x in inputs]
 

@@ -264,6 +264,12 @@ class EventSequenceToVoxelGrid_Pytorch(object):
         return self._col_stage
 
 
+def _chunk_is_sorted(t, lo: int, hi: int) -> bool:
+    """EventSequence.is_sorted restricted to stamps [lo, hi) PLUS the pair straddling `lo`, so that the chunk-wise
+    results over a partition of [0, n) AND together equal numpy.all(t[:-1] <= t[1:])."""
+    return bool(numpy.all(t[max(lo - 1, 0):hi - 1] <= t[max(lo, 1):hi]))
+
+
 class _ColumnStage:
     """Pinned staging of packed event columns (t 8 B, x/y int16, p int8), kept between calls like _PinnedStage;
     the dtype conversions of the .npz columns (uint16 -> int16, uint8 -> int8; the reference's `.long()` of
@@ -302,8 +308,7 @@ class _ColumnStage:
             # the sortedness scan of EventSequence.is_sorted runs here, chunk by chunk on the staging threads,
             # while the chunk is in cache anyway (one single-threaded pass over 10 M stamps costs more than staging)
             d0, d1, window, lo, hi, k = task
-            t = window[0]
-            if not numpy.all(t[max(lo - 1, 0):hi - 1] <= t[max(lo, 1):hi]):
+            if not _chunk_is_sorted(window[0], lo, hi):
                 unsorted.add(k)
             for view, col in zip(views, window):
                 numpy.copyto(view[d0:d1], col[lo:hi], casting="unsafe")

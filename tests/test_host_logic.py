@@ -144,3 +144,19 @@ def test_pyramid_shapes_and_tf32_gate():
     assert ops.pyramid_level_shapes(92, 160, 4) == [(92, 160), (46, 80), (23, 40), (11, 20)]
     assert ops.tf32_supported(256, 36, 44) and ops.tf32_supported(256, 92, 160)
     assert not ops.tf32_supported(16, 9, 13) and not ops.tf32_supported(512, 36, 44)
+
+
+def test_chunked_sortedness_scan_equals_global_scan():
+    """The packed-column ingest checks EventSequence.is_sorted chunk by chunk on its staging threads."""
+    from eemflow_b200.event_utils import _chunk_is_sorted
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n = int(rng.integers(1, 60))
+        t = np.sort(rng.random(n))
+        if n > 1 and rng.random() < 0.5:
+            i = int(rng.integers(0, n - 1))
+            t[i], t[i + 1] = t[i + 1] + 1e-3, t[i]
+        want = bool(np.all(t[:-1] <= t[1:]))
+        for chunk in (1, 2, 3, 7, 64):
+            got = all(_chunk_is_sorted(t, lo, min(n, lo + chunk)) for lo in range(0, n, chunk))
+            assert got == want, (n, chunk)

@@ -1,23 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the EEMFlow hot path on B200: frame-pairs/s for voxelize + corr + lookup + warp.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workloads a,b,...]
 
-One "step" is one pass of the hot path over one batch of synthetic frame pairs, BASELINE.json
-configs[1] (MVSEC dt1 shape) per GPU:
-  * 2*B event windows (260x346, 30 000 events each, [N,4] float64 rows) -> 5-bin voxel grids, normalised
-  * CorrBlock on [B,256,36,44] feature maps: 4-level all-pairs pyramid (TF32 tcgen05) + `lookups`
+One "step" is one pass of the hot path over one batch of synthetic frame pairs per GPU:
+  * 2*B event windows ([N,4] float64 rows) -> voxel grids, normalised
+  * CorrBlock on [B,256,h,w] feature maps: 4-level all-pairs pyramid (TF32 tcgen05) + `lookups`
     (default 12 = ERAFT's iterations, model/eraft.py:140) radius-4 window lookups
-  * the EEMFlow_cdc op sequence on its 5 pyramid levels at the padded 320x384 size: local 9x9
-    correlation (53 kept channels), upsample2d_flow_as, WarpingLayer_no_div, CDC blend, warp, and the 5
-    final flow upsamples to 260x346 (model/EEMFlow/EEMFlow+.py:158-234 without the cuDNN convs)
-Weak scaling: every rank processes its own B pairs (independent units, no data-path collective);
-at N > 1 the per-step result flows are all-gathered over NCCL and a metric accumulator all-reduced.
+  * the EEMFlow_cdc op sequence on its 5 pyramid levels at the padded size: local 9x9 correlation
+    (53 kept channels), upsample2d_flow_as, WarpingLayer_no_div, CDC blend, warp, and the 5 final flow
+    upsamples (model/EEMFlow/EEMFlow+.py:158-234 without the cuDNN convs)
+  * the masked end-point-error statistics of the final flow (test_mvsec.py:291-346), accumulated on the device
+The headline workload (top-level keys of the JSON line) is BASELINE.json configs[1]: MVSEC dt1 shape, 260x346,
+30 000 events per window, 5 bins, batch 32.  The HREM-shaped configs[2] / configs[3] (720x1280, 10 M / 40 M events
+per window, 15 bins, 92x160 feature maps) are run in the same invocation and reported under "workloads", each with
+its own value / e2e / roofline (dominant kernel family of THAT workload) / cpu_baseline.
+Weak scaling: every rank processes its own B pairs (independent units, no data-path collective); at N > 1 the
+result flows of every rank are delivered to rank 0 each step (written straight into rank 0's memory over NVLink by
+the kernel that produces them when peer memory is available, NCCL gather otherwise) and the metric accumulators
+are all-reduced once.  N = 1 and N > 1 time the SAME captured step.
 
 `value` times device-resident inputs with CUDA events; `e2e` runs the same step through the public
-reference-shaped API from HOST buffers (numpy events, pinned feature maps) including H2D and D2H.
-`--impl reference` times the CPU oracle port (the reference's own ATen calls, all host threads) on
-a bounded sample of the same workload.  Prints ONE JSON line on rank 0.
+reference-shaped API from HOST buffers including H2D and D2H.  `--impl reference` times the CPU oracle port (the
+reference's own ATen calls, all host threads) on the same configuration.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -30,6 +35,7 @@ import sys
 import threading
 import time
 from pathlib import Path
+from types import SimpleNamespace
 
 import numpy as np
 import torch
@@ -38,41 +44,41 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
-H, W, NB = 260, 346, 5                 # MVSEC sensor, a_meshflow / mvsec configs use 5 bins
-EVENTS_PER_WINDOW = 30_000             # MVSEC dt1
-FH, FW, FD = 36, 44, 256               # ERAFT feature map of the 288x352 padded input
+FD = 256                               # ERAFT feature channels
 LEVELS, RADIUS = 4, 4
-# EEMFlow_cdc pyramid (C, h, w) for the 320x384 padded MVSEC input, coarse -> fine
-EEM_LEVELS = [(64, 5, 6), (64, 10, 12), (64, 20, 24), (64, 40, 48), (32, 80, 96)]
 # the 53 correlation channels EEMFlow_cdc keeps (model/EEMFlow/EEMFlow+.py:89-97)
 EEMFLOW_CDC_INDEX = [0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 21, 22, 23, 24, 26, 28, 29, 30, 31, 32, 33, 34, 36, 38, 39, 40,
                      41, 42, 44, 46, 47, 48, 49, 50, 51, 52, 54, 56, 57, 58, 59, 60, 62, 64, 66, 68, 70, 72, 74, 76, 78, 80]
 
-
-# Alternative workloads (parity-test shapes of BASELINE.json, not the driver's bench line): selected
-# with --workload; the constants above are the default, BASELINE configs[1].
+HREM_LEVELS = [(64, 12, 20), (64, 24, 40), (64, 48, 80), (64, 96, 160), (32, 192, 320)]
 WORKLOADS = {
-    "mvsec_dt1": {},
+    # configs[1]: MVSEC dt1 shape -- 260x346 sensor, 30 000 events / window, 5 bins, ERAFT feature map of
+    # the 288x352 padded input, EEMFlow_cdc pyramid (C, h, w) of the 320x384 padded input
+    "mvsec_dt1": dict(H=260, W=346, NB=5, EVENTS_PER_WINDOW=30_000, FH=36, FW=44,
+                      EEM_LEVELS=[(64, 5, 6), (64, 10, 12), (64, 20, 24), (64, 40, 48), (32, 80, 96)], batch=32, cpu_batch=32),
     # configs[2]: HREM dt1 shape -- 720p-class stream, ~10M events/window, 15-bin grids, 92x160 ERAFT
     # feature maps (736x1280 padded / 8), EEMFlow_cdc pyramid of the 768x1280 padded input
-    "hrem_dt1": dict(H=720, W=1280, NB=15, EVENTS_PER_WINDOW=10_000_000, FH=92, FW=160,
-                     EEM_LEVELS=[(64, 12, 20), (64, 24, 40), (64, 48, 80), (64, 96, 160), (32, 192, 320)], batch=2, cpu_batch=1),
+    "hrem_dt1": dict(H=720, W=1280, NB=15, EVENTS_PER_WINDOW=10_000_000, FH=92, FW=160, EEM_LEVELS=HREM_LEVELS, batch=2, cpu_batch=1),
     # configs[3]: HREM dt4 -- 4x longer windows
-    "hrem_dt4": dict(H=720, W=1280, NB=15, EVENTS_PER_WINDOW=40_000_000, FH=92, FW=160,
-                     EEM_LEVELS=[(64, 12, 20), (64, 24, 40), (64, 48, 80), (64, 96, 160), (32, 192, 320)], batch=1, cpu_batch=1),
+    "hrem_dt4": dict(H=720, W=1280, NB=15, EVENTS_PER_WINDOW=40_000_000, FH=92, FW=160, EEM_LEVELS=HREM_LEVELS, batch=1, cpu_batch=1),
 }
+METRIC = "frame-pairs/sec (voxelize+corr+lookup+warp)"
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="mvsec_dt1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="mvsec_dt1", choices=sorted(WORKLOADS), help="headline workload (top-level keys)")
+    ap.add_argument("--workloads", default=None,
+                    help="comma-separated extra workloads reported under \"workloads\" (default: the HREM shapes when the "
+                         "headline is mvsec_dt1; 'none' disables)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=None, help="frame pairs per GPU per step (default 32; 2 / 1 for the HREM workloads)")
+    ap.add_argument("--batch", type=int, default=None, help="frame pairs per GPU per step of the headline workload")
     ap.add_argument("--lookups", type=int, default=12, help="CorrBlock lookups per pair (ERAFT iterations)")
-    ap.add_argument("--cpu-batch", type=int, default=None, help="frame pairs per CPU-baseline sample step")
+    ap.add_argument("--cpu-batch", type=int, default=None, help="frame pairs per CPU step (default: the whole batch for mvsec_dt1)")
+    ap.add_argument("--corr", default="tf32", choices=["tf32", "tf32_f16", "fp32"], help="CorrBlock precision / storage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--events-format", default="rows", choices=["rows", "columns"],
@@ -81,17 +87,49 @@ def parse_args():
     return ap.parse_args()
 
 
+def workload(name, batch=None, cpu_batch=None):
+    wl = SimpleNamespace(name=name, **WORKLOADS[name])
+    if batch is not None:
+        wl.batch = batch
+    if cpu_batch is not None:
+        wl.cpu_batch = cpu_batch
+    wl.cpu_batch = min(wl.cpu_batch, wl.batch)
+    return wl
+
+
+def config_of(wl, args, world):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": f"{wl.name}_{wl.H}x{wl.W}_batch{wl.batch}_voxelize+corrblock4x4+eemflow_cdc_ops",
+            "pairs_per_gpu": wl.batch, "windows_per_pair": 2, "events_per_window": wl.EVENTS_PER_WINDOW,
+            "voxel": f"{wl.NB}x{wl.H}x{wl.W}", "fmap": f"{FD}x{wl.FH}x{wl.FW}", "corr_levels": LEVELS, "radius": RADIUS,
+            "lookups_per_pair": args.lookups, "eemflow_levels": [list(l) for l in wl.EEM_LEVELS],
+            "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
+            "pairs_per_step_reference_arm": wl.cpu_batch,
+            "l2": "no explicit flush: a step streams > 1 GB (the correlation volume alone is written then gathered 12x) >> 126 MB L2"}
+
+
 # ------------------------------------------------------------------------------------------------
 # synthetic inputs (seeded; SURVEY 8d)
 # ------------------------------------------------------------------------------------------------
-def make_events(rng, n, h, w):
-    t = np.sort(rng.uniform(0.0, 0.05, size=n)) * 1e6
+def make_events(rng, n, h, w, pin=False):
+    """t: sorted uniform stamps in [0, 50 ms) as microseconds relative to the first event (drawn as normalised
+    cumulative exponential gaps = the order statistics of n uniforms, O(n) instead of a sort); x, y uniform;
+    p in {-1, +1}.  [n, 4] float64 rows, in pinned memory when `pin` (a loader with pin_memory=True)."""
+    out = torch.empty((n, 4), dtype=torch.float64, pin_memory=pin).numpy()
+    gaps = rng.standard_exponential(n + 1)
+    t = np.cumsum(gaps[:n])
+    t *= 0.05e6 / (t[-1] + gaps[n])
     t -= t[0]
-    return np.stack([t, rng.integers(0, w, size=n).astype(np.float64), rng.integers(0, h, size=n).astype(np.float64),
-                     2.0 * rng.integers(0, 2, size=n) - 1.0], axis=1)
+    out[:, 0] = t
+    out[:, 1] = rng.integers(0, w, size=n)
+    out[:, 2] = rng.integers(0, h, size=n)
+    out[:, 3] = rng.integers(0, 2, size=n)
+    out[:, 3] *= 2.0
+    out[:, 3] -= 1.0
+    return out
 
 
-def make_host_inputs(B: int, lookups: int, seed: int, pin: bool):
+def make_host_inputs(wl, B, lookups, seed, pin):
     rng = np.random.default_rng(seed)
     g = torch.Generator().manual_seed(seed)
 
@@ -99,14 +137,14 @@ def make_host_inputs(B: int, lookups: int, seed: int, pin: bool):
         x = torch.randn(*shape, generator=g) * scale
         return x.pin_memory() if pin else x
 
-    inp = {"events": [make_events(rng, EVENTS_PER_WINDOW, H, W) for _ in range(2 * B)]}
-    inp["f1"], inp["f2"] = t(B, FD, FH, FW), t(B, FD, FH, FW)
-    base = torch.stack(torch.meshgrid(torch.arange(FH), torch.arange(FW), indexing="ij")[::-1], 0).float()
-    inp["coords"] = [(base[None] + t(B, 2, FH, FW, scale=3.0)) for _ in range(lookups)]
+    inp = {"events": [make_events(rng, wl.EVENTS_PER_WINDOW, wl.H, wl.W, pin) for _ in range(2 * B)]}
+    inp["f1"], inp["f2"] = t(B, FD, wl.FH, wl.FW), t(B, FD, wl.FH, wl.FW)
+    base = torch.stack(torch.meshgrid(torch.arange(wl.FH), torch.arange(wl.FW), indexing="ij")[::-1], 0).float()
+    inp["coords"] = [(base[None] + t(B, 2, wl.FH, wl.FW, scale=3.0)) for _ in range(lookups)]
     if pin:
         inp["coords"] = [c.pin_memory() for c in inp["coords"]]
     inp["eem"] = []
-    for (c, h, w) in EEM_LEVELS:
+    for (c, h, w) in wl.EEM_LEVELS:
         inp["eem"].append({"f1": t(B, c, h, w), "f2": t(B, c, h, w), "p1": t(B, 32, h, w), "p2": t(B, 32, h, w),
                            "inter": t(B, 2, h, w, scale=1.5), "mask": torch.sigmoid(t(B, 1, h, w)),
                            "flow": t(B, 2, h, w, scale=2.0)})
@@ -114,52 +152,62 @@ def make_host_inputs(B: int, lookups: int, seed: int, pin: bool):
         for lv in inp["eem"]:
             for k in lv:
                 lv[k] = lv[k].pin_memory()
+    inp["flow_gt"] = t(B, 2, wl.H, wl.W, scale=2.0)
     return inp
 
 
-def h2d_bytes(inp, columns: bool = False) -> int:
+def h2d_bytes(inp, columns=False):
     ev_bytes = sum(13 * e.shape[0] for e in inp["events"]) if columns else sum(e.nbytes for e in inp["events"])
     n = ev_bytes + inp["f1"].numel() * 4 * 2 + sum(c.numel() * 4 for c in inp["coords"])
     for lv in inp["eem"]:
         n += sum(v.numel() * 4 for v in lv.values())
-    return n
+    return n, ev_bytes
 
 
 # ------------------------------------------------------------------------------------------------
 # the step, B200 arm
 # ------------------------------------------------------------------------------------------------
 class B200Step:
-    def __init__(self, inp, dev, lookups):
+    FAMILIES = ("voxelize", "corr_pyramid", "corr_lookup", "eemflow_ops", "metrics")
+
+    def __init__(self, wl, inp, dev, lookups, corr):
         import eemflow_b200 as E
         from eemflow_b200 import ops
-        from eemflow_b200.correlation import EEMFLOW_CDC_INDEX
-        self.E, self.ops, self.index = E, ops, EEMFLOW_CDC_INDEX
-        self.dev, self.lookups = dev, lookups
+        from eemflow_b200.eval_utils import flow_error_stats
+        self.E, self.ops, self.flow_error_stats = E, ops, flow_error_stats
+        self.wl, self.dev, self.lookups, self.corr = wl, dev, lookups, corr
         self.host = inp
         self.B = inp["f1"].shape[0]
-        self.target = torch.empty(self.B, 1, H, W, device=dev)
-        self.enc = E.EventSequenceToVoxelGrid_Pytorch(NB, gpu=True, gpu_nr=dev.index or 0, normalize=True, forkserver=False)
-        self.seqs = [E.EventSequence(None, {"height": H, "width": W}, features=e) for e in inp["events"]]
+        self.target = torch.empty(self.B, 1, wl.H, wl.W, device=dev)
+        self.seqs = [E.EventSequence(None, {"height": wl.H, "width": wl.W}, features=e) for e in inp["events"]]
         self.columns = None       # packed-column copy of the same events (--events-format columns)
         # device-resident copies for the kernel-only number
-        ev = np.concatenate(inp["events"], 0)
-        self.d_events = torch.from_numpy(ev).to(dev)
+        self.d_events = torch.cat([torch.from_numpy(e).to(dev) for e in inp["events"]], 0)
         counts = [e.shape[0] for e in inp["events"]]
         self.d_offsets = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int64, device=dev)
         self.max_n = max(counts)
         self.d = {"f1": inp["f1"].to(dev), "f2": inp["f2"].to(dev), "coords": [c.to(dev) for c in inp["coords"]],
                   "eem": [{k: v.to(dev) for k, v in lv.items()} for lv in inp["eem"]]}
+        self.flow_gt = inp["flow_gt"].to(dev)
+        self.metric_acc = torch.zeros((self.B, 5), dtype=torch.float64, device=dev)
+        self.flow_out = None      # optional destination of the final flow (e.g. a slot of rank 0's result buffer)
         self.out_host = None
         self.flow_host = None
         self.lanes = None
 
-    # ---- the four kernel families of a step; each is also captured as its own CUDA graph ----------
+    # ---- the kernel families of a step; each is also captured as its own CUDA graph ----------
     def fam_voxelize(self):
-        self.grids = self.ops.voxelize(self.d_events, self.d_offsets, self.max_n, NB, H, W, normalize=True)
+        wl = self.wl
+        self.grids = self.ops.voxelize(self.d_events, self.d_offsets, self.max_n, wl.NB, wl.H, wl.W, normalize=True)
+
+    def fam_voxel_vote(self):
+        """K1 alone (zero-init + votes -> raw grid), for the voxelization roofline."""
+        wl = self.wl
+        self.raw = self.ops.voxelize(self.d_events, self.d_offsets, self.max_n, wl.NB, wl.H, wl.W, normalize=False)
 
     def fam_corr_pyramid(self, d=None):
         d = d or self.d
-        self.blk = self.E.CorrBlock(d["f1"], d["f2"], num_levels=LEVELS, radius=RADIUS, precision="tf32")
+        self.blk = self.E.CorrBlock(d["f1"], d["f2"], num_levels=LEVELS, radius=RADIUS, precision=self.corr)
 
     def fam_corr_lookup(self, d=None):
         d = d or self.d
@@ -169,9 +217,10 @@ class B200Step:
     def fam_eemflow_ops(self, d=None):
         d = d or self.d
         E = self.E
+        index = EEMFLOW_CDC_INDEX
         flows = []
         lv = d["eem"][0]
-        E.correlation_select(lv["f1"], lv["f2"], self.index)
+        E.correlation_select(lv["f1"], lv["f2"], index)
         flow = lv["flow"]
         flows.append(flow)
         for lv in d["eem"][1:]:
@@ -179,13 +228,17 @@ class B200Step:
             E.WarpingLayer_no_div()(lv["p2"], flow_up)
             flow_up = E.cdc_blend(flow_up, lv["inter"], lv["mask"])
             f2w = E.warp(lv["f2"], flow_up)
-            E.correlation_select(lv["f1"], f2w, self.index)
+            E.correlation_select(lv["f1"], f2w, index)
             flow = flow_up
             flows.append(flow)
-        finals = [E.upsample2d_flow_as(f.clone(), self.target, mode="bilinear", if_rate=True) for f in flows]
+        finals = [E.upsample2d_flow_as(f.clone(), self.target, mode="bilinear", if_rate=True) for f in flows[:-1]]
+        finals.append(E.upsample2d_flow_as(flows[-1].clone(), self.target, mode="bilinear", if_rate=True, out=self.flow_out))
         self.flow = finals[-1]
 
-    FAMILIES = ("voxelize", "corr_pyramid", "corr_lookup", "eemflow_ops")
+    def fam_metrics(self):
+        # EPE sums / counts of this rank's pairs, accumulated on the device like the reference's evaluation loop
+        # accumulates its AEE sums (test_mvsec.py:291-346); reduced over the ranks once at the end of the run
+        self.metric_acc.add_(self.flow_error_stats(self.flow_gt, self.flow))
 
     def resident(self):
         """One step with inputs already in HBM; returns (last lookup, final flow)."""
@@ -193,35 +246,38 @@ class B200Step:
         self.fam_corr_pyramid()
         self.fam_corr_lookup()
         self.fam_eemflow_ops()
+        self.fam_metrics()
         return self.out, self.flow
 
     class _Lane:
         """Streams, device input buffers, pinned result buffers and a voxel encoder of one in-flight step."""
 
     def _make_lane(self):
-        dev, ln = self.dev, B200Step._Lane()
+        dev, wl, ln = self.dev, self.wl, B200Step._Lane()
         ln.d = {"f1": torch.empty_like(self.d["f1"]), "f2": torch.empty_like(self.d["f2"]),
                 "coords": [torch.empty_like(c) for c in self.d["coords"]],
                 "eem": [{k: torch.empty_like(v) for k, v in lv.items()} for lv in self.d["eem"]]}
         ln.main, ln.h2d, ln.d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        ln.enc = self.E.EventSequenceToVoxelGrid_Pytorch(NB, gpu=True, gpu_nr=dev.index or 0, normalize=True, forkserver=False)
-        out_shape = (self.B, LEVELS * (2 * RADIUS + 1) ** 2, FH, FW)
+        ln.enc = self.E.EventSequenceToVoxelGrid_Pytorch(wl.NB, gpu=True, gpu_nr=dev.index or 0, normalize=True, forkserver=False)
+        out_shape = (self.B, LEVELS * (2 * RADIUS + 1) ** 2, wl.FH, wl.FW)
         ln.out_host = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
-        ln.flow_host = torch.empty((self.B, 2, H, W), dtype=torch.float32, pin_memory=True)
+        ln.flow_host = torch.empty((self.B, 2, wl.H, wl.W), dtype=torch.float32, pin_memory=True)
         return ln
+
+    N_LANES = 3
 
     def end_to_end(self, i=0):
         """Same step through the public API from HOST buffers: numpy events, pinned feature maps in,
         last correlation features + final flow out to pinned host memory.
 
-        Two steps are in flight (lane = i % 2), each on its own streams and buffers, so the copies of one step
-        overlap the kernels of the other as in any double-buffered serving loop; every step still uploads all of
+        N_LANES steps are in flight (lane = i % N_LANES), each on its own streams and buffers, so the copies of one
+        step overlap the kernels of the others as in any multi-buffered serving loop; every step still uploads all of
         its inputs and reads back its results.  Within a lane the pinned tensors go up on a copy stream while the
         host stages the event rows, and the results come back on a third stream."""
         if self.lanes is None:
-            self.lanes = [self._make_lane(), self._make_lane()]
-        ln = self.lanes[i % 2]
-        hi, d = self.host, ln.d
+            self.lanes = [self._make_lane() for _ in range(self.N_LANES)]
+        ln = self.lanes[i % self.N_LANES]
+        hi, d, wl = self.host, ln.d, self.wl
         with torch.cuda.stream(ln.main):
             cur = ln.main
             ln.h2d.wait_stream(cur)               # the lane's previous step is done with these device buffers
@@ -233,7 +289,7 @@ class B200Step:
                 corr_in = torch.cuda.Event()
                 corr_in.record()
             if self.columns is not None:          # stages the events while the copies above are on the link
-                ln.enc.voxelize_columns(self.columns, H, W)
+                ln.enc.voxelize_columns(self.columns, wl.H, wl.W)
             else:
                 ln.enc.voxelize_batch(self.seqs)
             with torch.cuda.stream(ln.h2d):       # queued behind the event rows: arrives under voxelize/corr/lookup
@@ -252,6 +308,7 @@ class B200Step:
                 out.record_stream(ln.d2h)
             cur.wait_event(eem_in)
             self.fam_eemflow_ops(d)
+            self.fam_metrics()
             ln.flow_host.copy_(self.flow, non_blocking=True)
             cur.wait_stream(ln.d2h)
             self.flow.record_stream(cur)
@@ -269,16 +326,16 @@ class B200Step:
 # ------------------------------------------------------------------------------------------------
 # the step, CPU reference arm (oracle port: the reference's own ATen calls)
 # ------------------------------------------------------------------------------------------------
-def reference_step(inp, lookups):
+def reference_step(wl, inp, lookups):
     from oracle import ref_ops as R
     idx = EEMFLOW_CDC_INDEX
     for e in inp["events"]:
-        R.voxelize(e, NB, H, W, normalize=True)
+        R.voxelize(e, wl.NB, wl.H, wl.W, normalize=True)
     pyr = R.corr_pyramid(inp["f1"], inp["f2"], LEVELS)
     for c in inp["coords"][:lookups]:
         R.corr_lookup(pyr, c, RADIUS)
     B = inp["f1"].shape[0]
-    target = torch.empty(B, 1, H, W)
+    target = torch.empty(B, 1, wl.H, wl.W)
     lv = inp["eem"][0]
     R.correlation(lv["f1"], lv["f2"], 4, index=idx)
     flow = lv["flow"]
@@ -291,23 +348,31 @@ def reference_step(inp, lookups):
         R.correlation(lv["f1"], f2w, 4, index=idx)
         flow = flow_up
         flows.append(flow)
-    return [R.upsample2d_flow_as(f.clone(), target, if_rate=True) for f in flows][-1]
+    final = [R.upsample2d_flow_as(f.clone(), target, if_rate=True) for f in flows][-1]
+    for b in range(B):      # Test.flow_error per sample, dense evaluation (test_mvsec.py:291-346)
+        R.flow_error(inp["flow_gt"][b:b + 1], final[b:b + 1], None, False, "dense")
+    return final
 
 
-def time_reference(cpu_batch, lookups, steps, warmup, budget_s=25.0):
+def time_reference(wl, lookups, steps, warmup, budget_s):
+    """Times `steps` CPU steps after `warmup` untimed ones; stops early only when the time budget is spent."""
     torch.set_num_threads(os.cpu_count() or 1)
-    inp = make_host_inputs(cpu_batch, lookups, seed=1234, pin=False)
-    for _ in range(max(1, min(warmup, 2))):
-        reference_step(inp, lookups)
-    times = []
+    inp = make_host_inputs(wl, wl.cpu_batch, lookups, seed=1234, pin=False)
     t_all = time.perf_counter()
+    done_warm = 0
+    for _ in range(warmup):
+        reference_step(wl, inp, lookups)
+        done_warm += 1
+        if time.perf_counter() - t_all > 0.4 * budget_s:
+            break
+    times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        reference_step(inp, lookups)
+        reference_step(wl, inp, lookups)
         times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_all > budget_s and len(times) >= 3:
+        if time.perf_counter() - t_all > budget_s:
             break
-    return times
+    return times, done_warm
 
 
 # ------------------------------------------------------------------------------------------------
@@ -419,170 +484,116 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def lookup_algorithmic_bytes(B):
-    """per position 4*L*81 written + 8 coords + 4*sum_l min((2r+2)^2, P_l) volume taps read."""
-    P = FH * FW
-    taps, h, w = 0, FH, FW
+# roofline of the dominant kernel family (DESIGN.md section 4 defines the algorithmic bytes)
+# ------------------------------------------------------------------------------------------------
+def lookup_algorithmic_bytes(wl, B, corr):
+    """K5, per position: 4*L*81 written + 8 coords + s*sum_l min((2r+2)^2, P_l) volume taps read, s = bytes per
+    stored volume element (4 for the f32 pyramid, 2 for the fp16 working pyramid)."""
+    s = 2 if corr == "tf32_f16" else 4
+    P = wl.FH * wl.FW
+    taps, h, w = 0, wl.FH, wl.FW
     for _ in range(LEVELS):
         taps += min((2 * RADIUS + 2) ** 2, h * w)
         h, w = h // 2, w // 2
-    return B * P * (4 * LEVELS * (2 * RADIUS + 1) ** 2 + 8 + 4 * taps)
+    return B * P * (4 * LEVELS * (2 * RADIUS + 1) ** 2 + 8 + s * taps)
 
 
-def ncu_traffic(kernel, args):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of
-    this very command (profiles/r01/ncu_full_summary_v5.json); only quoted for the workload it was captured on."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01", "ncu_full_summary_v5.json")
-    if args.workload != "mvsec_dt1" or args.batch != 32 or not os.path.exists(path):
-        return None, None
-    try:
-        with open(path) as fh:
-            d = json.load(fh)[kernel]
-        return int(d["dram_rd"] + d["dram_wr"]), "profiles/r01/prof_%s_v5_raw.csv (ncu --set full, one launch)" % kernel
-    except (KeyError, ValueError, TypeError):
-        return None, None
+def voxel_algorithmic_bytes(wl, B):
+    """K1, per window: 32*N event-row bytes read + 4*nb*H*W grid bytes written once."""
+    return 2 * B * (32 * wl.EVENTS_PER_WINDOW + 4 * wl.NB * wl.H * wl.W)
+
+
+def ncu_traffic(kernel, wl, B, corr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this
+    very command (profiles/r0N/ncu_full_summary*.json); only quoted for the workload/batch it was captured on."""
+    for rel in ("profiles/r02/ncu_full_summary.json", "profiles/r01/ncu_full_summary_v5.json"):
+        path = ROOT / rel
+        if not path.exists():
+            continue
+        try:
+            d = json.loads(path.read_text())
+            meta = d.get("_meta", {"workload": "mvsec_dt1", "batch": 32, "corr": "tf32"})
+            if meta.get("workload") != wl.name or meta.get("batch") != B or meta.get("corr", "tf32") != corr:
+                continue
+            k = d[kernel]
+            return int(k["dram_rd"] + k["dram_wr"]), f"{rel} [{kernel}] (ncu --set full, one launch)"
+        except (KeyError, ValueError, TypeError):
+            continue
+    return None, None
 
 
 def peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
         p = json.loads(f.read_text())
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def main():
-    args = parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    if args.batch is None:
-        args.batch = wl.pop("batch", 32)
-    if args.cpu_batch is None:
-        args.cpu_batch = wl.pop("cpu_batch", 2)
-    wl.pop("batch", None), wl.pop("cpu_batch", None)
-    globals().update(wl)          # H, W, NB, EVENTS_PER_WINDOW, FH, FW, EEM_LEVELS of the chosen workload
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": f"{args.workload}_{H}x{W}_batch{args.batch}_voxelize+corrblock4x4+eemflow_cdc_ops",
-              "pairs_per_gpu": args.batch, "windows_per_pair": 2, "events_per_window": EVENTS_PER_WINDOW,
-              "voxel": f"{NB}x{H}x{W}", "fmap": f"{FD}x{FH}x{FW}", "corr_levels": LEVELS, "radius": RADIUS,
-              "lookups_per_pair": args.lookups, "eemflow_levels": EEM_LEVELS,
-              "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
-              "l2": "no explicit flush: a step streams > 1 GB (the correlation volume alone is written then gathered 12x) >> 126 MB L2"}
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        times = time_reference(args.cpu_batch, args.lookups, args.steps, args.warmup, budget_s=120.0)
-        ms = 1e3 * statistics.mean(times)
-        val = args.cpu_batch / statistics.mean(times)
-        cores = os.cpu_count() or 1
-        sample = f"{args.cpu_batch} frame pairs per step (of the {args.batch}-pair batch), {len(times)} timed steps"
-        line = {"impl": "reference", "metric": "frame-pairs/sec (voxelize+corr+lookup+warp)", "value": val, "unit": "frame-pairs/s",
-                "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 event times)", "data": "synthetic",
-                "config": dict(config, pairs_per_step=args.cpu_batch),
-                "cpu_baseline": {"value": val, "unit": "frame-pairs/s", "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": val, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
-        return
-
+# ------------------------------------------------------------------------------------------------
+# one workload on the B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_clocks):
     from eemflow_b200 import _lib
     from eemflow_b200 import dist as edist
-    assert torch.cuda.is_available(), "bench.py (b200 arm) needs a CUDA device; there is no CPU fallback"
-    rank, world, local_rank = edist.init_from_env("nccl")
-    dev = torch.device("cuda", local_rank if world > 1 else 0)
-    torch.cuda.set_device(dev)
     lib = _lib.lib()
-
-    inp = make_host_inputs(args.batch, args.lookups, seed=100 + rank, pin=True)
-    step = B200Step(inp, dev, args.lookups)
+    B = wl.batch
+    inp = make_host_inputs(wl, B, args.lookups, seed=100 + rank, pin=True)
+    step = B200Step(wl, inp, dev, args.lookups, args.corr)
     if args.events_format == "columns":
         step.columns = [{"t": np.ascontiguousarray(e[:, 0]), "x": e[:, 1].astype(np.int16), "y": e[:, 2].astype(np.int16),
                          "p": e[:, 3].astype(np.int8)} for e in inp["events"]]
 
-    def eager_step():
-        out, flow = step.resident()
-        if world > 1:                       # result gather only; nothing on the data path
-            edist.gather_batch(flow, total=world * args.batch)
-        return out, flow
+    # N > 1: nothing on the data path is exchanged.  The result flows go to rank 0 every step: the kernel that
+    # produces the final flow writes it straight into rank 0's result buffer over NVLink (peer memory), or -- when
+    # peer memory cannot be set up -- an NCCL gather on a communication stream overlaps the next step.  The step is
+    # captured twice (two result slots) and the replays alternate, so rank 0 may read step i's flows while step i+1
+    # is being written.  Metric accumulators are reduced once, at the end of the run.
+    sink = edist.ResultSink((B, 2, wl.H, wl.W), torch.float32, dev, dst=0, slots=2) if world > 1 else None
 
-    for _ in range(max(3, args.warmup)):
-        eager_step()
+    for _ in range(max(3, warmup)):
+        step.resident()
     torch.cuda.synchronize()
 
-    # The step is ~55 short kernels; issued one by one from Python the launch path is as long as the
-    # GPU work, so the resident step is captured once into a CUDA graph and replayed (the graph holds
-    # exactly the launches of one eager step; buffers live in a shared private pool).  The four kernel
-    # families are additionally captured as their own graphs for the per-family split.
+    # The step is ~55 short kernels; issued one by one from Python the launch path is as long as the GPU work, so
+    # the resident step is captured once into a CUDA graph and replayed (the graph holds exactly the launches of one
+    # eager step).  The kernel families are additionally captured as their own graphs for the per-family split.
+    n_graphs = 2 if world > 1 else 1
+    graphs, flows = [], []
+    launches_per_step = 0
+    for k in range(n_graphs):
+        step.flow_out = sink.slot(k) if (sink is not None and sink.direct) else None
+        launches_a = lib.eem_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            _, f = step.resident()
+        launches_per_step = lib.eem_launch_count() - launches_a
+        graphs.append(g)
+        flows.append(f)
+    step.flow_out = None
     pool = torch.cuda.graph_pool_handle()
-    launches_a = lib.eem_launch_count()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, pool=pool):
-        g_out, g_flow = step.resident()
-    launches_per_step = lib.eem_launch_count() - launches_a
     fam_graphs = {}
-    for name in B200Step.FAMILIES:
+    for name in B200Step.FAMILIES + ("voxel_vote",):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, pool=pool):
             getattr(step, "fam_" + name)()
         fam_graphs[name] = g
-
-    # N > 1: nothing on the data path is exchanged.  The result gather (flows of all ranks, rank order) and the
-    # metric reduction run on a communication stream and overlap the next step's kernels; the timed region ends
-    # only after the last gather has completed.  The step is captured twice (same kernels, two sets of output
-    # buffers) and the replays alternate, so the collective reads step i's flow while step i+1 writes the other
-    # buffer -- no snapshot copy, and nothing but graph launches and event waits on the compute stream.
-    graphs, flows = [graph], [g_flow]
-    if world > 1:
-        from eemflow_b200.eval_utils import flow_error_stats
-        comm = torch.cuda.Stream(dev)
-        gathered = [torch.empty((world * args.batch,) + tuple(g_flow.shape[1:]), device=dev) for _ in range(2)]
-        flow_read = [None, None]
-        flow_gt = torch.zeros_like(g_flow).add_(0.5)
-        metric_acc = torch.zeros((args.batch, 5), dtype=torch.float64, device=dev)
-        with_metrics = os.environ.get("EEM_BENCH_METRICS", "1") != "0"     # timing experiments only
-
-        def step_with_metrics():
-            _, flow = step.resident()
-            if with_metrics:
-                # EPE sums / counts of this rank's pairs, accumulated on the device like the reference's evaluation
-                # loop accumulates its AEE sums (test_mvsec.py:291-346); reduced over the ranks once, in drain()
-                metric_acc.add_(flow_error_stats(flow_gt, flow))
-            return flow
-
-        graphs, flows = [], []
-        for _ in range(2):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):              # own memory pool: replays overlap with the collective
-                f = step_with_metrics()
-            graphs.append(g)
-            flows.append(f)
-        metric_acc.zero_()
+    step.metric_acc.zero_()
     step_no = [0]
 
     def timed_step():
-        k = step_no[0] % len(graphs)
+        k = step_no[0] % n_graphs
         step_no[0] += 1
-        if world == 1:
-            graph.replay()
-            return
-        cur = torch.cuda.current_stream(dev)
-        if flow_read[k] is not None:
-            cur.wait_event(flow_read[k])            # the gather issued two steps ago has read flows[k]
+        if sink is not None:
+            sink.before_write(k)
         graphs[k].replay()
-        if os.environ.get("EEM_BENCH_GATHER", "1") != "0":     # timing experiments only
-            ready = torch.cuda.Event()
-            ready.record(cur)
-            with torch.cuda.stream(comm):
-                comm.wait_event(ready)
-                edist.gather_batch(flows[k], total=world * args.batch, out=gathered[k])
-                flow_read[k] = torch.cuda.Event()
-                flow_read[k].record(comm)
+        if sink is not None:
+            sink.after_write(k, flows[k])
 
     def drain():
-        if world > 1:
-            torch.cuda.current_stream(dev).wait_stream(comm)
-            edist.reduce_metrics(metric_acc)            # the one metric collective of the run
+        if sink is not None:
+            sink.drain()
+            edist.reduce_metrics(step.metric_acc)            # the one metric collective of the run
 
     for _ in range(3):
         timed_step()
@@ -590,66 +601,84 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    sampler = ClockSampler(dev.index or 0)
-    if rank == 0:
+    sampler = ClockSampler(dev.index or 0) if (rank == 0 and sample_clocks) else None
+    if sampler:
         sampler.start()
     torch.cuda.synchronize()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         timed_step()
     drain()
     t_stop.record()
-    if rank == 0:                       # the steps are only enqueued so far: the device is executing them right now
+    if sampler:                         # the steps are only enqueued so far: the device is executing them right now
         for _ in range(4):
             sampler.poke()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     elapsed_ms = edist.max_over_ranks(t_start.elapsed_time(t_stop), dev)
-    launches = launches_per_step * args.steps
+    launches = launches_per_step * steps
 
-    # Same K steps again as four family graphs with CUDA events between the replays (events cannot be
-    # timed inside one replayed graph): per-family split and the dominant kernel's launch duration.
+    # Same K steps again as family graphs with CUDA events between the replays (events cannot be timed inside one
+    # replayed graph): per-family split and the dominant kernel's launch duration.
     def mark():
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         return e
 
+    names = B200Step.FAMILIES + ("voxel_vote",)
     marks = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         marks.append(mark())
-        for name in B200Step.FAMILIES:
+        for name in names:
             fam_graphs[name].replay()
             marks.append(mark())
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
 
-    fam = {name: 0.0 for name in B200Step.FAMILIES}
-    for s_ in range(args.steps):
-        m = marks[5 * s_: 5 * s_ + 5]
-        for k_, name in enumerate(B200Step.FAMILIES):
+    nm = len(names) + 1
+    fam = {name: 0.0 for name in names}
+    for s_ in range(steps):
+        m = marks[nm * s_: nm * s_ + nm]
+        for k_, name in enumerate(names):
             fam[name] += m[k_].elapsed_time(m[k_ + 1])
-    total_fam = sum(fam.values())
-    lookup_ms = fam["corr_lookup"] / (args.steps * args.lookups)
+    fam_ms = {k: v / steps for k, v in fam.items()}
+    vote_ms = fam_ms.pop("voxel_vote")
+    total_fam = sum(fam_ms.values())
     peak, peak_src = peaks()
-    algo = lookup_algorithmic_bytes(args.batch)
-    achieved = algo / (lookup_ms * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic("corr_lookup_kernel", args)
-    roofline = {"kernel": "corr_lookup_kernel<4>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    dominant = max(fam_ms, key=fam_ms.get)
+    # the roofline is quoted for the dominant family's kernel when that family is one kernel (voxelize -> K1 vote
+    # pass, corr_lookup -> K5); for the multi-kernel families the larger of the two single-kernel families is used
+    if dominant not in ("voxelize", "corr_lookup"):
+        dominant = "voxelize" if fam_ms["voxelize"] >= fam_ms["corr_lookup"] else "corr_lookup"
+    if dominant == "corr_lookup":
+        kernel = "corr_lookup_packed_kernel<4>" if args.corr == "tf32_f16" else "corr_lookup_kernel<4>"
+        ncu_key = "corr_lookup_packed_kernel" if args.corr == "tf32_f16" else "corr_lookup_kernel"
+        launch_ms = fam_ms["corr_lookup"] / args.lookups
+        algo = lookup_algorithmic_bytes(wl, B, args.corr)
+        timing = f"CUDA events around a graph replay of the {args.lookups} lookups, K steps, same inputs as the timed region"
+    else:
+        kernel, ncu_key = "K1 voxel vote (eem_voxelize, normalize=0: zero-init + votes -> raw grid)", "voxel_vote"
+        launch_ms = vote_ms
+        algo = voxel_algorithmic_bytes(wl, B)
+        timing = "CUDA events around a graph replay of one un-normalised eem_voxelize call over the step's 2B windows, K steps"
+    achieved = algo / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(ncu_key, wl, B, args.corr)
+    roofline = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo,
-                "avg_launch_ms": lookup_ms, "share_of_step": fam["corr_lookup"] / total_fam,
-                "timing": "CUDA events around a graph replay of the 12 lookups, K steps, same inputs as the timed region",
-                "family_ms_per_step": {k: v / args.steps for k, v in fam.items()}}
+                "algorithmic_bytes_per_launch": algo, "avg_launch_ms": launch_ms,
+                "share_of_step": fam_ms[dominant] / total_fam, "timing": timing,
+                "family_ms_per_step": fam_ms, "voxel_vote_ms": vote_ms,
+                "voxel_vote_frac_of_hbm_peak": voxel_algorithmic_bytes(wl, B) / (vote_ms * 1e-3) / 1e9 / peak}
 
-    value = args.batch * world * args.steps / (elapsed_ms * 1e-3)
+    value = B * world * steps / (elapsed_ms * 1e-3)
 
     # end to end through the public API from host buffers
     e2e = None
-    if not args.no_e2e:
-        k = max(5, args.steps // 2)
-        for i in range(max(6, args.warmup)):
+    if do_e2e:
+        k = max(5, steps // 2)
+        for i in range(max(2 * B200Step.N_LANES, warmup)):
             step.end_to_end(i)
         torch.cuda.synchronize()
         if world > 1:
@@ -657,28 +686,100 @@ def main():
         t0 = time.perf_counter()
         for i in range(k):
             flow = step.end_to_end(i)
-            if world > 1:
-                torch.cuda.current_stream().wait_stream(step.lanes[i % 2].main)
-                edist.gather_batch(flow, total=world * args.batch)
+            if sink is not None:
+                torch.cuda.current_stream().wait_stream(step.lanes[i % B200Step.N_LANES].main)
+                sink.push(i % 2, flow)
+        if sink is not None:
+            sink.drain()
         torch.cuda.synchronize()
         dt = edist.max_over_ranks(time.perf_counter() - t0, dev)
-        e2e = {"value": args.batch * world * k / dt, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d_bytes(inp, args.events_format == "columns"), "events_format": args.events_format,
+        total_b, ev_b = h2d_bytes(inp, args.events_format == "columns")
+        e2e = {"value": B * world * k / dt, "unit": "frame-pairs/s", "h2d_bytes_per_step": total_b,
+               "h2d_event_bytes_per_step": ev_b, "events_format": args.events_format,
                "d2h_bytes_per_step": step.d2h_bytes(), "steps": k, "ms_per_step": 1e3 * dt / k,
+               "h2d_gbs_per_rank": total_b / (dt / k) / 1e9,
                "timer": "host perf_counter around synchronize (host staging + H2D + kernels + D2H)"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times = time_reference(args.cpu_batch, args.lookups, steps=12, warmup=1, budget_s=20.0)
-        cpu = {"value": args.cpu_batch / statistics.mean(times), "unit": "frame-pairs/s", "cores": os.cpu_count() or 1,
-               "kind": "port", "sample": f"{args.cpu_batch} frame pairs per step x {len(times)} steps of the same workload, "
+    if do_cpu and rank == 0 and world == 1:
+        times, _ = time_reference(wl, args.lookups, steps=12, warmup=1, budget_s=25.0)
+        cpu = {"value": wl.cpu_batch / statistics.mean(times), "unit": "frame-pairs/s", "cores": os.cpu_count() or 1,
+               "kind": "port", "sample": f"{wl.cpu_batch} frame pairs per step x {len(times)} steps of the same workload, "
                                          f"oracle/ref_ops.py (the reference's ATen calls), torch threads = {torch.get_num_threads()}"}
 
+    res = {"value": value, "ms_per_step": elapsed_ms / steps, "steps": steps, "warmup": max(3, warmup), "clocks": clocks,
+           "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+           "result_gather": None if sink is None else sink.describe()}
+    if sink is not None:
+        sink.close()
+    del step, graphs, fam_graphs, inp
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    head = workload(args.workload, args.batch, args.cpu_batch)
+    if args.workloads is None:
+        extra = ["hrem_dt1", "hrem_dt4"] if args.workload == "mvsec_dt1" else []
+    else:
+        extra = [w for w in args.workloads.split(",") if w and w != "none"]
+    extra = [w for w in extra if w != args.workload]
+    dtype = {"tf32": "f32 (tf32 tensor-core volume, f64 event times)", "fp32": "f32 (f64 event times)",
+             "tf32_f16": "f32 (tf32 tensor-core volume stored as fp16, f64 event times)"}[args.corr]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+
+        def ref_line(wl, steps, warmup, budget):
+            times, done_warm = time_reference(wl, args.lookups, steps, warmup, budget_s=budget)
+            val = wl.cpu_batch / statistics.mean(times)
+            sample = f"{wl.cpu_batch} frame pairs per step (of the {wl.batch}-pair batch), {len(times)} timed steps"
+            return {"value": val, "unit": "frame-pairs/s", "steps": len(times), "warmup": done_warm,
+                    "ms_per_step": 1e3 * statistics.mean(times), "config": config_of(wl, args, world),
+                    "cpu_baseline": {"value": val, "unit": "frame-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+                    "e2e": {"value": val, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+        r = ref_line(head, args.steps, args.warmup, 240.0)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frame-pairs/s", "n_gpus": args.gpus,
+                "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 event times)", "data": "synthetic",
+                "config": r["config"], "cpu_baseline": r["cpu_baseline"], "e2e": r["e2e"]}
+        if extra:
+            line["workloads"] = {name: ref_line(workload(name), min(args.steps, 3), 1, 60.0) for name in extra}
+        print(json.dumps(line), flush=True)
+        return
+
+    from eemflow_b200 import dist as edist
+    assert torch.cuda.is_available(), "bench.py (b200 arm) needs a CUDA device; there is no CPU fallback"
+    rank, world, local_rank = edist.init_from_env("nccl")
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    edist.pin_host_threads(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+
+    r = run_b200(head, args, rank, world, dev, args.steps, args.warmup, not args.no_e2e, not args.no_cpu_baseline, True)
+    subs = {}
+    for name in extra:
+        wl = workload(name)
+        s = run_b200(wl, args, rank, world, dev, max(3, min(args.steps, 10)), min(args.warmup, 3), not args.no_e2e,
+                     not args.no_cpu_baseline, False)
+        s["config"] = config_of(wl, args, world)
+        s["unit"] = "frame-pairs/s"
+        subs[name] = s
+
     if rank == 0:
-        line = {"metric": "frame-pairs/sec (voxelize+corr+lookup+warp)", "value": value, "unit": "frame-pairs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core volume, f64 event times)",
-                "data": "synthetic", "config": dict(config, launch="CUDA graph replay of one step"), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu}
+        line = {"metric": METRIC, "value": r["value"], "unit": "frame-pairs/s", "n_gpus": world,
+                "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": dict(config_of(head, args, world)), "launch": "CUDA graph replay of one step",
+                "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],
+                "roofline": r["roofline"], "cpu_baseline": r["cpu_baseline"], "result_gather": r["result_gather"]}
+        if subs:
+            line["workloads"] = subs
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -148,8 +148,10 @@ def backwarp(x, flow, convention, mask_mode=L.MASK_NONE):
         return ops.backwarp(x, flow, convention, mask_mode)
 
 
-def bilinear_resize(x, size, align_corners, scale0=1.0, scale1=1.0, scale_rest=1.0):
+def bilinear_resize(x, size, align_corners, scale0=1.0, scale1=1.0, scale_rest=1.0, out=None):
     if needs_grad(x):
+        if out is not None:
+            raise NotImplementedError("eemflow_b200: `out=` is an inference-only option of the flow resize")
         return ResizeFn.apply(x, tuple(size), align_corners, scale0, scale1, scale_rest)
     with torch.no_grad():
-        return ops.bilinear_resize(x, size, align_corners, scale0, scale1, scale_rest)
+        return ops.bilinear_resize(x, size, align_corners, scale0, scale1, scale_rest, out=out)

@@ -15,10 +15,16 @@ from . import ops
 
 
 def _default_precision(D: int, H: int, W: int) -> str:
+    """The reference forms the volume with fp32 torch.matmul (model/corr.py:58), where TF32 is off unless the
+    user sets torch.backends.cuda.matmul.allow_tf32.  The drop-in follows the same switch: exact fp32 by default,
+    the tcgen05 TF32 kernel when the user allowed TF32 (or asked for it with precision= / the environment
+    variable EEMFLOW_B200_CORR_PRECISION = fp32 | tf32 | tf32_f16) and the shape is one the tensor-core path takes."""
     env = os.environ.get("EEMFLOW_B200_CORR_PRECISION")
     if env:
         return env
-    return "tf32" if ops.tf32_supported(D, H, W) else "fp32"
+    if torch.backends.cuda.matmul.allow_tf32 and ops.tf32_supported(D, H, W):
+        return "tf32"
+    return "fp32"
 
 
 class CorrBlock:
@@ -43,11 +49,11 @@ class CorrBlock:
                 self.corr_pyramid = ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision)
 
     def __call__(self, coords):
+        if torch.is_grad_enabled() and coords.requires_grad:     # never a silent zero gradient
+            raise NotImplementedError(
+                "eemflow_b200.CorrBlock gives no gradient to the lookup coordinates; detach them as the "
+                "reference's callers do (model/eraft.py:141)")
         if ag.needs_grad(*self.corr_pyramid):
-            if torch.is_grad_enabled() and coords.requires_grad:
-                raise NotImplementedError(
-                    "eemflow_b200.CorrBlock gives no gradient to the lookup coordinates; detach them as the "
-                    "reference's callers do (model/eraft.py:141)")
             return ag.CorrLookupFn.apply(coords, self.radius, *self.corr_pyramid)
         with torch.no_grad():
             return ops.corr_lookup(self.corr_pyramid, coords, self.radius)

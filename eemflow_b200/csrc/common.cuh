@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 
 #include "../../include/eemflow_b200.h"
 
@@ -47,6 +48,30 @@ void count_launch();
     if (e_ != cudaSuccess)                                                                  \
       return ::eem::fail(EEM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));            \
   } while (0)
+
+// Opt-in for more than 48 KiB of dynamic shared memory.  cudaFuncSetAttribute applies to the CURRENT device's
+// context only, so the "already configured" cache is kept per device: a process that touches a second GPU
+// (nn.DataParallel as in train_EEMFlow_HREM.py:117, a voxelizer with gpu_nr=1, a model moved to cuda:1) sets the
+// attribute there as well.  One instance (a function-local static) per kernel instantiation.
+constexpr int kMaxDevices = 64;
+struct DynSmemOptIn {
+  std::mutex mu;
+  size_t configured[kMaxDevices] = {};
+  template <class Kernel>
+  cudaError_t ensure(Kernel kernel, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices)
+      return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    std::lock_guard<std::mutex> lock(mu);
+    if (bytes > configured[dev]) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e == cudaSuccess) configured[dev] = bytes;
+    }
+    return e;
+  }
+};
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -200,15 +200,8 @@ int launch_lookup(const LookupParams& p, cudaStream_t stream) {
   using S = LookupSmem<R, PB>;
   const size_t smem = (size_t)p.L * S::kPerLevelBytes;
   dim3 grid((unsigned)ceil_div(p.H * p.W, PB), (unsigned)p.B);
-  static std::mutex mu;
-  static size_t configured = 0;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (smem > configured) {
-      EEM_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<R, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-  }
+  static DynSmemOptIn optin;
+  EEM_CHECK_CUDA(optin.ensure(corr_lookup_kernel<R, PB>, smem));
   corr_lookup_kernel<R, PB><<<grid, S::kThreads, smem, stream>>>(p);
   return EEM_OK;
 }
@@ -338,15 +331,8 @@ template <int R>
 int launch_lookup_backward(const LookupBwdParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int K = 2 * R + 1;
   const size_t smem = ((size_t)p.L * K * K * 33 + 2 * (size_t)p.L * kPosPerBlock * K) * 4 + (size_t)p.L * kPosPerBlock * 2 * 4;
-  static std::mutex mu;
-  static size_t configured = 0;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (smem > configured) {
-      EEM_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_backward_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-  }
+  static DynSmemOptIn optin;
+  EEM_CHECK_CUDA(optin.ensure(corr_lookup_backward_kernel<R>, smem));
   corr_lookup_backward_kernel<R><<<grid, 256, smem, stream>>>(p);
   return EEM_OK;
 }

@@ -849,16 +849,13 @@ int encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, 
   return EEM_OK;
 }
 
-// One function (hence one set of statics) per kernel instantiation: the > 48 KiB dynamic shared memory
-// opt-in is done once per instantiation, which also keeps it out of CUDA-graph capture.
+// One function (hence one opt-in cache) per kernel instantiation: the > 48 KiB dynamic shared memory opt-in is
+// done once per instantiation AND device (the warm-up call before a CUDA-graph capture does it).
 template <int BK, int BN, int CL>
 cudaError_t launch_tf32(cudaLaunchConfig_t cfg, const Tf32Params& p) {
   constexpr size_t kSmem = sizeof(Tf32Smem<BK, BN>) + 1024;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(corr_tf32_kernel<BK, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-  });
+  static DynSmemOptIn optin;
+  const cudaError_t attr_err = optin.ensure(corr_tf32_kernel<BK, BN, CL>, kSmem);
   if (attr_err != cudaSuccess) return attr_err;
   cfg.dynamicSmemBytes = kSmem;
   return cudaLaunchKernelEx(&cfg, corr_tf32_kernel<BK, BN, CL>, p);
@@ -867,11 +864,8 @@ cudaError_t launch_tf32(cudaLaunchConfig_t cfg, const Tf32Params& p) {
 template <int BK, int BN>
 cudaError_t launch_tf32_pair(cudaLaunchConfig_t cfg, const Tf32Params& p) {
   constexpr size_t kSmem = sizeof(Tf32PairSmem<BK, BN>) + 1024;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(corr_tf32_pair_kernel<BK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-  });
+  static DynSmemOptIn optin;
+  const cudaError_t attr_err = optin.ensure(corr_tf32_pair_kernel<BK, BN>, kSmem);
   if (attr_err != cudaSuccess) return attr_err;
   cfg.dynamicSmemBytes = kSmem;
   return cudaLaunchKernelEx(&cfg, corr_tf32_pair_kernel<BK, BN>, p);
@@ -962,15 +956,8 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
       }
     }
     const size_t smem = pyr_floats * sizeof(float);
-    static std::mutex mu;
-    static size_t configured = 48 * 1024;
-    {
-      std::lock_guard<std::mutex> lock(mu);
-      if (smem > configured) {
-        EEM_CHECK_CUDA(cudaFuncSetAttribute(pool_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-      }
-    }
+    static DynSmemOptIn optin;
+    if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(pool_pyramid_kernel, smem));
     int64_t blocks = planes;
     const int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;

@@ -288,11 +288,8 @@ local_corr_vec_kernel(const __grid_constant__ LocalCorrParams p) {
 template <unsigned MA, unsigned MB, unsigned MC, unsigned MD_, unsigned ME>
 int launch_vec(const LocalCorrParams& p, int B, int H, int W, cudaStream_t stream) {
   const size_t smem = 2 * (size_t)kStageFloats * sizeof(float);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(local_corr_vec_kernel<MA, MB, MC, MD_, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  });
+  static DynSmemOptIn optin;
+  const cudaError_t attr_err = optin.ensure(local_corr_vec_kernel<MA, MB, MC, MD_, ME>, smem);
   if (attr_err != cudaSuccess) return fail(EEM_ERR_CUDA, "local_corr_vec_kernel attribute: %s", cudaGetErrorString(attr_err));
   dim3 grid((unsigned)ceil_div(W, VW), (unsigned)ceil_div(H, VH), (unsigned)B);
   local_corr_vec_kernel<MA, MB, MC, MD_, ME><<<grid, kThreads, smem, stream>>>(p);

@@ -979,9 +979,12 @@ ClusterPlan cluster_plan(int64_t vox, int n_windows, int64_t n_total) {
   if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return pl;
   if (pl.smem > (size_t)optin) return pl;
   static std::mutex mu;
-  static size_t configured = 0;
-  static int cached_clusters = 0;
+  static size_t configured_dev[kMaxDevices] = {};       // per device: the attribute lives in the device's context
+  static int cached_clusters_dev[kMaxDevices] = {};
+  if (dev < 0 || dev >= kMaxDevices) return pl;
   std::lock_guard<std::mutex> lock(mu);
+  size_t& configured = configured_dev[dev];
+  int& cached_clusters = cached_clusters_dev[dev];
   if (pl.smem > configured || cached_clusters == 0) {
     if (cudaFuncSetAttribute(voxel_cluster_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) {
       cudaGetLastError();

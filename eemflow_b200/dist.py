@@ -96,3 +96,129 @@ def max_over_ranks(value: float, device: torch.device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def pin_host_threads(local_rank: int, local_world: int) -> list[int]:
+    """Give this rank its own contiguous share of the host cores (os.sched_setaffinity) and size the host thread
+    pools to it.  Eight ranks that each run an 8-thread staging pool on the same 32 cores (torchrun gives no
+    affinity) thrash each other: round 1 measured per-rank host->device throughput falling from 44 to 13.5 GB/s.
+    Returns the cores now owned (empty list when the platform offers no affinity call)."""
+    if local_world <= 1 or not hasattr(os, "sched_getaffinity"):
+        return []
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+        per = max(1, len(avail) // local_world)
+        mine = avail[local_rank * per:(local_rank + 1) * per] or avail
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return []
+    torch.set_num_threads(max(1, len(mine)))
+    from . import event_utils
+    event_utils.set_staging_threads(max(1, len(mine) - 1))
+    return mine
+
+
+class ResultSink:
+    """Delivery of every rank's per-step result (e.g. the final flows `[B_r, 2, H, W]`) to ONE rank.
+
+    The reference gathers results with nn.DataParallel (train_EEMFlow_HREM.py:116-117); evaluation consumes them on
+    one process.  Here rank `dst` owns a buffer `[slots, world, *shape]`:
+
+      direct   (peer memory available: torch symmetric memory over NVLink / NVSwitch)  every rank maps dst's buffer
+               into its own address space; `slot(k)` is this rank's slice of slot k, and the kernel that produces the
+               result writes it there (its stores travel over NVLink).  No collective kernel runs at all, nothing
+               competes with the step for SMs, and dst's HBM only sees the incoming writes.
+      gather   (fallback) `after_write` / `push` enqueue an NCCL gather to dst on a communication stream, overlapped
+               with the next step; `before_write` makes the producer wait until the previous gather has read the slot.
+
+    Slots alternate (step k uses slot k % slots) so that dst may consume step i while step i+1 is being produced.
+    """
+
+    def __init__(self, shape, dtype, device, dst: int = 0, slots: int = 2):
+        assert dist.is_initialized()
+        self.world, self.rank, self.dst, self.slots = dist.get_world_size(), dist.get_rank(), dst, slots
+        self.shape, self.dtype, self.device = tuple(shape), dtype, device
+        self.direct = False
+        self.peer = None
+        self.why = ""
+        ok = 0
+        if os.environ.get("EEM_RESULT_SINK", "direct") == "direct" and device.type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                full = (slots, self.world) + self.shape
+                self._buf = symm_mem.empty(full, dtype=dtype, device=device)
+                self._hdl = symm_mem.rendezvous(self._buf, dist.group.WORLD)
+                self.peer = self._hdl.get_buffer(dst, full, dtype)
+                ok = 1
+            except Exception as e:           # no peer memory on this platform: fall back to NCCL
+                self.why = f"{type(e).__name__}: {e}"[:200]
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # all ranks take the same path
+        self.direct = bool(flag.item())
+        self.cuda = device.type == "cuda"
+        if not self.direct:
+            self.peer = None
+            self.comm = torch.cuda.Stream(device) if self.cuda else None
+            self.read_done = [None] * slots
+            self.gathered = None
+            if self.rank == dst:
+                self.gathered = torch.empty((slots, self.world) + self.shape, dtype=dtype, device=device)
+
+    def slot(self, k: int) -> torch.Tensor:
+        """This rank's slice of result slot k in dst's memory (direct mode only)."""
+        assert self.direct
+        return self.peer[k % self.slots, self.rank]
+
+    def buffer(self) -> torch.Tensor | None:
+        """On dst: `[slots, world, *shape]`; elsewhere None."""
+        if self.rank != self.dst:
+            return None
+        return self.peer if self.direct else self.gathered
+
+    def before_write(self, k: int) -> None:
+        if not self.direct and self.cuda and self.read_done[k % self.slots] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.read_done[k % self.slots])
+
+    def after_write(self, k: int, local: torch.Tensor) -> None:
+        """`local` has been produced on the current stream (direct mode: already written through slot(k))."""
+        if self.direct:
+            return
+        if not self.cuda:                 # host tensors (gloo): a synchronous gather
+            self._gather(k, local)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            self._gather(k, local)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+            self.read_done[k % self.slots] = ev
+
+    def push(self, k: int, local: torch.Tensor) -> None:
+        """Deliver a result that lives in this rank's own memory."""
+        if self.direct:
+            self.slot(k).copy_(local, non_blocking=True)       # device-to-peer copy over NVLink
+        else:
+            self.before_write(k)
+            self.after_write(k, local)
+
+    def _gather(self, k: int, local: torch.Tensor) -> None:
+        if self.rank == self.dst:
+            dist.gather(local.contiguous(), list(self.gathered[k % self.slots].unbind(0)), dst=self.dst)
+        else:
+            dist.gather(local.contiguous(), None, dst=self.dst)
+
+    def drain(self) -> None:
+        if not self.direct and self.comm is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)
+
+    def describe(self) -> dict:
+        return {"mode": "direct peer-memory stores over NVLink (no collective kernel)" if self.direct else "NCCL gather to one rank",
+                "dst": self.dst, "slots": self.slots, "fallback_reason": self.why or None}
+
+    def close(self) -> None:
+        self.peer = None
+        self._buf = None
+        self._hdl = None

@@ -78,6 +78,17 @@ def _is_dataframe(obj) -> bool:
 _STAGE_CHUNK_ROWS = 1 << 17      # 4 MiB of [*,4] float64 rows per staging task
 _STAGE_FLUSH_ROWS = 1 << 18      # issue the host->device copy every 8 MiB staged
 _stage_pool = None
+_stage_threads = None
+
+
+def set_staging_threads(n: int) -> None:
+    """Size of the staging pool (default: min(8, usable cores - 1)).  Multi-rank launchers give every rank its share
+    of the cores (eemflow_b200.dist.pin_host_threads) so the pools of different ranks do not oversubscribe the host."""
+    global _stage_pool, _stage_threads
+    _stage_threads = max(1, int(n))
+    if _stage_pool is not None:
+        _stage_pool.shutdown(wait=True)
+        _stage_pool = None
 
 
 def _staging_pool():
@@ -86,8 +97,19 @@ def _staging_pool():
     if _stage_pool is None:
         import os
         from concurrent.futures import ThreadPoolExecutor
-        _stage_pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1)), thread_name_prefix="eem-stage")
+        usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
+        n = _stage_threads if _stage_threads is not None else max(1, min(8, usable - 1))
+        _stage_pool = ThreadPoolExecutor(max_workers=n, thread_name_prefix="eem-stage")
     return _stage_pool
+
+
+def _is_pinned(a: numpy.ndarray) -> bool:
+    """True when the array already lives in page-locked host memory (e.g. produced by a DataLoader with
+    pin_memory=True, or a view of a pinned torch tensor): the DMA engine can read it directly."""
+    try:
+        return bool(a.flags.c_contiguous and a.dtype == numpy.float64 and torch.from_numpy(a).is_pinned())
+    except (TypeError, ValueError, RuntimeError):
+        return False
 
 
 class _PinnedStage:
@@ -120,7 +142,18 @@ class _PinnedStage:
         numpy.cumsum(counts, out=off_host[1:len(arrays) + 1])
         with torch.cuda.device(device):
             off = self.off[:len(arrays) + 1].to(device, non_blocking=True)
-            if total <= _STAGE_CHUNK_ROWS:
+            if total > 0 and all(_is_pinned(a) for a in arrays):
+                # page-locked caller arrays: no staging pass, one DMA per window straight from the caller's memory
+                key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+                buf = self.dev_buf.get(key)
+                if buf is None or buf.shape[0] < total:
+                    buf = self.dev_buf[key] = torch.empty((total, 4), dtype=torch.float64, device=device)
+                ev = buf[:total]
+                pos = 0
+                for a, n in zip(arrays, counts):
+                    ev[pos:pos + n].copy_(torch.from_numpy(a), non_blocking=True)
+                    pos += n
+            elif total <= _STAGE_CHUNK_ROWS:
                 pos = 0
                 for a, n in zip(arrays, counts):
                     host[pos:pos + n] = a  # astype('float') + from_numpy of the reference, in one copy
@@ -157,8 +190,12 @@ class _PinnedStage:
 class EventSequenceToVoxelGrid_Pytorch(object):
     """Time-bilinear polarity voxel grid; signature of utils/transformers.py:20.
 
-    Extra keyword arguments (all optional, defaults keep the reference behaviour):
-      deterministic  sort-by-voxel mode, bit-exact against the reference's CPU result
+    Extra keyword arguments (all optional).  The defaults keep the reference's results for every input the
+    reference accepts; the one deviation is for CORRUPT input: a vote whose flat index falls outside the grid is
+    dropped silently unless strict=True (the reference's index_add_ raises IndexError there).
+      deterministic  sort-by-voxel mode, bit-exact against the reference's CPU result for time-sorted input
+                     (unsorted windows are argsort-ed first like EventSequence does; ties between equal stamps
+                     may then be ordered differently, which changes the fp32 summation order only)
       strict         raise IndexError (after a sync) if a vote fell outside the grid, like the
                      reference's index_add_ does
       compute_device CUDA device the kernels run on when gpu=False (default cuda:gpu_nr)

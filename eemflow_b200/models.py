@@ -350,6 +350,14 @@ class GraphedInference:
         self.model.change_imagesize(img_size)
 
     def __call__(self, events1, events2, **kwargs):
+        for name, value in kwargs.items():
+            if isinstance(value, torch.Tensor):
+                # a tensor would be baked into the graph by address: replays would silently reuse stale data
+                raise TypeError(f"GraphedInference: tensor keyword argument `{name}` is not supported "
+                                "(e.g. ERAFT's flow_init warm start); call the model directly for that")
+        if self.model.training:
+            raise RuntimeError("GraphedInference replays an inference forward: call model.eval() first "
+                               "(a train-mode forward would update BatchNorm statistics on every warm-up and replay)")
         key = (tuple(events1.shape), events1.dtype, events1.device, tuple(sorted(kwargs.items())), getattr(self.model, "image_size", None))
         entry = self._captured.get(key)
         if entry is None:

@@ -239,11 +239,16 @@ def warp_blend(flow_init: torch.Tensor, inter_flow: torch.Tensor, mask: torch.Te
 
 # ------------------------------------------------------------------------------------------ K8/K9
 def bilinear_resize(x: torch.Tensor, size: tuple[int, int], align_corners: bool, scale0: float = 1.0,
-                    scale1: float = 1.0, scale_rest: float = 1.0) -> torch.Tensor:
+                    scale1: float = 1.0, scale_rest: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """`out` (optional) receives the result in place of a fresh tensor; it may live in a PEER GPU's memory (a slot of
+    another rank's result buffer mapped into this process): the kernel's stores then travel over NVLink."""
     x = L.require_cuda(x, "x")
     B, Cc, h, w = x.shape
     H, W = int(size[0]), int(size[1])
-    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    else:
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, Cc, H, W)
     with torch.cuda.device(x.device):
         L.check(L.lib().eem_bilinear_resize(x.data_ptr(), B, Cc, h, w, out.data_ptr(), H, W, int(bool(align_corners)),
                                             float(scale0), float(scale1), float(scale_rest), L.stream_ptr(x.device)))

@@ -59,23 +59,24 @@ class WarpingLayer_no_div(nn.Module):
         return ag.backwarp(x, flow, L.WARP_HALFPIX, L.MASK_GE1)
 
 
-def upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate=False):
+def upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate=False, out=None):
     """Resize `inputs` to target_as's spatial size (align_corners=True); with if_rate scale u by w/w_ and
-    v by h/h_ -- and, like the reference (cdc_utils.py:85-86), scale `inputs` itself IN PLACE."""
+    v by h/h_ -- and, like the reference (cdc_utils.py:85-86), scale `inputs` itself IN PLACE.
+    `out` (extra, optional): write the result there (inference only; may be peer-GPU memory, see ops.bilinear_resize)."""
     if mode != "bilinear":
         raise NotImplementedError("eemflow_b200.upsample2d_flow_as implements mode='bilinear' only")
     _, _, h, w = target_as.shape
     if if_rate:
         _, _, h_, w_ = inputs.shape
         u_scale, v_scale = (w / w_), (h / h_)
-        res = ag.bilinear_resize(inputs, (h, w), align_corners=True, scale0=u_scale, scale1=v_scale)
+        res = ag.bilinear_resize(inputs, (h, w), align_corners=True, scale0=u_scale, scale1=v_scale, out=out)
         if inputs.is_contiguous() and inputs.dtype == torch.float32 and not ag.needs_grad(inputs):
             ops.scale_uv_(inputs, u_scale, v_scale)
         else:  # autograd-tracked or exotic view: keep the side effect with (tiny) torch in-place ops
             inputs[:, 0, :, :] *= u_scale
             inputs[:, 1, :, :] *= v_scale
         return res
-    return ag.bilinear_resize(inputs, (h, w), align_corners=True)
+    return ag.bilinear_resize(inputs, (h, w), align_corners=True, out=out)
 
 
 def upsample_flow(flow, orig_size):

@@ -30,7 +30,21 @@ def _worker(rank, world, port, total, q):
     got2 = edist.gather_batch(local * 1.0)                     # sizes exchanged by all_gather
     acc = edist.reduce_metrics(torch.tensor([float(rank + 1), 10.0]))
     mx = edist.max_over_ranks(3.0 + rank, torch.device("cpu"))
-    q.put((rank, torch.equal(got, full), torch.equal(got2, full), acc.tolist(), mx))
+    # result delivery to one rank (NCCL-gather fallback of ResultSink, here on gloo with host tensors)
+    sink_ok = True
+    if total % world == 0:
+        sink = edist.ResultSink(tuple(local.shape), torch.float32, torch.device("cpu"), dst=0, slots=2)
+        assert not sink.direct and sink.describe()["mode"].startswith("NCCL gather")
+        for k in range(3):
+            sink.before_write(k)
+            sink.push(k, local + float(k))
+        sink.drain()
+        buf = sink.buffer()
+        if rank == 0:
+            sink_ok = torch.equal(buf[0].reshape(full.shape), full + 2.0) and torch.equal(buf[1].reshape(full.shape), full + 1.0)
+        else:
+            sink_ok = buf is None
+    q.put((rank, torch.equal(got, full) and sink_ok, torch.equal(got2, full), acc.tolist(), mx))
     dist.destroy_process_group()
 
 

@@ -111,23 +111,51 @@ def test_batched_windows_ragged(V):
         assert np.array_equal(det[k], ref), k
 
 
-def test_full_size_hrem_checksum(V):
-    """BASELINE size (10M events, 15x720x1280): size-independent property -- the grid's total and its
-    per-bin totals equal the sums of the per-event vote weights (computed vectorised on the CPU)."""
-    rng = np.random.default_rng(9)
-    n, nb, h, w = 10_000_000, 15, 720, 1280
-    ev = make_events(rng, n, h, w)
-    out = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev, h, w))
-    v = ref_ops.voxel_votes(ev, nb, h, w)
-    per_bin = np.zeros(nb)
-    for idx, val in ((v["idx_left"], v["val_left"]), (v["idx_right"], v["val_right"])):
-        ok = idx >= 0
-        per_bin += np.bincount(idx[ok] // (h * w), weights=val[ok].astype(np.float64), minlength=nb)
-    got = out.double().sum(dim=(1, 2)).cpu().numpy()
-    assert np.allclose(got, per_bin, rtol=0, atol=2.0), (got - per_bin)   # ~1e6 fp32 adds per bin
-    # and the event count per pixel column is conserved: |votes| sum to the number of events per bin pair
-    absum = out.abs().double().sum().item()
-    assert absum <= n + 1.0
+def _full_size_case(n, seed, clustered=False):
+    rng = np.random.default_rng(seed)
+    nb, h, w = 15, 720, 1280
+    ev = make_events(rng, n, h, w, clustered)
+    ref_raw, dropped, _ = c_oracle.voxelize(ev, nb, h, w, normalize=False)      # per-voxel CPU oracle (plain C)
+    assert dropped == 0
+    return ev, ref_raw, nb, h, w
+
+
+@pytest.mark.parametrize("clustered", [False, True])
+def test_full_size_hrem_dt1_per_voxel(V, clustered):
+    """BASELINE configs[2] size (10 M events, 15x720x1280), EVERY voxel against the C oracle: deterministic mode
+    bit-exact, atomic mode <= 1e-5 relative, normalised <= 1e-5 relative; rows and packed columns."""
+    ev, ref_raw, nb, h, w = _full_size_case(10_000_000, 9 + int(clustered), clustered)
+    out_d = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True)(Seq(ev, h, w)).cpu().numpy()
+    assert np.array_equal(out_d, ref_raw)                                                         # bit-exact
+    del out_d
+    out_a = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
+    assert rel_close(out_a, ref_raw).all(), np.abs(out_a - ref_raw).max()
+    del out_a
+    cols = [{"t": np.ascontiguousarray(ev[:, 0]), "x": ev[:, 1].astype(np.int16), "y": ev[:, 2].astype(np.int16),
+             "p": ev[:, 3].astype(np.int8)}]
+    out_c = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_columns(cols, h, w)[0].cpu().numpy()
+    assert np.array_equal(out_c, ref_raw)                                                         # packed columns, bit-exact
+    out_ca = V(nb, gpu=True, normalize=False, forkserver=False).voxelize_columns(cols, h, w)[0].cpu().numpy()
+    assert rel_close(out_ca, ref_raw).all(), np.abs(out_ca - ref_raw).max()
+    del out_c, out_ca
+    ref_norm, _, _ = c_oracle.voxelize(ev, nb, h, w, normalize=True)
+    out_n = V(nb, gpu=True, normalize=True, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
+    assert rel_close(out_n, ref_norm).all(), np.abs(out_n - ref_norm).max()
+
+
+def test_full_size_hrem_dt4_per_voxel(V):
+    """BASELINE configs[3] size (40 M events per window: the auto-selected path for event-dominated windows),
+    every voxel against the C oracle: atomic <= 1e-5 relative, deterministic bit-exact, normalised <= 1e-5."""
+    ev, ref_raw, nb, h, w = _full_size_case(40_000_000, 19)
+    out_a = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
+    assert rel_close(out_a, ref_raw).all(), np.abs(out_a - ref_raw).max()
+    del out_a
+    out_d = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True)(Seq(ev, h, w)).cpu().numpy()
+    assert np.array_equal(out_d, ref_raw)
+    del out_d
+    ref_norm, _, _ = c_oracle.voxelize(ev, nb, h, w, normalize=True)
+    out_n = V(nb, gpu=True, normalize=True, forkserver=False)(Seq(ev, h, w)).cpu().numpy()
+    assert rel_close(out_n, ref_norm).all(), np.abs(out_n - ref_norm).max()
 
 
 def test_device_contract_and_errors(V):

@@ -25,6 +25,7 @@ EEM_ERR_UNSUPPORTED = -5
 
 VOXEL_ATOMIC, VOXEL_DETERMINISTIC = 0, 1
 CORR_FP32, CORR_TF32 = 0, 1
+PRECISIONS = ("fp32", "tf32", "tf32_f16")
 WARP_EXACT, WARP_HALFPIX = 0, 1
 MASK_NONE, MASK_GE1, MASK_9999 = 0, 1, 2
 
@@ -43,6 +44,11 @@ SIGNATURES = {
     "eem_voxel_normalize": (_i, [_vp, _i, _i64, _vp, _vp, _sz, _vp]),
     "eem_corr_pyramid_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "eem_corr_pyramid": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_vp), _i, _vp, _sz, _vp]),
+    "eem_corr_packed_layout": (_i, [_i, _i, _i, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "eem_corr_pyramid_packed_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "eem_corr_pyramid_packed": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "eem_corr_lookup_packed": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "eem_corr_pyramid_unpack": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp), _vp]),
     "eem_avg_pool2x2": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "eem_corr_lookup": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eem_local_corr": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, _vp, _vp]),

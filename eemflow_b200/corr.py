@@ -31,8 +31,13 @@ class CorrBlock:
     """RAFT all-pairs correlation: volume + avg-pool pyramid at construction, window lookup on call.
 
     `corr_pyramid` keeps the reference's attribute contract: a list of `[B*H*W, 1, H_l, W_l]`
-    float32 tensors.  `precision` ("tf32" | "fp32") is the one extra knob: tcgen05 TF32 tensor
-    cores (default where the shape allows) or exact fp32 FMA.
+    float32 tensors.  `precision` is the one extra knob:
+      "fp32"      exact fp32 FMA (the default, like the reference's fp32 matmul)
+      "tf32"      tcgen05 TF32 tensor cores, f32 pyramid tensors
+      "tf32_f16"  tcgen05 TF32 tensor cores, fp32 accumulation, the pyramid kept as the fp16 WORKING pyramid
+                  (4x4-pixel tiles, all levels of a position in one row: half the bytes written by the GEMM and read
+                  by every lookup).  `corr_pyramid` is then materialised lazily -- only if somebody reads the
+                  attribute.  Inference only: under autograd this falls back to "tf32".
     """
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, precision=None):
@@ -41,18 +46,42 @@ class CorrBlock:
         batch, dim, ht, wd = fmap1.shape
         if precision is None:
             precision = _default_precision(dim, ht, wd)
-        self.precision = precision
+        if precision not in ("fp32", "tf32", "tf32_f16"):
+            raise ValueError(f"eemflow_b200.CorrBlock: unknown precision {precision!r}")
+        self._packed = None
+        self._pyramid = None
+        self._shape = (batch, ht, wd)
         if ag.needs_grad(fmap1, fmap2):
-            self.corr_pyramid = list(ag.CorrPyramidFn.apply(fmap1, fmap2, num_levels, precision))
+            if precision == "tf32_f16":
+                precision = "tf32"
+            self._pyramid = list(ag.CorrPyramidFn.apply(fmap1, fmap2, num_levels, precision))
         else:
             with torch.no_grad():
-                self.corr_pyramid = ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision)
+                if precision == "tf32_f16":
+                    self._packed = ops.corr_pyramid_packed(fmap1, fmap2, num_levels)
+                else:
+                    self._pyramid = ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision)
+        self.precision = precision
+
+    @property
+    def corr_pyramid(self):
+        if self._pyramid is None:           # fp16 working pyramid: build the reference-shaped f32 tensors on demand
+            with torch.no_grad():
+                self._pyramid = ops.corr_pyramid_unpack(self._packed, *self._shape, self.num_levels)
+        return self._pyramid
+
+    @corr_pyramid.setter
+    def corr_pyramid(self, value):
+        self._pyramid, self._packed = list(value), None
 
     def __call__(self, coords):
         if torch.is_grad_enabled() and coords.requires_grad:     # never a silent zero gradient
             raise NotImplementedError(
                 "eemflow_b200.CorrBlock gives no gradient to the lookup coordinates; detach them as the "
                 "reference's callers do (model/eraft.py:141)")
+        if self._packed is not None:
+            with torch.no_grad():
+                return ops.corr_lookup_packed(self._packed, coords, self.num_levels, self.radius)
         if ag.needs_grad(*self.corr_pyramid):
             return ag.CorrLookupFn.apply(coords, self.radius, *self.corr_pyramid)
         with torch.no_grad():

@@ -14,7 +14,10 @@
 #include <cstdlib>
 #include <mutex>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "packed_layout.cuh"
 
 namespace eem {
 namespace {
@@ -216,6 +219,184 @@ int launch_lookup_any(const LookupParams& p, cudaStream_t stream) {
     return (v != nullptr && atoi(v) == 16) ? 16 : 32;
   }();
   return pb == 32 ? launch_lookup<R, 32>(p, stream) : launch_lookup<R, 16>(p, stream);
+}
+
+// ---- lookup on the packed fp16 working pyramid (packed_layout.cuh) ----------------------------------------------
+// Same outputs as corr_lookup_kernel, different input: every level of a source position is stored as 4x4-pixel
+// tiles of fp16 (32 B = one sector each) in ONE row per position.  A CTA owns 32 consecutive positions.  Phases:
+// (1) window geometry per (position, level) -- identical arithmetic to the f32 kernel; (2) ONE gather phase: the
+// NT x NT tiles that cover a position's (2r+2)^2 tap window are copied sector by sector with 16-byte cp.async
+// (zero-filled when the tile lies outside the map; cells of a partial last tile are zeros in the volume itself),
+// all levels back to back, every load in flight before anything is consumed; (3) interpolation in fp32 with
+// warp = (level, 3 window columns), lane = position, so each store instruction writes 32 consecutive positions of
+// one output channel (128 B).  Per position the kernel fetches ~10.6 sectors per full-size level instead of the
+// 16 + that the f32 row-major volume costs, and half the bytes per tap.
+struct PackedLookupParams {
+  const uint16_t* packed;
+  int h[kMaxLevels], w[kMaxLevels], tx[kMaxLevels], ty[kMaxLevels], off[kMaxLevels];
+  int row;
+  int B, H, W, L;
+  const float* coords;
+  float* out;
+};
+
+template <int R>
+struct PackedSmem {
+  static constexpr int K = 2 * R + 1, T = K + 1;
+  static constexpr int NT = (T + 6) / 4;                    // tiles per dimension covering T taps at any phase 0..3
+  static constexpr int PB = 32;
+  static constexpr int kPatchBytes = NT * NT * 32;
+  // + 16 B: consecutive positions start 4 banks apart (mod 32), so the 8-byte reads of a half-warp conflict 2-way at most
+  static constexpr int kStrideBytes = kPatchBytes + 16;
+  static constexpr int kColsPerTask = 3, kGroups = (K + kColsPerTask - 1) / kColsPerTask;
+  static constexpr int kThreads = 32 * 4 * kGroups;          // one interpolation task per warp for a 4-level pyramid
+  static constexpr int kPerLevelBytes = PB * kStrideBytes + 2 * PB * K * 4 + PB * 2 * 4;
+};
+
+template <int R>
+__global__ void __launch_bounds__(PackedSmem<R>::kThreads)
+corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
+  using S = PackedSmem<R>;
+  constexpr int K = S::K, T = S::T, NT = S::NT, PB = S::PB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int P = p.H * p.W;
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * PB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npos = min(PB, P - i0);
+  const int L = p.L;
+
+  auto patch_of = [&](int l) { return smem_raw + (size_t)l * S::kPerLevelBytes; };
+  auto fx_of = [&](int l) { return reinterpret_cast<float*>(patch_of(l) + PB * S::kStrideBytes); };
+  auto fy_of = [&](int l) { return fx_of(l) + PB * K; };
+  auto org_of = [&](int l) { return reinterpret_cast<int*>(fy_of(l) + PB * K); };
+
+  // 1) window geometry, one thread per (position, level): same arithmetic as corr_lookup_kernel
+  for (int t = threadIdx.x; t < PB * L; t += blockDim.x) {
+    const int l = t / PB, pos = t % PB;
+    const int hl = p.h[l], wl = p.w[l];
+    float cx = 0.f, cy = 0.f;
+    if (pos < npos) {
+      cx = __ldg(p.coords + ((int64_t)b * 2 + 0) * P + i0 + pos);
+      cy = __ldg(p.coords + ((int64_t)b * 2 + 1) * P + i0 + pos);
+    }
+    const float inv = 1.0f / (float)(1 << l);
+    const float lx = cx * inv, ly = cy * inv;
+    const float ox = floorf(fminf(fmaxf(roundtrip(lx - (float)R, wl), -1.0e6f), 1.0e6f));
+    const float oy = floorf(fminf(fmaxf(roundtrip(ly - (float)R, hl), -1.0e6f), 1.0e6f));
+    org_of(l)[pos * 2 + 0] = (int)ox;
+    org_of(l)[pos * 2 + 1] = (int)oy;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      fx_of(l)[pos * K + a] = roundtrip(lx + (float)(a - R), wl) - (ox + (float)a);
+      fy_of(l)[pos * K + a] = roundtrip(ly + (float)(a - R), hl) - (oy + (float)a);
+    }
+  }
+  __syncthreads();
+
+  // 2) gather: unit = (level, position, tile slot); consecutive threads take consecutive slots of a position, i.e.
+  //    neighbouring 32-byte sectors of the same tile row
+  {
+    constexpr int kUnitsPerLevel = PB * NT * NT;
+    for (int u = threadIdx.x; u < L * kUnitsPerLevel; u += blockDim.x) {
+      const int l = u / kUnitsPerLevel, rem = u - l * kUnitsPerLevel;
+      const int pos = rem / (NT * NT), slot = rem - pos * (NT * NT);
+      if (pos >= npos || p.h[l] * p.w[l] == 0) continue;
+      const int sy = slot / NT, sx = slot - sy * NT;
+      const int txx = (org_of(l)[pos * 2 + 0] >> 2) + sx, tyy = (org_of(l)[pos * 2 + 1] >> 2) + sy;   // >> : floor for negatives
+      const bool ok = (unsigned)txx < (unsigned)p.tx[l] && (unsigned)tyy < (unsigned)p.ty[l];
+      const uint16_t* src = p.packed + ((int64_t)b * P + i0 + pos) * p.row + p.off[l] + (ok ? (tyy * p.tx[l] + txx) * 16 : 0);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(patch_of(l) + pos * S::kStrideBytes + slot * 32);
+      const int nbytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16), "l"(src + 8), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+
+  // 3) interpolate: task = (level, group of G adjacent window columns), lane = position
+  constexpr int G = S::kColsPerTask, kGroups = S::kGroups;
+  const int n_warps = blockDim.x >> 5;
+  if (lane < npos) {
+    for (int task = warp; task < L * kGroups; task += n_warps) {
+      const int l = task / kGroups, a0 = (task - l * kGroups) * G;
+      float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a0 * K) * P + i0 + lane;
+      if (p.h[l] * p.w[l] == 0) {            // level pooled away: an empty map contributes zeros
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (a0 + g < K)
+#pragma unroll
+            for (int c = 0; c < K; ++c) st_stream(o + (int64_t)(g * K + c) * P, 0.f);
+        continue;
+      }
+      const unsigned char* patch = patch_of(l) + lane * S::kStrideBytes;
+      const int sx0 = org_of(l)[lane * 2 + 0] & 3, sy0 = org_of(l)[lane * 2 + 1] & 3;
+      const int q0 = sx0 + a0;                                  // first tap column of this task inside the patch
+      const int tq = q0 >> 2, tq1 = min(tq + 1, NT - 1);       // the G+1 = 4 taps span at most two tiles
+      const unsigned sh = (unsigned)(q0 & 3) * 16u;
+      const float* fyp = fy_of(l) + lane * K;
+      float fx[G], prev[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) fx[g] = (a0 + g < K) ? fx_of(l)[lane * K + a0 + g] : 0.f;
+      auto load_row = [&](int rr, float (&t)[G + 1]) {
+        const int py = sy0 + rr;
+        const unsigned char* rowp = patch + ((py >> 2) * NT) * 32 + (py & 3) * 8;
+        const uint64_t lo = *reinterpret_cast<const uint64_t*>(rowp + tq * 32);
+        const uint64_t hi = *reinterpret_cast<const uint64_t*>(rowp + tq1 * 32);
+        const uint64_t v = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
+        const float2 ab = __half22float2(*reinterpret_cast<const __half2*>(&v));
+        const uint32_t v_hi = (uint32_t)(v >> 32);
+        const float2 cd = __half22float2(*reinterpret_cast<const __half2*>(&v_hi));
+        t[0] = ab.x; t[1] = ab.y; t[2] = cd.x; t[3] = cd.y;
+      };
+      static_assert(G == 3, "load_row unpacks G + 1 = 4 taps");
+      {
+        float t[G + 1];
+        load_row(0, t);
+#pragma unroll
+        for (int g = 0; g < G; ++g) prev[g] = t[g] + fx[g] * (t[g + 1] - t[g]);
+      }
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        float t[G + 1];
+        load_row(c + 1, t);
+        const float fy = fyp[c];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float cur = t[g] + fx[g] * (t[g + 1] - t[g]);
+          if (a0 + g < K) st_stream(o + (int64_t)(g * K + c) * P, prev[g] + fy * (cur - prev[g]));
+          prev[g] = cur;
+        }
+      }
+    }
+  }
+}
+
+template <int R>
+int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
+  using S = PackedSmem<R>;
+  const size_t smem = (size_t)p.L * S::kPerLevelBytes;
+  dim3 grid((unsigned)ceil_div(p.H * p.W, S::PB), (unsigned)p.B);
+  static DynSmemOptIn optin;
+  if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_kernel<R>, smem));
+  corr_lookup_packed_kernel<R><<<grid, S::kThreads, smem, stream>>>(p);
+  return EEM_OK;
+}
+
+// packed fp16 level -> the reference's f32 [B*P, h_l*w_l] tensor (lazily materialised `corr_pyramid`)
+__global__ void __launch_bounds__(256)
+corr_unpack_level_kernel(const uint16_t* __restrict__ packed, int64_t rows, int row_elems, int off, int h, int w, int tiles_x,
+                         float* __restrict__ out) {
+  const int64_t plane = (int64_t)h * w, total = rows * plane;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / plane;
+    const int cell = (int)(i - r * plane);
+    const int y = cell / w, x = cell - y * w;
+    const __half v = *reinterpret_cast<const __half*>(packed + r * row_elems + off + packed_cell(y, x, tiles_x));
+    out[i] = __half2float(v);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -454,6 +635,59 @@ int eem_avg_pool2x2_backward(const float* grad_out, int64_t n_planes, int h, int
   if (cap > 0 && blocks > cap) blocks = cap;
   avg_pool2x2_backward_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(grad_out, n_planes, h, w, grad_in, accumulate);
   EEM_CHECK_LAUNCH("avg_pool2x2_backward_kernel");
+  return EEM_OK;
+}
+
+int eem_corr_lookup_packed(const void* packed, int B, int H, int W, int num_levels, int radius, const float* coords,
+                           float* out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(packed && coords && out, "eem_corr_lookup_packed: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && H > 0 && W > 0, "eem_corr_lookup_packed: sizes must be > 0");
+  EEM_CHECK_ARG(num_levels > 0 && num_levels <= kMaxLevels, "eem_corr_lookup_packed: num_levels must be in [1,%d]", kMaxLevels);
+  EEM_CHECK_ARG(B <= 65535, "eem_corr_lookup_packed: batch > 65535 not supported in one call");
+  EEM_CHECK_ALIGNED(packed, 32);
+  const PackedLayout pl = packed_layout(H, W, num_levels);
+  PackedLookupParams p{};
+  p.packed = static_cast<const uint16_t*>(packed);
+  for (int l = 0; l < num_levels; ++l) {
+    p.h[l] = pl.h[l]; p.w[l] = pl.w[l]; p.tx[l] = pl.tx[l]; p.ty[l] = pl.ty[l]; p.off[l] = pl.off[l];
+  }
+  p.row = pl.row;
+  p.B = B; p.H = H; p.W = W; p.L = num_levels;
+  p.coords = coords;
+  p.out = out;
+  cudaStream_t stream = as_stream(stream_);
+  int rc = EEM_OK;
+  switch (radius) {
+    case 4: rc = launch_lookup_packed<4>(p, stream); break;
+    case 3: rc = launch_lookup_packed<3>(p, stream); break;
+    case 2: rc = launch_lookup_packed<2>(p, stream); break;
+    case 1: rc = launch_lookup_packed<1>(p, stream); break;
+    default:
+      return fail(EEM_ERR_UNSUPPORTED, "eem_corr_lookup_packed: radius %d not in {1,2,3,4}", radius);
+  }
+  if (rc != EEM_OK) return rc;
+  EEM_CHECK_LAUNCH("corr_lookup_packed_kernel");
+  return EEM_OK;
+}
+
+int eem_corr_pyramid_unpack(const void* packed, int B, int H, int W, int num_levels, float* const* levels,
+                            eem_stream_t stream_) {
+  EEM_CHECK_ARG(packed && levels, "eem_corr_pyramid_unpack: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && H > 0 && W > 0, "eem_corr_pyramid_unpack: sizes must be > 0");
+  EEM_CHECK_ARG(num_levels > 0 && num_levels <= kMaxLevels, "eem_corr_pyramid_unpack: num_levels must be in [1,%d]", kMaxLevels);
+  const PackedLayout pl = packed_layout(H, W, num_levels);
+  const int64_t rows = (int64_t)B * H * W;
+  for (int l = 0; l < num_levels; ++l) {
+    const int64_t total = rows * pl.h[l] * pl.w[l];
+    if (total == 0) continue;
+    EEM_CHECK_ARG(levels[l] != nullptr, "eem_corr_pyramid_unpack: levels[%d] is NULL", l);
+    int64_t blocks = ceil_div(total, 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (cap > 0 && blocks > cap) blocks = cap;
+    corr_unpack_level_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(static_cast<const uint16_t*>(packed), rows, pl.row,
+                                                                                 pl.off[l], pl.h[l], pl.w[l], pl.tx[l], levels[l]);
+    EEM_CHECK_LAUNCH("corr_unpack_level_kernel");
+  }
   return EEM_OK;
 }
 

@@ -23,6 +23,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "packed_layout.cuh"
 
 namespace eem {
 namespace {
@@ -87,6 +88,69 @@ pool_pyramid_kernel(const __grid_constant__ PoolPyramidParams p) {
       __syncthreads();
       cur = nxt;
     }
+  }
+}
+
+// Operand of the packed (fp16 working pyramid) GEMM: for every (b, d) plane ONE row holding fmap2 and all of its
+// pooled levels in the tile order of packed_layout.cuh, zeros in the padding -- [B*D, row] fp32, the "N side" of
+// the GEMM, so that output column c of the GEMM is element c of the packed row of a source position.  A group of
+// threads (a warp for MVSEC-sized planes, the CTA for large ones) stages the plane in shared memory, pools it level
+// by level there (same ((a+b)+c)+d order as the per-level kernel) and writes the row coalesced.
+struct PoolPackedParams {
+  const float* in;       // [n_planes, P0]
+  float* out;            // [n_planes, row]
+  int64_t n_planes;
+  PackedLayout pl;
+  int smem_floats;       // per group: sum_l h_l*w_l
+};
+
+template <bool kWarpGroups>
+__global__ void __launch_bounds__(256)
+pool_pyramid_packed_kernel(const __grid_constant__ PoolPackedParams p) {
+  extern __shared__ __align__(16) float pk_smem[];
+  const int gsize = kWarpGroups ? 32 : (int)blockDim.x;
+  const int gid = kWarpGroups ? (int)(threadIdx.x >> 5) : 0;
+  const int groups_per_cta = kWarpGroups ? (int)(blockDim.x >> 5) : 1;
+  const int t = kWarpGroups ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  auto gsync = [&] { if (kWarpGroups) __syncwarp(); else __syncthreads(); };
+  float* base = pk_smem + (size_t)gid * p.smem_floats;
+  const PackedLayout& pl = p.pl;
+  const int P0 = pl.h[0] * pl.w[0];
+  for (int64_t plane = (int64_t)blockIdx.x * groups_per_cta + gid; plane < p.n_planes; plane += (int64_t)gridDim.x * groups_per_cta) {
+    const float* src = p.in + plane * P0;
+    if ((P0 & 3) == 0) {
+      for (int i = t * 4; i < P0; i += gsize * 4)
+        *reinterpret_cast<float4*>(base + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+    } else {
+      for (int i = t; i < P0; i += gsize) base[i] = __ldg(src + i);
+    }
+    gsync();
+    float* cur = base;
+    for (int l = 1; l < pl.L; ++l) {
+      const int hi = pl.h[l - 1], wi = pl.w[l - 1], ho = pl.h[l], wo = pl.w[l];
+      float* nxt = cur + hi * wi;
+      for (int r = t; r < ho * wo; r += gsize) {
+        const int y = r / wo, x = r - y * wo;
+        const float* s4 = cur + (2 * y) * wi + 2 * x;
+        nxt[r] = (((s4[0] + s4[1]) + s4[wi]) + s4[wi + 1]) * 0.25f;
+      }
+      gsync();
+      cur = nxt;
+    }
+    float* dst = p.out + plane * pl.row;
+    cur = base;
+    for (int l = 0; l < pl.L; ++l) {
+      const int h = pl.h[l], w = pl.w[l], tx = pl.tx[l];
+      float* d = dst + pl.off[l];
+      for (int e = t; e < pl.len[l]; e += gsize) {
+        const int tile = e >> 4, r = (e >> 2) & 3, c = e & 3;
+        const int tyi = tile / tx, txi = tile - tyi * tx;
+        const int y = 4 * tyi + r, x = 4 * txi + c;
+        d[e] = (y < h && x < w) ? cur[y * w + x] : 0.0f;
+      }
+      cur += h * w;
+    }
+    gsync();      // the group's staging area is reused by its next plane
   }
 }
 
@@ -181,6 +245,10 @@ struct Tf32Params {
   int cluster;                        // CTAs per cluster sharing one fmap1 stream (1, 2 or 4)
   float scale;
   uint32_t desc_lo, desc_hi;          // constant smem-descriptor fields (desc_fields)
+  // packed (fp16 working pyramid) mode: M side = fmap1 positions (L = 1, Pl[0] = P), N side = the concatenated,
+  // tile-ordered level operand with `row` columns; out16[(b*P + i)*row + column]
+  uint16_t* out16;
+  int row;
   uint32_t debug;                     // EEM_TF32_DEBUG bits (timing experiments only): 1 skip MMA, 2 skip stores, 4 skip streamed loads, 8 skip TMEM loads
 };
 
@@ -659,7 +727,7 @@ struct __align__(1024) Tf32PairSmem {
   uint32_t tmem_base;
 };
 
-template <int BK, int BN>
+template <int BK, int BN, bool kPacked>
 __global__ void __launch_bounds__(kTf32Threads, 1)
 corr_tf32_pair_kernel(const __grid_constant__ Tf32Params p) {
   using C = PairCfg<BK, BN>;
@@ -791,7 +859,28 @@ corr_tf32_pair_kernel(const __grid_constant__ Tf32Params p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&s.acc_empty[acc]);
-      if (j_ok) {
+      if constexpr (kPacked) {
+        // packed mode: TMEM lane = fmap1 position i (this lane's output ROW), the 128 registers = 128 consecutive
+        // elements of that position's packed row.  Scale, round to fp16 (saturating), and write them as eight
+        // 32-byte stores (one full sector each, 256 contiguous bytes per lane).
+        if (j_ok) {                                      // here: row i = it.m0 + quarter*32 + lane < P
+          uint16_t* o16 = p.out16 + ((int64_t)it.b * p.P + j) * p.row + i_base;
+          const int n_valid = p.row - i_base;            // columns of the packed row left from i_base
+#pragma unroll
+          for (int q = 0; q < BN / 2 / 16; ++q) {
+            uint32_t h[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float a = __uint_as_float(v[q * 16 + 2 * e]) * scale, b2 = __uint_as_float(v[q * 16 + 2 * e + 1]) * scale;
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(b2), "f"(a));
+            }
+            if (q * 16 < n_valid)
+              asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+                           ::"l"(o16 + q * 16), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]),
+                           "l"(stream_out) : "memory");
+          }
+        }
+      } else if (j_ok) {
         const int n_valid = p.P - i_base;    // >= 128 on interior tiles
 #pragma unroll
         for (int r = 0; r < BN / 2; ++r) {
@@ -861,14 +950,14 @@ cudaError_t launch_tf32(cudaLaunchConfig_t cfg, const Tf32Params& p) {
   return cudaLaunchKernelEx(&cfg, corr_tf32_kernel<BK, BN, CL>, p);
 }
 
-template <int BK, int BN>
+template <int BK, int BN, bool kPacked = false>
 cudaError_t launch_tf32_pair(cudaLaunchConfig_t cfg, const Tf32Params& p) {
   constexpr size_t kSmem = sizeof(Tf32PairSmem<BK, BN>) + 1024;
   static DynSmemOptIn optin;
-  const cudaError_t attr_err = optin.ensure(corr_tf32_pair_kernel<BK, BN>, kSmem);
+  const cudaError_t attr_err = optin.ensure(corr_tf32_pair_kernel<BK, BN, kPacked>, kSmem);
   if (attr_err != cudaSuccess) return attr_err;
   cfg.dynamicSmemBytes = kSmem;
-  return cudaLaunchKernelEx(&cfg, corr_tf32_pair_kernel<BK, BN>, p);
+  return cudaLaunchKernelEx(&cfg, corr_tf32_pair_kernel<BK, BN, kPacked>, p);
 }
 
 struct LevelDims {
@@ -1106,6 +1195,123 @@ int eem_corr_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H
   }
   if (err != cudaSuccess) return fail(EEM_ERR_CUDA, "corr_tf32_kernel launch: %s", cudaGetErrorString(err));
   EEM_CHECK_LAUNCH("corr_tf32_kernel");
+  return EEM_OK;
+}
+
+// ---- packed fp16 working pyramid (see packed_layout.cuh) ------------------------------------------------------
+int eem_corr_packed_layout(int H, int W, int num_levels, int64_t* level_offset, int64_t* level_elems, int64_t* row_elems) {
+  EEM_CHECK_ARG(H > 0 && W > 0 && num_levels > 0 && num_levels <= kPackedMaxLevels, "eem_corr_packed_layout: bad shape");
+  const PackedLayout pl = packed_layout(H, W, num_levels);
+  for (int l = 0; l < num_levels; ++l) {
+    if (level_offset) level_offset[l] = pl.off[l];
+    if (level_elems) level_elems[l] = pl.len[l];
+  }
+  if (row_elems) *row_elems = pl.row;
+  return EEM_OK;
+}
+
+size_t eem_corr_pyramid_packed_workspace_bytes(int B, int D, int H, int W, int num_levels) {
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || num_levels <= 0 || num_levels > kPackedMaxLevels) return 0;
+  return align_up((size_t)B * D * packed_layout(H, W, num_levels).row * sizeof(float), 256);
+}
+
+int eem_corr_pyramid_packed(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int num_levels,
+                            void* packed, void* workspace, size_t workspace_bytes, eem_stream_t stream_) {
+  EEM_CHECK_ARG(fmap1 && fmap2 && packed, "eem_corr_pyramid_packed: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0, "eem_corr_pyramid_packed: sizes must be > 0");
+  EEM_CHECK_ARG(num_levels > 0 && num_levels <= kPackedMaxLevels, "eem_corr_pyramid_packed: num_levels must be in [1,%d]", kPackedMaxLevels);
+  EEM_CHECK_ARG(B <= 65535, "eem_corr_pyramid_packed: batch > 65535 not supported in one call");
+  EEM_CHECK_ALIGNED(fmap1, 16);
+  EEM_CHECK_ALIGNED(fmap2, 16);
+  EEM_CHECK_ALIGNED(packed, 32);
+  const int P = H * W;
+  if (!((P % 4 == 0) && (D % 32 == 0) && (D <= kMaxD)))
+    return fail(EEM_ERR_UNSUPPORTED,
+                "eem_corr_pyramid_packed: needs H*W %% 4 == 0, D %% 32 == 0 and D <= %d (got H*W=%d, D=%d)", kMaxD, P, D);
+  const PackedLayout pl = packed_layout(H, W, num_levels);
+  const size_t need = eem_corr_pyramid_packed_workspace_bytes(B, D, H, W, num_levels);
+  if (workspace == nullptr || workspace_bytes < need)
+    return fail(EEM_ERR_WORKSPACE, "eem_corr_pyramid_packed: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+  EEM_CHECK_ALIGNED(workspace, 256);
+  cudaStream_t stream = as_stream(stream_);
+  const int64_t planes = (int64_t)B * D;
+  const int sms = sm_count();
+  if (sms <= 0) return fail(EEM_ERR_CUDA, "eem_corr_pyramid_packed: cannot query SM count");
+
+  // 1) the tile-ordered, zero-padded operand [fmap2 | pool(fmap2) | ...] per (b, d) plane
+  {
+    PoolPackedParams pp{};
+    pp.in = fmap2;
+    pp.out = static_cast<float*>(workspace);
+    pp.n_planes = planes;
+    pp.pl = pl;
+    int fl = 0;
+    for (int l = 0; l < num_levels; ++l) fl += pl.h[l] * pl.w[l];
+    pp.smem_floats = (fl + 3) & ~3;
+    const size_t per_group = (size_t)pp.smem_floats * sizeof(float);
+    const bool warp_groups = per_group * 8 <= 72 * 1024;          // 8 warps per CTA, one plane each, <= 3 CTAs per SM
+    const size_t smem = warp_groups ? per_group * 8 : per_group;
+    if (smem > 200 * 1024)
+      return fail(EEM_ERR_UNSUPPORTED, "eem_corr_pyramid_packed: a %dx%d feature plane does not fit the pooling kernel's shared memory", H, W);
+    int64_t blocks = warp_groups ? ceil_div(planes, 8) : planes;
+    const int64_t cap = (int64_t)sms * (warp_groups ? 3 : (smem > 100 * 1024 ? 1 : 2));
+    if (blocks > cap) blocks = cap;
+    if (warp_groups) {
+      static DynSmemOptIn optin;
+      if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(pool_pyramid_packed_kernel<true>, smem));
+      pool_pyramid_packed_kernel<true><<<(unsigned)blocks, 256, smem, stream>>>(pp);
+    } else {
+      static DynSmemOptIn optin;
+      if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(pool_pyramid_packed_kernel<false>, smem));
+      pool_pyramid_packed_kernel<false><<<(unsigned)blocks, 256, smem, stream>>>(pp);
+    }
+    EEM_CHECK_LAUNCH("pool_pyramid_packed_kernel");
+  }
+
+  // 2) one batched GEMM: M = fmap1 positions (128 per CTA, 256 per CTA pair, resident panel), N = packed columns
+  const int bk = 32, bn = 256;
+  Tf32Params p{};
+  desc_fields(32u * bk * 4u, 512, 1, &p.desc_lo, &p.desc_hi);
+  if (const char* v = getenv("EEM_TF32_DEBUG")) p.debug = (uint32_t)atoi(v);
+  int rc = encode_map(&p.map_lvl[0], fmap1, planes, P, P, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, bk);
+  if (rc != EEM_OK) return rc;
+  rc = encode_map(&p.map_f1, static_cast<const float*>(workspace), planes, pl.row, pl.row, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, bk);
+  if (rc != EEM_OK) return rc;
+  p.out16 = static_cast<uint16_t*>(packed);
+  p.row = pl.row;
+  p.Pl[0] = P;
+  p.mt_cum[0] = 0;
+  p.mt_cum[1] = (int)ceil_div(P, BM);
+  p.B = B; p.D = D; p.P = P; p.L = 1;
+  p.n_tiles = (int)ceil_div(pl.row, bn);
+  if (sms < 2) return fail(EEM_ERR_UNSUPPORTED, "eem_corr_pyramid_packed: needs at least one SM pair");
+  p.cluster = 2;
+  p.gpb = (int)ceil_div(p.mt_cum[1], 2);
+  p.n_items = (int64_t)B * p.gpb;
+  p.scale = 1.0f / sqrtf((float)D);
+  if (p.n_items * p.n_tiles >= (int64_t)0x7fffffff)
+    return fail(EEM_ERR_UNSUPPORTED, "eem_corr_pyramid_packed: too many tiles in one call; split the batch");
+  int usable = sms;
+  if (const char* v = getenv("EEM_TF32_MAX_SMS")) {
+    const int cap = atoi(v);
+    if (cap >= 2 && cap < usable) usable = cap;
+  }
+  int64_t clusters = usable / 2;
+  if (clusters > p.n_items * p.n_tiles) clusters = p.n_items * p.n_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  cfg.blockDim = dim3(kTf32Threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t err = launch_tf32_pair<32, 256, true>(cfg, p);
+  if (err != cudaSuccess) return fail(EEM_ERR_CUDA, "corr_tf32_pair_kernel(packed) launch: %s", cudaGetErrorString(err));
+  EEM_CHECK_LAUNCH("corr_tf32_pair_kernel(packed)");
   return EEM_OK;
 }
 

@@ -139,6 +139,67 @@ def tf32_supported(D: int, H: int, W: int) -> bool:
     return (H * W) % 4 == 0 and D % 32 == 0 and D <= 256
 
 
+def packed_row_elems(H: int, W: int, num_levels: int) -> tuple[int, list[int], list[int]]:
+    """(elements per source position, level offsets, padded level sizes) of the fp16 working pyramid."""
+    off = (C.c_int64 * num_levels)()
+    ln = (C.c_int64 * num_levels)()
+    row = C.c_int64(0)
+    L.check(L.lib().eem_corr_packed_layout(H, W, num_levels, off, ln, C.byref(row)))
+    return int(row.value), [int(v) for v in off], [int(v) for v in ln]
+
+
+def corr_pyramid_packed(fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4,
+                        out: torch.Tensor | None = None) -> torch.Tensor:
+    """All-pairs correlation pyramid as the fp16 WORKING pyramid: `[B*H*W, row]` float16, every level of a source
+    position in one row, 4x4-pixel tiles (csrc/packed_layout.cuh).  TF32 tensor-core contraction with fp32
+    accumulation, rounded once to fp16 on the way out.  Feed it to `corr_lookup_packed`; `corr_pyramid_unpack`
+    recovers the reference's f32 `corr_pyramid` tensors (model/corr.py:13-27) when somebody wants to look at them."""
+    fmap1 = L.require_cuda(fmap1, "fmap1")
+    fmap2 = L.require_cuda(fmap2, "fmap2")
+    assert fmap1.shape == fmap2.shape and fmap1.dim() == 4
+    B, D, H, W = fmap1.shape
+    dev = _dev(fmap1)
+    row, _, _ = packed_row_elems(H, W, num_levels)
+    if out is None:
+        out = torch.empty((B * H * W, row), dtype=torch.float16, device=dev)
+    else:
+        assert out.is_cuda and out.dtype == torch.float16 and out.is_contiguous() and tuple(out.shape) == (B * H * W, row)
+    lib = L.lib()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.eem_corr_pyramid_packed_workspace_bytes(B, D, H, W, num_levels)
+        ws = L.workspace.get(dev, ws_bytes, "corr_packed")
+        L.check(lib.eem_corr_pyramid_packed(fmap1.data_ptr(), fmap2.data_ptr(), B, D, H, W, num_levels, out.data_ptr(),
+                                            L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
+    return out
+
+
+def corr_lookup_packed(packed: torch.Tensor, coords: torch.Tensor, num_levels: int, radius: int = 4,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+    """CorrBlock.__call__ (model/corr.py:29-50) on the fp16 working pyramid: coords [B,2,H,W] -> [B, L*(2r+1)^2, H, W] f32."""
+    coords = L.require_cuda(coords, "coords")
+    B, two, H, W = coords.shape
+    assert two == 2
+    assert packed.is_cuda and packed.dtype == torch.float16 and packed.is_contiguous()
+    assert packed.shape[0] == B * H * W, "packed pyramid does not match coords"
+    k = (2 * radius + 1) ** 2
+    if out is None:
+        out = torch.empty((B, num_levels * k, H, W), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        L.check(L.lib().eem_corr_lookup_packed(packed.data_ptr(), B, H, W, num_levels, radius, coords.data_ptr(),
+                                               out.data_ptr(), L.stream_ptr(coords.device)))
+    return out
+
+
+def corr_pyramid_unpack(packed: torch.Tensor, B: int, H: int, W: int, num_levels: int) -> list[torch.Tensor]:
+    """fp16 working pyramid -> the reference's list of [B*H*W, 1, H_l, W_l] float32 tensors."""
+    assert packed.is_cuda and packed.dtype == torch.float16 and packed.is_contiguous()
+    dev = packed.device
+    out = [torch.empty((B * H * W, 1, h, w), dtype=torch.float32, device=dev) for (h, w) in pyramid_level_shapes(H, W, num_levels)]
+    with torch.cuda.device(dev):
+        L.check(L.lib().eem_corr_pyramid_unpack(packed.data_ptr(), B, H, W, num_levels, L.ptr_array(out), L.stream_ptr(dev)))
+    return out
+
+
 def avg_pool2x2(x: torch.Tensor) -> torch.Tensor:
     """F.avg_pool2d(x, 2, stride=2) for [N, C, h, w] (model/corr.py:25-27)."""
     x = L.require_cuda(x, "x")

@@ -145,6 +145,33 @@ EEM_API int eem_avg_pool2x2(const float* in, int64_t n_planes, int h, int w, flo
 EEM_API int eem_corr_lookup(const float* const* levels, int B, int H, int W, int num_levels,
                             int radius, const float* coords, float* out, eem_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K3p / K5p  fp16 WORKING pyramid: the same pyramid as K3 (TF32 contraction, fp32 accumulation), rounded once to
+ * fp16 and laid out for the window lookup instead of for inspection -- half the bytes written by the GEMM and read
+ * by each of the ~12 lookups per pair that follow (model/eraft.py:140-142).
+ * replaces: model/corr.py:13-27 + :52-60 (build) and :29-50 (lookup) when the caller only consumes the lookups.
+ *
+ * packed : [B*H*W, row_elems] fp16 (uint16 storage), 32-byte aligned.  Row (b*P + i) holds ALL levels of source
+ *          position i back to back; level l starts at element level_offset[l] and stores its H_l x W_l map as
+ *          4x4-pixel tiles (tile-row-major; row-major inside a tile; 16 fp16 = one 32-byte sector per tile):
+ *            element(y, x) = level_offset[l] + (((y/4) * ceil(W_l/4) + x/4) * 16 + (y%4)*4 + x%4)
+ *          cells of the last tile row/column beyond the map are zeros; each level is padded to a multiple of
+ *          32 elements (level_elems[l]).  eem_corr_packed_layout returns these numbers (HOST arrays of num_levels).
+ * eem_corr_pyramid_packed needs H*W % 4 == 0, D % 32 == 0, D <= 256 (EEM_ERR_UNSUPPORTED otherwise).
+ * eem_corr_lookup_packed has the output contract of eem_corr_lookup (K5).
+ * eem_corr_pyramid_unpack expands `packed` into the f32 level tensors of K3 (levels: HOST array of DEVICE pointers).
+ * ------------------------------------------------------------------------------------------ */
+EEM_API int eem_corr_packed_layout(int H, int W, int num_levels, int64_t* level_offset,
+                                   int64_t* level_elems, int64_t* row_elems);
+EEM_API size_t eem_corr_pyramid_packed_workspace_bytes(int B, int D, int H, int W, int num_levels);
+EEM_API int eem_corr_pyramid_packed(const float* fmap1, const float* fmap2, int B, int D, int H, int W,
+                                    int num_levels, void* packed, void* workspace,
+                                    size_t workspace_bytes, eem_stream_t stream);
+EEM_API int eem_corr_lookup_packed(const void* packed, int B, int H, int W, int num_levels, int radius,
+                                   const float* coords, float* out, eem_stream_t stream);
+EEM_API int eem_corr_pyramid_unpack(const void* packed, int B, int H, int W, int num_levels,
+                                    float* const* levels, eem_stream_t stream);
+
 /* K5b generic pixel-coordinate bilinear sampler
  * replaces: bilinear_sampler (model/model_utils.py:7-21) = normalise with (S-1) + F.grid_sample(align_corners=True)
  * img [N,C,H,W], coords [N,Ho,Wo,2] (x, y) in pixels -> out [N,C,Ho,Wo]; mask_out (optional, [N,Ho,Wo,1])

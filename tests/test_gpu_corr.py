@@ -110,6 +110,73 @@ def test_bench_config_b32_tf32_full(E):
     assert (ours - ref).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("B,D,H,W,L", [(2, 256, 36, 44, 4), (1, 256, 32, 32, 4), (1, 128, 23, 40, 4), (3, 64, 17, 20, 4),
+                                       (1, 32, 12, 20, 2), (1, 32, 8, 2, 2), (32, 256, 36, 44, 4)])
+def test_packed_fp16_pyramid_and_lookup(E, B, D, H, W, L):
+    """precision="tf32_f16": TF32 contraction stored as the fp16 working pyramid (4x4-pixel tiles, csrc/packed_layout.cuh).
+    (1) the lazily materialised `corr_pyramid` against the CPU oracle, every element: <= 1e-2 sigma max and
+    <= 2e-3 sigma RMS (TF32 inputs + one fp16 rounding of the fp32 accumulator); (2) the packed lookup against the
+    oracle lookup on those same (fp16-valued) levels: <= 1e-5 -- the gather/interpolation is exact fp32 arithmetic on
+    identical taps, including partial tiles, odd level sizes, out-of-map windows and the reference's NaN on a 1-wide
+    level; (3) the BASELINE configs[1] size B = 32."""
+    from eemflow_b200 import ops
+    gen = torch.Generator().manual_seed(B * 100 + H + L)
+    f1 = torch.randn(B, D, H, W, generator=gen)
+    f2 = torch.randn(B, D, H, W, generator=gen)
+    coords = ref_ops.coords_grid(B, H, W) + 3.0 * torch.randn(B, 2, H, W, generator=gen)
+    coords[0, :, 0, 0] = torch.tensor([-50.0, 3.0])           # a window entirely outside the map
+    coords[0, :, -1, -1] = torch.tensor([W + 2.5, H - 0.25])   # straddling the right/bottom edge
+    ref_pyr = ref_ops.corr_pyramid(f1, f2, L)
+    blk = E.CorrBlock(f1.cuda(), f2.cuda(), num_levels=L, radius=4, precision="tf32_f16")
+    assert blk._packed is not None and blk._packed.dtype == torch.float16
+    row, offs, lens = ops.packed_row_elems(H, W, L)
+    assert tuple(blk._packed.shape) == (B * H * W, row)
+    ours_first = blk(coords.cuda()).cpu()                      # lookup BEFORE anybody touched corr_pyramid
+    assert blk._pyramid is None                                # ... did not materialise the f32 tensors
+    levels = [lvl.cpu() for lvl in blk.corr_pyramid]
+    for l, (lvl, ref) in enumerate(zip(levels, ref_pyr)):
+        assert tuple(lvl.shape) == tuple(ref.shape)
+        if ref.numel() == 0:
+            continue
+        d = lvl - ref
+        sigma = max(ref.std().item(), 1e-6)
+        assert d.abs().max().item() <= 1e-2 * sigma, (l, d.abs().max().item(), sigma)
+        assert d.pow(2).mean().sqrt().item() <= 2e-3 * sigma, l
+    ref = ref_ops.corr_lookup(levels, coords, 4)
+    assert tuple(ours_first.shape) == tuple(ref.shape)
+    assert torch.equal(torch.isnan(ours_first), torch.isnan(ref))
+    err = (ours_first - ref).nan_to_num(0.0).abs().max().item()
+    assert err <= 1e-5, err
+    # padding cells of the packed rows are exact zeros (partial tiles / level padding)
+    pk = blk._packed.float().cpu().view(B * H * W, row)
+    h, w = H, W
+    for l in range(L):
+        tx, ty = (w + 3) // 4, (h + 3) // 4
+        blockv = pk[:, offs[l]:offs[l] + lens[l]]
+        if h * w > 0:
+            tiles = blockv[:, :tx * ty * 16].view(-1, ty, tx, 4, 4).permute(0, 1, 3, 2, 4).reshape(-1, ty * 4, tx * 4)
+            assert torch.equal(tiles[:, :h, :w].reshape(B * H * W, 1, h, w), levels[l])
+            assert tiles[:, h:, :].abs().max().item() == 0 if ty * 4 > h else True
+            assert tiles[:, :, w:].abs().max().item() == 0 if tx * 4 > w else True
+            assert blockv[:, tx * ty * 16:].abs().sum().item() == 0
+        h, w = h // 2, w // 2
+
+
+def test_packed_lookup_radius_variants(E):
+    from eemflow_b200 import ops
+    gen = torch.Generator().manual_seed(17)
+    f1 = torch.randn(1, 32, 12, 20, generator=gen)
+    f2 = torch.randn(1, 32, 12, 20, generator=gen)
+    coords = ref_ops.coords_grid(1, 12, 20) + 2.0 * torch.randn(1, 2, 12, 20, generator=gen)
+    for L, r in ((1, 4), (2, 3), (3, 2), (2, 1), (4, 4)):
+        blk = E.CorrBlock(f1.cuda(), f2.cuda(), num_levels=L, radius=r, precision="tf32_f16")
+        ours = blk(coords.cuda()).cpu()
+        ref = ref_ops.corr_lookup([lvl.cpu() for lvl in blk.corr_pyramid], coords, r)
+        assert tuple(ours.shape) == tuple(ref.shape) == (1, L * (2 * r + 1) ** 2, 12, 20)
+        assert torch.equal(torch.isnan(ours), torch.isnan(ref)), (L, r)
+        assert (ours - ref).nan_to_num(0.0).abs().max().item() <= 1e-5, (L, r)
+
+
 def test_lookup_radius_and_level_variants(E):
     gen = torch.Generator().manual_seed(7)
     f1 = torch.randn(1, 32, 12, 20, generator=gen)

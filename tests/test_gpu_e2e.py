@@ -71,7 +71,7 @@ def test_eemflow_cdc_trains_through_the_kernels():
     assert np.isfinite(losses).all()
 
 
-@pytest.mark.parametrize("precision,gate", [("fp32", 2e-4), ("tf32", 1e-3)])
+@pytest.mark.parametrize("precision,gate", [("fp32", 2e-4), ("tf32", 1e-3), ("tf32_f16", 1e-3)])
 def test_eraft_forward_from_events(golden, precision, gate):
     """ERAFT, the caller of CorrBlock: events -> voxel grids -> encoders -> all-pairs pyramid -> 12 x (lookup + GRU
     update) -> convex upsampling, against the REAL reference ERAFT on the CPU (tests/golden/e2e_eraft.npz).

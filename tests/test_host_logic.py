@@ -160,3 +160,18 @@ def test_chunked_sortedness_scan_equals_global_scan():
         for chunk in (1, 2, 3, 7, 64):
             got = all(_chunk_is_sorted(t, lo, min(n, lo + chunk)) for lo in range(0, n, chunk))
             assert got == want, (n, chunk)
+
+
+def test_packed_pyramid_layout_query():
+    """eem_corr_packed_layout (pure host function): 4x4-pixel tiles, every level padded to 32 elements, levels back to back."""
+    from eemflow_b200 import ops
+    for (H, W, L) in [(36, 44, 4), (92, 160, 4), (9, 13, 3), (8, 2, 2), (1, 1, 4)]:
+        row, offs, lens = ops.packed_row_elems(H, W, L)
+        h, w, off = H, W, 0
+        for l in range(L):
+            n = ((w + 3) // 4) * ((h + 3) // 4) * 16 if h * w > 0 else 0
+            n = (n + 31) // 32 * 32
+            assert offs[l] == off and lens[l] == n, (H, W, l)
+            off += n
+            h, w = h // 2, w // 2
+        assert row == off and row % 32 == 0

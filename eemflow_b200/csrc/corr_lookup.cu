@@ -225,101 +225,139 @@ int launch_lookup_any(const LookupParams& p, cudaStream_t stream) {
 // Same outputs as corr_lookup_kernel, different input: every level of a source position is stored as 4x4-pixel
 // tiles of fp16 (32 B = one sector each) in ONE row per position.  A CTA owns 32 consecutive positions.  Phases:
 // (1) window geometry per (position, level) -- identical arithmetic to the f32 kernel; (2) ONE gather phase: the
-// NT x NT tiles that cover a position's (2r+2)^2 tap window are copied sector by sector with 16-byte cp.async
-// (zero-filled when the tile lies outside the map; cells of a partial last tile are zeros in the volume itself),
-// all levels back to back, every load in flight before anything is consumed; (3) interpolation in fp32 with
+// window rows are copied out of the NT tiles per tile row that cover a position's (2r+2)^2 tap window with 8-byte
+// cp.async (zero-filled when the tile lies outside the map; cells of a partial last tile are zeros in the volume
+// itself), all levels back to back, every load in flight before anything is consumed; (3) interpolation in fp32 with
 // warp = (level, 3 window columns), lane = position, so each store instruction writes 32 consecutive positions of
 // one output channel (128 B).  Per position the kernel fetches ~10.6 sectors per full-size level instead of the
 // 16 + that the f32 row-major volume costs, and half the bytes per tap.
 struct PackedLookupParams {
   const uint16_t* packed;
   int h[kMaxLevels], w[kMaxLevels], tx[kMaxLevels], ty[kMaxLevels], off[kMaxLevels];
+  float rcp_w1[kMaxLevels], rcp_h1[kMaxLevels];     // RN(1 / (w_l - 1)), RN(1 / (h_l - 1)) (inf for a 1-wide map)
   int row;
   int B, H, W, L;
   const float* coords;
   float* out;
 };
 
+// roundtrip() with the IEEE division replaced by a multiply and two FMAs: q0 = RN(x * y), r = x - q0 * s1 (exact in
+// one FMA), q = RN(q0 + r * y) with y = RN(1 / s1) is the correctly rounded quotient x / s1 (Markstein's theorem; the
+// divisor is a small integer, results in the normal range), i.e. the same bits as __fdiv_rn without its ~10
+// instruction sequence and slow-path branch -- 20 of these per (position, level) made up half of the geometry phase.
+__device__ __forceinline__ float roundtrip_rcp(float p, float s1, float rcp_s1) {
+  const float x = __fmul_rn(2.0f, p);
+  const float q0 = __fmul_rn(x, rcp_s1);
+  const float r = __fmaf_rn(-q0, s1, x);
+  const float q = __fmaf_rn(r, rcp_s1, q0);
+  const float g = __fsub_rn(q, 1.0f);
+  return __fmul_rn(__fadd_rn(g, 1.0f), s1 * 0.5f);
+}
+
 template <int R>
 struct PackedSmem {
   static constexpr int K = 2 * R + 1, T = K + 1;
   static constexpr int NT = (T + 6) / 4;                    // tiles per dimension covering T taps at any phase 0..3
   static constexpr int PB = 32;
-  static constexpr int kPatchBytes = NT * NT * 32;
-  // + 16 B: consecutive positions start 4 banks apart (mod 32), so the 8-byte reads of a half-warp conflict 2-way at most
-  static constexpr int kStrideBytes = kPatchBytes + 16;
+  // Patch of one (level, position) in shared memory: T rows (the window's rows, row 0 = the window origin row) of
+  // NT*4 fp16 (the NT tiles that cover the window's columns; column 0 = first column of the first tile), row-major.
+  static constexpr int kRowBytes = NT * 8;
+  static constexpr int kPatchBytes = T * kRowBytes;
+  // + 8 B: consecutive positions start 2 banks apart (mod 32): the 4-byte tap reads of a warp conflict 2-way at most
+  static constexpr int kStrideBytes = kPatchBytes + ((kPatchBytes / 4) % 32 == 2 ? 0 : 8);
   static constexpr int kColsPerTask = 3, kGroups = (K + kColsPerTask - 1) / kColsPerTask;
   static constexpr int kThreads = 32 * 4 * kGroups;          // one interpolation task per warp for a 4-level pyramid
   static constexpr int kPerLevelBytes = PB * kStrideBytes + 2 * PB * K * 4 + PB * 2 * 4;
 };
 
+// The three phases of a batch of PB positions, shared by the one-batch-per-CTA kernel and the pipelined persistent one.
 template <int R>
-__global__ void __launch_bounds__(PackedSmem<R>::kThreads)
-corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
+struct PackedPhases {
   using S = PackedSmem<R>;
-  constexpr int K = S::K, T = S::T, NT = S::NT, PB = S::PB;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int P = p.H * p.W;
-  const int b = blockIdx.y;
-  const int i0 = blockIdx.x * PB;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int npos = min(PB, P - i0);
-  const int L = p.L;
+  static constexpr int K = S::K, T = S::T, NT = S::NT, PB = S::PB;
 
-  auto patch_of = [&](int l) { return smem_raw + (size_t)l * S::kPerLevelBytes; };
-  auto fx_of = [&](int l) { return reinterpret_cast<float*>(patch_of(l) + PB * S::kStrideBytes); };
-  auto fy_of = [&](int l) { return fx_of(l) + PB * K; };
-  auto org_of = [&](int l) { return reinterpret_cast<int*>(fy_of(l) + PB * K); };
+  static __device__ __forceinline__ unsigned char* patch_of(unsigned char* st, int l) { return st + (size_t)l * S::kPerLevelBytes; }
+  static __device__ __forceinline__ float* fx_of(unsigned char* st, int l) { return reinterpret_cast<float*>(patch_of(st, l) + PB * S::kStrideBytes); }
+  static __device__ __forceinline__ float* fy_of(unsigned char* st, int l) { return fx_of(st, l) + PB * K; }
+  static __device__ __forceinline__ int* org_of(unsigned char* st, int l) { return reinterpret_cast<int*>(fy_of(st, l) + PB * K); }
 
   // 1) window geometry, one thread per (position, level): same arithmetic as corr_lookup_kernel
-  for (int t = threadIdx.x; t < PB * L; t += blockDim.x) {
-    const int l = t / PB, pos = t % PB;
-    const int hl = p.h[l], wl = p.w[l];
-    float cx = 0.f, cy = 0.f;
-    if (pos < npos) {
-      cx = __ldg(p.coords + ((int64_t)b * 2 + 0) * P + i0 + pos);
-      cy = __ldg(p.coords + ((int64_t)b * 2 + 1) * P + i0 + pos);
-    }
-    const float inv = 1.0f / (float)(1 << l);
-    const float lx = cx * inv, ly = cy * inv;
-    const float ox = floorf(fminf(fmaxf(roundtrip(lx - (float)R, wl), -1.0e6f), 1.0e6f));
-    const float oy = floorf(fminf(fmaxf(roundtrip(ly - (float)R, hl), -1.0e6f), 1.0e6f));
-    org_of(l)[pos * 2 + 0] = (int)ox;
-    org_of(l)[pos * 2 + 1] = (int)oy;
+  static __device__ __forceinline__ void geometry(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos) {
+    const int P = p.H * p.W, L = p.L;
+    for (int t = threadIdx.x; t < PB * L; t += blockDim.x) {
+      const int l = t / PB, pos = t % PB;
+      const float sw = (float)(p.w[l] - 1), sh = (float)(p.h[l] - 1);
+      const float rw = p.rcp_w1[l], rh = p.rcp_h1[l];
+      float cx = 0.f, cy = 0.f;
+      if (pos < npos) {
+        cx = __ldg(p.coords + ((int64_t)b * 2 + 0) * P + i0 + pos);
+        cy = __ldg(p.coords + ((int64_t)b * 2 + 1) * P + i0 + pos);
+      }
+      const float inv = 1.0f / (float)(1 << l);
+      const float lx = cx * inv, ly = cy * inv;
+      const float ox = floorf(fminf(fmaxf(roundtrip_rcp(lx - (float)R, sw, rw), -1.0e6f), 1.0e6f));
+      const float oy = floorf(fminf(fmaxf(roundtrip_rcp(ly - (float)R, sh, rh), -1.0e6f), 1.0e6f));
+      org_of(st, l)[pos * 2 + 0] = (int)ox;
+      org_of(st, l)[pos * 2 + 1] = (int)oy;
+      float* fxp = fx_of(st, l) + pos * K;
+      float* fyp = fy_of(st, l) + pos * K;
 #pragma unroll
-    for (int a = 0; a < K; ++a) {
-      fx_of(l)[pos * K + a] = roundtrip(lx + (float)(a - R), wl) - (ox + (float)a);
-      fy_of(l)[pos * K + a] = roundtrip(ly + (float)(a - R), hl) - (oy + (float)a);
+      for (int a = 0; a < K; ++a) {
+        fxp[a] = roundtrip_rcp(lx + (float)(a - R), sw, rw) - (ox + (float)a);
+        fyp[a] = roundtrip_rcp(ly + (float)(a - R), sh, rh) - (oy + (float)a);
+      }
     }
   }
-  __syncthreads();
 
-  // 2) gather: unit = (level, position, tile slot); consecutive threads take consecutive slots of a position, i.e.
-  //    neighbouring 32-byte sectors of the same tile row
-  {
-    constexpr int kUnitsPerLevel = PB * NT * NT;
-    for (int u = threadIdx.x; u < L * kUnitsPerLevel; u += blockDim.x) {
-      const int l = u / kUnitsPerLevel, rem = u - l * kUnitsPerLevel;
-      const int pos = rem / (NT * NT), slot = rem - pos * (NT * NT);
-      if (pos >= npos || p.h[l] * p.w[l] == 0) continue;
-      const int sy = slot / NT, sx = slot - sy * NT;
-      const int txx = (org_of(l)[pos * 2 + 0] >> 2) + sx, tyy = (org_of(l)[pos * 2 + 1] >> 2) + sy;   // >> : floor for negatives
-      const bool ok = (unsigned)txx < (unsigned)p.tx[l] && (unsigned)tyy < (unsigned)p.ty[l];
-      const uint16_t* src = p.packed + ((int64_t)b * P + i0 + pos) * p.row + p.off[l] + (ok ? (tyy * p.tx[l] + txx) * 16 : 0);
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(patch_of(l) + pos * S::kStrideBytes + slot * 32);
-      const int nbytes = ok ? 16 : 0;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16), "l"(src + 8), "r"(nbytes) : "memory");
+  // 2) gather: unit = (level, position, window row); the thread copies that row's 8-byte piece out of each of the NT
+  //    tiles the window's columns touch (zero-filled when the tile lies outside the map; cells of a partial last tile
+  //    are zeros in the volume itself), so the patch in shared memory is a plain row-major image whose row 0 is the
+  //    window's first row.  Issues the copies and commits ONE cp.async group.
+  static __device__ __forceinline__ void gather(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos) {
+    const int P = p.H * p.W, L = p.L;
+    for (int u = threadIdx.x; u < PB * T; u += blockDim.x) {       // (position, window row): decoded once, then all levels
+      const int pos = u / T, rr = u - pos * T;
+      if (pos >= npos) continue;
+      const uint16_t* rowbase = p.packed + ((int64_t)b * P + i0 + pos) * p.row;
+      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(st + pos * S::kStrideBytes + rr * S::kRowBytes);
+      for (int l = 0; l < L; ++l) {
+        const int txl = p.tx[l], tyl = p.ty[l];
+        if (txl == 0 || tyl == 0) continue;                        // empty level
+        const int* org = org_of(st, l) + pos * 2;
+        const int py = org[1] + rr;                                // map row of this window row
+        const int ty = py >> 2, tx0 = org[0] >> 2;                 // >> : floor for negatives
+        const uint32_t dst = dst0 + l * S::kPerLevelBytes;
+        const bool row_ok = (unsigned)ty < (unsigned)tyl;
+        if (row_ok && tx0 >= 0 && tx0 + NT <= txl) {               // interior: NT consecutive tiles of one tile row
+          const uint16_t* src = rowbase + p.off[l] + ((ty * txl + tx0) * 16 + (py & 3) * 4);
+#pragma unroll
+          for (int sx = 0; sx < NT; ++sx)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + sx * 8), "l"(src + sx * 16) : "memory");
+        } else {
+          const uint16_t* src = rowbase + p.off[l] + (row_ok ? (ty * txl * 16 + (py & 3) * 4) : 0);
+#pragma unroll
+          for (int sx = 0; sx < NT; ++sx) {
+            const int tx = tx0 + sx;
+            const bool ok = row_ok && (unsigned)tx < (unsigned)txl;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + sx * 8), "l"(src + (ok ? tx * 16 : 0)), "r"(ok ? 8 : 0) : "memory");
+          }
+        }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
-  __syncthreads();
 
-  // 3) interpolate: task = (level, group of G adjacent window columns), lane = position
-  constexpr int G = S::kColsPerTask, kGroups = S::kGroups;
-  const int n_warps = blockDim.x >> 5;
-  if (lane < npos) {
+  // 3) interpolate: task = (level, group of G adjacent window columns), lane = position.  Per window row a thread
+  //    reads three 4-byte words (6 fp16: the G + 1 = 4 taps it needs start at an even or odd element), shifts them
+  //    into place with two funnel shifts, and forms G horizontal lerps + G vertical lerps; row addresses are
+  //    compile-time offsets of one per-task base pointer.
+  static __device__ __forceinline__ void interp(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos) {
+    constexpr int G = S::kColsPerTask, kGroups = S::kGroups;
+    static_assert(G == 3, "load_row unpacks G + 1 = 4 taps");
+    const int P = p.H * p.W, L = p.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    if (lane >= npos) return;
     for (int task = warp; task < L * kGroups; task += n_warps) {
       const int l = task / kGroups, a0 = (task - l * kGroups) * G;
       float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a0 * K) * P + i0 + lane;
@@ -331,33 +369,33 @@ corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
             for (int c = 0; c < K; ++c) st_stream(o + (int64_t)(g * K + c) * P, 0.f);
         continue;
       }
-      const unsigned char* patch = patch_of(l) + lane * S::kStrideBytes;
-      const int sx0 = org_of(l)[lane * 2 + 0] & 3, sy0 = org_of(l)[lane * 2 + 1] & 3;
-      const int q0 = sx0 + a0;                                  // first tap column of this task inside the patch
-      const int tq = q0 >> 2, tq1 = min(tq + 1, NT - 1);       // the G+1 = 4 taps span at most two tiles
-      const unsigned sh = (unsigned)(q0 & 3) * 16u;
-      const float* fyp = fy_of(l) + lane * K;
+      const int q0 = (org_of(st, l)[lane * 2 + 0] & 3) + a0;    // first tap column of this task inside the patch row
+      // 12 bytes per row from word q0/2 on.  For the last column group of a narrow window (r < 4) the third word may
+      // lie one word past the row: it only feeds taps that are never used, and the bytes read are still inside this
+      // stage's shared memory (the next row / the position's pad / the fraction arrays).
+      const unsigned char* base = patch_of(st, l) + lane * S::kStrideBytes + (q0 >> 1) * 4;
+      const unsigned sh = (unsigned)(q0 & 1) * 16u;
+      const float* fyp = fy_of(st, l) + lane * K;
       float fx[G], prev[G];
 #pragma unroll
-      for (int g = 0; g < G; ++g) fx[g] = (a0 + g < K) ? fx_of(l)[lane * K + a0 + g] : 0.f;
+      for (int g = 0; g < G; ++g) fx[g] = (a0 + g < K) ? fx_of(st, l)[lane * K + a0 + g] : 0.f;
       auto load_row = [&](int rr, float (&t)[G + 1]) {
-        const int py = sy0 + rr;
-        const unsigned char* rowp = patch + ((py >> 2) * NT) * 32 + (py & 3) * 8;
-        const uint64_t lo = *reinterpret_cast<const uint64_t*>(rowp + tq * 32);
-        const uint64_t hi = *reinterpret_cast<const uint64_t*>(rowp + tq1 * 32);
-        const uint64_t v = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
-        const float2 ab = __half22float2(*reinterpret_cast<const __half2*>(&v));
-        const uint32_t v_hi = (uint32_t)(v >> 32);
+        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(base + rr * S::kRowBytes);
+        const uint32_t x0 = rowp[0], x1 = rowp[1], x2 = rowp[2];
+        const uint32_t v_lo = __funnelshift_r(x0, x1, sh), v_hi = __funnelshift_r(x1, x2, sh);
+        const float2 ab = __half22float2(*reinterpret_cast<const __half2*>(&v_lo));
         const float2 cd = __half22float2(*reinterpret_cast<const __half2*>(&v_hi));
         t[0] = ab.x; t[1] = ab.y; t[2] = cd.x; t[3] = cd.y;
       };
-      static_assert(G == 3, "load_row unpacks G + 1 = 4 taps");
       {
         float t[G + 1];
         load_row(0, t);
 #pragma unroll
         for (int g = 0; g < G; ++g) prev[g] = t[g] + fx[g] * (t[g + 1] - t[g]);
       }
+      float* og[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) og[g] = o + (int64_t)(g * K) * P;
 #pragma unroll
       for (int c = 0; c < K; ++c) {
         float t[G + 1];
@@ -366,10 +404,80 @@ corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const float cur = t[g] + fx[g] * (t[g + 1] - t[g]);
-          if (a0 + g < K) st_stream(o + (int64_t)(g * K + c) * P, prev[g] + fy * (cur - prev[g]));
+          if (a0 + g < K) st_stream(og[g], prev[g] + fy * (cur - prev[g]));
+          og[g] += P;
           prev[g] = cur;
         }
       }
+    }
+  }
+};
+
+// One batch per CTA (the default).
+template <int R>
+__global__ void __launch_bounds__(PackedSmem<R>::kThreads)
+corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
+  using Ph = PackedPhases<R>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int P = p.H * p.W;
+  const int b = blockIdx.y, i0 = blockIdx.x * Ph::PB;
+  const int npos = min(Ph::PB, P - i0);
+  Ph::geometry(p, smem_raw, b, i0, npos);
+  __syncthreads();
+  Ph::gather(p, smem_raw, b, i0, npos);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  Ph::interp(p, smem_raw, b, i0, npos);
+}
+
+// Persistent, software-pipelined form (experiment, EEM_LOOKUP_PACKED_PIPE=1): a CTA walks batches blockIdx.x, blockIdx.x + gridDim.x, ...
+// with TWO shared-memory stages, so the tile gather of batch k+1 (64 KiB of 16-byte cp.async per CTA) is in flight
+// while batch k is interpolated and stored: HBM always has requests queued, and the barrier / copy-wait stalls of the
+// one-batch kernel (its CTAs spent most of their life waiting for their own gather) disappear.
+template <int R>
+__global__ void __launch_bounds__(PackedSmem<R>::kThreads, 1)
+corr_lookup_packed_pipe_kernel(const __grid_constant__ PackedLookupParams p, int batches_per_sample, int n_batches, int stage_bytes) {
+  using Ph = PackedPhases<R>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int P = p.H * p.W;
+  auto decode = [&](int bid, int& b, int& i0, int& npos) {
+    b = bid / batches_per_sample;
+    i0 = (bid - b * batches_per_sample) * Ph::PB;
+    npos = min(Ph::PB, P - i0);
+  };
+  const int step = gridDim.x;
+  int bid = blockIdx.x;
+  if (bid >= n_batches) return;
+  int b, i0, npos;
+  // prologue: batches 0 and 1 of this CTA
+  decode(bid, b, i0, npos);
+  Ph::geometry(p, smem_raw, b, i0, npos);
+  if (bid + step < n_batches) {
+    int b1, i1, n1;
+    decode(bid + step, b1, i1, n1);
+    Ph::geometry(p, smem_raw + stage_bytes, b1, i1, n1);
+    __syncthreads();
+    Ph::gather(p, smem_raw, b, i0, npos);
+    Ph::gather(p, smem_raw + stage_bytes, b1, i1, n1);
+  } else {
+    __syncthreads();
+    Ph::gather(p, smem_raw, b, i0, npos);
+  }
+  for (int k = 0; bid < n_batches; ++k, bid += step) {
+    unsigned char* st = smem_raw + (k & 1) * stage_bytes;
+    decode(bid, b, i0, npos);
+    if (bid + step < n_batches) asm volatile("cp.async.wait_group 1;" ::: "memory");   // batch k landed, k+1 may be in flight
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    Ph::interp(p, st, b, i0, npos);
+    const int nxt = bid + 2 * step;
+    if (nxt < n_batches) {                      // refill this stage with batch k+2
+      __syncthreads();                          // every warp is done reading the stage
+      int b2, i2, n2;
+      decode(nxt, b2, i2, n2);
+      Ph::geometry(p, st, b2, i2, n2);
+      __syncthreads();
+      Ph::gather(p, st, b2, i2, n2);
     }
   }
 }
@@ -377,11 +485,33 @@ corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
 template <int R>
 int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
   using S = PackedSmem<R>;
-  const size_t smem = (size_t)p.L * S::kPerLevelBytes;
-  dim3 grid((unsigned)ceil_div(p.H * p.W, S::PB), (unsigned)p.B);
+  const size_t stage = (size_t)p.L * S::kPerLevelBytes;
+  const int bps = (int)ceil_div(p.H * p.W, S::PB);
+  const int64_t n_batches = (int64_t)bps * p.B;
+  // Measured on B200 (MVSEC B = 32, 12 back-to-back launches): one batch per CTA with 4 CTAs (48 warps) per SM 39.0 us;
+  // the persistent two-stage pipeline with 2 CTAs (24 warps) per SM 45.3 us -- warp-level parallelism hides the gather
+  // latency better than the explicit pipeline with half the warps, so the simple kernel is the default and
+  // EEM_LOOKUP_PACKED_PIPE=1 selects the pipeline for comparisons.
+  static const bool force_simple = [] {
+    const char* v = getenv("EEM_LOOKUP_PACKED_PIPE");
+    return !(v != nullptr && atoi(v) == 1);
+  }();
+  if (2 * stage <= 220 * 1024 && n_batches < (int64_t)0x7fffffff && !force_simple) {
+    static DynSmemOptIn optin;
+    EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_pipe_kernel<R>, 2 * stage));
+    const int sms = sm_count();
+    if (sms <= 0) return fail(EEM_ERR_CUDA, "eem_corr_lookup_packed: cannot query SM count");
+    int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(2 * stage);      // CTAs that fit an SM's shared memory
+    if (per_sm > 2) per_sm = 2;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > n_batches) grid = n_batches;
+    corr_lookup_packed_pipe_kernel<R><<<(unsigned)grid, S::kThreads, 2 * stage, stream>>>(p, bps, (int)n_batches, (int)stage);
+    return EEM_OK;
+  }
+  dim3 grid((unsigned)bps, (unsigned)p.B);
   static DynSmemOptIn optin;
-  if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_kernel<R>, smem));
-  corr_lookup_packed_kernel<R><<<grid, S::kThreads, smem, stream>>>(p);
+  if (stage > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_kernel<R>, stage));
+  corr_lookup_packed_kernel<R><<<grid, S::kThreads, stage, stream>>>(p);
   return EEM_OK;
 }
 
@@ -650,6 +780,9 @@ int eem_corr_lookup_packed(const void* packed, int B, int H, int W, int num_leve
   p.packed = static_cast<const uint16_t*>(packed);
   for (int l = 0; l < num_levels; ++l) {
     p.h[l] = pl.h[l]; p.w[l] = pl.w[l]; p.tx[l] = pl.tx[l]; p.ty[l] = pl.ty[l]; p.off[l] = pl.off[l];
+    if (pl.h[l] * pl.w[l] == 0) p.tx[l] = p.ty[l] = 0;
+    p.rcp_w1[l] = (float)(1.0 / (double)(pl.w[l] - 1));      // correctly rounded reciprocal (inf for a 1-wide map)
+    p.rcp_h1[l] = (float)(1.0 / (double)(pl.h[l] - 1));
   }
   p.row = pl.row;
   p.B = B; p.H = H; p.W = W; p.L = num_levels;

@@ -118,36 +118,67 @@ pool_pyramid_packed_kernel(const __grid_constant__ PoolPackedParams p) {
   const int P0 = pl.h[0] * pl.w[0];
   for (int64_t plane = (int64_t)blockIdx.x * groups_per_cta + gid; plane < p.n_planes; plane += (int64_t)gridDim.x * groups_per_cta) {
     const float* src = p.in + plane * P0;
+    // asynchronous copies: all of a thread's loads are in flight at once (a plain load -> store loop with a
+    // run-time trip count keeps ONE 16-byte load per thread in flight and made this pass latency-bound)
     if ((P0 & 3) == 0) {
       for (int i = t * 4; i < P0; i += gsize * 4)
-        *reinterpret_cast<float4*>(base + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(base + i)), "l"(src + i) : "memory");
     } else {
-      for (int i = t; i < P0; i += gsize) base[i] = __ldg(src + i);
+      for (int i = t; i < P0; i += gsize)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(base + i)), "l"(src + i) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     gsync();
     float* cur = base;
     for (int l = 1; l < pl.L; ++l) {
       const int hi = pl.h[l - 1], wi = pl.w[l - 1], ho = pl.h[l], wo = pl.w[l];
       float* nxt = cur + hi * wi;
-      for (int r = t; r < ho * wo; r += gsize) {
-        const int y = r / wo, x = r - y * wo;
-        const float* s4 = cur + (2 * y) * wi + 2 * x;
-        nxt[r] = (((s4[0] + s4[1]) + s4[wi]) + s4[wi + 1]) * 0.25f;
+      if (ho * wo > 0) {
+        int y = t / wo, x = t - y * wo;                          // once per level, then incremental
+        for (int r = t; r < ho * wo; r += gsize) {
+          const float* s4 = cur + (2 * y) * wi + 2 * x;
+          nxt[r] = (((s4[0] + s4[1]) + s4[wi]) + s4[wi + 1]) * 0.25f;
+          x += gsize;
+          while (x >= wo) { x -= wo; ++y; }
+        }
       }
       gsync();
       cur = nxt;
     }
     float* dst = p.out + plane * pl.row;
     cur = base;
+    // write-out in tile order: thread t owns ROW r = t & 3 of the tiles t >> 2, t >> 2 + gsize / 4, ... (one 16-byte
+    // store per tile row, 8 tiles = 512 contiguous bytes per warp instruction) and walks (tile row, tile column)
+    // incrementally -- no division and ~1/4 of an instruction per element (a scalar version with a division per
+    // element made this pass instruction-bound: 29 M warp instructions for 18.6 M elements)
+    const int r = t & 3, tstep = gsize >> 2;
     for (int l = 0; l < pl.L; ++l) {
       const int h = pl.h[l], w = pl.w[l], tx = pl.tx[l];
+      const int n_tiles = tx * pl.ty[l];
       float* d = dst + pl.off[l];
-      for (int e = t; e < pl.len[l]; e += gsize) {
-        const int tile = e >> 4, r = (e >> 2) & 3, c = e & 3;
-        const int tyi = tile / tx, txi = tile - tyi * tx;
-        const int y = 4 * tyi + r, x = 4 * txi + c;
-        d[e] = (y < h && x < w) ? cur[y * w + x] : 0.0f;
+      if (n_tiles > 0) {
+        int tile = t >> 2;
+        int tyi = tile / tx, txi = tile - tyi * tx;            // once per level
+        for (; tile < n_tiles; tile += tstep) {
+          const int y = 4 * tyi + r, x = 4 * txi;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (y < h) {
+            const float* sp = cur + y * w + x;
+            if (x + 3 < w) {
+              v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            } else {
+              if (x < w) v.x = sp[0];
+              if (x + 1 < w) v.y = sp[1];
+              if (x + 2 < w) v.z = sp[2];
+            }
+          }
+          *reinterpret_cast<float4*>(d + tile * 16 + r * 4) = v;
+          txi += tstep;
+          while (txi >= tx) { txi -= tx; ++tyi; }
+        }
       }
+      for (int e = n_tiles * 16 + t; e < pl.len[l]; e += gsize) d[e] = 0.0f;     // level padding
       cur += h * w;
     }
     gsync();      // the group's staging area is reused by its next plane

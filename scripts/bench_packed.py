@@ -1,5 +1,6 @@
 """f32 pyramid + lookup vs the fp16 working pyramid (precision="tf32_f16") at the BASELINE shapes.
-CUDA-event medians; inputs/outputs are larger than L2 (no flush needed for the streaming kernels)."""
+CUDA-event time of `reps` back-to-back launches (median over `iters`), so launch latency is amortised as in the
+step graph; inputs/outputs are larger than L2."""
 import statistics
 import sys
 from pathlib import Path
@@ -11,7 +12,7 @@ sys.path.insert(0, str(ROOT))
 from eemflow_b200 import ops  # noqa: E402
 
 
-def timeit(fn, iters=20):
+def timeit(fn, iters=10, reps=6):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -19,10 +20,11 @@ def timeit(fn, iters=20):
     for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(reps):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / reps)
     return statistics.median(ts) * 1e3
 
 

@@ -203,9 +203,10 @@ def test_device_contract_and_errors(V):
     V(5, gpu=True, forkserver=False)(Seq(bad, 32, 48))            # non-strict: vote dropped, no error
 
 
-@pytest.mark.parametrize("path", ["pair", "direct", "cluster", "interleaved"])
+@pytest.mark.parametrize("path", ["pair", "direct", "cluster", "interleaved", "tiled"])
 def test_forced_vote_path_parity(golden, V, monkeypatch, path):
-    """The atomic mode has three implementations chosen by size: cluster-resident (a window's grid lives in the
+    """("tiled": the tile-binned exact kernel forced for the order-free mode as well.)
+    The atomic mode has three implementations chosen by size: cluster-resident (a window's grid lives in the
     shared memory of an 8-CTA cluster; MVSEC-sized windows), direct L2 atomics, and the pair layout (>= 2 events
     per voxel).  Force each one and repeat the parity checks, including the reference's row-wrap and
     dropped-vote corner cases (a forced cluster path falls back to direct for grids that do not fit)."""
@@ -245,6 +246,54 @@ def test_forced_vote_path_parity(golden, V, monkeypatch, path):
     with pytest.raises(IndexError):
         V(5, gpu=True, forkserver=False, strict=True)(Seq(bad, 32, 48))
     V(5, gpu=True, forkserver=False)(Seq(bad, 32, 48))
+
+
+@pytest.mark.parametrize("path,orderfree", [("radix", "0"), ("tiled", "1")])
+def test_forced_deterministic_and_orderfree_variants(golden, V, monkeypatch, path, orderfree):
+    """The deterministic mode's fallback (stable radix sort, bit-exact) and the tile path's shared-memory-atomic
+    variant (order-free, <= 1e-5 relative), forced through the environment."""
+    monkeypatch.setenv("EEM_VOXEL_PATH", path)
+    monkeypatch.setenv("EEM_VOXEL_ORDERFREE", orderfree)
+    g = golden("voxel")
+    rng = np.random.default_rng(33)
+    extra = [(make_events(rng, 300_000, 260, 346, True), 5, 260, 346), (make_events(rng, 400_000, 720, 1280, False), 15, 720, 1280)]
+    cases = [(g[f"{n}__events"], *(int(v) for v in g[f"{n}__shape"])) for n in cases_of(g)] + extra
+    for ev, nb, h, w in cases:
+        ref, _, _ = c_oracle.voxelize(ev, nb, h, w, normalize=False)
+        if path == "radix":
+            out = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True)(Seq(ev.copy(), h, w)).cpu().numpy()
+            assert np.array_equal(out, ref)
+        else:
+            out = V(nb, gpu=True, normalize=False, forkserver=False)(Seq(ev.copy(), h, w)).cpu().numpy()
+            assert rel_close(out, ref).all(), np.abs(out - ref).max()
+
+
+def test_deterministic_unusual_polarity_and_off_sensor_events(V):
+    """Tile-binned exact path, rare branches: polarity values other than +-1 (kept in the side array), p == 0 (-> -1),
+    x >= W (the reference's silent row wrap), votes that leave the grid (dropped and counted), unsorted stamps inside a
+    window handed straight to the C ABI layer (chunk ranges then overlap)."""
+    rng = np.random.default_rng(41)
+    nb, h, w = 7, 100, 150
+    ev = make_events(rng, 60_000, h, w)
+    ev[:, 3] = rng.choice([-1.0, 0.0, 1.0, 0.5, 2.0, -3.25], size=ev.shape[0])
+    ev[::97, 1] = w + rng.integers(0, 40, size=ev[::97].shape[0])          # wraps into the next row / bin
+    ev[5::1013, 2] = -3.0                                                  # flat index < 0 for the first bin: dropped
+    ref, dropped, _ = c_oracle.voxelize(ev, nb, h, w, normalize=False)
+    assert dropped > 0
+    out = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True)(Seq(ev.copy(), h, w)).cpu().numpy()
+    assert np.array_equal(out, ref)
+    with pytest.raises(IndexError):
+        V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True, strict=True)(Seq(ev.copy(), h, w))
+    # unsorted rows straight into ops.voxelize (EventSequence would sort them): still the reference's result,
+    # which votes in ROW order with first/last stamps taken from the first/last row
+    from eemflow_b200 import ops
+    perm = rng.permutation(ev.shape[0])
+    shuffled = np.ascontiguousarray(ev[perm])
+    ref_s, _, _ = c_oracle.voxelize(shuffled, nb, h, w, normalize=False)
+    d_ev = torch.from_numpy(shuffled).cuda()
+    off = torch.tensor([0, shuffled.shape[0]], dtype=torch.int64, device="cuda")
+    out_s = ops.voxelize(d_ev, off, shuffled.shape[0], nb, h, w, normalize=False, deterministic=True).cpu().numpy()[0]
+    assert np.array_equal(out_s, ref_s)
 
 
 def test_packed_columns_match_reference_loader_chain(V):

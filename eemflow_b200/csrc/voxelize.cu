@@ -677,7 +677,7 @@ inline TileWorkspace tile_workspace(int64_t n_total, int n_windows, int num_bins
 // Correctly rounded double division a / b through b's reciprocal: q0 = RN(a*y), r = a - q0*b (exact, one FMA),
 // q = RN(q0 + r*y) with y = RN(1/b) (Markstein).  Same bits as __ddiv_rn for the finite, normal-range stamps of an
 // event window, at 3 DFMA-class instructions instead of the ~25 of the IEEE division sequence; the deterministic
-// mode's bit-exactness tests (10 M / 40 M events against the C oracle) pin it.
+// mode's bit-exactness tests (10 M / 40 M events against the CPU reference restatement) pin it.
 __device__ __forceinline__ double div_by_rcp(double a, double b, double rcp_b) {
   const double q0 = __dmul_rn(a, rcp_b);
   const double r = __fma_rn(-q0, b, a);

@@ -78,7 +78,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=None, help="frame pairs per GPU per step of the headline workload")
     ap.add_argument("--lookups", type=int, default=12, help="CorrBlock lookups per pair (ERAFT iterations)")
     ap.add_argument("--cpu-batch", type=int, default=None, help="frame pairs per CPU step (default: the whole batch for mvsec_dt1)")
-    ap.add_argument("--corr", default="tf32", choices=["tf32", "tf32_f16", "fp32"], help="CorrBlock precision / storage")
+    ap.add_argument("--corr", default="tf32_f16", choices=["tf32", "tf32_f16", "fp32"], help="CorrBlock precision / storage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--events-format", default="rows", choices=["rows", "columns"],

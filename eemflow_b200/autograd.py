@@ -61,9 +61,9 @@ class CorrPyramidFn(torch.autograd.Function):
     """CorrBlock.__init__ under autograd (model/corr.py:13-27, 52-60): fmaps -> pyramid levels.
 
     Forward is the one fused kernel (level_l = fmap1^T pool^l(fmap2) / sqrt(D)).  Backward uses the same
-    linearity: d fmap1 = sum_l dV_l . pool^l(fmap2)^T, d pool^l(fmap2) = fmap1 . dV_l, folded back through
-    the pooling by the avg-pool backward kernel.  The four products are plain batched fp32 GEMMs and go to
-    cuBLAS (torch.bmm); everything else runs in this library's kernels.
+    linearity: d fmap1 = sum_l pool^l(fmap2) . dV_l^T, d pool^l(fmap2) = fmap1 . dV_l, folded back through
+    the pooling by the avg-pool backward kernel.  The products are exact-fp32 batched GEMMs in this library's own
+    kernel (eem_batched_gemm_f32; the 1/sqrt(D) scale and the sum over the levels are fused into it).
     """
 
     @staticmethod
@@ -79,7 +79,7 @@ class CorrPyramidFn(torch.autograd.Function):
         P = H * W
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         scale = ops.inv_sqrt_dim(D)
-        f1m = f1.reshape(B, D, P)
+        f1m = f1.contiguous().reshape(B, D, P)
         d1 = None
         d2_levels = []
         f2l = f2.contiguous()
@@ -87,12 +87,16 @@ class CorrPyramidFn(torch.autograd.Function):
             hl, wl = f2l.shape[-2:]
             d2 = None
             if g is not None and hl * wl > 0:
-                G = g.reshape(B, P, hl * wl)
-                if need1:
-                    t = torch.bmm(f2l.reshape(B, D, hl * wl), G.transpose(1, 2))
-                    d1 = t if d1 is None else d1.add_(t)
-                if need2:
-                    d2 = torch.bmm(f1m, G).view(B, D, hl, wl)
+                G = g.contiguous().reshape(B, P, hl * wl)
+                if need1:            # d1[b,d,i] (+)= s * sum_j f2l[b,d,j] * G[b,i,j]
+                    first = d1 is None
+                    if first:
+                        d1 = torch.empty((B, D, P), dtype=torch.float32, device=f1.device)
+                    ops.batched_gemm_(d1, f2l.reshape(B, D, hl * wl), G, b_transposed=True, alpha=scale, accumulate=not first)
+                if need2:            # d2[b,d,j] = s * sum_i f1[b,d,i] * G[b,i,j]
+                    d2 = torch.empty((B, D, hl * wl), dtype=torch.float32, device=f1.device)
+                    ops.batched_gemm_(d2, f1m, G, b_transposed=False, alpha=scale)
+                    d2 = d2.view(B, D, hl, wl)
             d2_levels.append((d2, (hl, wl)))
             if l + 1 < len(grad_levels):
                 f2l = ops.avg_pool2x2(f2l)
@@ -106,10 +110,11 @@ class CorrPyramidFn(torch.autograd.Function):
                     else:
                         ops.avg_pool2x2_backward_(d2, g2, accumulate=True)
                 g2 = d2
-            g2 = torch.zeros_like(f2) if g2 is None else g2.mul_(scale)
+            if g2 is None:
+                g2 = torch.zeros_like(f2)
         g1 = None
         if need1:
-            g1 = torch.zeros_like(f1) if d1 is None else d1.mul_(scale).view(B, D, H, W)
+            g1 = torch.zeros_like(f1) if d1 is None else d1.view(B, D, H, W)
         return g1, g2, None, None
 
 

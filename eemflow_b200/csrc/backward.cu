@@ -256,6 +256,72 @@ bilinear_resize_backward_kernel(const float* __restrict__ gout, int B, int C, in
   }
 }
 
+
+// ---- batched fp32 GEMM for the backward of the all-pairs pyramid ------------------------------------------------
+// level_l[b,i,j] = s * sum_d f1[b,d,i] * pool^l(f2)[b,d,j]  (model/corr.py:13-27, 52-60) gives
+//   d f1[b,d,i]          = s * sum_l sum_j pool^l(f2)[b,d,j] * dV_l[b,i,j]     C = A . B^T   (A = f2_l [D,P_l], B = dV_l [P,P_l])
+//   d pool^l(f2)[b,d,j]  = s * sum_i f1[b,d,i]           * dV_l[b,i,j]     C = A . B     (A = f1 [D,P],    B = dV_l [P,P_l])
+// (the reference gets these from autograd through torch.matmul; round 1 used torch.bmm -> cuBLAS).  Exact fp32 FFMA,
+// 64 x 64 x 16 shared-memory tiles, 4 x 4 outputs per thread, same inner loop as the forward's fp32 path.
+//   C[b] (M x N, ldc) = alpha * A[b] (M x K, row-major, lda) * op(B[b]) (+ C[b] when accumulate)
+//   op(B) = B (K x N, row-major, ldb) or B^T with B given N x K row-major (b_transposed)
+constexpr int GT = 64, GK = 16;
+
+template <bool kBT>
+__global__ void __launch_bounds__(256)
+batched_gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
+                        int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, float alpha,
+                        int accumulate) {
+  __shared__ __align__(16) float As[GK][GT + 4];
+  __shared__ __align__(16) float Bs[GK][GT + 4];
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  A += (int64_t)b * strideA;
+  B += (int64_t)b * strideB;
+  C += (int64_t)b * strideC;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    __syncthreads();
+    // A tile: rows m0..m0+63, columns k0..k0+15 (k contiguous in memory) -> As[k][m]
+    for (int t = threadIdx.x; t < GT * GK; t += 256) {
+      const int m = t / GK, k = t % GK;
+      As[k][m] = (m0 + m < M && k0 + k < K) ? __ldg(A + (int64_t)(m0 + m) * lda + k0 + k) : 0.f;
+    }
+    if (kBT) {      // B is N x K: rows n0..n0+63, columns k0.. (k contiguous) -> Bs[k][n]
+      for (int t = threadIdx.x; t < GT * GK; t += 256) {
+        const int n = t / GK, k = t % GK;
+        Bs[k][n] = (n0 + n < N && k0 + k < K) ? __ldg(B + (int64_t)(n0 + n) * ldb + k0 + k) : 0.f;
+      }
+    } else {        // B is K x N: rows k0.., columns n0..n0+63 (n contiguous) -> Bs[k][n]
+      for (int t = threadIdx.x; t < GT * GK; t += 256) {
+        const int k = t / GT, n = t % GT;
+        Bs[k][n] = (n0 + n < N && k0 + k < K) ? __ldg(B + (int64_t)(k0 + k) * ldb + n0 + n) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int m = m0 + ty * 4 + r;
+    if (m >= M) continue;
+    float* o = C + (int64_t)m * ldc + n0 + tx * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (n0 + tx * 4 + c < N) o[c] = accumulate ? fmaf(alpha, acc[r][c], o[c]) : alpha * acc[r][c];
+  }
+}
+
 }  // namespace
 }  // namespace eem
 
@@ -321,6 +387,21 @@ int eem_bilinear_resize_backward(const float* grad_out, int B, int C, int h, int
   bilinear_resize_backward_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream_)>>>(grad_out, B, C, h, w, H, W, align_corners ? 1 : 0,
                                                                                     scale0, scale1, scale_rest, grad_in);
   EEM_CHECK_LAUNCH("bilinear_resize_backward_kernel");
+  return EEM_OK;
+}
+
+int eem_batched_gemm_f32(const float* A, const float* B, float* C, int batch, int M, int N, int K, int64_t lda, int64_t ldb,
+                         int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, int b_transposed, float alpha,
+                         int accumulate, eem_stream_t stream_) {
+  EEM_CHECK_ARG(A && B && C, "eem_batched_gemm_f32: NULL pointer");
+  EEM_CHECK_ARG(batch > 0 && M > 0 && N > 0 && K > 0, "eem_batched_gemm_f32: sizes must be > 0");
+  EEM_CHECK_ARG(batch <= 65535 && (M + GT - 1) / GT <= 65535, "eem_batched_gemm_f32: batch or M too large for one launch");
+  dim3 grid((unsigned)((N + GT - 1) / GT), (unsigned)((M + GT - 1) / GT), (unsigned)batch);
+  if (b_transposed)
+    batched_gemm_f32_kernel<true><<<grid, 256, 0, as_stream(stream_)>>>(A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, accumulate);
+  else
+    batched_gemm_f32_kernel<false><<<grid, 256, 0, as_stream(stream_)>>>(A, B, C, M, N, K, lda, ldb, ldc, strideA, strideB, strideC, alpha, accumulate);
+  EEM_CHECK_LAUNCH("batched_gemm_f32_kernel");
   return EEM_OK;
 }
 

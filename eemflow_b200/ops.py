@@ -402,3 +402,19 @@ def avg_pool2x2_backward_(grad_fine: torch.Tensor, grad_coarse: torch.Tensor, ac
         L.check(L.lib().eem_avg_pool2x2_backward(L.ptr(grad_coarse) if grad_coarse.numel() else None, n * c, h, w,
                                                  grad_fine.data_ptr(), int(accumulate), L.stream_ptr(grad_fine.device)))
     return grad_fine
+
+
+def batched_gemm_(C_: torch.Tensor, A: torch.Tensor, B: torch.Tensor, *, b_transposed: bool, alpha: float = 1.0,
+                  accumulate: bool = False) -> torch.Tensor:
+    """C_[b] = alpha * A[b] @ (B[b].T if b_transposed else B[b]) (+ C_[b]), exact fp32, all [batch, rows, cols] contiguous."""
+    A = L.require_cuda(A, "A")
+    B = L.require_cuda(B, "B")
+    assert C_.is_cuda and C_.dtype == torch.float32 and C_.is_contiguous() and A.dim() == B.dim() == C_.dim() == 3
+    batch, M, K = A.shape
+    N = B.shape[1] if b_transposed else B.shape[2]
+    assert B.shape[0] == batch and (B.shape[2] if b_transposed else B.shape[1]) == K and tuple(C_.shape) == (batch, M, N)
+    with torch.cuda.device(A.device):
+        L.check(L.lib().eem_batched_gemm_f32(A.data_ptr(), B.data_ptr(), C_.data_ptr(), batch, M, N, K, A.shape[2], B.shape[2],
+                                             N, M * K, B.shape[1] * B.shape[2], M * N, int(b_transposed), float(alpha),
+                                             int(accumulate), L.stream_ptr(A.device)))
+    return C_

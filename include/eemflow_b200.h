@@ -261,6 +261,16 @@ EEM_API int eem_corr_lookup_backward(const float* grad_out, const float* coords,
 EEM_API int eem_avg_pool2x2_backward(const float* grad_out, int64_t n_planes, int h, int w, float* grad_in,
                                      int accumulate, eem_stream_t stream);
 
+/* Batched exact-fp32 GEMM used by the backward of K3 (the gradient of torch.matmul in model/corr.py:58 that the
+ * reference obtains from autograd during training, train_mvsec.py:251-258):
+ *   C[b] (M x N, row pitch ldc) = alpha * A[b] (M x K, row pitch lda) * op(B[b])  (+ C[b] when accumulate != 0)
+ *   op(B) = B given K x N row-major (b_transposed == 0) or B^T with B given N x K row-major (b_transposed != 0);
+ *   batch strides in elements.  d fmap1 = sum_l pool^l(fmap2) . dV_l^T and d pool^l(fmap2) = fmap1 . dV_l. */
+EEM_API int eem_batched_gemm_f32(const float* A, const float* B, float* C, int batch, int M, int N, int K,
+                                 int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                                 int64_t strideC, int b_transposed, float alpha, int accumulate,
+                                 eem_stream_t stream);
+
 /* grad_out [B,n_out,H,W] -> grad_f1, grad_f2 [B,C,H,W]; same index/scale meaning as eem_local_corr. */
 EEM_API int eem_local_corr_backward(const float* f1, const float* f2, const float* grad_out, int B,
                                     int C, int H, int W, int max_disp, const int* index, int n_out,

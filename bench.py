@@ -215,24 +215,25 @@ class B200Step:
             self.out = self.blk(c)
 
     def fam_eemflow_ops(self, d=None):
+        """The EEMFlow_cdc call sequence (EEMFlow+.py:158-234) on synthetic feature maps.  Like the reference, the flow of a
+        level is scaled IN PLACE by the upsample2d_flow_as of the next level before its own final upsampling; only the
+        coarsest flow (a persistent bench input) is cloned so that steps do not compound."""
         d = d or self.d
         E = self.E
         index = EEMFLOW_CDC_INDEX
-        flows = []
         lv = d["eem"][0]
         E.correlation_select(lv["f1"], lv["f2"], index)
-        flow = lv["flow"]
-        flows.append(flow)
+        flow = lv["flow"].clone()
+        flows = [flow]
         for lv in d["eem"][1:]:
-            flow_up = E.upsample2d_flow_as(flow.clone(), lv["p1"], mode="bilinear", if_rate=True)
+            flow_up = E.upsample2d_flow_as(flow, lv["p1"], mode="bilinear", if_rate=True)
             E.WarpingLayer_no_div()(lv["p2"], flow_up)
             flow_up = E.cdc_blend(flow_up, lv["inter"], lv["mask"])
             f2w = E.warp(lv["f2"], flow_up)
             E.correlation_select(lv["f1"], f2w, index)
             flow = flow_up
             flows.append(flow)
-        finals = [E.upsample2d_flow_as(f.clone(), self.target, mode="bilinear", if_rate=True) for f in flows[:-1]]
-        finals.append(E.upsample2d_flow_as(flows[-1].clone(), self.target, mode="bilinear", if_rate=True, out=self.flow_out))
+        finals = E.upsample2d_flows_as(flows, self.target, mode="bilinear", if_rate=True, out_last=self.flow_out)
         self.flow = finals[-1]
 
     def fam_metrics(self):
@@ -338,17 +339,17 @@ def reference_step(wl, inp, lookups):
     target = torch.empty(B, 1, wl.H, wl.W)
     lv = inp["eem"][0]
     R.correlation(lv["f1"], lv["f2"], 4, index=idx)
-    flow = lv["flow"]
+    flow = lv["flow"].clone()
     flows = [flow]
     for lv in inp["eem"][1:]:
-        flow_up = R.upsample2d_flow_as(flow.clone(), lv["p1"], if_rate=True)
+        flow_up = R.upsample2d_flow_as(flow, lv["p1"], if_rate=True)
         R.warping_layer_no_div(lv["p2"], flow_up)
         flow_up = R.cdc_blend(flow_up, lv["inter"], lv["mask"])
         f2w = R.warp_exact(lv["f2"], flow_up)
         R.correlation(lv["f1"], f2w, 4, index=idx)
         flow = flow_up
         flows.append(flow)
-    final = [R.upsample2d_flow_as(f.clone(), target, if_rate=True) for f in flows][-1]
+    final = [R.upsample2d_flow_as(f, target, if_rate=True) for f in flows][-1]
     for b in range(B):      # Test.flow_error per sample, dense evaluation (test_mvsec.py:291-346)
         R.flow_error(inp["flow_gt"][b:b + 1], final[b:b + 1], None, False, "dense")
     return final
@@ -619,6 +620,16 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
         torch.distributed.barrier()
     elapsed_ms = edist.max_over_ranks(t_start.elapsed_time(t_stop), dev)
     launches = launches_per_step * steps
+    gather_verified = None
+    if sink is not None:
+        # outside the timed region: rank 0's result buffer must hold every rank's last flows (checksums travel by NCCL)
+        mine = torch.stack([f.double().sum() for f in flows])
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        torch.distributed.all_gather(sums, mine)
+        buf = sink.buffer()
+        if rank == 0 and buf is not None:
+            gather_verified = all(abs(buf[k, r].double().sum().item() - sums[r][k].item()) <= 1e-6 * max(1.0, abs(sums[r][k].item()))
+                                  for k in range(n_graphs) for r in range(world))
 
     # Same K steps again as family graphs with CUDA events between the replays (events cannot be timed inside one
     # replayed graph): per-family split and the dominant kernel's launch duration.
@@ -709,7 +720,7 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
 
     res = {"value": value, "ms_per_step": elapsed_ms / steps, "steps": steps, "warmup": max(3, warmup), "clocks": clocks,
            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-           "result_gather": None if sink is None else sink.describe()}
+           "result_gather": None if sink is None else dict(sink.describe(), verified=gather_verified)}
     if sink is not None:
         sink.close()
     del step, graphs, fam_graphs, inp

@@ -5,7 +5,7 @@ Public surface (same names and call signatures as the reference, see INTEGRATION
     CorrBlock, bilinear_sampler, coords_grid, upflow8        corr.py
     SpatialCorrelationSampler, Correlation                   correlation.py
     warp, tensor_tools.torch_warp(_mask), WarpingLayer_no_div,
-    upsample2d_flow_as, upsample_flow, cdc_blend, InputPadder   warp.py
+    upsample2d_flow_as, upsample2d_flows_as (all predictions in one launch), upsample_flow, cdc_blend, InputPadder   warp.py
     event_mask, event_valid_from_volume, flow_error, motion_propagate   eval_utils.py
     EEMFlow_cdc                                              models.py (lazy: from eemflow_b200.models import ...)
 Everything computes in hand-written CUDA kernels reached through the C ABI of
@@ -16,12 +16,12 @@ from .correlation import Correlation, SpatialCorrelationSampler, correlation_sel
 from .eval_utils import event_mask, event_valid_from_volume, flow_error, motion_propagate
 from .event_utils import EventSequence, EventSequenceToVoxelGrid_Pytorch
 from .warp import (InputPadder, WarpingLayer_no_div, cdc_blend, tensor_tools, torch_warp, torch_warp_mask,
-                   upsample2d_flow_as, upsample_flow, warp)
+                   upsample2d_flow_as, upsample2d_flows_as, upsample_flow, warp)
 
 __all__ = [
     "EventSequence", "EventSequenceToVoxelGrid_Pytorch", "CorrBlock", "bilinear_sampler", "coords_grid", "upflow8",
     "SpatialCorrelationSampler", "Correlation", "correlation_select", "warp", "tensor_tools", "torch_warp",
-    "torch_warp_mask", "WarpingLayer_no_div", "upsample2d_flow_as", "upsample_flow", "cdc_blend", "InputPadder",
+    "torch_warp_mask", "WarpingLayer_no_div", "upsample2d_flow_as", "upsample2d_flows_as", "upsample_flow", "cdc_blend", "InputPadder",
     "event_mask", "event_valid_from_volume", "flow_error", "motion_propagate",
 ]
 __version__ = "0.1.0"

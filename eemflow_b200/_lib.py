@@ -56,6 +56,9 @@ SIGNATURES = {
     "eem_warp_blend": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "eem_bilinear_resize": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _vp]),
     "eem_bilinear_sample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "eem_bilinear_resize_multi": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _i, _i, C.POINTER(_vp), _i, _i, _i,
+                                       C.POINTER(_f), C.POINTER(_f), _f, _vp]),
+    "eem_scale_uv_inplace_multi": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp]),
     "eem_scale_uv_inplace": (_i, [_vp, _i, _i, _i, _i, _f, _f, _vp]),
     "eem_corr_lookup_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_vp), _vp]),
     "eem_avg_pool2x2_backward": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),

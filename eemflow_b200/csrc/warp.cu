@@ -211,6 +211,87 @@ scale_uv_kernel(float* __restrict__ flow, int B, int C, int64_t plane, float s0,
   }
 }
 
+// ---- several flow maps to one size in ONE launch -------------------------------------------------------------
+// The five flow predictions of EEMFlow_cdc are resized to the input size by five calls of upsample2d_flow_as
+// (model/EEMFlow/EEMFlow+.py:231-232), each followed by that function's in-place scaling of its input
+// (cdc_utils.py:85-86): ten launches of at most 23 MB here.  Same arithmetic per element as bilinear_resize_kernel /
+// scale_uv_kernel; blockIdx.z = (map, plane group), blockIdx.y of the scaling kernel = map.
+constexpr int kMaxResizeMaps = 8;
+struct ResizeMultiParams {
+  const float* in[kMaxResizeMaps];
+  float* out[kMaxResizeMaps];
+  int h[kMaxResizeMaps], w[kMaxResizeMaps];
+  float s0[kMaxResizeMaps], s1[kMaxResizeMaps];
+  int n, B, C, H, W, align_corners, gz;
+  float scale_rest;
+};
+
+template <int V>
+__global__ void __launch_bounds__(256)
+bilinear_resize_multi_kernel(const __grid_constant__ ResizeMultiParams p) {
+  const int X = (blockIdx.x * 32 + (threadIdx.x & 31)) * V;
+  const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (X >= p.W || Y >= p.H) return;
+  const int k = blockIdx.z / p.gz, z = blockIdx.z - k * p.gz;
+  const int h = p.h[k], w = p.w[k], C = p.C;
+  int xa[V], xb[V], y0, y1;
+  float la[V], lb[V], ly0, ly1;
+#pragma unroll
+  for (int i = 0; i < V; ++i) source_index(X + i, w, p.W, p.align_corners, xa[i], xb[i], la[i], lb[i]);
+  source_index(Y, h, p.H, p.align_corners, y0, y1, ly0, ly1);
+  const int64_t ip = (int64_t)h * w, op = (int64_t)p.H * p.W;
+  const int gz = p.gz, BC = p.B * C;
+  const float* r0 = p.in[k] + (int64_t)z * ip + y0 * w;
+  const float* r1 = p.in[k] + (int64_t)z * ip + y1 * w;
+  float* o = p.out[k] + (int64_t)z * op + (int64_t)Y * p.W + X;
+  const int64_t s_step = (int64_t)gz * ip, o_step = (int64_t)gz * op;
+  const float scale0 = p.s0[k], scale1 = p.s1[k];
+  int c = z % C;
+  const int c_step = gz % C;
+#pragma unroll 2
+  for (int bc = z; bc < BC; bc += gz) {
+    const float sc = c == 0 ? scale0 : (c == 1 ? scale1 : p.scale_rest);
+    float v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      v[i] = (ly0 * (la[i] * __ldg(r0 + xa[i]) + lb[i] * __ldg(r0 + xb[i])) +
+              ly1 * (la[i] * __ldg(r1 + xa[i]) + lb[i] * __ldg(r1 + xb[i]))) * sc;
+    if constexpr (V == 4) {
+      st_stream4(o, make_float4(v[0], v[1], v[2], v[3]));
+    } else if constexpr (V == 2) {
+      asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(o), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+      st_stream(o, v[0]);
+    }
+    r0 += s_step;
+    r1 += s_step;
+    o += o_step;
+    c += c_step;
+    if (c >= C) c -= C;
+  }
+}
+
+struct ScaleMultiParams {
+  float* flow[kMaxResizeMaps];
+  int64_t plane[kMaxResizeMaps];
+  float s0[kMaxResizeMaps], s1[kMaxResizeMaps];
+  int B, C;
+};
+
+__global__ void __launch_bounds__(256)
+scale_uv_multi_kernel(const __grid_constant__ ScaleMultiParams p) {
+  const int k = blockIdx.y;
+  const int64_t plane = p.plane[k], total = (int64_t)p.B * 2 * plane;
+  float* flow = p.flow[k];
+  const float s0 = p.s0[k], s1 = p.s1[k];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / (2 * plane), r = i % (2 * plane);
+    const int c = (int)(r / plane);
+    float* q = flow + ((int64_t)b * p.C + c) * plane + (r % plane);
+    *q = *q * (c == 0 ? s0 : s1);
+  }
+}
+
 // Thread = V horizontally adjacent output pixels (one V-wide streaming store), looping over a strided set of
 // planes so a few thousand fat CTAs cover the tensor instead of one tiny CTA per (tile, plane).
 template <int V>
@@ -317,6 +398,57 @@ int eem_bilinear_resize(const float* in, int B, int C, int h, int w, float* out,
   else if (V == 2) bilinear_resize_kernel<2><<<grid, 256, 0, stream>>>(in, B, C, h, w, out, H, W, ac, scale0, scale1, scale_rest);
   else bilinear_resize_kernel<1><<<grid, 256, 0, stream>>>(in, B, C, h, w, out, H, W, ac, scale0, scale1, scale_rest);
   EEM_CHECK_LAUNCH("bilinear_resize_kernel");
+  return EEM_OK;
+}
+
+int eem_bilinear_resize_multi(const float* const* ins, const int* hs, const int* ws, int n_maps, int B, int C,
+                              float* const* outs, int H, int W, int align_corners, const float* scale0, const float* scale1,
+                              float scale_rest, eem_stream_t stream_) {
+  EEM_CHECK_ARG(ins && hs && ws && outs && scale0 && scale1, "eem_bilinear_resize_multi: NULL pointer");
+  EEM_CHECK_ARG(n_maps > 0 && n_maps <= kMaxResizeMaps, "eem_bilinear_resize_multi: n_maps must be in [1,%d]", kMaxResizeMaps);
+  EEM_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "eem_bilinear_resize_multi: sizes must be > 0");
+  ResizeMultiParams p{};
+  int V = 4;
+  for (int k = 0; k < n_maps; ++k) {
+    EEM_CHECK_ARG(ins[k] && outs[k] && hs[k] > 0 && ws[k] > 0, "eem_bilinear_resize_multi: bad map %d", k);
+    p.in[k] = ins[k]; p.out[k] = outs[k]; p.h[k] = hs[k]; p.w[k] = ws[k]; p.s0[k] = scale0[k]; p.s1[k] = scale1[k];
+    const int v = (W % 4 == 0 && reinterpret_cast<uintptr_t>(outs[k]) % 16 == 0) ? 4
+                : (W % 2 == 0 && reinterpret_cast<uintptr_t>(outs[k]) % 8 == 0) ? 2 : 1;
+    if (v < V) V = v;
+  }
+  const int64_t bc = (int64_t)B * C;
+  const int64_t blocks_xy = ceil_div(W, 32 * V) * ceil_div(H, 8);
+  int64_t gz = ceil_div((int64_t)sm_count() * 8, blocks_xy * n_maps);
+  if (gz < 1) gz = 1;
+  if (gz > bc) gz = bc;
+  if (gz * n_maps > 65535) gz = 65535 / n_maps;
+  p.n = n_maps; p.B = B; p.C = C; p.H = H; p.W = W; p.align_corners = align_corners ? 1 : 0; p.gz = (int)gz; p.scale_rest = scale_rest;
+  dim3 grid((unsigned)ceil_div(W, 32 * V), (unsigned)ceil_div(H, 8), (unsigned)(gz * n_maps));
+  cudaStream_t stream = as_stream(stream_);
+  if (V == 4) bilinear_resize_multi_kernel<4><<<grid, 256, 0, stream>>>(p);
+  else if (V == 2) bilinear_resize_multi_kernel<2><<<grid, 256, 0, stream>>>(p);
+  else bilinear_resize_multi_kernel<1><<<grid, 256, 0, stream>>>(p);
+  EEM_CHECK_LAUNCH("bilinear_resize_multi_kernel");
+  return EEM_OK;
+}
+
+int eem_scale_uv_inplace_multi(float* const* flows, const int* hs, const int* ws, int n_maps, int B, int C,
+                               const float* scale0, const float* scale1, eem_stream_t stream_) {
+  EEM_CHECK_ARG(flows && hs && ws && scale0 && scale1, "eem_scale_uv_inplace_multi: NULL pointer");
+  EEM_CHECK_ARG(n_maps > 0 && n_maps <= kMaxResizeMaps, "eem_scale_uv_inplace_multi: n_maps must be in [1,%d]", kMaxResizeMaps);
+  EEM_CHECK_ARG(B > 0 && C >= 2, "eem_scale_uv_inplace_multi: need C >= 2 and a positive batch");
+  ScaleMultiParams p{};
+  int64_t largest = 0;
+  for (int k = 0; k < n_maps; ++k) {
+    EEM_CHECK_ARG(flows[k] && hs[k] > 0 && ws[k] > 0, "eem_scale_uv_inplace_multi: bad map %d", k);
+    p.flow[k] = flows[k]; p.plane[k] = (int64_t)hs[k] * ws[k]; p.s0[k] = scale0[k]; p.s1[k] = scale1[k];
+    if (p.plane[k] > largest) largest = p.plane[k];
+  }
+  p.B = B; p.C = C;
+  int64_t blocks = ceil_div((int64_t)B * 2 * largest, 256);
+  if (blocks > 1024) blocks = 1024;
+  scale_uv_multi_kernel<<<dim3((unsigned)blocks, (unsigned)n_maps), 256, 0, as_stream(stream_)>>>(p);
+  EEM_CHECK_LAUNCH("scale_uv_multi_kernel");
   return EEM_OK;
 }
 

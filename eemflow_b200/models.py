@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .correlation import EEMFLOW_CDC_INDEX, correlation_select
-from .warp import InputPadder, WarpingLayer_no_div, cdc_blend, upsample2d_flow_as, warp
+from .warp import InputPadder, WarpingLayer_no_div, cdc_blend, upsample2d_flow_as, upsample2d_flows_as, warp
 
 
 def _conv_lrelu(cin, cout, k=3, stride=1, groups=1):
@@ -143,7 +143,8 @@ class EEMFlow_cdc(nn.Module):
             cv = correlation_select(a, warp(b, flow_up), EEMFLOW_CDC_INDEX)
             feat = getattr(self, f"rconv{lvl}")(a)
             flows[lvl] = getattr(self, f"decoder{lvl}")(torch.cat([cv, feat, flow_up], 1)) + flow_up
-        predictions = [upsample2d_flow_as(flows[lvl], events1, mode="bilinear", if_rate=True) for lvl in (6, 5, 4, 3, 2)]
+        # EEMFlow+.py:231-232: five upsample2d_flow_as calls -> one resize launch + one in-place scaling launch
+        predictions = upsample2d_flows_as([flows[lvl] for lvl in (6, 5, 4, 3, 2)], events1, mode="bilinear", if_rate=True)
         return (events1, events2), predictions
 
 

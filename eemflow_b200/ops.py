@@ -325,6 +325,46 @@ def scale_uv_(flow: torch.Tensor, scale0: float, scale1: float) -> torch.Tensor:
     return flow
 
 
+def bilinear_resize_multi(xs: Sequence[torch.Tensor], size: tuple[int, int], align_corners: bool, scales: Sequence[tuple[float, float]],
+                          scale_rest: float = 1.0, outs: Sequence[torch.Tensor | None] | None = None) -> list[torch.Tensor]:
+    """bilinear_resize of several [B, C, h_k, w_k] maps (same B, C) to one size in ONE launch; scales[k] = (scale0, scale1)."""
+    xs = [L.require_cuda(x, "x") for x in xs]
+    n = len(xs)
+    B, Cc = xs[0].shape[:2]
+    H, W = int(size[0]), int(size[1])
+    assert all(x.shape[0] == B and x.shape[1] == Cc for x in xs) and len(scales) == n
+    res = []
+    for k in range(n):
+        o = None if outs is None else outs[k]
+        if o is None:
+            o = torch.empty((B, Cc, H, W), dtype=torch.float32, device=xs[0].device)
+        else:
+            assert o.is_cuda and o.dtype == torch.float32 and o.is_contiguous() and tuple(o.shape) == (B, Cc, H, W)
+        res.append(o)
+    hs = (C.c_int * n)(*[int(x.shape[2]) for x in xs])
+    ws = (C.c_int * n)(*[int(x.shape[3]) for x in xs])
+    s0 = (C.c_float * n)(*[float(s[0]) for s in scales])
+    s1 = (C.c_float * n)(*[float(s[1]) for s in scales])
+    with torch.cuda.device(xs[0].device):
+        L.check(L.lib().eem_bilinear_resize_multi(L.ptr_array(xs), hs, ws, n, B, Cc, L.ptr_array(res), H, W, int(bool(align_corners)),
+                                                  s0, s1, float(scale_rest), L.stream_ptr(xs[0].device)))
+    return res
+
+
+def scale_uv_multi_(flows: Sequence[torch.Tensor], scales: Sequence[tuple[float, float]]) -> None:
+    """In-place per-channel scale of channels 0/1 of several [B, C, h_k, w_k] maps in ONE launch."""
+    n = len(flows)
+    B, Cc = flows[0].shape[:2]
+    for f in flows:
+        assert f.is_cuda and f.dtype == torch.float32 and f.is_contiguous() and f.shape[0] == B and f.shape[1] == Cc
+    hs = (C.c_int * n)(*[int(f.shape[2]) for f in flows])
+    ws = (C.c_int * n)(*[int(f.shape[3]) for f in flows])
+    s0 = (C.c_float * n)(*[float(s[0]) for s in scales])
+    s1 = (C.c_float * n)(*[float(s[1]) for s in scales])
+    with torch.cuda.device(flows[0].device):
+        L.check(L.lib().eem_scale_uv_inplace_multi(L.ptr_array(flows), hs, ws, n, B, Cc, s0, s1, L.stream_ptr(flows[0].device)))
+
+
 def replicate_pad(x: torch.Tensor, pad: Sequence[int]) -> torch.Tensor:
     """F.pad(x, [left, right, top, bottom], mode='replicate') for [B,C,H,W]."""
     x = L.require_cuda(x, "x")

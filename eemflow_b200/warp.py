@@ -79,6 +79,28 @@ def upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate=False, out=No
     return ag.bilinear_resize(inputs, (h, w), align_corners=True, out=out)
 
 
+def upsample2d_flows_as(inputs, target_as, mode="bilinear", if_rate=False, out_last=None):
+    """`[upsample2d_flow_as(f, target_as, mode, if_rate) for f in inputs]` -- the five final predictions of EEMFlow_cdc
+    (model/EEMFlow/EEMFlow+.py:231-232) -- in two launches instead of ten: one kernel resizes all maps, one applies the
+    reference's in-place scaling of every input (cdc_utils.py:85-86).  Same results, same side effect.
+    `out_last` (optional): destination of the LAST map's result (may be peer-GPU memory, see ops.bilinear_resize)."""
+    if mode != "bilinear":
+        raise NotImplementedError("eemflow_b200.upsample2d_flows_as implements mode='bilinear' only")
+    inputs = list(inputs)
+    same = len({(tuple(f.shape[:2]), f.device, f.dtype) for f in inputs}) == 1
+    if (not same or len(inputs) > 8 or ag.needs_grad(*inputs)
+            or not all(f.is_cuda and f.is_contiguous() and f.dtype == torch.float32 for f in inputs)):
+        outs = [upsample2d_flow_as(f, target_as, mode, if_rate) for f in inputs[:-1]]
+        return outs + [upsample2d_flow_as(inputs[-1], target_as, mode, if_rate, out=out_last)]
+    _, _, h, w = target_as.shape
+    scales = [((w / f.shape[3]), (h / f.shape[2])) if if_rate else (1.0, 1.0) for f in inputs]
+    with torch.no_grad():
+        res = ops.bilinear_resize_multi(inputs, (h, w), True, scales, outs=[None] * (len(inputs) - 1) + [out_last])
+        if if_rate:
+            ops.scale_uv_multi_(inputs, scales)
+    return res
+
+
 def upsample_flow(flow, orig_size):
     """Meshflow -> dense flow: bilinear, align_corners=False, no magnitude rescale."""
     return ag.bilinear_resize(flow, tuple(orig_size), align_corners=False)

@@ -236,6 +236,16 @@ EEM_API int eem_bilinear_resize(const float* in, int B, int C, int h, int w, flo
 EEM_API int eem_scale_uv_inplace(float* flow, int B, int C, int h, int w, float scale0,
                                  float scale1, eem_stream_t stream);
 
+/* K8m  the same two operations for up to 8 maps of one batch in ONE launch each: EEMFlow_cdc resizes its five flow
+ * predictions to the input size with five upsample2d_flow_as calls (model/EEMFlow/EEMFlow+.py:231-232).
+ * ins/outs/flows, hs, ws, scale0, scale1: HOST arrays of n_maps entries (device pointers / sizes / per-map scales). */
+EEM_API int eem_bilinear_resize_multi(const float* const* ins, const int* hs, const int* ws, int n_maps, int B,
+                                      int C, float* const* outs, int H, int W, int align_corners,
+                                      const float* scale0, const float* scale1, float scale_rest,
+                                      eem_stream_t stream);
+EEM_API int eem_scale_uv_inplace_multi(float* const* flows, const int* hs, const int* ws, int n_maps, int B, int C,
+                                       const float* scale0, const float* scale1, eem_stream_t stream);
+
 /* K9  replicate padding.  replaces: InputPadder.pad (utils/image_utils.py:126-139, F.pad 'replicate')
  * in [B,C,H,W] -> out [B,C,H+top+bottom,W+left+right]. */
 EEM_API int eem_replicate_pad(const float* in, int B, int C, int H, int W, int left, int right,

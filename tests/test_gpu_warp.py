@@ -137,3 +137,31 @@ def test_resize_oracle_meshflow_shapes(E, h, w, H, W):
     ref = ref_ops.upsample_flow(fl, (H, W))
     got = E.upsample_flow(fl.cuda(), (H, W)).cpu()
     assert (got - ref).abs().max().item() <= 1e-5
+
+
+def test_upsample2d_flows_as_equals_the_list_of_calls():
+    """upsample2d_flows_as (all predictions of EEMFlow_cdc in one launch, EEMFlow+.py:231-232) == the reference's list
+    comprehension of upsample2d_flow_as calls: same outputs (<= 1e-5 against the CPU restatement, bit-identical to
+    our single-map kernel) and the same in-place scaling of every input."""
+    import eemflow_b200 as E
+    gen = torch.Generator().manual_seed(12)
+    shapes = [(5, 6), (10, 12), (20, 24), (40, 48), (80, 96)]
+    for if_rate in (True, False):
+        for (H, W) in ((260, 346), (64, 96)):
+            flows = [2.0 * torch.randn(3, 2, h, w, generator=gen) for (h, w) in shapes]
+            tgt = torch.zeros(3, 1, H, W)
+            ref_in = [f.clone() for f in flows]
+            ref = [ref_ops.upsample2d_flow_as(f, tgt, if_rate=if_rate) for f in ref_in]
+            a_in = [f.clone().cuda() for f in flows]
+            b_in = [f.clone().cuda() for f in flows]
+            multi = E.upsample2d_flows_as(a_in, tgt.cuda(), mode="bilinear", if_rate=if_rate)
+            single = [E.upsample2d_flow_as(f, tgt.cuda(), mode="bilinear", if_rate=if_rate) for f in b_in]
+            for k in range(len(flows)):
+                assert torch.equal(multi[k], single[k]), k
+                assert (multi[k].cpu() - ref[k]).abs().max().item() <= 1e-4 * max(1.0, ref[k].abs().max().item()), k
+                assert torch.equal(a_in[k], b_in[k])
+                assert (a_in[k].cpu() - ref_in[k]).abs().max().item() <= 1e-5 * max(1.0, ref_in[k].abs().max().item())
+    # destination of the last map given by the caller
+    out = torch.empty(3, 2, 64, 96, device="cuda")
+    res = E.upsample2d_flows_as([f.clone().cuda() for f in flows], torch.zeros(3, 1, 64, 96, device="cuda"), if_rate=True, out_last=out)
+    assert res[-1].data_ptr() == out.data_ptr()

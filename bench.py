@@ -79,6 +79,10 @@ def parse_args():
     ap.add_argument("--lookups", type=int, default=12, help="CorrBlock lookups per pair (ERAFT iterations)")
     ap.add_argument("--cpu-batch", type=int, default=None, help="frame pairs per CPU step (default: the whole batch for mvsec_dt1)")
     ap.add_argument("--corr", default="tf32_f16", choices=["tf32", "tf32_f16", "fp32"], help="CorrBlock precision / storage")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE configs[4] instead of the step bench: end-to-end EEMFlow_cdc inference at HREM resolution, global "
+                         "batch 1..256 sharded over the ranks, with the CPU path (batch 1) beside it; prints one JSON line")
+    ap.add_argument("--sweep-max-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--events-format", default="rows", choices=["rows", "columns"],
@@ -728,8 +732,114 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
     return res
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: end-to-end EEMFlow inference sweep, batch 1..256 at HREM resolution, 1..8 GPUs
+# ------------------------------------------------------------------------------------------------
+def cpu_model_forward(model, events1, events2):
+    """The EEMFlow_cdc forward (model/EEMFlow/EEMFlow+.py:158-234) on the CPU with the model's own (ATen CPU) convolutions
+    and the oracle's restatements of the hot-path ops -- the reference's CPU path for the same weights."""
+    from oracle import ref_ops as R
+    idx = EEMFLOW_CDC_INDEX
+    image1, _ = R.input_pad(events1, events1.shape, mode="chairs", eval_pad_rate=64)
+    image2, _ = R.input_pad(events2, events2.shape, mode="chairs", eval_pad_rate=64)
+    p1, p2 = model._pyramid(image1), model._pyramid(image2)
+    flows = {}
+    f16, f26 = p1[6], p2[6]
+    flow7_up = torch.zeros(f16.size(0), 2, f16.size(2), f16.size(3))
+    cv = R.correlation(f16, f26, 4, index=idx)
+    flows[6] = model.decoder6(torch.cat([cv, model.rconv6(f16), flow7_up], 1))
+    cdc = model.cdc_model
+    for lvl in (5, 4, 3, 2):
+        a, b = p1[lvl], p2[lvl]
+        proj = model.conv_1x1[lvl]
+        fa, fb = proj(a), proj(b)
+        flow_init = R.upsample2d_flow_as(flows[lvl + 1], fa, if_rate=True)
+        x_out = cdc.dense_estimator_mask(torch.cat((fa, R.warping_layer_no_div(fb, flow_init)), dim=1))
+        flow_up = R.cdc_blend(flow_init, x_out[:, :2].contiguous(), torch.sigmoid(x_out[:, 2:3]).contiguous())
+        cv = R.correlation(a, R.warp_exact(b, flow_up), 4, index=idx)
+        feat = getattr(model, f"rconv{lvl}")(a)
+        flows[lvl] = getattr(model, f"decoder{lvl}")(torch.cat([cv, feat, flow_up], 1)) + flow_up
+    return [R.upsample2d_flow_as(flows[lvl], events1, if_rate=True) for lvl in (6, 5, 4, 3, 2)]
+
+
+def run_sweep(args):
+    from eemflow_b200 import dist as edist
+    from eemflow_b200.models import EEMFlow_cdc
+    assert torch.cuda.is_available(), "bench.py --sweep needs a CUDA device"
+    rank, world, local_rank = edist.init_from_env("nccl")
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    nb, h, w = 15, 720, 1280
+    micro = 32                                  # a rank runs its shard in micro-batches of at most 32 pairs
+    torch.manual_seed(0)
+    model = EEMFlow_cdc(None, groups=3, n_first_channels=nb).to(dev).eval()
+    model.change_imagesize((h, w))
+    torch.backends.cudnn.benchmark = True
+    rows = []
+    B = 1
+    while B <= args.sweep_max_batch:
+        lo, hi = edist.shard_bounds(B, rank, world)
+        mine = hi - lo
+        chunks = [min(micro, mine - k) for k in range(0, mine, micro)]
+        inputs = [(torch.randn(c, nb, h, w, device=dev), torch.randn(c, nb, h, w, device=dev)) for c in sorted(set(chunks))]
+        by_size = {v1.shape[0]: (v1, v2) for v1, v2 in inputs}
+
+        def forward_all():
+            with torch.no_grad():
+                for c in chunks:
+                    v1, v2 = by_size[c]
+                    model(events1=v1, events2=v2)
+
+        for _ in range(2):
+            forward_all()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            forward_all()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(edist.max_over_ranks(a.elapsed_time(b), dev))
+        ms = statistics.median(ts)
+        rows.append({"global_batch": B, "pairs_per_rank_max": -(-B // world), "ms_per_forward": ms, "pairs_per_s": B / ms * 1e3,
+                     "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9})
+        del inputs, by_size
+        torch.cuda.empty_cache()
+        B *= 2
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cm = EEMFlow_cdc(None, groups=3, n_first_channels=nb).eval()
+        cm.load_state_dict(model.state_dict())
+        v1, v2 = torch.randn(1, nb, h, w), torch.randn(1, nb, h, w)
+        with torch.no_grad():
+            cpu_model_forward(cm, v1, v2)
+            t0 = time.perf_counter()
+            n = 0
+            while n < 3 and (n == 0 or time.perf_counter() - t0 < 20.0):
+                cpu_model_forward(cm, v1, v2)
+                n += 1
+            dt = (time.perf_counter() - t0) / n
+        cpu = {"value": 1.0 / dt, "unit": "frame-pairs/s", "cores": os.cpu_count() or 1, "kind": "port", "ms_per_forward": 1e3 * dt,
+               "sample": f"batch 1, {n} forwards, the model's ATen CPU convolutions + oracle/ref_ops.py hot-path ops"}
+    if rank == 0:
+        print(json.dumps({"metric": "frame-pairs/sec (end-to-end EEMFlow_cdc inference, HREM 720x1280, 15 bins)", "unit": "frame-pairs/s",
+                          "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "eemflow_cdc_inference_sweep_hrem_720x1280", "model": "EEMFlow_cdc(groups=3), random init",
+                                     "input": "voxel grids resident on the device", "micro_batch": micro,
+                                     "parallelism": f"batch-sharded x{world}"},
+                          "sweep": rows, "cpu_baseline": cpu}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    if args.sweep:
+        return run_sweep(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     head = workload(args.workload, args.batch, args.cpu_batch)

@@ -149,10 +149,22 @@ class _PinnedStage:
                 if buf is None or buf.shape[0] < total:
                     buf = self.dev_buf[key] = torch.empty((total, 4), dtype=torch.float64, device=device)
                 ev = buf[:total]
-                pos = 0
-                for a, n in zip(arrays, counts):
-                    ev[pos:pos + n].copy_(torch.from_numpy(a), non_blocking=True)
-                    pos += n
+                # windows that lie back to back in the caller's pinned buffer go up as ONE copy
+                pos, k = 0, 0
+                while k < len(arrays):
+                    j, rows = k, counts[k]
+                    while (j + 1 < len(arrays) and arrays[j + 1].ctypes.data == arrays[j].ctypes.data + arrays[j].nbytes):
+                        j += 1
+                        rows += counts[j]
+                    if j > k:       # a [rows, 4] view over the merged region of the caller's buffer
+                        import ctypes
+                        flat = (ctypes.c_double * (rows * 4)).from_address(arrays[k].ctypes.data)
+                        src = torch.from_numpy(numpy.frombuffer(flat, dtype=numpy.float64).reshape(rows, 4))
+                    else:
+                        src = torch.from_numpy(arrays[k])
+                    ev[pos:pos + rows].copy_(src, non_blocking=True)
+                    pos += rows
+                    k = j + 1
             elif total <= _STAGE_CHUNK_ROWS:
                 pos = 0
                 for a, n in zip(arrays, counts):

@@ -584,12 +584,13 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
         step.columns = [{"t": np.ascontiguousarray(e[:, 0]), "x": e[:, 1].astype(np.int16), "y": e[:, 2].astype(np.int16),
                          "p": e[:, 3].astype(np.int8)} for e in inp["events"]]
 
-    # N > 1: nothing on the data path is exchanged.  The result flows go to rank 0 every step: the kernel that
-    # produces the final flow writes it straight into rank 0's result buffer over NVLink (peer memory), or -- when
-    # peer memory cannot be set up -- an NCCL gather on a communication stream overlaps the next step.  The step is
-    # captured twice (two result slots) and the replays alternate, so rank 0 may read step i's flows while step i+1
-    # is being written.  Metric accumulators are reduced once, at the end of the run.
-    sink = edist.ResultSink((B, 2, wl.H, wl.W), torch.float32, dev, dst=0, slots=2) if world > 1 else None
+    # N > 1: nothing on the data path is exchanged.  The result flows go to rank 0 every step, on a communication
+    # stream that overlaps the next step: a device-to-peer copy into rank 0's result buffer (peer memory over NVLink,
+    # copy engines -- no collective kernel), or an NCCL gather when peer memory cannot be set up.  The step is captured
+    # twice (two sets of output buffers) and the replays alternate, so step i's flows are read by the delivery while
+    # step i+1 writes the other set.  Metric accumulators are reduced once, at the end of the run.
+    write_through = os.environ.get("EEM_RESULT_WRITE_THROUGH", "0") == "1"       # timing experiments: stores from the producing kernel
+    sink = edist.ResultSink((B, 2, wl.H, wl.W), torch.float32, dev, dst=0, slots=2, write_through=write_through) if world > 1 else None
 
     for _ in range(max(3, warmup)):
         step.resident()
@@ -602,7 +603,7 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
     graphs, flows = [], []
     launches_per_step = 0
     for k in range(n_graphs):
-        step.flow_out = sink.slot(k) if (sink is not None and sink.direct) else None
+        step.flow_out = sink.slot(k) if (sink is not None and sink.direct and sink.write_through) else None
         launches_a = lib.eem_launch_count()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -915,7 +916,9 @@ def main():
     rank, world, local_rank = edist.init_from_env("nccl")
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
-    edist.pin_host_threads(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    cores = edist.pin_host_threads(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    if world > 1:
+        print(f"[bench] rank {rank}: {len(cores)} host cores {cores[:4]}..{cores[-1:] if cores else []}", file=sys.stderr, flush=True)
 
     r = run_b200(head, args, rank, world, dev, args.steps, args.warmup, not args.no_e2e, not args.no_cpu_baseline, True)
     subs = {}

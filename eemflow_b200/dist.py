@@ -98,19 +98,47 @@ def max_over_ranks(value: float, device: torch.device) -> float:
     return float(t.item())
 
 
+def _gpu_local_cpus(device_index: int) -> set[int]:
+    """CPUs on the GPU's own NUMA node / PCIe root (NVML's ideal affinity), or an empty set when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        return {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+    except Exception:
+        return set()
+
+
 def pin_host_threads(local_rank: int, local_world: int) -> list[int]:
-    """Give this rank its own contiguous share of the host cores (os.sched_setaffinity) and size the host thread
-    pools to it.  Eight ranks that each run an 8-thread staging pool on the same 32 cores (torchrun gives no
-    affinity) thrash each other: round 1 measured per-rank host->device throughput falling from 44 to 13.5 GB/s.
-    Returns the cores now owned (empty list when the platform offers no affinity call)."""
+    """Give this rank its own share of the host cores ON ITS GPU'S NUMA NODE (os.sched_setaffinity) and size the host
+    thread pools to it.  Call it BEFORE allocating pinned memory: first touch then places the pages next to the GPU's
+    PCIe root, so the DMA does not cross the socket interconnect.  Eight ranks that each run an 8-thread staging pool
+    on the same 32 cores (torchrun gives no affinity) thrash each other: round 1 measured per-rank host->device
+    throughput falling from 44 to 13.5 GB/s.  Returns the cores now owned (empty when the platform offers no affinity call)."""
     if local_world <= 1 or not hasattr(os, "sched_getaffinity"):
         return []
     try:
         avail = sorted(os.sched_getaffinity(0))
-        per = max(1, len(avail) // local_world)
-        mine = avail[local_rank * per:(local_rank + 1) * per] or avail
+        local = sorted(set(avail) & _gpu_local_cpus(local_rank))
+        if local:
+            # the ranks whose GPUs share this CPU set split it among themselves, in rank order
+            sharers = [r for r in range(local_world) if sorted(set(avail) & _gpu_local_cpus(r)) == local]
+            pos, cnt = sharers.index(local_rank), len(sharers)
+            per = max(1, len(local) // cnt)
+            mine = local[pos * per:(pos + 1) * per] or local
+        else:
+            per = max(1, len(avail) // local_world)
+            mine = avail[local_rank * per:(local_rank + 1) * per] or avail
         os.sched_setaffinity(0, mine)
-    except OSError:
+    except (OSError, ValueError):
         return []
     torch.set_num_threads(max(1, len(mine)))
     from . import event_utils
@@ -125,17 +153,21 @@ class ResultSink:
     one process.  Here rank `dst` owns a buffer `[slots, world, *shape]`:
 
       direct   (peer memory available: torch symmetric memory over NVLink / NVSwitch)  every rank maps dst's buffer
-               into its own address space; `slot(k)` is this rank's slice of slot k, and the kernel that produces the
-               result writes it there (its stores travel over NVLink).  No collective kernel runs at all, nothing
-               competes with the step for SMs, and dst's HBM only sees the incoming writes.
+               into its own address space; `slot(k)` is this rank's slice of slot k.  `after_write` / `push` copy the
+               result there with a device-to-peer copy on a communication stream (copy engines over NVLink: no
+               collective kernel, no SM, nothing competes with the step), overlapped with the next step.  A producer
+               may also store into `slot(k)` directly from the kernel that forms the result (`write_through=True`);
+               with N - 1 ranks storing into ONE rank that puts dst's inbound link (161 MB per MVSEC step at 8 GPUs
+               = 0.21 ms at 770 GB/s) on every producer's critical path, so it is not the default.
       gather   (fallback) `after_write` / `push` enqueue an NCCL gather to dst on a communication stream, overlapped
                with the next step; `before_write` makes the producer wait until the previous gather has read the slot.
 
     Slots alternate (step k uses slot k % slots) so that dst may consume step i while step i+1 is being produced.
     """
 
-    def __init__(self, shape, dtype, device, dst: int = 0, slots: int = 2):
+    def __init__(self, shape, dtype, device, dst: int = 0, slots: int = 2, write_through: bool = False):
         assert dist.is_initialized()
+        self.write_through = write_through
         self.world, self.rank, self.dst, self.slots = dist.get_world_size(), dist.get_rank(), dst, slots
         self.shape, self.dtype, self.device = tuple(shape), dtype, device
         self.direct = False
@@ -156,11 +188,11 @@ class ResultSink:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # all ranks take the same path
         self.direct = bool(flag.item())
         self.cuda = device.type == "cuda"
+        self.comm = torch.cuda.Stream(device) if self.cuda else None
+        self.read_done = [None] * slots
+        self.gathered = None
         if not self.direct:
             self.peer = None
-            self.comm = torch.cuda.Stream(device) if self.cuda else None
-            self.read_done = [None] * slots
-            self.gathered = None
             if self.rank == dst:
                 self.gathered = torch.empty((slots, self.world) + self.shape, dtype=dtype, device=device)
 
@@ -176,13 +208,15 @@ class ResultSink:
         return self.peer if self.direct else self.gathered
 
     def before_write(self, k: int) -> None:
-        if not self.direct and self.cuda and self.read_done[k % self.slots] is not None:
+        """Call before `local` of slot k is overwritten: waits (on the current stream) until the delivery issued for it
+        has read it."""
+        if self.cuda and self.read_done[k % self.slots] is not None:
             torch.cuda.current_stream(self.device).wait_event(self.read_done[k % self.slots])
 
     def after_write(self, k: int, local: torch.Tensor) -> None:
-        """`local` has been produced on the current stream (direct mode: already written through slot(k))."""
-        if self.direct:
-            return
+        """`local` has been produced on the current stream: deliver it to dst on the communication stream."""
+        if self.direct and self.write_through:
+            return                        # the producing kernel stored into slot(k) itself
         if not self.cuda:                 # host tensors (gloo): a synchronous gather
             self._gather(k, local)
             return
@@ -191,18 +225,18 @@ class ResultSink:
         ready.record(cur)
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(ready)
-            self._gather(k, local)
+            if self.direct:
+                self.slot(k).copy_(local, non_blocking=True)       # device-to-peer copy over NVLink (copy engine)
+            else:
+                self._gather(k, local)
             ev = torch.cuda.Event()
             ev.record(self.comm)
             self.read_done[k % self.slots] = ev
 
     def push(self, k: int, local: torch.Tensor) -> None:
         """Deliver a result that lives in this rank's own memory."""
-        if self.direct:
-            self.slot(k).copy_(local, non_blocking=True)       # device-to-peer copy over NVLink
-        else:
-            self.before_write(k)
-            self.after_write(k, local)
+        self.before_write(k)
+        self.after_write(k, local)
 
     def _gather(self, k: int, local: torch.Tensor) -> None:
         if self.rank == self.dst:
@@ -211,12 +245,16 @@ class ResultSink:
             dist.gather(local.contiguous(), None, dst=self.dst)
 
     def drain(self) -> None:
-        if not self.direct and self.comm is not None:
+        if self.comm is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.comm)
 
     def describe(self) -> dict:
-        return {"mode": "direct peer-memory stores over NVLink (no collective kernel)" if self.direct else "NCCL gather to one rank",
-                "dst": self.dst, "slots": self.slots, "fallback_reason": self.why or None}
+        if self.direct:
+            mode = ("peer memory over NVLink: stores of the producing kernel (write-through)" if self.write_through else
+                    "peer memory over NVLink: device-to-peer copies on a communication stream (copy engines, no collective kernel)")
+        else:
+            mode = "NCCL gather to one rank on a communication stream"
+        return {"mode": mode, "dst": self.dst, "slots": self.slots, "fallback_reason": self.why or None}
 
     def close(self) -> None:
         self.peer = None

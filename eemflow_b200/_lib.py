@@ -39,6 +39,7 @@ SIGNATURES = {
     "eem_launch_count": (C.c_longlong, []),
     "eem_voxelize_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i, _i, _i]),
     "eem_voxelize": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "eem_voxelize_scaled": (_i, [_vp, C.c_double, _vp, _i, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eem_voxelize_soa": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "eem_voxel_normalize_workspace_bytes": (_sz, [_i, _i64]),
     "eem_voxel_normalize": (_i, [_vp, _i, _i64, _vp, _vp, _sz, _vp]),

@@ -35,14 +35,16 @@ struct EventRow {
 // get_compressed_events / EventSequence expand them (loader/loader_utils.py:26-37, 352-397).
 struct RowSource {
   const double* ev;
+  double mul;      // EventSequence's timestamp_multiplier (loader/loader_utils.py:367-368) applied on the fly; 1.0 = none (exact)
   __device__ __forceinline__ EventRow load(int64_t i) const {
     EventRow r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
                  : "=d"(r.t), "=d"(r.x), "=d"(r.y), "=d"(r.p)
                  : "l"(ev + 4 * i));
+    r.t = __dmul_rn(r.t, mul);
     return r;
   }
-  __device__ __forceinline__ double time(int64_t i) const { return __ldg(ev + 4 * i); }
+  __device__ __forceinline__ double time(int64_t i) const { return __dmul_rn(__ldg(ev + 4 * i), mul); }
 };
 
 struct SoaSource {
@@ -1868,9 +1870,18 @@ int eem_voxelize(const double* events, const int64_t* offsets, int n_windows, in
                  int64_t max_events_per_window, int num_bins, int height, int width, int mode,
                  int normalize, float* grid, int64_t* dropped, double* stats_out, void* workspace,
                  size_t workspace_bytes, eem_stream_t stream) {
+  return eem_voxelize_scaled(events, 1.0, offsets, n_windows, n_total, max_events_per_window, num_bins, height, width, mode,
+                             normalize, grid, dropped, stats_out, workspace, workspace_bytes, stream);
+}
+
+int eem_voxelize_scaled(const double* events, double timestamp_multiplier, const int64_t* offsets, int n_windows, int64_t n_total,
+                        int64_t max_events_per_window, int num_bins, int height, int width, int mode,
+                        int normalize, float* grid, int64_t* dropped, double* stats_out, void* workspace,
+                        size_t workspace_bytes, eem_stream_t stream) {
   EEM_CHECK_ARG(n_total <= 0 || events != nullptr, "eem_voxelize: NULL events");
+  EEM_CHECK_ARG(timestamp_multiplier > 0.0, "eem_voxelize_scaled: timestamp_multiplier must be > 0");
   EEM_CHECK_ALIGNED(events, 32);
-  return voxelize_impl(RowSource{events}, offsets, n_windows, n_total, max_events_per_window, num_bins, height, width,
+  return voxelize_impl(RowSource{events, timestamp_multiplier}, offsets, n_windows, n_total, max_events_per_window, num_bins, height, width,
                        mode, normalize, grid, dropped, stats_out, workspace, workspace_bytes, stream);
 }
 

@@ -62,6 +62,15 @@ def event_valid_from_volume(volume: torch.Tensor) -> torch.Tensor:
     return out[0] if single else out
 
 
+def center_crop(x: torch.Tensor, size: int = 256) -> torch.Tensor:
+    """The validation cropper of the MVSEC loader (loader/MVSEC.py:189-193: torchvision CenterCrop(256) on flow, voxel
+    grids and the event mask): a view of the last two dimensions, no copy; the same rounding as torchvision
+    (top = int(round((H - size) / 2)), left likewise)."""
+    h, w = x.shape[-2:]
+    top, left = int(round((h - size) / 2.0)), int(round((w - size) / 2.0))
+    return x[..., top:top + size, left:left + size]
+
+
 def flow_error_stats(flow_gt, flow_pred, event_img=None, max_row: int | None = None) -> torch.Tensor:
     """[B,2,H,W] x2 (+ [B,1,H,W] event image or None) -> float64 [B, 5] on the device:
     n_points, #(EE<1), #(EE<3 | EE<0.1|gt|), sum EE, sum |gt|."""

@@ -263,6 +263,52 @@ class EventSequenceToVoxelGrid_Pytorch(object):
         return grid
 
 
+    def voxelize_concat(self, groups, height, width, timestamp_multiplier=None):
+        """Voxelize windows that are CONCATENATIONS of several event arrays without concatenating them on the host:
+        `groups[k]` is a list of `[N_i, 4]` float64 arrays (ts, x, y, p), e.g. the four consecutive frames the dt4 loader
+        joins with `pandas.concat` (loader/MVSEC.py:245-262).  The arrays go up back to back and the group boundaries
+        become the window offsets; `timestamp_multiplier` (EventSequence's argument, 1e6 in the loaders) is applied on
+        the device.  Equals `__call__(EventSequence(concat, params, timestamp_multiplier=..., convert_to_relative=True))`
+        -- bit for bit in deterministic mode -- for arrays whose stamps are sorted across the group, which is what the
+        loader produces; an unsorted group takes the reference's host path (concatenate, sort, scale)."""
+        assert len(groups) > 0
+        assert (self.num_bins > 0)
+        assert (width > 0)
+        assert (height > 0)
+        arrays, totals, slow = [], [], []
+        for g, parts in enumerate(groups):
+            parts = [numpy.asarray(a) for a in parts]
+            assert all(a.ndim == 2 and a.shape[1] == 4 for a in parts)
+            n = sum(int(a.shape[0]) for a in parts)
+            if n == 0:
+                raise IndexError("index -1 is out of bounds for dimension 0 with size 0")
+            parts = [a for a in parts if a.shape[0] > 0]
+            ordered = all(bool(numpy.all(a[:-1, 0] <= a[1:, 0])) for a in parts) and \
+                all(parts[i][-1, 0] <= parts[i + 1][0, 0] for i in range(len(parts) - 1))
+            if not ordered:
+                slow.append(g)
+            arrays.extend(parts)
+            totals.append(n)
+        if slow:        # EventSequence semantics for unsorted input: concatenate + sort on the host, then the usual path
+            params = {'height': height, 'width': width}
+            seqs = [EventSequence(None, params, features=numpy.concatenate([numpy.asarray(a) for a in parts]).astype(numpy.float64),
+                                  timestamp_multiplier=timestamp_multiplier, convert_to_relative=True) for parts in groups]
+            return self.voxelize_batch(seqs)
+        with torch.no_grad():
+            ev, _, _ = self._stage.upload(arrays, self.compute_device)
+            goff = numpy.zeros(len(totals) + 1, dtype=numpy.int64)
+            numpy.cumsum(totals, out=goff[1:])
+            off = torch.from_numpy(goff).to(self.compute_device, non_blocking=True)
+            dropped = torch.zeros(1, dtype=torch.int64, device=self.compute_device) if self.strict else None
+            grid = ops.voxelize(ev, off, max(totals), self.num_bins, height, width, normalize=self.normalize,
+                                deterministic=self.deterministic, dropped=dropped,
+                                timestamp_multiplier=1.0 if timestamp_multiplier is None else float(timestamp_multiplier))
+            if self.strict and int(dropped.item()) != 0:
+                raise IndexError(f"index out of range in self ({int(dropped.item())} votes fell outside the voxel grid)")
+        if grid.device != self.device:
+            grid = grid.to(self.device)
+        return grid
+
     def voxelize_columns(self, windows, height, width):
         """Voxelize event windows given as packed columns, e.g. straight from an HREM `events{1,2}.npz`
         (x, y, t [int64 ns], p in {0,1}) without building the [N,4] float64 rows first.

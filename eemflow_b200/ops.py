@@ -24,8 +24,9 @@ def _dev(t: torch.Tensor) -> torch.device:
 def voxelize(events: torch.Tensor, offsets: torch.Tensor, max_events: int, num_bins: int, height: int,
              width: int, *, normalize: bool = True, deterministic: bool = False,
              dropped: torch.Tensor | None = None, out: torch.Tensor | None = None,
-             stats_out: torch.Tensor | None = None) -> torch.Tensor:
+             stats_out: torch.Tensor | None = None, timestamp_multiplier: float = 1.0) -> torch.Tensor:
     """Voxelize concatenated event windows.
+    timestamp_multiplier: EventSequence's multiplier (loader/loader_utils.py:367-368) applied on the device.
 
     events  : CUDA float64 [N, 4] rows (ts, x, y, p)  -- the reference's EventSequence.features layout
     offsets : CUDA int64 [n_windows + 1]
@@ -52,9 +53,9 @@ def voxelize(events: torch.Tensor, offsets: torch.Tensor, max_events: int, num_b
     with torch.cuda.device(dev):
         ws_bytes = lib.eem_voxelize_workspace_bytes(n_total, n_windows, num_bins, height, width, mode, int(normalize))
         ws = L.workspace.get(dev, ws_bytes, "voxel")
-        L.check(lib.eem_voxelize(events.data_ptr(), offsets.data_ptr(), n_windows, n_total, int(max_events),
-                                 num_bins, height, width, mode, int(normalize), out.data_ptr(), L.ptr(dropped),
-                                 L.ptr(stats_out), L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
+        L.check(lib.eem_voxelize_scaled(events.data_ptr(), float(timestamp_multiplier), offsets.data_ptr(), n_windows, n_total,
+                                        int(max_events), num_bins, height, width, mode, int(normalize), out.data_ptr(),
+                                        L.ptr(dropped), L.ptr(stats_out), L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
     return out
 
 

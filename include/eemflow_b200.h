@@ -85,6 +85,17 @@ EEM_API int eem_voxelize(const double* events, const int64_t* offsets, int n_win
                          int64_t* dropped, double* stats_out, void* workspace,
                          size_t workspace_bytes, eem_stream_t stream);
 
+/* K1 with EventSequence's `timestamp_multiplier` (loader/loader_utils.py:367-368) applied on the fly: stamps are
+ * multiplied by `timestamp_multiplier` in float64 as they are loaded (the relative conversion of :393-397 is implied:
+ * the voting subtracts the window's first stamp anyway, with the same roundings).  Together with windows that are merely
+ * CONSECUTIVE row ranges this voxelizes the dt4 concatenation of loader/MVSEC.py:245-262 (four frames' events joined and
+ * scaled by 1e6) without a host-side concatenate / scale pass.  timestamp_multiplier == 1 is eem_voxelize. */
+EEM_API int eem_voxelize_scaled(const double* events, double timestamp_multiplier, const int64_t* offsets,
+                                int n_windows, int64_t n_total, int64_t max_events_per_window, int num_bins,
+                                int height, int width, int mode, int normalize, float* grid,
+                                int64_t* dropped, double* stats_out, void* workspace,
+                                size_t workspace_bytes, eem_stream_t stream);
+
 /* K1 (packed columns)  Same voting, events given as separate columns -- 13 B/event instead of 32:
  *   t : float64 [N] with the values of EventSequence.features[:,0] (t_is_ns = 0), or the raw int64
  *       nanosecond stamps of an HREM .npz (t_is_ns = 1); the kernel then applies the reference's

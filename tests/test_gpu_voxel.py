@@ -296,6 +296,38 @@ def test_deterministic_unusual_polarity_and_off_sensor_events(V):
     assert np.array_equal(out_s, ref_s)
 
 
+def test_voxelize_concat_equals_the_dt4_loader_chain(V):
+    """dt4 windows (loader/MVSEC.py:245-262): four consecutive frames' events joined, EventSequence(x1e6, relative),
+    voxelized.  voxelize_concat does the join (consecutive device rows) and the x1e6 on the device: bit-exact in
+    deterministic mode, <= 1e-5 in the order-free mode; an unsorted group takes the host path and still matches."""
+    from eemflow_b200 import EventSequence
+    rng = np.random.default_rng(77)
+    h, w, nb = 260, 346, 5
+    groups = []
+    for g in range(3):
+        t0, parts = 1000.0 + 0.2 * g, []
+        for k in range(4):                                        # four frames of ~12.5 ms each, absolute seconds
+            n = int(rng.integers(20_000, 40_000))
+            t = np.sort(rng.uniform(t0 + 0.0125 * k, t0 + 0.0125 * (k + 1), size=n))
+            parts.append(np.stack([t, rng.integers(0, w, n).astype(np.float64), rng.integers(0, h, n).astype(np.float64),
+                                   2.0 * rng.integers(0, 2, n) - 1.0], axis=1))
+        groups.append(parts)
+    refs = []
+    for parts in groups:
+        seq = EventSequence(None, {"height": h, "width": w}, features=np.concatenate(parts), timestamp_multiplier=1e6,
+                            convert_to_relative=True)
+        refs.append(c_oracle.voxelize(seq.features, nb, h, w, normalize=False)[0])
+    det = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_concat(groups, h, w, timestamp_multiplier=1e6)
+    atom = V(nb, gpu=True, normalize=False, forkserver=False).voxelize_concat(groups, h, w, timestamp_multiplier=1e6)
+    for g in range(3):
+        assert np.array_equal(det[g].cpu().numpy(), refs[g]), g
+        assert rel_close(atom[g].cpu().numpy(), refs[g]).all(), g
+    shuffled = [groups[0][::-1]] + groups[1:]                      # frames in the wrong order: host path (sort), same result
+    det_s = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_concat(shuffled, h, w, timestamp_multiplier=1e6)
+    if len(np.unique(np.concatenate(groups[0])[:, 0])) == sum(p.shape[0] for p in groups[0]):
+        assert np.array_equal(det_s[0].cpu().numpy(), refs[0])
+
+
 def test_packed_columns_match_reference_loader_chain(V):
     """HREM .npz style columns (x, y, t [int64 ns], p in {0,1}) through eem_voxelize_soa vs the reference chain
     get_compressed_events -> EventSequence(x1e6, relative) -> voxelizer restated on the CPU: bit-exact in

@@ -176,3 +176,14 @@ def test_packed_pyramid_layout_query():
             off += n
             h, w = h // 2, w // 2
         assert row == off and row % 32 == 0
+
+
+def test_center_crop_matches_the_mvsec_cropper():
+    """loader/MVSEC.py:51,189-193: transforms.CenterCrop((256, 256)) on [.., 260, 346] tensors."""
+    import torch
+    from eemflow_b200 import center_crop
+    x = torch.arange(2 * 260 * 346, dtype=torch.float32).view(2, 260, 346)
+    out = center_crop(x, 256)
+    top, left = int(round((260 - 256) / 2.0)), int(round((346 - 256) / 2.0))
+    assert tuple(out.shape) == (2, 256, 256) and torch.equal(out, x[:, top:top + 256, left:left + 256])
+    assert out.data_ptr() == x[:, top:, left:].data_ptr()          # a view, no copy

@@ -267,7 +267,9 @@ struct PackedSmem {
   static constexpr int kStrideBytes = kPatchBytes + ((kPatchBytes / 4) % 32 == 2 ? 0 : 8);
   static constexpr int kColsPerTask = 3, kGroups = (K + kColsPerTask - 1) / kColsPerTask;
   static constexpr int kThreads = 32 * 4 * kGroups;          // one interpolation task per warp for a 4-level pyramid
-  static constexpr int kPerLevelBytes = PB * kStrideBytes + 2 * PB * K * 4 + PB * 2 * 4;
+  // per position: window origin (ox, oy), the NT tile columns of the window clamped into the map (one byte each) and
+  // a bit mask of the columns that really lie inside it -- everything the gather needs besides the window row
+  static constexpr int kPerLevelBytes = PB * kStrideBytes + 2 * PB * K * 4 + PB * 4 * 4;
 };
 
 // The three phases of a batch of PB positions, shared by the one-batch-per-CTA kernel and the pipelined persistent one.
@@ -297,8 +299,18 @@ struct PackedPhases {
       const float lx = cx * inv, ly = cy * inv;
       const float ox = floorf(fminf(fmaxf(roundtrip_rcp(lx - (float)R, sw, rw), -1.0e6f), 1.0e6f));
       const float oy = floorf(fminf(fmaxf(roundtrip_rcp(ly - (float)R, sh, rh), -1.0e6f), 1.0e6f));
-      org_of(st, l)[pos * 2 + 0] = (int)ox;
-      org_of(st, l)[pos * 2 + 1] = (int)oy;
+      {
+        const int oxi = (int)ox, tx0 = oxi >> 2, txl = p.tx[l];      // >> : floor for negatives
+        unsigned pack = 0, mask = 0;
+#pragma unroll
+        for (int sx = 0; sx < NT; ++sx) {
+          const int tx = tx0 + sx;
+          const bool ok = (unsigned)tx < (unsigned)txl;
+          pack |= (unsigned)(ok ? tx : 0) << (8 * sx);
+          mask |= (unsigned)ok << sx;
+        }
+        *reinterpret_cast<int4*>(org_of(st, l) + pos * 4) = make_int4(oxi, (int)oy, (int)pack, (int)mask);
+      }
       float* fxp = fx_of(st, l) + pos * K;
       float* fyp = fy_of(st, l) + pos * K;
 #pragma unroll
@@ -323,24 +335,17 @@ struct PackedPhases {
       for (int l = 0; l < L; ++l) {
         const int txl = p.tx[l], tyl = p.ty[l];
         if (txl == 0 || tyl == 0) continue;                        // empty level
-        const int* org = org_of(st, l) + pos * 2;
-        const int py = org[1] + rr;                                // map row of this window row
-        const int ty = py >> 2, tx0 = org[0] >> 2;                 // >> : floor for negatives
-        const uint32_t dst = dst0 + l * S::kPerLevelBytes;
+        const int4 g = *reinterpret_cast<const int4*>(org_of(st, l) + pos * 4);   // ox, oy, clamped tile columns, column mask
+        const int py = g.y + rr;                                   // map row of this window row
+        const int ty = py >> 2;                                    // >> : floor for negatives
         const bool row_ok = (unsigned)ty < (unsigned)tyl;
-        if (row_ok && tx0 >= 0 && tx0 + NT <= txl) {               // interior: NT consecutive tiles of one tile row
-          const uint16_t* src = rowbase + p.off[l] + ((ty * txl + tx0) * 16 + (py & 3) * 4);
+        const uint16_t* src = rowbase + p.off[l] + (row_ok ? (ty * txl * 16 + (py & 3) * 4) : 0);
+        const uint32_t dst = dst0 + l * S::kPerLevelBytes;
 #pragma unroll
-          for (int sx = 0; sx < NT; ++sx)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + sx * 8), "l"(src + sx * 16) : "memory");
-        } else {
-          const uint16_t* src = rowbase + p.off[l] + (row_ok ? (ty * txl * 16 + (py & 3) * 4) : 0);
-#pragma unroll
-          for (int sx = 0; sx < NT; ++sx) {
-            const int tx = tx0 + sx;
-            const bool ok = row_ok && (unsigned)tx < (unsigned)txl;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + sx * 8), "l"(src + (ok ? tx * 16 : 0)), "r"(ok ? 8 : 0) : "memory");
-          }
+        for (int sx = 0; sx < NT; ++sx) {
+          const unsigned tx = ((unsigned)g.z >> (8 * sx)) & 255u;
+          const bool ok = row_ok && (((unsigned)g.w >> sx) & 1u);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + sx * 8), "l"(src + tx * 16), "r"(ok ? 8 : 0) : "memory");
         }
       }
     }
@@ -369,7 +374,7 @@ struct PackedPhases {
             for (int c = 0; c < K; ++c) st_stream(o + (int64_t)(g * K + c) * P, 0.f);
         continue;
       }
-      const int q0 = (org_of(st, l)[lane * 2 + 0] & 3) + a0;    // first tap column of this task inside the patch row
+      const int q0 = (org_of(st, l)[lane * 4 + 0] & 3) + a0;    // first tap column of this task inside the patch row
       // 12 bytes per row from word q0/2 on.  For the last column group of a narrow window (r < 4) the third word may
       // lie one word past the row: it only feeds taps that are never used, and the bytes read are still inside this
       // stage's shared memory (the next row / the position's pad / the fraction arrays).
@@ -776,6 +781,8 @@ int eem_corr_lookup_packed(const void* packed, int B, int H, int W, int num_leve
   EEM_CHECK_ARG(B <= 65535, "eem_corr_lookup_packed: batch > 65535 not supported in one call");
   EEM_CHECK_ALIGNED(packed, 32);
   const PackedLayout pl = packed_layout(H, W, num_levels);
+  if (pl.tx[0] > 255)
+    return fail(EEM_ERR_UNSUPPORTED, "eem_corr_lookup_packed: feature maps wider than 1020 are not supported (got %d)", W);
   PackedLookupParams p{};
   p.packed = static_cast<const uint16_t*>(packed);
   for (int l = 0; l < num_levels; ++l) {

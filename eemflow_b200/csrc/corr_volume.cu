@@ -105,7 +105,7 @@ struct PoolPackedParams {
 };
 
 template <bool kWarpGroups>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kWarpGroups ? 256 : 1024)
 pool_pyramid_packed_kernel(const __grid_constant__ PoolPackedParams p) {
   extern __shared__ __align__(16) float pk_smem[];
   const int gsize = kWarpGroups ? 32 : (int)blockDim.x;
@@ -1294,7 +1294,9 @@ int eem_corr_pyramid_packed(const float* fmap1, const float* fmap2, int B, int D
     } else {
       static DynSmemOptIn optin;
       if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(pool_pyramid_packed_kernel<false>, smem));
-      pool_pyramid_packed_kernel<false><<<(unsigned)blocks, 256, smem, stream>>>(pp);
+      // a large plane (HREM: 59 KB in, 79 KB out) is one CTA's serial chain of load -> 3 pooling levels -> write-out:
+      // 1024 threads per plane shorten that chain 4x (B = 2 HREM pairs are only 512 planes on 148 SMs)
+      pool_pyramid_packed_kernel<false><<<(unsigned)blocks, 1024, smem, stream>>>(pp);
     }
     EEM_CHECK_LAUNCH("pool_pyramid_packed_kernel");
   }

@@ -284,10 +284,10 @@ struct PackedPhases {
   static __device__ __forceinline__ int* org_of(unsigned char* st, int l) { return reinterpret_cast<int*>(fy_of(st, l) + PB * K); }
 
   // 1) window geometry, one thread per (position, level): same arithmetic as corr_lookup_kernel
-  static __device__ __forceinline__ void geometry(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos) {
+  static __device__ __forceinline__ void geometry(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
     const int P = p.H * p.W, L = p.L;
-    for (int t = threadIdx.x; t < PB * L; t += blockDim.x) {
-      const int l = t / PB, pos = t % PB;
+    for (int t = threadIdx.x; t < PB * nl; t += blockDim.x) {
+      const int ls = t / PB, l = l0 + ls, pos = t % PB;      // ls: level slot in shared memory
       const float sw = (float)(p.w[l] - 1), sh = (float)(p.h[l] - 1);
       const float rw = p.rcp_w1[l], rh = p.rcp_h1[l];
       float cx = 0.f, cy = 0.f;
@@ -309,10 +309,10 @@ struct PackedPhases {
           pack |= (unsigned)(ok ? tx : 0) << (8 * sx);
           mask |= (unsigned)ok << sx;
         }
-        *reinterpret_cast<int4*>(org_of(st, l) + pos * 4) = make_int4(oxi, (int)oy, (int)pack, (int)mask);
+        *reinterpret_cast<int4*>(org_of(st, ls) + pos * 4) = make_int4(oxi, (int)oy, (int)pack, (int)mask);
       }
-      float* fxp = fx_of(st, l) + pos * K;
-      float* fyp = fy_of(st, l) + pos * K;
+      float* fxp = fx_of(st, ls) + pos * K;
+      float* fyp = fy_of(st, ls) + pos * K;
 #pragma unroll
       for (int a = 0; a < K; ++a) {
         fxp[a] = roundtrip_rcp(lx + (float)(a - R), sw, rw) - (ox + (float)a);
@@ -325,22 +325,23 @@ struct PackedPhases {
   //    tiles the window's columns touch (zero-filled when the tile lies outside the map; cells of a partial last tile
   //    are zeros in the volume itself), so the patch in shared memory is a plain row-major image whose row 0 is the
   //    window's first row.  Issues the copies and commits ONE cp.async group.
-  static __device__ __forceinline__ void gather(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos) {
+  static __device__ __forceinline__ void gather(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
     const int P = p.H * p.W, L = p.L;
     for (int u = threadIdx.x; u < PB * T; u += blockDim.x) {       // (position, window row): decoded once, then all levels
       const int pos = u / T, rr = u - pos * T;
       if (pos >= npos) continue;
       const uint16_t* rowbase = p.packed + ((int64_t)b * P + i0 + pos) * p.row;
       const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(st + pos * S::kStrideBytes + rr * S::kRowBytes);
-      for (int l = 0; l < L; ++l) {
+      for (int ls = 0; ls < nl; ++ls) {
+        const int l = l0 + ls;
         const int txl = p.tx[l], tyl = p.ty[l];
         if (txl == 0 || tyl == 0) continue;                        // empty level
-        const int4 g = *reinterpret_cast<const int4*>(org_of(st, l) + pos * 4);   // ox, oy, clamped tile columns, column mask
+        const int4 g = *reinterpret_cast<const int4*>(org_of(st, ls) + pos * 4);   // ox, oy, clamped tile columns, column mask
         const int py = g.y + rr;                                   // map row of this window row
         const int ty = py >> 2;                                    // >> : floor for negatives
         const bool row_ok = (unsigned)ty < (unsigned)tyl;
         const uint16_t* src = rowbase + p.off[l] + (row_ok ? (ty * txl * 16 + (py & 3) * 4) : 0);
-        const uint32_t dst = dst0 + l * S::kPerLevelBytes;
+        const uint32_t dst = dst0 + ls * S::kPerLevelBytes;
 #pragma unroll
         for (int sx = 0; sx < NT; ++sx) {
           const unsigned tx = ((unsigned)g.z >> (8 * sx)) & 255u;
@@ -356,15 +357,15 @@ struct PackedPhases {
   //    reads three 4-byte words (6 fp16: the G + 1 = 4 taps it needs start at an even or odd element), shifts them
   //    into place with two funnel shifts, and forms G horizontal lerps + G vertical lerps; row addresses are
   //    compile-time offsets of one per-task base pointer.
-  static __device__ __forceinline__ void interp(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos) {
+  static __device__ __forceinline__ void interp(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
     constexpr int G = S::kColsPerTask, kGroups = S::kGroups;
     static_assert(G == 3, "load_row unpacks G + 1 = 4 taps");
     const int P = p.H * p.W, L = p.L;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_warps = blockDim.x >> 5;
     if (lane >= npos) return;
-    for (int task = warp; task < L * kGroups; task += n_warps) {
-      const int l = task / kGroups, a0 = (task - l * kGroups) * G;
+    for (int task = warp; task < nl * kGroups; task += n_warps) {
+      const int ls = task / kGroups, l = l0 + ls, a0 = (task - ls * kGroups) * G;
       float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a0 * K) * P + i0 + lane;
       if (p.h[l] * p.w[l] == 0) {            // level pooled away: an empty map contributes zeros
 #pragma unroll
@@ -374,16 +375,16 @@ struct PackedPhases {
             for (int c = 0; c < K; ++c) st_stream(o + (int64_t)(g * K + c) * P, 0.f);
         continue;
       }
-      const int q0 = (org_of(st, l)[lane * 4 + 0] & 3) + a0;    // first tap column of this task inside the patch row
+      const int q0 = (org_of(st, ls)[lane * 4 + 0] & 3) + a0;    // first tap column of this task inside the patch row
       // 12 bytes per row from word q0/2 on.  For the last column group of a narrow window (r < 4) the third word may
       // lie one word past the row: it only feeds taps that are never used, and the bytes read are still inside this
       // stage's shared memory (the next row / the position's pad / the fraction arrays).
-      const unsigned char* base = patch_of(st, l) + lane * S::kStrideBytes + (q0 >> 1) * 4;
+      const unsigned char* base = patch_of(st, ls) + lane * S::kStrideBytes + (q0 >> 1) * 4;
       const unsigned sh = (unsigned)(q0 & 1) * 16u;
-      const float* fyp = fy_of(st, l) + lane * K;
+      const float* fyp = fy_of(st, ls) + lane * K;
       float fx[G], prev[G];
 #pragma unroll
-      for (int g = 0; g < G; ++g) fx[g] = (a0 + g < K) ? fx_of(st, l)[lane * K + a0 + g] : 0.f;
+      for (int g = 0; g < G; ++g) fx[g] = (a0 + g < K) ? fx_of(st, ls)[lane * K + a0 + g] : 0.f;
       auto load_row = [&](int rr, float (&t)[G + 1]) {
         const uint32_t* rowp = reinterpret_cast<const uint32_t*>(base + rr * S::kRowBytes);
         const uint32_t x0 = rowp[0], x1 = rowp[1], x2 = rowp[2];
@@ -421,18 +422,19 @@ struct PackedPhases {
 // One batch per CTA (the default).
 template <int R>
 __global__ void __launch_bounds__(PackedSmem<R>::kThreads)
-corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
+corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p, int levels_per_cta) {
   using Ph = PackedPhases<R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int P = p.H * p.W;
   const int b = blockIdx.y, i0 = blockIdx.x * Ph::PB;
   const int npos = min(Ph::PB, P - i0);
-  Ph::geometry(p, smem_raw, b, i0, npos);
+  const int l0 = blockIdx.z * levels_per_cta, nl = min(levels_per_cta, p.L - l0);   // this CTA's levels
+  Ph::geometry(p, smem_raw, b, i0, npos, l0, nl);
   __syncthreads();
-  Ph::gather(p, smem_raw, b, i0, npos);
+  Ph::gather(p, smem_raw, b, i0, npos, l0, nl);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  Ph::interp(p, smem_raw, b, i0, npos);
+  Ph::interp(p, smem_raw, b, i0, npos, l0, nl);
 }
 
 // Persistent, software-pipelined form (experiment, EEM_LOOKUP_PACKED_PIPE=1): a CTA walks batches blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -456,17 +458,17 @@ corr_lookup_packed_pipe_kernel(const __grid_constant__ PackedLookupParams p, int
   int b, i0, npos;
   // prologue: batches 0 and 1 of this CTA
   decode(bid, b, i0, npos);
-  Ph::geometry(p, smem_raw, b, i0, npos);
+  Ph::geometry(p, smem_raw, b, i0, npos, 0, p.L);
   if (bid + step < n_batches) {
     int b1, i1, n1;
     decode(bid + step, b1, i1, n1);
-    Ph::geometry(p, smem_raw + stage_bytes, b1, i1, n1);
+    Ph::geometry(p, smem_raw + stage_bytes, b1, i1, n1, 0, p.L);
     __syncthreads();
-    Ph::gather(p, smem_raw, b, i0, npos);
-    Ph::gather(p, smem_raw + stage_bytes, b1, i1, n1);
+    Ph::gather(p, smem_raw, b, i0, npos, 0, p.L);
+    Ph::gather(p, smem_raw + stage_bytes, b1, i1, n1, 0, p.L);
   } else {
     __syncthreads();
-    Ph::gather(p, smem_raw, b, i0, npos);
+    Ph::gather(p, smem_raw, b, i0, npos, 0, p.L);
   }
   for (int k = 0; bid < n_batches; ++k, bid += step) {
     unsigned char* st = smem_raw + (k & 1) * stage_bytes;
@@ -474,15 +476,15 @@ corr_lookup_packed_pipe_kernel(const __grid_constant__ PackedLookupParams p, int
     if (bid + step < n_batches) asm volatile("cp.async.wait_group 1;" ::: "memory");   // batch k landed, k+1 may be in flight
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    Ph::interp(p, st, b, i0, npos);
+    Ph::interp(p, st, b, i0, npos, 0, p.L);
     const int nxt = bid + 2 * step;
     if (nxt < n_batches) {                      // refill this stage with batch k+2
       __syncthreads();                          // every warp is done reading the stage
       int b2, i2, n2;
       decode(nxt, b2, i2, n2);
-      Ph::geometry(p, st, b2, i2, n2);
+      Ph::geometry(p, st, b2, i2, n2, 0, p.L);
       __syncthreads();
-      Ph::gather(p, st, b2, i2, n2);
+      Ph::gather(p, st, b2, i2, n2, 0, p.L);
     }
   }
 }
@@ -513,10 +515,19 @@ int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
     corr_lookup_packed_pipe_kernel<R><<<(unsigned)grid, S::kThreads, 2 * stage, stream>>>(p, bps, (int)n_batches, (int)stage);
     return EEM_OK;
   }
-  dim3 grid((unsigned)bps, (unsigned)p.B);
+  // levels per CTA (EEM_LOOKUP_PACKED_LPC, default all): fewer levels per CTA = smaller, more numerous CTAs whose
+  // geometry / gather / interpolation phases interleave on an SM
+  static const int lpc_env = [] {
+    const char* v = getenv("EEM_LOOKUP_PACKED_LPC");
+    return v != nullptr ? atoi(v) : 0;
+  }();
+  const int lpc = (lpc_env >= 1 && lpc_env < p.L) ? lpc_env : p.L;
+  const size_t smem = (size_t)lpc * S::kPerLevelBytes;
+  const int threads = 32 * ((lpc * S::kGroups + 0) > 0 ? lpc * S::kGroups : 1);
+  dim3 grid((unsigned)bps, (unsigned)p.B, (unsigned)ceil_div(p.L, lpc));
   static DynSmemOptIn optin;
-  if (stage > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_kernel<R>, stage));
-  corr_lookup_packed_kernel<R><<<grid, S::kThreads, stage, stream>>>(p);
+  if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_kernel<R>, smem));
+  corr_lookup_packed_kernel<R><<<grid, threads < 64 ? 64 : threads, smem, stream>>>(p, lpc);
   return EEM_OK;
 }
 

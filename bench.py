@@ -283,12 +283,36 @@ class B200Step:
         self.metric_acc.add_(self.flow_error_stats(self.flow_gt, self.flow))
 
     def resident(self):
-        """One step with inputs already in HBM; returns (last lookup, final flow)."""
-        self.fam_voxelize()
+        """One step with inputs already in HBM; returns (last lookup, final flow).
+
+        The three chains of a step are independent of each other -- event windows -> voxel grids; feature maps ->
+        pyramid -> 12 lookups; EEMFlow-level maps -> flows -> metrics -- so (unless EEM_BENCH_SERIAL=1) they are issued
+        on three streams and become three concurrent branches of the captured step graph: the small latency-bound
+        kernels of one chain fill the issue slots and SMs the other chains leave idle.  Same kernels, same results."""
+        if os.environ.get("EEM_BENCH_SERIAL", "0") == "1":
+            self.fam_voxelize()
+            self.fam_corr_pyramid()
+            self.fam_corr_lookup()
+            self.fam_eemflow_ops()
+            self.fam_metrics()
+            return self.out, self.flow
+        if getattr(self, "side", None) is None:
+            self.side = (torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev))
+        cur = torch.cuda.current_stream(self.dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        s1, s2 = self.side
+        s1.wait_event(fork)
+        s2.wait_event(fork)
+        with torch.cuda.stream(s1):
+            self.fam_voxelize()
+        with torch.cuda.stream(s2):
+            self.fam_eemflow_ops()
+            self.fam_metrics()
         self.fam_corr_pyramid()
         self.fam_corr_lookup()
-        self.fam_eemflow_ops()
-        self.fam_metrics()
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
         return self.out, self.flow
 
     class _Lane:
@@ -934,7 +958,9 @@ def main():
         line = {"metric": METRIC, "value": r["value"], "unit": "frame-pairs/s", "n_gpus": world,
                 "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-                "config": dict(config_of(head, args, world)), "launch": "CUDA graph replay of one step",
+                "config": dict(config_of(head, args, world)),
+                "launch": "CUDA graph replay of one step; its three independent chains (voxelize | pyramid + lookups | EEMFlow ops + metrics) are concurrent branches of the graph"
+                          if os.environ.get("EEM_BENCH_SERIAL", "0") != "1" else "CUDA graph replay of one step, kernels in series",
                 "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],
                 "roofline": r["roofline"], "cpu_baseline": r["cpu_baseline"], "result_gather": r["result_gather"]}
         if subs:

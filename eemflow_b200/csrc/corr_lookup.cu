@@ -326,28 +326,29 @@ struct PackedPhases {
   //    are zeros in the volume itself), so the patch in shared memory is a plain row-major image whose row 0 is the
   //    window's first row.  Issues the copies and commits ONE cp.async group.
   static __device__ __forceinline__ void gather(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
-    // unit = ONE 8-byte copy: (level, position, window row, tile column), tile column fastest, then the window row.
-    // The 32 copies of a warp instruction then fill 256 CONTIGUOUS bytes of a patch (8 rows x 32 B: two shared-memory
-    // wavefronts; with a thread per (position, row) issuing its 4 columns one after the other every instruction wrote
-    // 8 bytes at a 32-byte stride -- 10.8 wavefronts per LDGSTS in ncu) and read whole 128-byte lines of the volume
-    // (4 adjacent tiles x 4 rows of a tile row).
-    const int P = p.H * p.W;
-    const int total = nl * PB * T * NT;
-    for (int u = threadIdx.x; u < total; u += blockDim.x) {
-      const int sx = u % NT, v = u / NT;
-      const int rr = v % T, w2 = v / T;
-      const int pos = w2 % PB, ls = w2 / PB;
-      const int l = l0 + ls;
-      const int txl = p.tx[l], tyl = p.ty[l];
-      if (pos >= npos || txl == 0 || tyl == 0) continue;
-      const int4 g = *reinterpret_cast<const int4*>(org_of(st, ls) + pos * 4);   // ox, oy, clamped tile columns, column mask
-      const int py = g.y + rr;                                   // map row of this window row
-      const int ty = py >> 2;                                    // >> : floor for negatives
-      const bool ok = (unsigned)ty < (unsigned)tyl && (((unsigned)g.w >> sx) & 1u);
-      const unsigned tx = ((unsigned)g.z >> (8 * sx)) & 255u;
-      const uint16_t* src = p.packed + ((int64_t)b * P + i0 + pos) * p.row + p.off[l] + (ok ? ((ty * txl + (int)tx) * 16 + (py & 3) * 4) : 0);
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(patch_of(st, ls) + pos * S::kStrideBytes + rr * S::kRowBytes + sx * 8);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(ok ? 8 : 0) : "memory");
+    const int P = p.H * p.W, L = p.L;
+    for (int u = threadIdx.x; u < PB * T; u += blockDim.x) {       // (position, window row): decoded once, then all levels
+      const int pos = u / T, rr = u - pos * T;
+      if (pos >= npos) continue;
+      const uint16_t* rowbase = p.packed + ((int64_t)b * P + i0 + pos) * p.row;
+      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(st + pos * S::kStrideBytes + rr * S::kRowBytes);
+      for (int ls = 0; ls < nl; ++ls) {
+        const int l = l0 + ls;
+        const int txl = p.tx[l], tyl = p.ty[l];
+        if (txl == 0 || tyl == 0) continue;                        // empty level
+        const int4 g = *reinterpret_cast<const int4*>(org_of(st, ls) + pos * 4);   // ox, oy, clamped tile columns, column mask
+        const int py = g.y + rr;                                   // map row of this window row
+        const int ty = py >> 2;                                    // >> : floor for negatives
+        const bool row_ok = (unsigned)ty < (unsigned)tyl;
+        const uint16_t* src = rowbase + p.off[l] + (row_ok ? (ty * txl * 16 + (py & 3) * 4) : 0);
+        const uint32_t dst = dst0 + ls * S::kPerLevelBytes;
+#pragma unroll
+        for (int sx = 0; sx < NT; ++sx) {
+          const unsigned tx = ((unsigned)g.z >> (8 * sx)) & 255u;
+          const bool ok = row_ok && (((unsigned)g.w >> sx) & 1u);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + sx * 8), "l"(src + tx * 16), "r"(ok ? 8 : 0) : "memory");
+        }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }

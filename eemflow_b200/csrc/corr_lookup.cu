@@ -522,7 +522,12 @@ int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
     return v != nullptr ? atoi(v) : 0;
   }();
   const int lpc = (lpc_env >= 1 && lpc_env < p.L) ? lpc_env : p.L;
-  const size_t smem = (size_t)lpc * S::kPerLevelBytes;
+  // EEM_LOOKUP_PACKED_PAD_KB (timing experiments only): extra dynamic shared memory per CTA, i.e. fewer CTAs per SM
+  static const size_t pad_bytes = [] {
+    const char* v = getenv("EEM_LOOKUP_PACKED_PAD_KB");
+    return v != nullptr ? (size_t)atoi(v) * 1024 : (size_t)0;
+  }();
+  const size_t smem = (size_t)lpc * S::kPerLevelBytes + pad_bytes;
   const int threads = 32 * ((lpc * S::kGroups + 0) > 0 ? lpc * S::kGroups : 1);
   dim3 grid((unsigned)bps, (unsigned)p.B, (unsigned)ceil_div(p.L, lpc));
   static DynSmemOptIn optin;

@@ -1072,9 +1072,11 @@ voxel_plane_kernel(const int64_t* __restrict__ offsets, int nb, int H, int W, co
           while (true) {
             if (pending) atomicMin(&claim[pix], (uint32_t)tid);
             __syncthreads();
-            if (pending && claim[pix] == (uint32_t)tid) {
+            // (a loser may read the claim word while the winner resets it: both accesses are volatile / atomic, and
+            // either value it can see -- the winner's id or "free" -- differs from its own id)
+            if (pending && *reinterpret_cast<volatile uint32_t*>(&claim[pix]) == (uint32_t)tid) {
               plane[pix] = __fadd_rn(plane[pix], v);
-              claim[pix] = 0xffffffffu;
+              atomicExch(&claim[pix], 0xffffffffu);
               pending = false;
             }
             if (!__syncthreads_or((int)pending)) break;

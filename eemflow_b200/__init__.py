@@ -15,13 +15,14 @@ from .corr import CorrBlock, bilinear_sampler, coords_grid, upflow8
 from .correlation import Correlation, SpatialCorrelationSampler, correlation_select
 from .eval_utils import center_crop, event_mask, event_valid_from_volume, flow_error, motion_propagate
 from .event_utils import EventSequence, EventSequenceToVoxelGrid_Pytorch
-from .warp import (InputPadder, WarpingLayer_no_div, cdc_blend, tensor_tools, torch_warp, torch_warp_mask,
-                   upsample2d_flow_as, upsample2d_flows_as, upsample_flow, warp)
+from .warp import (InputPadder, WarpingLayer_no_div, blend_warp, cdc_blend, tensor_tools, torch_warp, torch_warp_mask,
+                   upsample2d_flow_as, upsample2d_flows_as, upsample_flow, upsample_warp_no_div, warp)
 
 __all__ = [
     "EventSequence", "EventSequenceToVoxelGrid_Pytorch", "CorrBlock", "bilinear_sampler", "coords_grid", "upflow8",
     "SpatialCorrelationSampler", "Correlation", "correlation_select", "warp", "tensor_tools", "torch_warp",
-    "torch_warp_mask", "WarpingLayer_no_div", "upsample2d_flow_as", "upsample2d_flows_as", "upsample_flow", "cdc_blend", "InputPadder",
+    "torch_warp_mask", "WarpingLayer_no_div", "upsample2d_flow_as", "upsample2d_flows_as", "upsample_flow",
+    "upsample_warp_no_div", "blend_warp", "cdc_blend", "InputPadder",
     "event_mask", "event_valid_from_volume", "flow_error", "motion_propagate", "center_crop",
 ]
 __version__ = "0.1.0"

@@ -54,6 +54,8 @@ SIGNATURES = {
     "eem_corr_lookup": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eem_local_corr": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, _vp, _vp]),
     "eem_backwarp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "eem_upsample_flow_warp": (_i, [_vp, _i, _i, _f, _f, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "eem_blend_flow_warp": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eem_warp_blend": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "eem_bilinear_resize": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _vp]),
     "eem_bilinear_sample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -211,6 +211,79 @@ scale_uv_kernel(float* __restrict__ flow, int B, int C, int64_t plane, float s0,
   }
 }
 
+// ---- fused EEMFlow-level chains -------------------------------------------------------------------------------------
+// Per pyramid level EEMFlow_cdc runs  upsample2d_flow_as -> WarpingLayer_no_div  (cdc_utils.py:156-160) and, after its
+// estimator convolutions,  CDC blend -> EEMFlow_cdc.warp  (cdc_utils.py:173, EEMFlow+.py:181...): in both pairs the
+// second op only needs the first op's per-pixel flow.  The fused kernels compute that flow per thread with the SAME
+// expressions as bilinear_resize_kernel / warp_blend_kernel, write it out once (the channel-chunk-0 thread) and warp
+// the feature map with it: one launch and one flow round trip less per pair.
+struct FusedWarpParams {
+  const float* x;            // [B,C,H,W] map to warp
+  float* out;                // [B,C,H,W]
+  float* flow_out;           // [B,2,H,W] the flow the warp used
+  // kUpsample: coarse flow [B,2,h,w] resized with align_corners=True, channels scaled by s0 / s1; HALFPIX warp + >= 1.0 mask
+  const float* coarse;
+  int h, w;
+  float s0, s1;
+  // !kUpsample: flow = torch_warp(flow_init, inter) * (1 - m) + flow_init * m; EXACT warp, no mask
+  const float* flow_init;
+  const float* inter;
+  const float* mk;
+  int B, C, H, W;
+};
+
+template <bool kUpsample>
+__global__ void __launch_bounds__(256)
+fused_flow_warp_kernel(const __grid_constant__ FusedWarpParams p) {
+  const int px = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int py = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int H = p.H, W = p.W, C = p.C;
+  if (px >= W || py >= H) return;
+  const int chunks = (C + kWarpChunk - 1) / kWarpChunk;
+  const int b = blockIdx.z / chunks, c0 = (blockIdx.z % chunks) * kWarpChunk;
+  const int64_t plane = (int64_t)H * W, pix = (int64_t)py * W + px;
+  float u, v;
+  if (kUpsample) {
+    int xa, xb, y0, y1;
+    float la, lb, ly0, ly1;
+    source_index(px, p.w, W, 1, xa, xb, la, lb);
+    source_index(py, p.h, H, 1, y0, y1, ly0, ly1);
+    const int64_t ip = (int64_t)p.h * p.w;
+    const float* r0 = p.coarse + (int64_t)b * 2 * ip + y0 * p.w;
+    const float* r1 = p.coarse + (int64_t)b * 2 * ip + y1 * p.w;
+    u = (ly0 * (la * __ldg(r0 + xa) + lb * __ldg(r0 + xb)) + ly1 * (la * __ldg(r1 + xa) + lb * __ldg(r1 + xb))) * p.s0;
+    r0 += ip;
+    r1 += ip;
+    v = (ly0 * (la * __ldg(r0 + xa) + lb * __ldg(r0 + xb)) + ly1 * (la * __ldg(r1 + xa) + lb * __ldg(r1 + xb))) * p.s1;
+  } else {
+    const float iu = p.inter[((int64_t)b * 2 + 0) * plane + pix];
+    const float iv = p.inter[((int64_t)b * 2 + 1) * plane + pix];
+    const Bilin sb = make_bilin((float)px + iu, (float)py + iv, H, W, EEM_WARP_HALFPIX);
+    const float m = p.mk[(int64_t)b * plane + pix];
+    const int64_t off0 = ((int64_t)b * 2 + 0) * plane, off1 = off0 + plane;
+    u = sample(p.flow_init + off0, sb, W) * (1.f - m) + p.flow_init[off0 + pix] * m;
+    v = sample(p.flow_init + off1, sb, W) * (1.f - m) + p.flow_init[off1 + pix] * m;
+  }
+  if (c0 == 0) {
+    p.flow_out[((int64_t)b * 2 + 0) * plane + pix] = u;
+    p.flow_out[((int64_t)b * 2 + 1) * plane + pix] = v;
+  }
+  const Bilin s = make_bilin((float)px + u, (float)py + v, H, W, kUpsample ? EEM_WARP_HALFPIX : EEM_WARP_EXACT);
+  float m = 1.f;
+  if (kUpsample) m = ones_sample(s) >= 1.0f ? 1.f : 0.f;
+  float r[kWarpChunk];
+#pragma unroll
+  for (int k = 0; k < kWarpChunk; ++k) {
+    const int c = min(c0 + k, C - 1);
+    r[k] = sample(p.x + ((int64_t)b * C + c) * plane, s, W);
+  }
+#pragma unroll
+  for (int k = 0; k < kWarpChunk; ++k) {
+    const int c = c0 + k;
+    if (c < C) st_stream(p.out + ((int64_t)b * C + c) * plane + pix, kUpsample ? r[k] * m : r[k]);
+  }
+}
+
 // ---- several flow maps to one size in ONE launch -------------------------------------------------------------
 // The five flow predictions of EEMFlow_cdc are resized to the input size by five calls of upsample2d_flow_as
 // (model/EEMFlow/EEMFlow+.py:231-232), each followed by that function's in-place scaling of its input
@@ -364,6 +437,37 @@ int eem_backwarp(const float* x, const float* flow, int B, int C, int H, int W, 
   dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)gz);
   backwarp_kernel<<<grid, 256, 0, as_stream(stream_)>>>(x, flow, B, C, H, W, convention, mask_mode, out, mask_out);
   EEM_CHECK_LAUNCH("backwarp_kernel");
+  return EEM_OK;
+}
+
+int eem_upsample_flow_warp(const float* coarse_flow, int h, int w, float scale0, float scale1, const float* x, int B, int C,
+                           int H, int W, float* flow_out, float* out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(coarse_flow && x && flow_out && out, "eem_upsample_flow_warp: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && h > 0 && w > 0, "eem_upsample_flow_warp: sizes must be > 0");
+  const int64_t gz = (int64_t)B * ceil_div(C, kWarpChunk);
+  EEM_CHECK_ARG(gz <= 65535, "eem_upsample_flow_warp: B*ceil(C/%d) = %lld exceeds 65535; split the batch", kWarpChunk, (long long)gz);
+  FusedWarpParams p{};
+  p.x = x; p.out = out; p.flow_out = flow_out; p.coarse = coarse_flow; p.h = h; p.w = w; p.s0 = scale0; p.s1 = scale1;
+  p.B = B; p.C = C; p.H = H; p.W = W;
+  dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)gz);
+  fused_flow_warp_kernel<true><<<grid, 256, 0, as_stream(stream_)>>>(p);
+  EEM_CHECK_LAUNCH("fused_flow_warp_kernel<upsample>");
+  return EEM_OK;
+}
+
+int eem_blend_flow_warp(const float* flow_init, const float* inter_flow, const float* m, const float* x, int B, int C, int H,
+                        int W, float* flow_out, float* out, eem_stream_t stream_) {
+  EEM_CHECK_ARG(flow_init && inter_flow && m && x && flow_out && out, "eem_blend_flow_warp: NULL pointer");
+  EEM_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "eem_blend_flow_warp: sizes must be > 0");
+  EEM_CHECK_ARG(flow_out != flow_init, "eem_blend_flow_warp: flow_out must not alias flow_init (it is gathered from)");
+  const int64_t gz = (int64_t)B * ceil_div(C, kWarpChunk);
+  EEM_CHECK_ARG(gz <= 65535, "eem_blend_flow_warp: B*ceil(C/%d) = %lld exceeds 65535; split the batch", kWarpChunk, (long long)gz);
+  FusedWarpParams p{};
+  p.x = x; p.out = out; p.flow_out = flow_out; p.flow_init = flow_init; p.inter = inter_flow; p.mk = m;
+  p.B = B; p.C = C; p.H = H; p.W = W;
+  dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)gz);
+  fused_flow_warp_kernel<false><<<grid, 256, 0, as_stream(stream_)>>>(p);
+  EEM_CHECK_LAUNCH("fused_flow_warp_kernel<blend>");
   return EEM_OK;
 }
 

@@ -17,7 +17,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .correlation import EEMFLOW_CDC_INDEX, correlation_select
-from .warp import InputPadder, WarpingLayer_no_div, cdc_blend, upsample2d_flow_as, upsample2d_flows_as, warp
+from .warp import (InputPadder, WarpingLayer_no_div, blend_warp, cdc_blend, upsample2d_flow_as, upsample2d_flows_as,
+                   upsample_warp_no_div, warp)
 
 
 def _conv_lrelu(cin, cout, k=3, stride=1, groups=1):
@@ -80,14 +81,24 @@ class _CdcUpsampler(nn.Module):
         self.upsample_output_conv = nn.Sequential(_conv_lrelu(3, 16), _conv_lrelu(16, 16, stride=2), _conv_lrelu(16, 32),
                                                   _conv_lrelu(32, 32, stride=2))
 
-    def forward(self, flow_init, feature_1, feature_2):
+    def forward(self, flow_init, feature_1, feature_2, warp_target=None):
+        """cdc_utils.py:156-174.  Returns (flow_up, warped, pre_scale):
+        `warped` = EEMFlow_cdc.warp(warp_target, flow_up) when the caller passes the map it is going to warp with the
+        result (EEMFlow+.py:181...), fused with the blend; `pre_scale` = the in-place scaling of `flow_init` that the
+        reference's upsample2d_flow_as would have applied here and that is deferred to the final upsampling (None when
+        no resize was needed)."""
+        pre_scale = None
         if flow_init.shape[-2:] != feature_1.shape[-2:]:
-            flow_init = upsample2d_flow_as(flow_init, feature_1, mode="bilinear", if_rate=True)   # scales its input in place
-        feature_2_warp = self.warping_layer(feature_2, flow_init)
+            flow_init, feature_2_warp, pre_scale = upsample_warp_no_div(flow_init, feature_1, feature_2)
+        else:
+            feature_2_warp = self.warping_layer(feature_2, flow_init)
         x_out = self.dense_estimator_mask(torch.cat((feature_1, feature_2_warp), dim=1))
         inter_flow = x_out[:, :2].contiguous()
         inter_mask = torch.sigmoid(x_out[:, 2:3]).contiguous()
-        return cdc_blend(flow_init, inter_flow, inter_mask)
+        if warp_target is None:
+            return cdc_blend(flow_init, inter_flow, inter_mask), None, pre_scale
+        flow_up, warped = blend_warp(flow_init, inter_flow, inter_mask, warp_target)
+        return flow_up, warped, pre_scale
 
 
 class EEMFlow_cdc(nn.Module):
@@ -136,15 +147,20 @@ class EEMFlow_cdc(nn.Module):
         flow7_up = torch.zeros(f16.size(0), 2, f16.size(2), f16.size(3), device=f16.device, dtype=f16.dtype)
         cv = correlation_select(f16, f26, EEMFLOW_CDC_INDEX)
         flows[6] = self.decoder6(torch.cat([cv, self.rconv6(f16), flow7_up], 1))
+        pre_scales = {}
         for lvl in (5, 4, 3, 2):
             a, b = p1[lvl], p2[lvl]
             proj = self.conv_1x1[lvl]
-            flow_up = self.cdc_model(flows[lvl + 1], proj(a), proj(b))
-            cv = correlation_select(a, warp(b, flow_up), EEMFLOW_CDC_INDEX)
+            # upsample + WarpingLayer_no_div in one launch, blend + warp in one launch; the reference's in-place scaling of
+            # flows[lvl + 1] (upsample2d_flow_as side effect) is deferred to the final upsampling below
+            flow_up, b_warp, pre_scales[lvl + 1] = self.cdc_model(flows[lvl + 1], proj(a), proj(b), warp_target=b)
+            cv = correlation_select(a, b_warp, EEMFLOW_CDC_INDEX)
             feat = getattr(self, f"rconv{lvl}")(a)
             flows[lvl] = getattr(self, f"decoder{lvl}")(torch.cat([cv, feat, flow_up], 1)) + flow_up
         # EEMFlow+.py:231-232: five upsample2d_flow_as calls -> one resize launch + one in-place scaling launch
-        predictions = upsample2d_flows_as([flows[lvl] for lvl in (6, 5, 4, 3, 2)], events1, mode="bilinear", if_rate=True)
+        order = (6, 5, 4, 3, 2)
+        predictions = upsample2d_flows_as([flows[lvl] for lvl in order], events1, mode="bilinear", if_rate=True,
+                                          pre_scales=[pre_scales.get(lvl) for lvl in order])
         return (events1, events2), predictions
 
 

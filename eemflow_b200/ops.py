@@ -299,6 +299,37 @@ def warp_blend(flow_init: torch.Tensor, inter_flow: torch.Tensor, mask: torch.Te
     return out
 
 
+def upsample_flow_warp(coarse_flow: torch.Tensor, x: torch.Tensor, scale0: float, scale1: float):
+    """(upsample2d_flow_as(coarse_flow, x, if_rate) without its in-place side effect, WarpingLayer_no_div(x, that flow)) in one launch."""
+    coarse_flow = L.require_cuda(coarse_flow, "coarse_flow")
+    x = L.require_cuda(x, "x")
+    B, Cc, H, W = x.shape
+    assert coarse_flow.shape[0] == B and coarse_flow.shape[1] == 2
+    h, w = coarse_flow.shape[2:]
+    flow = torch.empty((B, 2, H, W), dtype=torch.float32, device=x.device)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().eem_upsample_flow_warp(coarse_flow.data_ptr(), h, w, float(scale0), float(scale1), x.data_ptr(), B, Cc, H, W,
+                                               flow.data_ptr(), out.data_ptr(), L.stream_ptr(x.device)))
+    return flow, out
+
+
+def blend_flow_warp(flow_init: torch.Tensor, inter_flow: torch.Tensor, mask: torch.Tensor, x: torch.Tensor):
+    """(cdc blend(flow_init, inter_flow, mask), EEMFlow_cdc.warp(x, that flow)) in one launch."""
+    flow_init = L.require_cuda(flow_init, "flow_init")
+    inter_flow = L.require_cuda(inter_flow, "inter_flow")
+    mask = L.require_cuda(mask, "mask")
+    x = L.require_cuda(x, "x")
+    B, Cc, H, W = x.shape
+    assert tuple(flow_init.shape) == (B, 2, H, W) and inter_flow.shape == flow_init.shape and tuple(mask.shape) == (B, 1, H, W)
+    flow = torch.empty_like(flow_init)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().eem_blend_flow_warp(flow_init.data_ptr(), inter_flow.data_ptr(), mask.data_ptr(), x.data_ptr(), B, Cc, H, W,
+                                            flow.data_ptr(), out.data_ptr(), L.stream_ptr(x.device)))
+    return flow, out
+
+
 # ------------------------------------------------------------------------------------------ K8/K9
 def bilinear_resize(x: torch.Tensor, size: tuple[int, int], align_corners: bool, scale0: float = 1.0,
                     scale1: float = 1.0, scale_rest: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -79,26 +79,62 @@ def upsample2d_flow_as(inputs, target_as, mode="bilinear", if_rate=False, out=No
     return ag.bilinear_resize(inputs, (h, w), align_corners=True, out=out)
 
 
-def upsample2d_flows_as(inputs, target_as, mode="bilinear", if_rate=False, out_last=None):
+def upsample2d_flows_as(inputs, target_as, mode="bilinear", if_rate=False, out_last=None, pre_scales=None):
     """`[upsample2d_flow_as(f, target_as, mode, if_rate) for f in inputs]` -- the five final predictions of EEMFlow_cdc
     (model/EEMFlow/EEMFlow+.py:231-232) -- in two launches instead of ten: one kernel resizes all maps, one applies the
     reference's in-place scaling of every input (cdc_utils.py:85-86).  Same results, same side effect.
-    `out_last` (optional): destination of the LAST map's result (may be peer-GPU memory, see ops.bilinear_resize)."""
+    `out_last` (optional): destination of the LAST map's result (may be peer-GPU memory, see ops.bilinear_resize).
+    `pre_scales` (optional): per map `(su, sv)` or None -- an in-place scaling of that input which an EARLIER
+    upsample2d_flow_as(if_rate=True) call of the reference would already have applied (the per-level call of
+    cdc_utils.py:156-160) and which the caller deferred (`upsample_warp_no_div`): it is folded into this call's resize
+    and into its in-place scaling, so the inputs end up exactly as the reference leaves them."""
     if mode != "bilinear":
         raise NotImplementedError("eemflow_b200.upsample2d_flows_as implements mode='bilinear' only")
     inputs = list(inputs)
+    pre = [(1.0, 1.0) if (pre_scales is None or pre_scales[k] is None) else tuple(pre_scales[k]) for k in range(len(inputs))]
     same = len({(tuple(f.shape[:2]), f.device, f.dtype) for f in inputs}) == 1
     if (not same or len(inputs) > 8 or ag.needs_grad(*inputs)
             or not all(f.is_cuda and f.is_contiguous() and f.dtype == torch.float32 for f in inputs)):
+        for f, (su, sv) in zip(inputs, pre):           # apply the deferred scalings the way the reference would have
+            if (su, sv) != (1.0, 1.0):
+                f[:, 0, :, :] *= su
+                f[:, 1, :, :] *= sv
         outs = [upsample2d_flow_as(f, target_as, mode, if_rate) for f in inputs[:-1]]
         return outs + [upsample2d_flow_as(inputs[-1], target_as, mode, if_rate, out=out_last)]
     _, _, h, w = target_as.shape
-    scales = [((w / f.shape[3]), (h / f.shape[2])) if if_rate else (1.0, 1.0) for f in inputs]
+    rates = [((w / f.shape[3]), (h / f.shape[2])) if if_rate else (1.0, 1.0) for f in inputs]
+    scales = [(r[0] * q[0], r[1] * q[1]) for r, q in zip(rates, pre)]
     with torch.no_grad():
         res = ops.bilinear_resize_multi(inputs, (h, w), True, scales, outs=[None] * (len(inputs) - 1) + [out_last])
-        if if_rate:
+        if any(sc != (1.0, 1.0) for sc in scales):
             ops.scale_uv_multi_(inputs, scales)
     return res
+
+
+def upsample_warp_no_div(flow, feature_as, feature_to_warp):
+    """`flow_up = upsample2d_flow_as(flow, feature_as, if_rate=True)` then `WarpingLayer_no_div()(feature_to_warp, flow_up)`
+    (model/EEMFlow/cdc_utils.py:156-160) in ONE launch.  Returns (flow_up, warped, (su, sv)).  The reference's in-place
+    scaling of `flow` by (su, sv) is NOT applied here: hand the pair to `upsample2d_flows_as(pre_scales=...)` (or scale
+    `flow` yourself) if `flow` is used again, as EEMFlow_cdc does for its final predictions."""
+    _, _, h, w = feature_as.shape
+    _, _, h_, w_ = flow.shape
+    su, sv = (w / w_), (h / h_)
+    if ag.needs_grad(flow, feature_to_warp) or not (flow.is_cuda and feature_to_warp.is_cuda):
+        flow_up = ag.bilinear_resize(flow, (h, w), align_corners=True, scale0=su, scale1=sv)
+        return flow_up, ag.backwarp(feature_to_warp, flow_up, L.WARP_HALFPIX, L.MASK_GE1), (su, sv)
+    with torch.no_grad():
+        flow_up, warped = ops.upsample_flow_warp(flow, feature_to_warp, su, sv)
+    return flow_up, warped, (su, sv)
+
+
+def blend_warp(flow_init, inter_flow, inter_mask, x):
+    """`flow_up = cdc_blend(flow_init, inter_flow, inter_mask)` (cdc_utils.py:173) then `warp(x, flow_up)`
+    (EEMFlow+.py:137-149) in ONE launch.  Returns (flow_up, warped)."""
+    if ag.needs_grad(flow_init, inter_flow, inter_mask, x):
+        flow_up = cdc_blend(flow_init, inter_flow, inter_mask)
+        return flow_up, warp(x, flow_up)
+    with torch.no_grad():
+        return ops.blend_flow_warp(flow_init, inter_flow, inter_mask, x)
 
 
 def upsample_flow(flow, orig_size):

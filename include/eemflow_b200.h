@@ -229,6 +229,20 @@ EEM_API int eem_backwarp(const float* x, const float* flow, int B, int C, int H,
 EEM_API int eem_warp_blend(const float* flow_init, const float* inter_flow, const float* m,
                            int B, int H, int W, float* out, eem_stream_t stream);
 
+/* K7c fused per-level chains of EEMFlow_cdc (same arithmetic as the separate calls, one launch and one flow round trip less):
+ *   eem_upsample_flow_warp : flow_out = upsample2d_flow_as(coarse_flow, [H,W], if_rate) WITHOUT the in-place side effect
+ *                            (scale0 = W/w, scale1 = H/h), out = WarpingLayer_no_div(x, flow_out)
+ *                            replaces: model/EEMFlow/cdc_utils.py:156-160 (K8 followed by K7 HALFPIX + MASK_GE1)
+ *   eem_blend_flow_warp    : flow_out = K7b blend(flow_init, inter_flow, m), out = EEMFlow_cdc.warp(x, flow_out)
+ *                            replaces: cdc_utils.py:173 followed by EEMFlow+.py:137-149 (K7b followed by K7 EXACT)
+ * coarse_flow [B,2,h,w]; flow_init, inter_flow, flow_out [B,2,H,W]; m [B,1,H,W]; x, out [B,C,H,W]. */
+EEM_API int eem_upsample_flow_warp(const float* coarse_flow, int h, int w, float scale0, float scale1,
+                                   const float* x, int B, int C, int H, int W, float* flow_out, float* out,
+                                   eem_stream_t stream);
+EEM_API int eem_blend_flow_warp(const float* flow_init, const float* inter_flow, const float* m,
+                                const float* x, int B, int C, int H, int W, float* flow_out, float* out,
+                                eem_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K8  bilinear resize of flow / meshflow maps
  * replaces: upsample2d_flow_as (model/EEMFlow/cdc_utils.py:80-103; utils_luo/tools.py:3215-3229)

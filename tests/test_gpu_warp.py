@@ -165,3 +165,51 @@ def test_upsample2d_flows_as_equals_the_list_of_calls():
     out = torch.empty(3, 2, 64, 96, device="cuda")
     res = E.upsample2d_flows_as([f.clone().cuda() for f in flows], torch.zeros(3, 1, 64, 96, device="cuda"), if_rate=True, out_last=out)
     assert res[-1].data_ptr() == out.data_ptr()
+
+
+def test_fused_level_chains_equal_the_separate_calls():
+    """upsample_warp_no_div == upsample2d_flow_as + WarpingLayer_no_div and blend_warp == cdc_blend + warp
+    (model/EEMFlow/cdc_utils.py:156-174, EEMFlow+.py:181): against the CPU restatement <= 1e-5 and against our own
+    separate kernels (same arithmetic: <= 1e-6, masks identical); the deferred in-place scaling handed to
+    upsample2d_flows_as(pre_scales=...) leaves outputs and inputs as the reference's call sequence does."""
+    import eemflow_b200 as E
+    gen = torch.Generator().manual_seed(21)
+    for (B, C, h, w, H, W) in ((2, 32, 10, 12, 20, 24), (1, 64, 12, 20, 24, 40), (3, 5, 5, 6, 10, 12)):
+        flow = 2.0 * torch.randn(B, 2, h, w, generator=gen)
+        p1 = torch.randn(B, 32, H, W, generator=gen)
+        p2 = torch.randn(B, 32, H, W, generator=gen)
+        f2 = torch.randn(B, C, H, W, generator=gen)
+        inter = 1.5 * torch.randn(B, 2, H, W, generator=gen)
+        mask = torch.sigmoid(torch.randn(B, 1, H, W, generator=gen))
+        # reference sequence (CPU restatement), including the in-place scaling of `flow`
+        r_flow = flow.clone()
+        r_up = ref_ops.upsample2d_flow_as(r_flow, p1, if_rate=True)
+        r_w = ref_ops.warping_layer_no_div(p2, r_up)
+        r_blend = ref_ops.cdc_blend(r_up, inter, mask)
+        r_f2w = ref_ops.warp_exact(f2, r_blend.clone())
+        # fused
+        d_flow = flow.clone().cuda()
+        up, wl, sc = E.upsample_warp_no_div(d_flow, p1.cuda(), p2.cuda())
+        blend, f2w = E.blend_warp(up, inter.cuda(), mask.cuda(), f2.cuda())
+        assert torch.equal(d_flow.cpu(), flow)                           # no side effect yet
+        assert sc == (W / w, H / h)
+        # separate kernels
+        s_flow = flow.clone().cuda()
+        s_up = E.upsample2d_flow_as(s_flow, p1.cuda(), mode="bilinear", if_rate=True)
+        s_wl = E.WarpingLayer_no_div()(p2.cuda(), s_up)
+        s_blend = E.cdc_blend(s_up, inter.cuda(), mask.cuda())
+        s_f2w = E.warp(f2.cuda(), s_blend)
+        # The >= 1.0 validity mask of WarpingLayer_no_div thresholds a weight sum that is 1 +- 1 ulp for interior samples,
+        # so it is exact only for an IDENTICAL input flow (tests above); here the flow comes from our resize kernel, whose
+        # last-ulp differences to ATen's interpolate flip isolated knife-edge pixels -- in the separate path just the same.
+        for got, sep, ref, flips in ((up, s_up, r_up, 0.0), (wl, s_wl, r_w, 0.03), (blend, s_blend, r_blend, 0.0), (f2w, s_f2w, r_f2w, 0.0)):
+            assert (got - sep).abs().max().item() <= 1e-6 * max(1.0, sep.abs().max().item())
+            bad = ((got.cpu() - ref).abs() > 1e-4 * max(1.0, ref.abs().max().item())).any(dim=1)      # per pixel
+            assert bad.float().mean().item() <= flips, (tuple(got.shape), bad.float().mean().item())
+        assert torch.equal(wl == 0, s_wl == 0)
+        # deferred scaling through the final upsampling: same prediction, same final state of the coarse flow
+        tgt = torch.zeros(B, 1, 2 * H, 2 * W)
+        r_final = ref_ops.upsample2d_flow_as(r_flow, tgt, if_rate=True)       # r_flow was scaled in place above, and is again here
+        (final,) = E.upsample2d_flows_as([d_flow], tgt.cuda(), if_rate=True, pre_scales=[sc])
+        assert (final.cpu() - r_final).abs().max().item() <= 1e-4 * max(1.0, r_final.abs().max().item())
+        assert (d_flow.cpu() - r_flow).abs().max().item() <= 1e-5 * max(1.0, r_flow.abs().max().item())

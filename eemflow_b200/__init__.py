@@ -15,6 +15,7 @@ from .corr import CorrBlock, bilinear_sampler, coords_grid, upflow8
 from .correlation import Correlation, SpatialCorrelationSampler, correlation_select
 from .eval_utils import center_crop, event_mask, event_valid_from_volume, flow_error, motion_propagate
 from .event_utils import EventSequence, EventSequenceToVoxelGrid_Pytorch
+from .ops import local_corr_precision, set_local_corr_precision
 from .warp import (InputPadder, WarpingLayer_no_div, blend_warp, cdc_blend, tensor_tools, torch_warp, torch_warp_mask,
                    upsample2d_flow_as, upsample2d_flows_as, upsample_flow, upsample_warp_no_div, warp)
 
@@ -24,5 +25,6 @@ __all__ = [
     "torch_warp_mask", "WarpingLayer_no_div", "upsample2d_flow_as", "upsample2d_flows_as", "upsample_flow",
     "upsample_warp_no_div", "blend_warp", "cdc_blend", "InputPadder",
     "event_mask", "event_valid_from_volume", "flow_error", "motion_propagate", "center_crop",
+    "set_local_corr_precision", "local_corr_precision",
 ]
 __version__ = "0.1.0"

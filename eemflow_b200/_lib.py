@@ -53,6 +53,8 @@ SIGNATURES = {
     "eem_avg_pool2x2": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "eem_corr_lookup": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eem_local_corr": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, _vp, _vp]),
+    "eem_local_corr_tf32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, _vp, _vp]),
+    "eem_local_corr_tf32_supported": (_i, [_i, _i, _i, _i, _i]),
     "eem_backwarp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eem_upsample_flow_warp": (_i, [_vp, _i, _i, _f, _f, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eem_blend_flow_warp": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

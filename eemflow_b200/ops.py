@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Sequence
 
 import torch
@@ -249,9 +250,41 @@ def bilinear_sample(img: torch.Tensor, coords: torch.Tensor, mask: bool = False)
 
 
 # ------------------------------------------------------------------------------------------ K6
+LOCAL_CORR_PRECISIONS = ("fp32", "tf32")
+_local_corr_precision: str | None = None
+
+
+def set_local_corr_precision(precision: str | None) -> None:
+    """Arithmetic of the local 9x9 correlation in inference: "fp32" (FFMA, what the reference's sampler computes;
+    the default) or "tf32" (tcgen05 banded GEMM, ~1e-3 relative).  None restores the default, which the
+    environment variable EEMFLOW_B200_LOCAL_CORR_PRECISION can override."""
+    global _local_corr_precision
+    if precision is not None and precision not in LOCAL_CORR_PRECISIONS:
+        raise ValueError(f"local-correlation precision must be one of {LOCAL_CORR_PRECISIONS}, got {precision!r}")
+    _local_corr_precision = precision
+
+
+def local_corr_precision() -> str:
+    if _local_corr_precision is not None:
+        return _local_corr_precision
+    env = os.environ.get("EEMFLOW_B200_LOCAL_CORR_PRECISION")
+    if env:
+        if env not in LOCAL_CORR_PRECISIONS:
+            raise ValueError(f"EEMFLOW_B200_LOCAL_CORR_PRECISION must be one of {LOCAL_CORR_PRECISIONS}, got {env!r}")
+        return env
+    return "fp32"
+
+
+def local_corr_tf32_supported(B: int, Cc: int, H: int, W: int, max_disp: int = 4) -> bool:
+    return bool(L.lib().eem_local_corr_tf32_supported(B, Cc, H, W, max_disp))
+
+
 def local_corr(f1: torch.Tensor, f2: torch.Tensor, max_disp: int = 4, index: Sequence[int] | None = None,
-               scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
-    """Local (2*md+1)^2 correlation, optional fused channel select and scale -> [B, n_out, H, W]."""
+               scale: float = 1.0, out: torch.Tensor | None = None, precision: str | None = None) -> torch.Tensor:
+    """Local (2*md+1)^2 correlation, optional fused channel select and scale -> [B, n_out, H, W].
+
+    precision None follows `local_corr_precision()`.  "tf32" runs the tcgen05 kernel on the shapes it takes
+    (W % 4 == 0) and the exact FFMA kernel on the others (the coarsest 5x6 level of the MVSEC pyramid)."""
     f1 = L.require_cuda(f1, "f1")
     f2 = L.require_cuda(f2, "f2")
     assert f1.shape == f2.shape and f1.dim() == 4
@@ -264,9 +297,15 @@ def local_corr(f1: torch.Tensor, f2: torch.Tensor, max_disp: int = 4, index: Seq
         idx = (C.c_int * n_out)(*[int(v) for v in index])
     if out is None:
         out = torch.empty((B, n_out, H, W), dtype=torch.float32, device=f1.device)
+    precision = precision or local_corr_precision()
+    if precision not in LOCAL_CORR_PRECISIONS:
+        raise ValueError(f"local-correlation precision must be one of {LOCAL_CORR_PRECISIONS}, got {precision!r}")
+    use_tc = (precision == "tf32" and local_corr_tf32_supported(B, Cc, H, W, max_disp)
+              and f1.data_ptr() % 16 == 0 and f2.data_ptr() % 16 == 0)
+    fn = L.lib().eem_local_corr_tf32 if use_tc else L.lib().eem_local_corr
     with torch.cuda.device(f1.device):
-        L.check(L.lib().eem_local_corr(f1.data_ptr(), f2.data_ptr(), B, Cc, H, W, max_disp, idx, n_out,
-                                       float(scale), out.data_ptr(), L.stream_ptr(f1.device)))
+        L.check(fn(f1.data_ptr(), f2.data_ptr(), B, Cc, H, W, max_disp, idx, n_out,
+                   float(scale), out.data_ptr(), L.stream_ptr(f1.device)))
     return out
 
 

@@ -205,6 +205,17 @@ EEM_API int eem_local_corr(const float* f1, const float* f2, int B, int C, int H
                            int max_disp, const int* index, int n_out, float scale, float* out,
                            eem_stream_t stream);
 
+/* K6t  the same operator with the channel contraction on the tensor cores (tcgen05 kind::tf32, fp32 accumulate):
+ * a banded GEMM per 4-row x 32-pixel block of f1 against the 12 x 40 window of f2 around it, operands read by TMA
+ * straight from the NCHW maps (csrc/local_corr_tc.cu).  Opt-in: products are rounded to TF32 (the sampler the
+ * reference calls computes them in fp32), results agree with eem_local_corr to ~1e-3 relative.
+ * Same arguments and errors as eem_local_corr; additionally EEM_ERR_UNSUPPORTED unless W % 4 == 0 and f1 / f2 are
+ * 16-byte aligned (eem_local_corr_tf32_supported() answers that without a device). */
+EEM_API int eem_local_corr_tf32(const float* f1, const float* f2, int B, int C, int H, int W,
+                                int max_disp, const int* index, int n_out, float scale, float* out,
+                                eem_stream_t stream);
+EEM_API int eem_local_corr_tf32_supported(int B, int C, int H, int W, int max_disp);
+
 /* ------------------------------------------------------------------------------------------
  * K7  backward warp (bilinear, zero padding)
  * replaces: EEMFlow_cdc.warp (model/EEMFlow/EEMFlow+.py:137-149)          -> EEM_WARP_EXACT

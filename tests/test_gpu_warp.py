@@ -55,6 +55,62 @@ def test_local_corr_oracle_eemflow_shapes(E, B, C, H, W):
     assert torch.equal(sel, out[:, EEMFLOW_CDC_INDEX])
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 10, 12), (2, 64, 20, 24), (2, 64, 40, 48), (1, 32, 80, 96), (1, 64, 96, 160),
+                                     (1, 19, 33, 36), (3, 40, 7, 100), (1, 8, 3, 4)])
+def test_local_corr_tf32_tensor_core(E, B, C, H, W):
+    """The tcgen05 banded-GEMM form of the local correlation (csrc/local_corr_tc.cu).  With inputs that are exactly
+    representable in TF32 (low 13 mantissa bits cleared) the products are exact, so it must agree with the oracle
+    like the FFMA kernel does (1e-5: accumulation order only) -- this pins every index of the band extraction,
+    the zero padding and the ragged edges.  With full-precision inputs the stated tolerance is 2e-3 of the
+    per-pixel feature energy |f1||f2|/C (TF32 rounds each factor to 10+1 bits: <= 2^-10 relative per product)."""
+    from eemflow_b200 import ops
+    from eemflow_b200.correlation import EEMFLOW_CDC_INDEX, EEMFLOW_INDEX
+    gen = torch.Generator().manual_seed(7 * C + H)
+    f1 = torch.randn(B, C, H, W, generator=gen)
+    f2 = torch.randn(B, C, H, W, generator=gen)
+
+    def tf32_exact(x):
+        return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+    a, b = tf32_exact(f1), tf32_exact(f2)
+    ref = ref_ops.correlation(a, b, 4)
+    assert ops.local_corr_tf32_supported(B, C, H, W)
+    out = ops.local_corr(a.cuda(), b.cuda(), scale=1.0 / C, precision="tf32").cpu()
+    assert (out - ref).abs().max().item() <= 1e-5
+    for idx in (EEMFLOW_CDC_INDEX, EEMFLOW_INDEX, [80, 0, 40]):
+        sel = ops.local_corr(a.cuda(), b.cuda(), index=idx, scale=1.0 / C, precision="tf32").cpu()
+        assert torch.equal(sel, out[:, idx])
+    # full-precision inputs: TF32 rounding only
+    ref = ref_ops.correlation(f1, f2, 4)
+    out = ops.local_corr(f1.cuda(), f2.cuda(), scale=1.0 / C, precision="tf32").cpu()
+    energy = (f1.norm(dim=1, keepdim=True) * torch.nn.functional.max_pool2d(f2.norm(dim=1, keepdim=True), 9, 1, 4)) / C
+    assert ((out - ref).abs() / energy.clamp_min(1e-6)).max().item() <= 2e-3
+    exact = ops.local_corr(f1.cuda(), f2.cuda(), scale=1.0 / C, precision="fp32").cpu()
+    assert (exact - ref).abs().max().item() <= 1e-5
+
+
+def test_local_corr_precision_switch(E):
+    """`set_local_corr_precision` routes Correlation / correlation_select; shapes the tensor-core kernel does not take
+    (W % 4 != 0) run the exact kernel whatever the switch says."""
+    from eemflow_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    f1, f2 = torch.randn(2, 32, 12, 16, generator=gen).cuda(), torch.randn(2, 32, 12, 16, generator=gen).cuda()
+    exact = E.Correlation(4)(f1, f2)
+    try:
+        E.set_local_corr_precision("tf32")
+        assert E.local_corr_precision() == "tf32"
+        fast = E.Correlation(4)(f1, f2)
+        assert not torch.equal(fast, exact) and (fast - exact).abs().max().item() <= 5e-3
+        g1, g2 = torch.randn(1, 16, 5, 6, generator=gen).cuda(), torch.randn(1, 16, 5, 6, generator=gen).cuda()
+        assert not ops.local_corr_tf32_supported(1, 16, 5, 6)
+        assert torch.equal(E.Correlation(4)(g1, g2), ops.local_corr(g1, g2, scale=1.0 / 16, precision="fp32"))
+    finally:
+        E.set_local_corr_precision(None)
+    assert E.local_corr_precision() == "fp32"
+    with pytest.raises(ValueError):
+        E.set_local_corr_precision("bf16")
+
+
 # ------------------------------------------------------------------------------------ warps
 def _mask_knife_edge(x, flo):
     """The reference thresholds grid_sample(ones) at 1.0 (cdc_utils.py:77) / 0.9999 (tools.py:2251); for an

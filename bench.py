@@ -79,6 +79,8 @@ def parse_args():
     ap.add_argument("--lookups", type=int, default=12, help="CorrBlock lookups per pair (ERAFT iterations)")
     ap.add_argument("--cpu-batch", type=int, default=None, help="frame pairs per CPU step (default: the whole batch for mvsec_dt1)")
     ap.add_argument("--corr", default="tf32_f16", choices=["tf32", "tf32_f16", "fp32"], help="CorrBlock precision / storage")
+    ap.add_argument("--local-corr", default="fp32", choices=["fp32", "tf32"],
+                    help="arithmetic of the local 9x9 correlations: FFMA kernel or the tcgen05 banded GEMM (TF32 products)")
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE configs[4] instead of the step bench: end-to-end EEMFlow_cdc inference at HREM resolution, global "
                          "batch 1..256 sharded over the ranks, with the CPU path (batch 1) beside it; prints one JSON line")
@@ -920,6 +922,8 @@ def main():
     extra = [w for w in extra if w != args.workload]
     dtype = {"tf32": "f32 (tf32 tensor-core volume, f64 event times)", "fp32": "f32 (f64 event times)",
              "tf32_f16": "f32 (tf32 tensor-core volume stored as fp16, f64 event times)"}[args.corr]
+    if args.local_corr == "tf32":
+        dtype = dtype.replace("f64 event times", "tf32 tensor-core local correlation, f64 event times")
 
     if args.impl == "reference":
         if rank != 0:
@@ -946,7 +950,9 @@ def main():
         return
 
     from eemflow_b200 import dist as edist
+    import eemflow_b200
     assert torch.cuda.is_available(), "bench.py (b200 arm) needs a CUDA device; there is no CPU fallback"
+    eemflow_b200.set_local_corr_precision(args.local_corr)
     rank, world, local_rank = edist.init_from_env("nccl")
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)

@@ -283,70 +283,87 @@ struct PackedPhases {
   static __device__ __forceinline__ float* fy_of(unsigned char* st, int l) { return fx_of(st, l) + PB * K; }
   static __device__ __forceinline__ int* org_of(unsigned char* st, int l) { return reinterpret_cast<int*>(fy_of(st, l) + PB * K); }
 
-  // 1) window geometry, one thread per (position, level): same arithmetic as corr_lookup_kernel
+  // 1) window geometry, one thread per (position, level, axis): same arithmetic as corr_lookup_kernel.  The x and the
+  //    y half of a (position, level) are independent (origin + K fractions each), so they run on different warps: the
+  //    phase is a dependent chain of ~10 coordinate round trips per thread and sits on the CTA's critical path.
   static __device__ __forceinline__ void geometry(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
-    const int P = p.H * p.W, L = p.L;
-    for (int t = threadIdx.x; t < PB * nl; t += blockDim.x) {
-      const int ls = t / PB, l = l0 + ls, pos = t % PB;      // ls: level slot in shared memory
-      const float sw = (float)(p.w[l] - 1), sh = (float)(p.h[l] - 1);
-      const float rw = p.rcp_w1[l], rh = p.rcp_h1[l];
-      float cx = 0.f, cy = 0.f;
-      if (pos < npos) {
-        cx = __ldg(p.coords + ((int64_t)b * 2 + 0) * P + i0 + pos);
-        cy = __ldg(p.coords + ((int64_t)b * 2 + 1) * P + i0 + pos);
-      }
-      const float inv = 1.0f / (float)(1 << l);
-      const float lx = cx * inv, ly = cy * inv;
-      const float ox = floorf(fminf(fmaxf(roundtrip_rcp(lx - (float)R, sw, rw), -1.0e6f), 1.0e6f));
-      const float oy = floorf(fminf(fmaxf(roundtrip_rcp(ly - (float)R, sh, rh), -1.0e6f), 1.0e6f));
-      {
-        const int oxi = (int)ox, tx0 = oxi >> 2, txl = p.tx[l];      // >> : floor for negatives
-        unsigned pack = 0, mask = 0;
+    const int P = p.H * p.W;
+    const int per_axis = PB * nl;
+    for (int t = threadIdx.x; t < 2 * per_axis; t += blockDim.x) {
+      const int axis = t >= per_axis ? 1 : 0, r = t - axis * per_axis;      // warp-uniform: PB is a warp
+      const int ls = r / PB, l = l0 + ls, pos = r % PB;                     // ls: level slot in shared memory
+      const float s1 = (float)((axis ? p.h[l] : p.w[l]) - 1);
+      const float rc = axis ? p.rcp_h1[l] : p.rcp_w1[l];
+      float c = 0.f;
+      if (pos < npos) c = __ldg(p.coords + ((int64_t)b * 2 + axis) * P + i0 + pos);
+      const float lc = c * (1.0f / (float)(1 << l));
+      const float o = floorf(fminf(fmaxf(roundtrip_rcp(lc - (float)R, s1, rc), -1.0e6f), 1.0e6f));
+      int* org = org_of(st, ls) + pos * 4;
+      float* frac = (axis ? fy_of(st, ls) : fx_of(st, ls)) + pos * K;
+      if (axis == 0) {
+        // record of (position, level) for the gather and the interpolation: .x = (ox & 3) | in-map mask of the NT tile
+        // columns << 4, .y = oy (written by the y thread), .z / .w = byte offsets (tile column * 32, 0 when outside the
+        // map) of the tile columns as four 16-bit fields
+        const int oxi = (int)o, tx0 = oxi >> 2, txl = p.tx[l];      // >> : floor for negatives
+        unsigned lo = 0, hi = 0, mask = 0;
 #pragma unroll
         for (int sx = 0; sx < NT; ++sx) {
           const int tx = tx0 + sx;
           const bool ok = (unsigned)tx < (unsigned)txl;
-          pack |= (unsigned)(ok ? tx : 0) << (8 * sx);
+          const unsigned field = (unsigned)(ok ? tx * 32 : 0) << (16 * (sx & 1));
+          if (sx < 2) lo |= field; else hi |= field;
           mask |= (unsigned)ok << sx;
         }
-        *reinterpret_cast<int4*>(org_of(st, ls) + pos * 4) = make_int4(oxi, (int)oy, (int)pack, (int)mask);
+        org[0] = (oxi & 3) | (int)(mask << 4);
+        *reinterpret_cast<int2*>(org + 2) = make_int2((int)lo, (int)hi);
+      } else {
+        org[1] = (int)o;
       }
-      float* fxp = fx_of(st, ls) + pos * K;
-      float* fyp = fy_of(st, ls) + pos * K;
 #pragma unroll
-      for (int a = 0; a < K; ++a) {
-        fxp[a] = roundtrip_rcp(lx + (float)(a - R), sw, rw) - (ox + (float)a);
-        fyp[a] = roundtrip_rcp(ly + (float)(a - R), sh, rh) - (oy + (float)a);
-      }
+      for (int a = 0; a < K; ++a) frac[a] = roundtrip_rcp(lc + (float)(a - R), s1, rc) - (o + (float)a);
     }
   }
 
-  // 2) gather: unit = (level, position, window row); the thread copies that row's 8-byte piece out of each of the NT
-  //    tiles the window's columns touch (zero-filled when the tile lies outside the map; cells of a partial last tile
+  // 2) gather: unit = (position, window row), all levels; the thread copies that row's 8-byte piece out of each of the
+  //    NT tiles the window's columns touch (zero-filled when the tile lies outside the map; cells of a partial last tile
   //    are zeros in the volume itself), so the patch in shared memory is a plain row-major image whose row 0 is the
-  //    window's first row.  Issues the copies and commits ONE cp.async group.
+  //    window's first row.  Everything position-dependent comes out of the geometry record with a handful of integer
+  //    instructions (32-bit byte offsets from the position's row, one 64-bit multiply-add per copy); the level loop is
+  //    unrolled so the per-level constants are direct constant-bank operands.  Issues the copies and commits ONE
+  //    cp.async group.
   static __device__ __forceinline__ void gather(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
-    const int P = p.H * p.W, L = p.L;
+    const int P = p.H * p.W;
     for (int u = threadIdx.x; u < PB * T; u += blockDim.x) {       // (position, window row): decoded once, then all levels
       const int pos = u / T, rr = u - pos * T;
       if (pos >= npos) continue;
-      const uint16_t* rowbase = p.packed + ((int64_t)b * P + i0 + pos) * p.row;
+      const unsigned char* rowbase = reinterpret_cast<const unsigned char*>(p.packed + ((int64_t)b * P + i0 + pos) * p.row);
       const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(st + pos * S::kStrideBytes + rr * S::kRowBytes);
-      for (int ls = 0; ls < nl; ++ls) {
+      const uint32_t org0 = (uint32_t)__cvta_generic_to_shared(org_of(st, 0) + pos * 4);
+#pragma unroll
+      for (int ls = 0; ls < kMaxLevels; ++ls) {
+        if (ls >= nl) break;
         const int l = l0 + ls;
         const int txl = p.tx[l], tyl = p.ty[l];
         if (txl == 0 || tyl == 0) continue;                        // empty level
-        const int4 g = *reinterpret_cast<const int4*>(org_of(st, ls) + pos * 4);   // ox, oy, clamped tile columns, column mask
+        int4 g;                                                    // (ox & 3) | mask << 4, oy, tile-column byte offsets
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g.x), "=r"(g.y), "=r"(g.z), "=r"(g.w) : "r"(org0 + ls * S::kPerLevelBytes));
         const int py = g.y + rr;                                   // map row of this window row
         const int ty = py >> 2;                                    // >> : floor for negatives
         const bool row_ok = (unsigned)ty < (unsigned)tyl;
-        const uint16_t* src = rowbase + p.off[l] + (row_ok ? (ty * txl * 16 + (py & 3) * 4) : 0);
+        const unsigned live = row_ok ? ((unsigned)g.x >> 4) : 0u;  // tile columns to fetch
+        const unsigned roff = (unsigned)p.off[l] * 2u + (row_ok ? (unsigned)(ty * txl * 32 + (py & 3) * 8) : 0u);
         const uint32_t dst = dst0 + ls * S::kPerLevelBytes;
 #pragma unroll
         for (int sx = 0; sx < NT; ++sx) {
-          const unsigned tx = ((unsigned)g.z >> (8 * sx)) & 255u;
-          const bool ok = row_ok && (((unsigned)g.w >> sx) & 1u);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + sx * 8), "l"(src + tx * 16), "r"(ok ? 8 : 0) : "memory");
+          const unsigned field = ((sx < 2 ? (unsigned)g.z : (unsigned)g.w) >> (16 * (sx & 1))) & 0xffffu;
+          const unsigned char* src;
+          asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(src) : "r"(roff + field), "l"(rowbase));
+          asm volatile(
+              "{\n"
+              ".reg .pred q;\n"
+              "setp.eq.u32 q, %2, 0;\n"
+              "cp.async.ca.shared.global [%0], [%1], 8, q;\n"       // q = ignore-src: the 8 bytes are zero-filled
+              "}\n" ::"r"(dst + sx * 8), "l"(src), "r"(live & (1u << sx)) : "memory");
         }
       }
     }
@@ -399,9 +416,6 @@ struct PackedPhases {
 #pragma unroll
         for (int g = 0; g < G; ++g) prev[g] = t[g] + fx[g] * (t[g + 1] - t[g]);
       }
-      float* og[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) og[g] = o + (int64_t)(g * K) * P;
 #pragma unroll
       for (int c = 0; c < K; ++c) {
         float t[G + 1];
@@ -410,8 +424,10 @@ struct PackedPhases {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const float cur = t[g] + fx[g] * (t[g + 1] - t[g]);
-          if (a0 + g < K) st_stream(og[g], prev[g] + fy * (cur - prev[g]));
-          og[g] += P;
+          // output channel (a0 + g) * K + c: one 32 x 32 -> 64-bit multiply-add per store address
+          float* dst;
+          asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(dst) : "r"(P), "r"((g * K + c) * 4), "l"(o));
+          if (a0 + g < K) st_stream(dst, prev[g] + fy * (cur - prev[g]));
           prev[g] = cur;
         }
       }
@@ -422,19 +438,18 @@ struct PackedPhases {
 // One batch per CTA (the default).
 template <int R>
 __global__ void __launch_bounds__(PackedSmem<R>::kThreads)
-corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p, int levels_per_cta) {
+corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
   using Ph = PackedPhases<R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int P = p.H * p.W;
   const int b = blockIdx.y, i0 = blockIdx.x * Ph::PB;
   const int npos = min(Ph::PB, P - i0);
-  const int l0 = blockIdx.z * levels_per_cta, nl = min(levels_per_cta, p.L - l0);   // this CTA's levels
-  Ph::geometry(p, smem_raw, b, i0, npos, l0, nl);
+  Ph::geometry(p, smem_raw, b, i0, npos, 0, p.L);
   __syncthreads();
-  Ph::gather(p, smem_raw, b, i0, npos, l0, nl);
+  Ph::gather(p, smem_raw, b, i0, npos, 0, p.L);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  Ph::interp(p, smem_raw, b, i0, npos, l0, nl);
+  Ph::interp(p, smem_raw, b, i0, npos, 0, p.L);
 }
 
 // Persistent, software-pipelined form (experiment, EEM_LOOKUP_PACKED_PIPE=1): a CTA walks batches blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -515,24 +530,17 @@ int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
     corr_lookup_packed_pipe_kernel<R><<<(unsigned)grid, S::kThreads, 2 * stage, stream>>>(p, bps, (int)n_batches, (int)stage);
     return EEM_OK;
   }
-  // levels per CTA (EEM_LOOKUP_PACKED_LPC, default all): fewer levels per CTA = smaller, more numerous CTAs whose
-  // geometry / gather / interpolation phases interleave on an SM
-  static const int lpc_env = [] {
-    const char* v = getenv("EEM_LOOKUP_PACKED_LPC");
-    return v != nullptr ? atoi(v) : 0;
-  }();
-  const int lpc = (lpc_env >= 1 && lpc_env < p.L) ? lpc_env : p.L;
   // EEM_LOOKUP_PACKED_PAD_KB (timing experiments only): extra dynamic shared memory per CTA, i.e. fewer CTAs per SM
   static const size_t pad_bytes = [] {
     const char* v = getenv("EEM_LOOKUP_PACKED_PAD_KB");
     return v != nullptr ? (size_t)atoi(v) * 1024 : (size_t)0;
   }();
-  const size_t smem = (size_t)lpc * S::kPerLevelBytes + pad_bytes;
-  const int threads = 32 * ((lpc * S::kGroups + 0) > 0 ? lpc * S::kGroups : 1);
-  dim3 grid((unsigned)bps, (unsigned)p.B, (unsigned)ceil_div(p.L, lpc));
+  const size_t smem = (size_t)p.L * S::kPerLevelBytes + pad_bytes;
+  const int threads = 32 * p.L * S::kGroups;                    // one interpolation task per warp
+  dim3 grid((unsigned)bps, (unsigned)p.B, 1);
   static DynSmemOptIn optin;
   if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_kernel<R>, smem));
-  corr_lookup_packed_kernel<R><<<grid, threads < 64 ? 64 : threads, smem, stream>>>(p, lpc);
+  corr_lookup_packed_kernel<R><<<grid, threads < 64 ? 64 : (threads > S::kThreads ? S::kThreads : threads), smem, stream>>>(p);
   return EEM_OK;
 }
 

@@ -11,6 +11,7 @@
 // float4 and three f2 float4 (12 consecutive columns) from shared memory and issues 36 FMAs, so
 // the loop is FMA-bound rather than LDS-bound.  Channels stream through shared memory in chunks
 // of 8 with the f2 halo (+-4) loaded once per chunk.
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 
@@ -285,6 +286,113 @@ local_corr_vec_kernel(const __grid_constant__ LocalCorrParams p) {
   }
 }
 
+// ---- small maps (the coarsest pyramid levels: 5x6, 10x12, 12x20) -------------------------------------------------
+// With a few hundred pixels per sample the tiled kernels above run 8 strictly serial load -> barrier -> FMA rounds per
+// CTA on a fraction of the SMs (16-18 us for < 1 MB of data).  Here a CTA owns (sample, dy): it pulls ALL channels of
+// f1 and of the f2 rows y + dy (zero rows outside the map, zero halo columns) into shared memory with every copy in
+// flight at once, then thread = (pixel, channel quarter) accumulates the nine dx of its pixel over its channels and
+// the quarters are summed in a fixed order through shared memory: one memory round trip instead of eight.
+constexpr int kSmallMaxPix = 256;
+constexpr int kSmallGroups = 4;
+
+struct SmallPlan {
+  bool ok;
+  int pixp, threads;     // pixels rounded up to a warp multiple; pixp * kSmallGroups threads
+  size_t smem;
+};
+
+inline SmallPlan small_plan(int C, int H, int W) {
+  SmallPlan s{false, 0, 0, 0};
+  const int hw = H * W;
+  if (hw > kSmallMaxPix) return s;
+  s.pixp = (hw + 31) / 32 * 32;
+  s.threads = s.pixp * kSmallGroups;
+  // f1 [C][hw] | f2 [C][H][W + 2 MD] | partial sums [groups - 1][ND][pixp]
+  s.smem = ((size_t)C * hw + (size_t)C * H * (W + 2 * MD) + (size_t)(kSmallGroups - 1) * ND * s.pixp) * sizeof(float);
+  s.ok = s.smem <= 160 * 1024;
+  return s;
+}
+
+__global__ void __launch_bounds__(kSmallMaxPix * kSmallGroups)
+local_corr_small_kernel(const __grid_constant__ LocalCorrParams p, int pixp) {
+  extern __shared__ __align__(16) float smem[];
+  const int dyi = blockIdx.x, dy = dyi - MD, b = blockIdx.y;
+  unsigned row_mask = 0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) row_mask |= (unsigned)(p.slot[dyi * ND + d] >= 0) << d;
+  if (row_mask == 0) return;                       // no selected displacement in this row (block-uniform)
+  const int H = p.H, W = p.W, C = p.C, hw = H * W, W2 = W + 2 * MD;
+  float* s1 = smem;
+  float* s2 = s1 + C * hw;
+  float* part = s2 + C * H * W2;
+  const float* f1 = p.f1 + (int64_t)b * C * hw;
+  const float* f2 = p.f2 + (int64_t)b * C * hw;
+  const int nthr = blockDim.x;
+
+  for (int i = threadIdx.x; i < C * hw; i += nthr) {
+    const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(s1 + i);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d1), "l"(f1 + i) : "memory");
+    const int c = i / hw, r = i - c * hw, y = r / W, x = r - y * W;
+    const int y2 = y + dy;
+    const bool ok = y2 >= 0 && y2 < H;
+    const uint32_t d2 = (uint32_t)__cvta_generic_to_shared(s2 + (c * H + y) * W2 + MD + x);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d2), "l"(f2 + (ok ? i + dy * W : 0)), "r"(ok ? 4 : 0) : "memory");
+  }
+  for (int i = threadIdx.x; i < C * H * 2 * MD; i += nthr) {      // halo columns (disjoint from the copies above)
+    const int row = i / (2 * MD), k = i - row * (2 * MD);
+    s2[row * W2 + (k < MD ? k : W + k)] = 0.f;
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int pix = threadIdx.x % pixp, g = threadIdx.x / pixp;
+  const bool live = pix < hw;
+  float acc[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) acc[d] = 0.f;
+  if (live) {
+    const int y = pix / W, x = pix - y * W;
+    const int cpg = (C + kSmallGroups - 1) / kSmallGroups;
+    const int c_end = min(C, (g + 1) * cpg);
+    const float* a = s1 + pix;
+    const float* w = s2 + y * W2 + x;
+#pragma unroll 4
+    for (int c = g * cpg; c < c_end; ++c) {
+      const float av = a[c * hw];
+      const float* row = w + c * H * W2;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) acc[d] = fmaf(av, row[d], acc[d]);
+    }
+  }
+  if (g > 0) {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) part[((g - 1) * ND + d) * pixp + pix] = acc[d];
+  }
+  __syncthreads();
+  if (g != 0 || !live) return;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const int slot = p.slot[dyi * ND + d];
+    if (slot < 0) continue;
+    float v = acc[d];
+#pragma unroll
+    for (int q = 0; q < kSmallGroups - 1; ++q) v += part[(q * ND + d) * pixp + pix];
+    p.out[((int64_t)b * p.n_out + slot) * hw + pix] = v * p.scale;
+  }
+}
+
+int launch_small(const LocalCorrParams& p, const SmallPlan& sp, cudaStream_t stream) {
+  static DynSmemOptIn optin;
+  if (sp.smem > 48 * 1024) {
+    const cudaError_t attr_err = optin.ensure(local_corr_small_kernel, sp.smem);
+    if (attr_err != cudaSuccess) return fail(EEM_ERR_CUDA, "local_corr_small_kernel attribute: %s", cudaGetErrorString(attr_err));
+  }
+  local_corr_small_kernel<<<dim3(ND, (unsigned)p.B), sp.threads, sp.smem, stream>>>(p, sp.pixp);
+  EEM_CHECK_LAUNCH("local_corr_small_kernel");
+  return EEM_OK;
+}
+
 template <unsigned MA, unsigned MB, unsigned MC, unsigned MD_, unsigned ME>
 int launch_vec(const LocalCorrParams& p, int B, int H, int W, cudaStream_t stream) {
   const size_t smem = 2 * (size_t)kStageFloats * sizeof(float);
@@ -326,6 +434,15 @@ extern "C" int eem_local_corr(const float* f1, const float* f2, int B, int C, in
         return fail(EEM_ERR_UNSUPPORTED, "eem_local_corr: repeated channel %d in index list", index[k]);
       p.slot[index[k]] = (signed char)k;
     }
+  }
+  {
+    // small maps: whole-map-per-CTA kernel (EEM_LC_SMALL=0 switches it off for comparisons)
+    static const bool small_on = [] {
+      const char* v = getenv("EEM_LC_SMALL");
+      return !(v != nullptr && atoi(v) == 0);
+    }();
+    const SmallPlan sp = small_plan(C, H, W);
+    if (small_on && sp.ok) return launch_small(p, sp, as_stream(stream_));
   }
   const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) |
                                         reinterpret_cast<uintptr_t>(out)) % 16 == 0);

@@ -5,24 +5,27 @@
 // (fp32 accumulate) instead of FFMA.  Opt-in: the products carry 10-bit mantissas, the reference's are fp32.
 //
 // Formulation.  For a block of 4 image rows x 32 pixels of f1 (M = 128 TMEM lanes) and ONE row of 64 pixels of f2
-// starting 4 pixels left of the block (N = 64 TMEM columns),
-//     D[(r, j)][n] = sum_c f1[c, y0 + r, x0 + j] * f2[c, y2, x0 - 4 + n]
-// holds, on the diagonal band n = j + dx + 4 (dx = -4..4), the nine displacements of vertical offset dy = y2 - (y0 + r).
+// starting 8 pixels left of the block (N = 64 TMEM columns),
+//     D[(r, j)][n] = sum_c f1[c, y0 + r, x0 + j] * f2[c, y2, x0 - 8 + n]
+// holds, on the diagonal band n = j + dx + 8 (dx = -4..4), the nine displacements of vertical offset dy = y2 - (y0 + r).
+// (8, not 4: a TMA box whose first byte is not 32-byte aligned is delivered at half rate or less -- measured 33.8 us
+// against 18.9 us for the 40 x 48 x 64-channel level -- and x0 - 8 keeps every f2 box sector-aligned.)
 // A job is (sample, 32-pixel column, 4-row block k of f1, 4-row block m = k - 1 | k | k + 1 of f2): 4 f2 rows x 64
-// columns = 256 TMEM columns, accumulated over C in stages of 32 channels.  Every (dy, dx) of every pixel is
-// produced by exactly one job, so jobs are independent and nothing is accumulated in global memory; f2 rows /
-// columns outside the image are zero-filled by TMA, which is the reference's zero padding.
+// columns = ONE 256-column operand (M = 128, N = 256 MMAs), accumulated over C in stages of 32 channels.  Every
+// (dy, dx) of every pixel is produced by exactly one job, so jobs are independent and nothing is accumulated in global
+// memory; f2 rows / columns outside the image are zero-filled by TMA, which is the reference's zero padding.
 //
-// Both operands are read "MN-major" straight from the NCHW fp32 maps: a TMA box is [32 channels][1 row][32 pixels]
-// (4 KiB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), the same canonical layout corr_volume.cu uses.  Per stage: 4 boxes of
-// f1 + 8 boxes of f2 = 48 KiB, 16 MMAs of 128 x 64 x 8.
+// Both operands are read "MN-major" straight from the NCHW fp32 maps: a TMA box is [4 rows][32 channels][32 pixels]
+// (16 KiB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), i.e. four of the canonical 4-KiB operand groups corr_volume.cu uses.
+// Per stage: 1 box of f1 + 2 boxes of f2 = 48 KiB, 4 MMAs of 128 x 256 x 8.
 //
-// Roles (192 threads, one persistent CTA per SM): warps 0-3 epilogue (warp r = f1 row r of the block = TMEM lane
-// quarter r), warp 4 TMA producer, warp 5 MMA issuer.  TMEM holds two 256-column accumulators so the epilogue of
-// job i overlaps the MMAs of job i + 1.  The epilogue pulls the 40 live columns of a (row r, f2 row s) pair out of
-// TMEM, stages them in shared memory (pitch 44: conflict-free 16-byte row writes and conflict-free diagonal reads)
-// and each lane picks its own diagonal: lane j reads column j + d, so a warp stores 32 consecutive pixels of one
-// output channel per instruction (128-byte coalesced).
+// Roles (320 threads, one persistent CTA per SM, a contiguous range of jobs each): warps 0-7 epilogue (warp w -> f1
+// row w % 4 of the block = TMEM lane quarter, f2 rows 2 * (w / 4) and 2 * (w / 4) + 1 of the job), warp 8 TMA producer,
+// warp 9 MMA issuer.  TMEM holds two 256-column accumulators so the epilogue of job i overlaps the MMAs of job i + 1.
+// The epilogue pulls columns 0 .. 47 of a (row r, f2 row s) pair out of TMEM, stages the 40 live ones in shared memory
+// (pitch 44: conflict-free 16-byte row writes and conflict-free diagonal reads) and each lane picks its own diagonal:
+// lane j reads staged column j + d, so a warp stores 32 consecutive pixels of one output channel per instruction
+// (128-byte coalesced).
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -43,7 +46,9 @@ constexpr int kEpiWarps = 8;                             // two per TMEM lane qu
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kPitch = 44;                                // staging row pitch (floats)
-constexpr int kLive = 40;                                 // columns j + d + ... of a 64-column row that the band touches
+constexpr int kF2Shift = 8;                               // f2 boxes start 8 px (32 B: one sector) left of the f1 block
+constexpr int kLive = 40;                                 // columns 4 .. 43 of a 64-column row are the ones the band touches
+constexpr int kLd = 48;                                   // columns pulled out of TMEM per row (32 + 16)
 // kind::tf32, fp32 accumulate, both operands MN-major, M = 128, N = 256 (the four f2 rows of a job are 8 consecutive
 // boxes, i.e. ONE 256-column operand: f1 is read from shared memory once per k-step instead of once per f2 row)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
@@ -78,9 +83,9 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// the 40 live columns of one f2 row (32 from the left 32-pixel group, 8 from the right one, 128 columns further)
-// of this warp's 32 lanes -> 40 registers per lane (the wait is the caller's)
-__device__ __forceinline__ void tmem_ld40(uint32_t (&v)[kLive], uint32_t taddr) {
+// columns 0 .. 47 of one f2 row (32 from the left 32-pixel group, 16 from the right one, 128 columns further) of this
+// warp's 32 lanes -> 48 registers per lane (the wait is the caller's); the band lives in columns 4 .. 43
+__device__ __forceinline__ void tmem_ld48(uint32_t (&v)[kLd], uint32_t taddr) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -91,8 +96,9 @@ __device__ __forceinline__ void tmem_ld40(uint32_t (&v)[kLive], uint32_t taddr) 
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-      : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39])
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+        "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47])
       : "r"(taddr + 128));
 }
 
@@ -107,6 +113,8 @@ __device__ __forceinline__ void st_stream_if(float* ptr, float v, bool pred) {
       : "memory");
 }
 
+// Jobs are numbered ((sample * ntx + column) * nby + k) * 3 + pass; a CTA owns a contiguous range, decoded once and
+// then advanced with carries (no division in the per-job loops of the three roles).
 struct Job {
   int b, x0, k, pass;   // f1 rows 4k .. 4k+3, f2 rows 4(k + pass - 1) ..
   __device__ __forceinline__ void decode(const LcTcParams& p, int job) {
@@ -117,6 +125,16 @@ struct Job {
     x0 = (t % p.ntx) * 32;
     b = t / p.ntx;
   }
+  __device__ __forceinline__ void next(const LcTcParams& p) {
+    if (++pass == 3) {
+      pass = 0;
+      if (++k == p.nby) {
+        k = 0;
+        x0 += 32;
+        if (x0 >= p.ntx * 32) { x0 = 0; ++b; }
+      }
+    }
+  }
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -125,6 +143,8 @@ local_corr_tf32_kernel(const __grid_constant__ LcTcParams p) {
   LcTcSmem& s = *reinterpret_cast<LcTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = (p.C + kBK - 1) / kBK;
+  const int per_cta = (p.n_jobs + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int job_begin = min((int)blockIdx.x * per_cta, p.n_jobs), job_end = min(job_begin + per_cta, p.n_jobs);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -146,21 +166,26 @@ local_corr_tf32_kernel(const __grid_constant__ LcTcParams p) {
     const uint64_t keep = policy_evict_last();   // every box is re-read by the neighbouring jobs
     int stage = 0;
     uint32_t phase = 0;
-    for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x) {
-      Job j;
-      j.decode(p, job);
+    Job j;
+    j.decode(p, job_begin);
+    for (int job = job_begin; job < job_end; ++job, j.next(p)) {
       const int y1 = 4 * j.k, y2 = 4 * (j.k + j.pass - 1);
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&s.empty[stage], phase ^ 1);
         if (p.debug & 4) {
           if (elect_one()) mbar_arrive(&s.full[stage]);
         } else if (elect_one()) {
-          mbar_expect_tx(&s.full[stage], kStageBytes);
+          // timing experiments: 16 skips the f1 box, 32 the f2 boxes, 64 loads the f2 boxes 128-byte aligned (wrong data)
+          const uint32_t bytes = ((p.debug & 16) ? 0u : kABoxes * kBoxBytes) + ((p.debug & 32) ? 0u : kBBoxes * kBoxBytes);
+          const int xs = (p.debug & 64) ? 0 : kF2Shift;
+          mbar_expect_tx(&s.full[stage], bytes);
           uint8_t* dst = s.ring[stage];
           // one box = 32 px x 32 channels x 4 rows (16 KiB), written as [row][channel][32 px]: four 4-KiB operand groups
-          tma_load_4d(dst, &p.map1, j.x0, kb * kBK, y1, j.b, &s.full[stage], keep);
-          tma_load_4d(dst + kABoxes * kBoxBytes, &p.map2, j.x0 - kMD, kb * kBK, y2, j.b, &s.full[stage], keep);
-          tma_load_4d(dst + (kABoxes + 4) * kBoxBytes, &p.map2, j.x0 - kMD + 32, kb * kBK, y2, j.b, &s.full[stage], keep);
+          if (!(p.debug & 16)) tma_load_4d(dst, &p.map1, j.x0, kb * kBK, y1, j.b, &s.full[stage], keep);
+          if (!(p.debug & 32)) {
+            tma_load_4d(dst + kABoxes * kBoxBytes, &p.map2, j.x0 - xs, kb * kBK, y2, j.b, &s.full[stage], keep);
+            tma_load_4d(dst + (kABoxes + 4) * kBoxBytes, &p.map2, j.x0 - xs + 32, kb * kBK, y2, j.b, &s.full[stage], keep);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -170,7 +195,7 @@ local_corr_tf32_kernel(const __grid_constant__ LcTcParams p) {
     // ===== MMA issuer =====
     int stage = 0;
     uint32_t phase = 0, n = 0;
-    for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++n) {
+    for (int job = job_begin; job < job_end; ++job, ++n) {
       const uint32_t acc = n & 1;
       mbar_wait(&s.acc_empty[acc], ((n >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -204,9 +229,9 @@ local_corr_tf32_kernel(const __grid_constant__ LcTcParams p) {
     const int r = warp & 3, half = warp >> 2;
     const int64_t plane = (int64_t)p.H * p.W;
     uint32_t n = 0;
-    for (int job = blockIdx.x; job < p.n_jobs; job += gridDim.x, ++n) {
-      Job j;
-      j.decode(p, job);
+    Job j;
+    j.decode(p, job_begin);
+    for (int job = job_begin; job < job_end; ++job, ++n, j.next(p)) {
       const uint32_t acc = n & 1;
       const int dy0 = 4 * (j.pass - 1) + 2 * half - r, dy1 = dy0 + 1;          // warp-uniform
       const unsigned mask0 = (dy0 >= -kMD && dy0 <= kMD && !(p.debug & 8)) ? p.row_mask[dy0 + kMD] : 0u;
@@ -215,9 +240,9 @@ local_corr_tf32_kernel(const __grid_constant__ LcTcParams p) {
       tc_fence_after();
       // f2 row q of the job, pixel column n (0..63): TMEM column (n / 32) * 128 + q * 32 + n % 32
       const uint32_t taddr = tmem + ((uint32_t)(r * 32) << 16) + acc * kAccCols + half * 64;
-      uint32_t v0[kLive], v1[kLive];
-      if (mask0) tmem_ld40(v0, taddr);
-      if (mask1) tmem_ld40(v1, taddr + 32);
+      uint32_t v0[kLd], v1[kLd];
+      if (mask0) tmem_ld48(v0, taddr);
+      if (mask1) tmem_ld48(v1, taddr + 32);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -226,11 +251,12 @@ local_corr_tf32_kernel(const __grid_constant__ LcTcParams p) {
       const int y = 4 * j.k + r, x = j.x0 + lane;
       const bool px_ok = y < p.H && x < p.W && !(p.debug & 2);
       float* obase = p.out + (int64_t)j.b * p.n_out * plane + (int64_t)y * p.W + x;
-      auto extract = [&](const uint32_t (&v)[kLive], int dy) {
+      auto extract = [&](const uint32_t (&v)[kLd], int dy) {
+        // staging column c = TMEM column c + 4: pixel j, displacement column d sits at TMEM column j + d + 4
 #pragma unroll
         for (int q = 0; q < kLive / 4; ++q)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + 16 * q), "r"(v[4 * q]), "r"(v[4 * q + 1]),
-                       "r"(v[4 * q + 2]), "r"(v[4 * q + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + 16 * q), "r"(v[4 * q + 4]), "r"(v[4 * q + 5]),
+                       "r"(v[4 * q + 6]), "r"(v[4 * q + 7]) : "memory");
         __syncwarp();
         int sl[12];
 #pragma unroll

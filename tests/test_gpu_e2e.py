@@ -17,7 +17,10 @@ class Seq:
         self.features, self.image_height, self.image_width = features, h, w
 
 
-def test_eemflow_cdc_forward_from_events(golden):
+@pytest.mark.parametrize("local_corr", ["fp32", "tf32"])
+def test_eemflow_cdc_forward_from_events(golden, local_corr):
+    """local_corr="tf32": the five local 9x9 correlations on the tcgen05 banded-GEMM kernel (TF32 products, fp32
+    accumulation) -- same end-to-end gate as the north star states for the TF32 correlation volume."""
     import eemflow_b200 as E
     from eemflow_b200.models import EEMFlow_cdc
     assert torch.cuda.is_available(), "GPU tests selected but no CUDA device is visible"
@@ -27,6 +30,7 @@ def test_eemflow_cdc_forward_from_events(golden):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
+        E.set_local_corr_precision(local_corr)
         enc = E.EventSequenceToVoxelGrid_Pytorch(nb, gpu=True, normalize=True, forkserver=False)
         v1 = enc(Seq(g["events1"].copy(), h, w))[None]
         v2 = enc(Seq(g["events2"].copy(), h, w))[None]
@@ -43,8 +47,9 @@ def test_eemflow_cdc_forward_from_events(golden):
             assert tuple(f.shape) == ref.shape == (1, 2, h, w)
             d = np.abs(f.cpu().numpy() - ref)
             rel = d.mean() / np.abs(ref).mean()
-            assert rel <= 1e-3, (k, rel, d.max())
+            assert rel <= 1e-3, (local_corr, k, rel, d.max())
     finally:
+        E.set_local_corr_precision(None)
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 

@@ -41,7 +41,9 @@ def test_local_corr_golden(golden, E, name):
         assert np.abs(sel.cpu().numpy() - ref[:, idx]).max() <= 1e-5
 
 
-@pytest.mark.parametrize("B,C,H,W", [(2, 64, 5, 6), (2, 64, 40, 48), (1, 32, 80, 96), (1, 64, 96, 160), (1, 32, 192, 320), (1, 19, 33, 37)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 5, 6), (2, 64, 40, 48), (1, 32, 80, 96), (1, 64, 96, 160), (1, 32, 192, 320), (1, 19, 33, 37),
+                                     # whole-map-per-CTA kernel (<= 256 pixels): coarsest MVSEC / HREM levels, ragged, 1 x 1, the limit
+                                     (32, 64, 10, 12), (2, 64, 12, 20), (3, 41, 7, 9), (2, 8, 1, 1), (1, 5, 16, 16), (1, 3, 2, 128)])
 def test_local_corr_oracle_eemflow_shapes(E, B, C, H, W):
     """EEMFlow_cdc pyramid shapes at MVSEC (pad 320x384) and HREM (pad 768x1280), plus a ragged one."""
     gen = torch.Generator().manual_seed(C + H)

@@ -79,8 +79,9 @@ def parse_args():
     ap.add_argument("--lookups", type=int, default=12, help="CorrBlock lookups per pair (ERAFT iterations)")
     ap.add_argument("--cpu-batch", type=int, default=None, help="frame pairs per CPU step (default: the whole batch for mvsec_dt1)")
     ap.add_argument("--corr", default="tf32_f16", choices=["tf32", "tf32_f16", "fp32"], help="CorrBlock precision / storage")
-    ap.add_argument("--local-corr", default="fp32", choices=["fp32", "tf32"],
-                    help="arithmetic of the local 9x9 correlations: FFMA kernel or the tcgen05 banded GEMM (TF32 products)")
+    ap.add_argument("--local-corr", default="tf32", choices=["fp32", "tf32"],
+                    help="arithmetic of the local 9x9 correlations: the tcgen05 banded GEMM (TF32 products, fp32 accumulation; the "
+                         "same end-to-end gate as the TF32 correlation volume, tests/test_gpu_e2e.py) or the exact FFMA kernel")
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE configs[4] instead of the step bench: end-to-end EEMFlow_cdc inference at HREM resolution, global "
                          "batch 1..256 sharded over the ranks, with the CPU path (batch 1) beside it; prints one JSON line")

@@ -1374,6 +1374,179 @@ voxel_cluster_kernel(const Src ev, const int64_t* __restrict__ offsets, int n_wi
   cluster.sync();   // keep every CTA's shared memory alive until all peers are done with it
 }
 
+// ---- cluster-resident NORMALISATION (windows whose grid fits the shared memory of one 8-CTA cluster) ------------------
+// K2 as two kernels reads every voxel twice and writes it once, with a launch boundary in between because the
+// statistics are a whole-window reduction.  For MVSEC-sized windows (5 x 260 x 346 fp32 = 1.8 MB) one 8-CTA cluster
+// holds a whole window in its shared memory (8 x 225 KB): every CTA pulls its eighth in ONCE while accumulating the
+// non-zero statistics, the partials are exchanged over distributed shared memory (cluster barrier, rank-ordered sum, so
+// the result does not depend on scheduling), and the normalised values are written back from shared memory -- one
+// launch, 8 bytes of traffic per voxel instead of 12.  Same arithmetic as voxel_stats_kernel / finish_stats_at /
+// voxel_apply_kernel.  (The votes themselves stay L2 atomics: shared memory has no float RED, see cluster_plan().)
+__global__ void __launch_bounds__(kClusterThreads, 1)
+voxel_normalize_cluster_kernel(float* __restrict__ grid, int n_windows, int64_t vox, int slice, double* __restrict__ stats_out) {
+  extern __shared__ __align__(16) float cl_smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / kClusterSize, n_clusters = gridDim.x / kClusterSize;
+  float* mine = cl_smem;
+  double* red = reinterpret_cast<double*>(cl_smem + slice);     // slice is a multiple of 4 floats
+  double* partial = red + 96;
+  float* ms = reinterpret_cast<float*>(partial + 3);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int w = cluster_id; w < n_windows; w += n_clusters) {
+    float* g = grid + (int64_t)w * vox + (int64_t)rank * slice;
+    const int64_t left = vox - (int64_t)rank * slice;             // cells of this slice inside the window
+    const int valid = (int)(left < 0 ? 0 : (left < slice ? left : slice));
+    const int nvec = valid / 4;                                   // the caller guarantees 16-byte aligned windows
+    double c = 0, s = 0, q = 0;
+    constexpr int kU = 7;                                         // loads in flight per thread (MVSEC: 2 rounds of 7)
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += kClusterThreads * kU) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * kClusterThreads;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nvec) v[u] = __ldcs(reinterpret_cast<const float4*>(g) + i);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * kClusterThreads;
+        if (i < nvec) *reinterpret_cast<float4*>(mine + 4 * i) = v[u];
+        accum_stat(v[u].x, c, s, q);                              // zeros (also the padding ones) do not count
+        accum_stat(v[u].y, c, s, q);
+        accum_stat(v[u].z, c, s, q);
+        accum_stat(v[u].w, c, s, q);
+      }
+    }
+    for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads) {
+      const float v = g[i];
+      mine[i] = v;
+      accum_stat(v, c, s, q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      red[warp] = c;
+      red[32 + warp] = s;
+      red[64 + warp] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double bc = 0, bs = 0, bq = 0;
+      for (int k = 0; k < kClusterThreads / 32; ++k) {
+        bc += red[k];
+        bs += red[32 + k];
+        bq += red[64 + k];
+      }
+      partial[0] = bc;
+      partial[1] = bs;
+      partial[2] = bq;
+    }
+    cluster.sync();
+    if (threadIdx.x == 0) {
+      double tc = 0, ts = 0, tq = 0;
+      for (int r = 0; r < kClusterSize; ++r) {       // rank order: every CTA derives identical statistics
+        const double* pr = cluster.map_shared_rank(partial, r);
+        tc += pr[0];
+        ts += pr[1];
+        tq += pr[2];
+      }
+      float m_ = 0.0f, sd_ = 0.0f;                    // same arithmetic as finish_stats_at
+      if (tc > 0) {
+        const double m = ts / tc;
+        m_ = (float)m;
+        if (tc > 1) {
+          double var = (tq - ts * m) / (tc - 1.0);
+          if (var < 0) var = 0;
+          sd_ = (float)sqrt(var);
+        } else {
+          sd_ = __int_as_float(0x7fc00000);
+        }
+      }
+      ms[0] = m_;
+      ms[1] = sd_;
+      if (stats_out != nullptr && rank == 0) {
+        stats_out[3 * w + 0] = tc;
+        stats_out[3 * w + 1] = (double)m_;
+        stats_out[3 * w + 2] = (double)sd_;
+      }
+    }
+    __syncthreads();
+    const float mean = ms[0], sd = ms[1];
+    const bool divide = sd > 0.0f;
+    for (int i = threadIdx.x; i < nvec; i += kClusterThreads) {
+      float4 v = *reinterpret_cast<const float4*>(mine + 4 * i);
+      v.x = normalize_one(v.x, mean, sd, divide);
+      v.y = normalize_one(v.y, mean, sd, divide);
+      v.z = normalize_one(v.z, mean, sd, divide);
+      v.w = normalize_one(v.w, mean, sd, divide);
+      st_stream4(g + 4 * i, v);
+    }
+    for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads) g[i] = normalize_one(mine[i], mean, sd, divide);
+    cluster.sync();   // `partial` / `ms` are rewritten for the next window only after every peer has read them
+  }
+}
+
+struct NormClusterPlan {
+  bool ok;
+  int slice;
+  size_t smem;
+  int max_clusters;
+};
+
+// Possible when a window fits the cluster's shared memory and its slices are 16-byte aligned; EEM_VOXEL_NORM=split
+// forces the two-kernel path (comparisons).
+NormClusterPlan norm_cluster_plan(const float* grid, int64_t vox) {
+  NormClusterPlan pl{false, 0, 0, 0};
+  if (const char* v = getenv("EEM_VOXEL_NORM")) {
+    if (v[0] == 's') return pl;
+  }
+  if (vox >= (1ll << 31) || vox % 4 != 0 || (reinterpret_cast<uintptr_t>(grid) & 15) != 0) return pl;
+  pl.slice = (int)align_up((size_t)ceil_div(vox, kClusterSize), 4);
+  pl.smem = (size_t)pl.slice * sizeof(float) + kClusterScratchBytes;
+  int dev = 0, optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return pl;
+  if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return pl;
+  if (pl.smem > (size_t)optin) return pl;
+  static std::mutex mu;
+  static size_t configured_dev[kMaxDevices] = {};       // per device: the attribute lives in the device's context
+  static int clusters_dev[kMaxDevices] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (pl.smem > configured_dev[dev] || clusters_dev[dev] == 0) {
+    if (cudaFuncSetAttribute(voxel_normalize_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem) != cudaSuccess) {
+      cudaGetLastError();
+      return pl;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kClusterSize, 1, 1);
+    cfg.blockDim = dim3(kClusterThreads, 1, 1);
+    cfg.dynamicSmemBytes = pl.smem;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kClusterSize;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, voxel_normalize_cluster_kernel, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return pl;
+    }
+    configured_dev[dev] = pl.smem;
+    clusters_dev[dev] = n;
+    if (getenv("EEM_VOXEL_DEBUG")) fprintf(stderr, "[eemflow_b200] cluster normalisation: %d co-resident clusters of %d CTAs (%zu B smem)\n", n, kClusterSize, pl.smem);
+  }
+  pl.max_clusters = clusters_dev[dev];
+  pl.ok = true;
+  return pl;
+}
+
 int bit_length(uint64_t v) {
   int b = 0;
   while (v) {
@@ -1585,6 +1758,27 @@ ClusterPlan cluster_plan(int64_t vox, int n_windows, int64_t n_total) {
 }
 
 int launch_normalize(float* grid, int n_windows, int64_t vox, double* stats_out, char* ws, cudaStream_t stream) {
+  {
+    const NormClusterPlan pl = norm_cluster_plan(grid, vox);
+    if (pl.ok) {
+      const int n_clusters = n_windows < pl.max_clusters ? n_windows : pl.max_clusters;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(n_clusters * kClusterSize), 1, 1);
+      cfg.blockDim = dim3(kClusterThreads, 1, 1);
+      cfg.dynamicSmemBytes = pl.smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = kClusterSize;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      EEM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, voxel_normalize_cluster_kernel, grid, n_windows, vox, pl.slice, stats_out));
+      EEM_CHECK_LAUNCH("voxel_normalize_cluster_kernel");
+      return EEM_OK;
+    }
+  }
   const StatLayout L = stat_layout(n_windows);
   StatPartial* partials = reinterpret_cast<StatPartial*>(ws + L.partials);
   unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + L.tickets);

@@ -95,6 +95,46 @@ def test_oracle_parity(V, n, nb, h, w, clustered):
     assert rel_close(out_n, ref_norm).all(), np.abs(out_n - ref_norm).max()
 
 
+@pytest.mark.parametrize("n_windows,shape", [(40, (5, 64, 96)), (3, (5, 260, 346)), (2, (15, 60, 62)), (1, (1, 1, 4))])
+def test_normalize_cluster_path_matches_split_path(n_windows, shape):
+    """K2 for windows that fit one 8-CTA cluster's shared memory (one launch: load + statistics, DSMEM exchange, apply)
+    against the two-kernel path (EEM_VOXEL_NORM=split) and the oracle's formula: non-zero count exact, mean / std and the
+    normalised voxels <= 1e-6 relative (the two paths add the same fp64 terms in a different order).  40 windows: more
+    than the resident clusters, so clusters loop; all-zero, one-non-zero (std = NaN -> v - mean) and dense windows."""
+    import os
+    from eemflow_b200 import ops
+    gen = torch.Generator().manual_seed(n_windows)
+    grid = torch.randn((n_windows,) + shape, generator=gen)
+    grid[torch.rand(grid.shape, generator=gen) < 0.7] = 0.0
+    if n_windows >= 3:
+        grid[1].zero_()                                   # no events at all
+        grid[2].zero_()
+        grid[2].view(-1)[3] = 2.5                         # a single non-zero voxel
+    outs, stats = {}, {}
+    for mode in ("cluster", "split"):
+        os.environ["EEM_VOXEL_NORM"] = mode
+        try:
+            g = grid.cuda()
+            st = torch.zeros(n_windows, 3, dtype=torch.float64, device="cuda")
+            ops.voxel_normalize_(g, st)
+            outs[mode], stats[mode] = g.cpu(), st.cpu()
+        finally:
+            os.environ.pop("EEM_VOXEL_NORM", None)
+    assert torch.equal(stats["cluster"][:, 0], stats["split"][:, 0])
+    assert torch.equal(stats["cluster"][:, 0], (grid.flatten(1) != 0).sum(1).double())
+    for k in range(n_windows):
+        nz = grid[k][grid[k] != 0].double()
+        if nz.numel() > 1:
+            mean, std = nz.mean().item(), nz.std().item()
+            assert abs(stats["cluster"][k, 1].item() - mean) <= 1e-6 * max(1.0, abs(mean))
+            assert abs(stats["cluster"][k, 2].item() - std) <= 1e-6 * std
+    a, b = outs["cluster"], outs["split"]
+    assert torch.equal(a == 0, b == 0) and torch.equal(torch.isnan(a), torch.isnan(b))
+    assert ((a - b).abs() <= 1e-6 * b.abs().clamp_min(1.0)).all()
+    if n_windows >= 3:
+        assert a[1].abs().max().item() == 0.0 and a[2].view(-1)[3].item() == 0.0     # 2.5 - mean(2.5)
+
+
 def test_batched_windows_ragged(V):
     rng = np.random.default_rng(5)
     h, w, nb = 64, 96, 5

@@ -239,6 +239,7 @@ struct PackedLookupParams {
   int B, H, W, L;
   const float* coords;
   float* out;
+  int debug;       // EEM_LOOKUP_DEBUG (timing experiments only): 1 no output stores, 2 no tile copies, 4 no interpolation
 };
 
 // roundtrip() with the IEEE division replaced by a multiply and two FMAs: q0 = RN(x * y), r = x - q0 * s1 (exact in
@@ -273,7 +274,7 @@ struct PackedSmem {
 };
 
 // The three phases of a batch of PB positions, shared by the one-batch-per-CTA kernel and the pipelined persistent one.
-template <int R>
+template <int R, bool kDbg = false>
 struct PackedPhases {
   using S = PackedSmem<R>;
   static constexpr int K = S::K, T = S::T, NT = S::NT, PB = S::PB;
@@ -363,7 +364,7 @@ struct PackedPhases {
               ".reg .pred q;\n"
               "setp.eq.u32 q, %2, 0;\n"
               "cp.async.ca.shared.global [%0], [%1], 8, q;\n"       // q = ignore-src: the 8 bytes are zero-filled
-              "}\n" ::"r"(dst + sx * 8), "l"(src), "r"(live & (1u << sx)) : "memory");
+              "}\n" ::"r"(dst + sx * 8), "l"(src), "r"((kDbg && (p.debug & 2)) ? 0u : (live & (1u << sx))) : "memory");
         }
       }
     }
@@ -380,7 +381,7 @@ struct PackedPhases {
     const int P = p.H * p.W, L = p.L;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_warps = blockDim.x >> 5;
-    if (lane >= npos) return;
+    if (lane >= npos || (kDbg && (p.debug & 4))) return;
     for (int task = warp; task < nl * kGroups; task += n_warps) {
       const int ls = task / kGroups, l = l0 + ls, a0 = (task - ls * kGroups) * G;
       float* o = p.out + ((int64_t)b * L * K * K + (int64_t)l * K * K + a0 * K) * P + i0 + lane;
@@ -427,7 +428,7 @@ struct PackedPhases {
           // output channel (a0 + g) * K + c: one 32 x 32 -> 64-bit multiply-add per store address
           float* dst;
           asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(dst) : "r"(P), "r"((g * K + c) * 4), "l"(o));
-          if (a0 + g < K) st_stream(dst, prev[g] + fy * (cur - prev[g]));
+          if (a0 + g < K && !(kDbg && (p.debug & 1))) st_stream(dst, prev[g] + fy * (cur - prev[g]));
           prev[g] = cur;
         }
       }
@@ -436,10 +437,10 @@ struct PackedPhases {
 };
 
 // One batch per CTA (the default).
-template <int R>
+template <int R, bool kDbg>
 __global__ void __launch_bounds__(PackedSmem<R>::kThreads)
 corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
-  using Ph = PackedPhases<R>;
+  using Ph = PackedPhases<R, kDbg>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int P = p.H * p.W;
   const int b = blockIdx.y, i0 = blockIdx.x * Ph::PB;
@@ -538,9 +539,16 @@ int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)p.L * S::kPerLevelBytes + pad_bytes;
   const int threads = 32 * p.L * S::kGroups;                    // one interpolation task per warp
   dim3 grid((unsigned)bps, (unsigned)p.B, 1);
+  const int nthreads = threads < 64 ? 64 : (threads > S::kThreads ? S::kThreads : threads);
+  if (p.debug != 0) {                      // phase-ablation build of the kernel (EEM_LOOKUP_DEBUG, timing experiments only)
+    static DynSmemOptIn optin_dbg;
+    if (smem > 48 * 1024) EEM_CHECK_CUDA(optin_dbg.ensure(corr_lookup_packed_kernel<R, true>, smem));
+    corr_lookup_packed_kernel<R, true><<<grid, nthreads, smem, stream>>>(p);
+    return EEM_OK;
+  }
   static DynSmemOptIn optin;
-  if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_kernel<R>, smem));
-  corr_lookup_packed_kernel<R><<<grid, threads < 64 ? 64 : (threads > S::kThreads ? S::kThreads : threads), smem, stream>>>(p);
+  if (smem > 48 * 1024) EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_kernel<R, false>, smem));
+  corr_lookup_packed_kernel<R, false><<<grid, nthreads, smem, stream>>>(p);
   return EEM_OK;
 }
 
@@ -819,6 +827,7 @@ int eem_corr_lookup_packed(const void* packed, int B, int H, int W, int num_leve
   p.B = B; p.H = H; p.W = W; p.L = num_levels;
   p.coords = coords;
   p.out = out;
+  if (const char* dbg = getenv("EEM_LOOKUP_DEBUG")) p.debug = atoi(dbg);
   cudaStream_t stream = as_stream(stream_);
   int rc = EEM_OK;
   switch (radius) {

@@ -1409,15 +1409,19 @@ voxel_normalize_cluster_kernel(float* __restrict__ grid, int n_windows, int64_t 
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < nvec) v[u] = __ldcs(reinterpret_cast<const float4*>(g) + i);
       }
+      int cnt = 0;
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int i = i0 + u * kClusterThreads;
         if (i < nvec) *reinterpret_cast<float4*>(mine + 4 * i) = v[u];
-        accum_stat(v[u].x, c, s, q);                              // zeros (also the padding ones) do not count
-        accum_stat(v[u].y, c, s, q);
-        accum_stat(v[u].z, c, s, q);
-        accum_stat(v[u].w, c, s, q);
+        // zeros (also the padding ones) contribute nothing: four voxels are summed in fp32 (relative error 1e-7 of a
+        // partial of at most four terms), the running sums stay fp64 -- a quarter of the fp64 instructions
+        const float4 f = v[u];
+        cnt += (f.x != 0.0f) + (f.y != 0.0f) + (f.z != 0.0f) + (f.w != 0.0f);
+        s += (double)((f.x + f.y) + (f.z + f.w));
+        q += (double)fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, f.w * f.w)));
       }
+      c += (double)cnt;
     }
     for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads) {
       const float v = g[i];
@@ -1479,12 +1483,25 @@ voxel_normalize_cluster_kernel(float* __restrict__ grid, int n_windows, int64_t 
     __syncthreads();
     const float mean = ms[0], sd = ms[1];
     const bool divide = sd > 0.0f;
+    // (v - mean) / sd as q0 = c * r, rem = c - q0 * sd (exact, one FMA), q = q0 + rem * r with r = RN(1 / sd): the
+    // correctly rounded quotient (Markstein), i.e. the bits of __fdiv_rn in 3 instructions; huge / tiny sd (where the
+    // intermediate products could leave the normal range) take the IEEE division
+    const bool fast_div = divide && sd > 1.0e-15f && sd < 1.0e15f;
+    const float rcp = fast_div ? __frcp_rn(sd) : 0.0f;
+    auto norm = [&](float v) {
+      if (v == 0.0f) return v;
+      const float cv = __fsub_rn(v, mean);
+      if (!divide) return cv;
+      if (!fast_div || !(fabsf(cv) < 1.0e15f && fabsf(cv) > 1.0e-15f)) return __fdiv_rn(cv, sd);
+      const float q0 = __fmul_rn(cv, rcp);
+      return __fmaf_rn(__fmaf_rn(-q0, sd, cv), rcp, q0);
+    };
     for (int i = threadIdx.x; i < nvec; i += kClusterThreads) {
       float4 v = *reinterpret_cast<const float4*>(mine + 4 * i);
-      v.x = normalize_one(v.x, mean, sd, divide);
-      v.y = normalize_one(v.y, mean, sd, divide);
-      v.z = normalize_one(v.z, mean, sd, divide);
-      v.w = normalize_one(v.w, mean, sd, divide);
+      v.x = norm(v.x);
+      v.y = norm(v.y);
+      v.z = norm(v.z);
+      v.w = norm(v.w);
       st_stream4(g + 4 * i, v);
     }
     for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads) g[i] = normalize_one(mine[i], mean, sd, divide);

@@ -16,7 +16,10 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdio>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "packed_layout.cuh"
 
 namespace eem {
@@ -287,10 +290,12 @@ struct PackedPhases {
   // 1) window geometry, one thread per (position, level, axis): same arithmetic as corr_lookup_kernel.  The x and the
   //    y half of a (position, level) are independent (origin + K fractions each), so they run on different warps: the
   //    phase is a dependent chain of ~10 coordinate round trips per thread and sits on the CTA's critical path.
-  static __device__ __forceinline__ void geometry(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
+  //    (tid, nthr): the calling thread's index in the group of threads that shares the phase, and the group's size
+  static __device__ __forceinline__ void geometry(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl,
+                                                  int tid, int nthr) {
     const int P = p.H * p.W;
     const int per_axis = PB * nl;
-    for (int t = threadIdx.x; t < 2 * per_axis; t += blockDim.x) {
+    for (int t = tid; t < 2 * per_axis; t += nthr) {
       const int axis = t >= per_axis ? 1 : 0, r = t - axis * per_axis;      // warp-uniform: PB is a warp
       const int ls = r / PB, l = l0 + ls, pos = r % PB;                     // ls: level slot in shared memory
       const float s1 = (float)((axis ? p.h[l] : p.w[l]) - 1);
@@ -332,9 +337,10 @@ struct PackedPhases {
   //    instructions (32-bit byte offsets from the position's row, one 64-bit multiply-add per copy); the level loop is
   //    unrolled so the per-level constants are direct constant-bank operands.  Issues the copies and commits ONE
   //    cp.async group.
-  static __device__ __forceinline__ void gather(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
+  static __device__ __forceinline__ void gather(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl,
+                                                int tid, int nthr) {
     const int P = p.H * p.W;
-    for (int u = threadIdx.x; u < PB * T; u += blockDim.x) {       // (position, window row): decoded once, then all levels
+    for (int u = tid; u < PB * T; u += nthr) {                     // (position, window row): decoded once, then all levels
       const int pos = u / T, rr = u - pos * T;
       if (pos >= npos) continue;
       const unsigned char* rowbase = reinterpret_cast<const unsigned char*>(p.packed + ((int64_t)b * P + i0 + pos) * p.row);
@@ -375,12 +381,13 @@ struct PackedPhases {
   //    reads three 4-byte words (6 fp16: the G + 1 = 4 taps it needs start at an even or odd element), shifts them
   //    into place with two funnel shifts, and forms G horizontal lerps + G vertical lerps; row addresses are
   //    compile-time offsets of one per-task base pointer.
-  static __device__ __forceinline__ void interp(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl) {
+  //    (warp, n_warps): the calling warp's index among the warps that share the interpolation, and their number
+  static __device__ __forceinline__ void interp(const PackedLookupParams& p, unsigned char* st, int b, int i0, int npos, int l0, int nl,
+                                                int warp, int n_warps) {
     constexpr int G = S::kColsPerTask, kGroups = S::kGroups;
     static_assert(G == 3, "load_row unpacks G + 1 = 4 taps");
     const int P = p.H * p.W, L = p.L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_warps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
     if (lane >= npos || (kDbg && (p.debug & 4))) return;
     for (int task = warp; task < nl * kGroups; task += n_warps) {
       const int ls = task / kGroups, l = l0 + ls, a0 = (task - ls * kGroups) * G;
@@ -445,62 +452,97 @@ corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
   const int P = p.H * p.W;
   const int b = blockIdx.y, i0 = blockIdx.x * Ph::PB;
   const int npos = min(Ph::PB, P - i0);
-  Ph::geometry(p, smem_raw, b, i0, npos, 0, p.L);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  Ph::geometry(p, smem_raw, b, i0, npos, 0, p.L, tid, nthr);
   __syncthreads();
-  Ph::gather(p, smem_raw, b, i0, npos, 0, p.L);
+  Ph::gather(p, smem_raw, b, i0, npos, 0, p.L, tid, nthr);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  Ph::interp(p, smem_raw, b, i0, npos, 0, p.L);
+  Ph::interp(p, smem_raw, b, i0, npos, 0, p.L, tid >> 5, nthr >> 5);
 }
 
-// Persistent, software-pipelined form (experiment, EEM_LOOKUP_PACKED_PIPE=1): a CTA walks batches blockIdx.x, blockIdx.x + gridDim.x, ...
-// with TWO shared-memory stages, so the tile gather of batch k+1 (64 KiB of 16-byte cp.async per CTA) is in flight
-// while batch k is interpolated and stored: HBM always has requests queued, and the barrier / copy-wait stalls of the
-// one-batch kernel (its CTAs spent most of their life waiting for their own gather) disappear.
+// Persistent, warp-specialised form: the phases of the one-batch kernel run on DIFFERENT warps of a CTA and are coupled by
+// mbarriers over a ring of shared-memory stages, so the geometry / tile copies of batch k+1 (and the DRAM latency of its
+// copies) overlap the interpolation and the output stores of batch k inside every SM -- in the one-batch kernel these
+// phases are serial per CTA and only overlap by chance between the CTAs of an SM (measured there: skeleton 10.4 us +
+// tile copies 8 us + interpolation 7 us + output stores 9.4 us ~ the whole 34.7 us, scripts/lookup_ablation.py).
+//   warps 0 .. kConsWarps-1   consumers: wait full[s], interpolate stage s (one (level, column group) task per warp),
+//                             store, arrive empty[s]
+//   the last n_prod_warps warps producers: wait empty[s], window geometry of the batch into stage s, producer barrier,
+//                             issue the tile copies (one cp.async group per batch); full[s'] of the PREVIOUS batch is
+//                             signalled once its group has landed (cp.async.wait_group 1), so the producers always run
+//                             one batch ahead of the data they wait for.
+// A CTA walks batches blockIdx.x, blockIdx.x + gridDim.x, ...
+constexpr int kWsMaxProdWarps = 12;
+// default configuration, (producer warps * 16 + stages) * 16 + CTAs per SM (0: one-batch kernel).  Measured on B200, MVSEC
+// B = 32, graph of 12 launches: one-batch kernel 34.8 us; 3 stages x 1 CTA per SM with 4 / 8 / 12 producer warps 37.1 /
+// 32.3 / 31.6 us; 2 stages x 2 CTAs (8 producer warps) 36.7; 4 stages x 1 CTA 39.6 (213 KiB of shared memory leave the
+// 8-byte tile-row copies too little L1).  In the step graph 8 and 12 producer warps are equal (0.822 / 0.823 ms).
+constexpr int kWsDefault = (8 * 16 + 3) * 16 + 1;
+
 template <int R>
-__global__ void __launch_bounds__(PackedSmem<R>::kThreads, 1)
-corr_lookup_packed_pipe_kernel(const __grid_constant__ PackedLookupParams p, int batches_per_sample, int n_batches, int stage_bytes) {
+__global__ void __launch_bounds__(PackedSmem<R>::kThreads + kWsMaxProdWarps * 32)
+corr_lookup_packed_ws_kernel(const __grid_constant__ PackedLookupParams p, int batches_per_sample, int n_batches, int stage_bytes,
+                             int n_stages, int n_prod_warps) {
   using Ph = PackedPhases<R>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * stage_bytes);
+  uint64_t* empty = full + n_stages;
   const int P = p.H * p.W;
+  const int n_cons_warps = (int)(blockDim.x >> 5) - n_prod_warps;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      tc::mbar_init(&full[i], n_prod_warps * 32);
+      tc::mbar_init(&empty[i], n_cons_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   auto decode = [&](int bid, int& b, int& i0, int& npos) {
     b = bid / batches_per_sample;
     i0 = (bid - b * batches_per_sample) * Ph::PB;
     npos = min(Ph::PB, P - i0);
   };
-  const int step = gridDim.x;
-  int bid = blockIdx.x;
-  if (bid >= n_batches) return;
-  int b, i0, npos;
-  // prologue: batches 0 and 1 of this CTA
-  decode(bid, b, i0, npos);
-  Ph::geometry(p, smem_raw, b, i0, npos, 0, p.L);
-  if (bid + step < n_batches) {
-    int b1, i1, n1;
-    decode(bid + step, b1, i1, n1);
-    Ph::geometry(p, smem_raw + stage_bytes, b1, i1, n1, 0, p.L);
-    __syncthreads();
-    Ph::gather(p, smem_raw, b, i0, npos, 0, p.L);
-    Ph::gather(p, smem_raw + stage_bytes, b1, i1, n1, 0, p.L);
+  const int first = blockIdx.x, step = gridDim.x;
+  if (warp >= n_cons_warps) {
+    // ===== producers =====
+    const int ptid = (int)threadIdx.x - n_cons_warps * 32, pn = n_prod_warps * 32;
+    int s = 0, prev_s = -1;
+    uint32_t parity = 1;                       // a fresh barrier passes a wait on the phase "before" its first one
+    for (int bid = first; bid < n_batches; bid += step) {
+      int b, i0, npos;
+      decode(bid, b, i0, npos);
+      tc::mbar_wait(&empty[s], parity);
+      unsigned char* st = smem_raw + (size_t)s * stage_bytes;
+      Ph::geometry(p, st, b, i0, npos, 0, p.L, ptid, pn);
+      asm volatile("bar.sync 1, %0;" ::"r"(pn) : "memory");      // records complete before the copies read them
+      Ph::gather(p, st, b, i0, npos, 0, p.L, ptid, pn);
+      if (prev_s >= 0) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");                     // the previous batch's copies have landed
+        __threadfence_block();
+        tc::mbar_arrive(&full[prev_s]);
+      }
+      prev_s = s;
+      if (++s == n_stages) { s = 0; parity ^= 1; }
+    }
+    if (prev_s >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __threadfence_block();
+      tc::mbar_arrive(&full[prev_s]);
+    }
   } else {
-    __syncthreads();
-    Ph::gather(p, smem_raw, b, i0, npos, 0, p.L);
-  }
-  for (int k = 0; bid < n_batches; ++k, bid += step) {
-    unsigned char* st = smem_raw + (k & 1) * stage_bytes;
-    decode(bid, b, i0, npos);
-    if (bid + step < n_batches) asm volatile("cp.async.wait_group 1;" ::: "memory");   // batch k landed, k+1 may be in flight
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    Ph::interp(p, st, b, i0, npos, 0, p.L);
-    const int nxt = bid + 2 * step;
-    if (nxt < n_batches) {                      // refill this stage with batch k+2
-      __syncthreads();                          // every warp is done reading the stage
-      int b2, i2, n2;
-      decode(nxt, b2, i2, n2);
-      Ph::geometry(p, st, b2, i2, n2, 0, p.L);
-      __syncthreads();
-      Ph::gather(p, st, b2, i2, n2, 0, p.L);
+    // ===== consumers =====
+    int s = 0;
+    uint32_t parity = 0;
+    for (int bid = first; bid < n_batches; bid += step) {
+      int b, i0, npos;
+      decode(bid, b, i0, npos);
+      tc::mbar_wait(&full[s], parity);
+      Ph::interp(p, smem_raw + (size_t)s * stage_bytes, b, i0, npos, 0, p.L, warp, n_cons_warps);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&empty[s]);
+      if (++s == n_stages) { s = 0; parity ^= 1; }
     }
   }
 }
@@ -511,25 +553,31 @@ int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
   const size_t stage = (size_t)p.L * S::kPerLevelBytes;
   const int bps = (int)ceil_div(p.H * p.W, S::PB);
   const int64_t n_batches = (int64_t)bps * p.B;
-  // Measured on B200 (MVSEC B = 32, 12 back-to-back launches): one batch per CTA with 4 CTAs (48 warps) per SM 39.0 us;
-  // the persistent two-stage pipeline with 2 CTAs (24 warps) per SM 45.3 us -- warp-level parallelism hides the gather
-  // latency better than the explicit pipeline with half the warps, so the simple kernel is the default and
-  // EEM_LOOKUP_PACKED_PIPE=1 selects the pipeline for comparisons.
-  static const bool force_simple = [] {
-    const char* v = getenv("EEM_LOOKUP_PACKED_PIPE");
-    return !(v != nullptr && atoi(v) == 1);
+  // EEM_LOOKUP_PACKED_WS = "<stages>x<CTAs per SM>" (e.g. 2x2, 4x1) selects the persistent warp-specialised kernel, 0 the
+  // one-batch kernel.
+  const int ws_cfg = [] {                  // read per call (tests switch between the two kernels inside one process)
+    const char* v = getenv("EEM_LOOKUP_PACKED_WS");
+    if (v == nullptr) return kWsDefault;
+    int a = 0, c = 0, w = 4;
+    const int n = sscanf(v, "%dx%dx%d", &a, &c, &w);            // stages x CTAs per SM [x producer warps]
+    if (n >= 2 && a >= 2 && a <= 8 && c >= 1 && c <= 4 && w >= 1 && w <= kWsMaxProdWarps)
+      return (w * 16 + a) * 16 + c;                            // >= 2 stages: full[k-1] is signalled after batch k is issued
+    return 0;
   }();
-  if (2 * stage <= 220 * 1024 && n_batches < (int64_t)0x7fffffff && !force_simple) {
-    static DynSmemOptIn optin;
-    EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_pipe_kernel<R>, 2 * stage));
+  if (ws_cfg != 0 && p.debug == 0 && n_batches < (int64_t)0x7fffffff) {
+    const int n_stages = (ws_cfg / 16) % 16, per_sm = ws_cfg % 16, prod = ws_cfg / 256;
+    const size_t smem = (size_t)n_stages * stage + 2 * (size_t)n_stages * sizeof(uint64_t);
     const int sms = sm_count();
-    if (sms <= 0) return fail(EEM_ERR_CUDA, "eem_corr_lookup_packed: cannot query SM count");
-    int64_t per_sm = (int64_t)(220 * 1024) / (int64_t)(2 * stage);      // CTAs that fit an SM's shared memory
-    if (per_sm > 2) per_sm = 2;
-    int64_t grid = (int64_t)sms * per_sm;
-    if (grid > n_batches) grid = n_batches;
-    corr_lookup_packed_pipe_kernel<R><<<(unsigned)grid, S::kThreads, 2 * stage, stream>>>(p, bps, (int)n_batches, (int)stage);
-    return EEM_OK;
+    if (smem <= 227 * 1024 && sms > 0) {
+      static DynSmemOptIn optin;
+      EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_ws_kernel<R>, smem));
+      int cons = p.L * S::kGroups;
+      if (cons > S::kThreads / 32) cons = S::kThreads / 32;
+      int64_t grid = (int64_t)sms * per_sm;
+      if (grid > n_batches) grid = n_batches;
+      corr_lookup_packed_ws_kernel<R><<<(unsigned)grid, (cons + prod) * 32, smem, stream>>>(p, bps, (int)n_batches, (int)stage, n_stages, prod);
+      return EEM_OK;
+    }
   }
   // EEM_LOOKUP_PACKED_PAD_KB (timing experiments only): extra dynamic shared memory per CTA, i.e. fewer CTAs per SM
   static const size_t pad_bytes = [] {

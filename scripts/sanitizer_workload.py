@@ -23,6 +23,16 @@ coords = (torch.stack(torch.meshgrid(torch.arange(17), torch.arange(20), indexin
 for r in (4, 2):
     blk = E.CorrBlock(f1, f2, num_levels=4, radius=r, precision="tf32_f16"); out = blk(coords); _ = blk.corr_pyramid
 blk = E.CorrBlock(f1, f2, num_levels=4, radius=4, precision="tf32"); out = blk(coords)
+# warp-specialised persistent lookup with more batches than 3 x SMs: the stage ring wraps (mbarrier phases flip)
+if torch.cuda.get_device_properties(0).multi_processor_count * 4 <= 12 * 50:
+    g1 = torch.randn(12, 32, 36, 44, generator=g_).cuda(); g2 = torch.randn(12, 32, 36, 44, generator=g_).cuda()
+    cc = (torch.stack(torch.meshgrid(torch.arange(36), torch.arange(44), indexing='ij')[::-1], 0).float()[None].repeat(12,1,1,1) + 3*torch.randn(12,2,36,44, generator=g_)).cuda()
+    blk = E.CorrBlock(g1, g2, num_levels=4, radius=4, precision="tf32_f16"); out = blk(cc); out = blk(cc + 0.5)
+# local correlation: whole-map kernel, tcgen05 banded GEMM (ragged sizes)
+for (B, C, H, W) in ((2, 24, 5, 6), (1, 40, 9, 12), (2, 40, 21, 36)):
+    a_, b_ = torch.randn(B, C, H, W, generator=g_).cuda(), torch.randn(B, C, H, W, generator=g_).cuda()
+    ops.local_corr(a_, b_, scale=1.0 / C, precision="fp32")
+    ops.local_corr(a_, b_, index=list(range(0, 81, 2)), scale=1.0 / C, precision="tf32")
 # backward GEMM + multi resize
 a = f1.clone().requires_grad_(True); b = f2.clone().requires_grad_(True)
 E.CorrBlock(a, b, num_levels=3, radius=4, precision="fp32")(coords).sum().backward()

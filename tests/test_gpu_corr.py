@@ -162,6 +162,33 @@ def test_packed_fp16_pyramid_and_lookup(E, B, D, H, W, L):
         h, w = h // 2, w // 2
 
 
+@pytest.mark.parametrize("B,H,W,L,r", [(12, 36, 44, 4, 4), (3, 17, 20, 4, 4), (2, 92, 160, 4, 4), (5, 24, 31, 3, 2), (1, 8, 8, 4, 1)])
+def test_packed_lookup_warp_specialised_equals_one_batch_kernel(E, B, H, W, L, r):
+    """The persistent warp-specialised lookup (producer warps: window geometry + tile copies, consumer warps: interpolation,
+    coupled by mbarriers over a ring of stages -- the default) runs the same per-element arithmetic as the one-batch
+    kernel, so the two must agree BIT FOR BIT; (12, 36, 44) has more batches than 3 x SMs, so the stage ring wraps and
+    the barrier phases flip; the other shapes have ragged last batches, three levels, small radii, degenerate levels."""
+    import os
+    from eemflow_b200 import ops
+    gen = torch.Generator().manual_seed(B * H + W)
+    D = 32
+    f1 = torch.randn(B, D, H, W, generator=gen).cuda()
+    f2 = torch.randn(B, D, H, W, generator=gen).cuda()
+    base = torch.stack(torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")[::-1], 0).float()
+    coords = (base[None] + 4.0 * torch.randn(B, 2, H, W, generator=gen)).cuda()
+    packed = ops.corr_pyramid_packed(f1, f2, L)
+    outs = {}
+    for cfg in ("0", "3x1x8", "2x2x4", "3x1x12"):
+        os.environ["EEM_LOOKUP_PACKED_WS"] = cfg
+        try:
+            outs[cfg] = ops.corr_lookup_packed(packed, coords, L, r).clone()
+        finally:
+            os.environ.pop("EEM_LOOKUP_PACKED_WS", None)
+    outs["default"] = ops.corr_lookup_packed(packed, coords, L, r)
+    for cfg, o in outs.items():
+        assert torch.equal(torch.nan_to_num(o, nan=-7.0), torch.nan_to_num(outs["0"], nan=-7.0)), cfg
+
+
 def test_packed_lookup_radius_variants(E):
     from eemflow_b200 import ops
     gen = torch.Generator().manual_seed(17)

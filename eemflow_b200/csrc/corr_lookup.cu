@@ -461,40 +461,42 @@ corr_lookup_packed_kernel(const __grid_constant__ PackedLookupParams p) {
   Ph::interp(p, smem_raw, b, i0, npos, 0, p.L, tid >> 5, nthr >> 5);
 }
 
-// Persistent, warp-specialised form: the phases of the one-batch kernel run on DIFFERENT warps of a CTA and are coupled by
-// mbarriers over a ring of shared-memory stages, so the geometry / tile copies of batch k+1 (and the DRAM latency of its
-// copies) overlap the interpolation and the output stores of batch k inside every SM -- in the one-batch kernel these
-// phases are serial per CTA and only overlap by chance between the CTAs of an SM (measured there: skeleton 10.4 us +
-// tile copies 8 us + interpolation 7 us + output stores 9.4 us ~ the whole 34.7 us, scripts/lookup_ablation.py).
-//   warps 0 .. kConsWarps-1   consumers: wait full[s], interpolate stage s (one (level, column group) task per warp),
-//                             store, arrive empty[s]
-//   the last n_prod_warps warps producers: wait empty[s], window geometry of the batch into stage s, producer barrier,
-//                             issue the tile copies (one cp.async group per batch); full[s'] of the PREVIOUS batch is
-//                             signalled once its group has landed (cp.async.wait_group 1), so the producers always run
-//                             one batch ahead of the data they wait for.
+// Persistent, warp-specialised form: the three phases of the one-batch kernel run on DIFFERENT warps of a CTA and are
+// coupled by mbarriers over a ring of shared-memory stages, so the window geometry of batch k+2, the tile copies of batch
+// k+1 (and their DRAM latency) and the interpolation + output stores of batch k overlap inside every SM -- in the
+// one-batch kernel the phases are serial per CTA and only overlap by chance between the CTAs of an SM (measured there:
+// geometry + copy issue 10.4 us, tile copies + 8 us, interpolation + 7 us, output stores + 9.4 us ~ the whole 34.7 us,
+// scripts/lookup_ablation.py).
+//   warps [0, n_cons)            consumers: wait full[s], interpolate stage s (one (level, column group) task per warp),
+//                                store, arrive empty[s]
+//   the next n_geo warps         geometry: wait empty[s], window geometry of the batch into stage s, arrive ready[s]
+//   the last n_copy warps        copies: wait ready[s], issue the tile copies (one cp.async group per batch); full[s'] of
+//                                the PREVIOUS batch is signalled once its group has landed (cp.async.wait_group 1), so the
+//                                copy warps always run one batch ahead of the data they wait for.
 // A CTA walks batches blockIdx.x, blockIdx.x + gridDim.x, ...
-constexpr int kWsMaxProdWarps = 12;
-// default configuration, (producer warps * 16 + stages) * 16 + CTAs per SM (0: one-batch kernel).  Measured on B200, MVSEC
-// B = 32, graph of 12 launches: one-batch kernel 34.8 us; 3 stages x 1 CTA per SM with 4 / 8 / 12 producer warps 37.1 /
-// 32.3 / 31.6 us; 2 stages x 2 CTAs (8 producer warps) 36.7; 4 stages x 1 CTA 39.6 (213 KiB of shared memory leave the
-// 8-byte tile-row copies too little L1).  In the step graph 8 and 12 producer warps are equal (0.822 / 0.823 ms).
-constexpr int kWsDefault = (8 * 16 + 3) * 16 + 1;
+constexpr int kWsMaxProdWarps = 18;
+// default configuration (0: one-batch kernel), see ws_config()
+struct WsConfig {
+  int stages, per_sm, geo_warps, copy_warps;
+};
 
-template <int R>
+template <int R, bool kDbg>
 __global__ void __launch_bounds__(PackedSmem<R>::kThreads + kWsMaxProdWarps * 32)
 corr_lookup_packed_ws_kernel(const __grid_constant__ PackedLookupParams p, int batches_per_sample, int n_batches, int stage_bytes,
-                             int n_stages, int n_prod_warps) {
-  using Ph = PackedPhases<R>;
+                             int n_stages, int n_geo_warps, int n_copy_warps) {
+  using Ph = PackedPhases<R, kDbg>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * stage_bytes);
   uint64_t* empty = full + n_stages;
+  uint64_t* ready = empty + n_stages;
   const int P = p.H * p.W;
-  const int n_cons_warps = (int)(blockDim.x >> 5) - n_prod_warps;
+  const int n_cons_warps = (int)(blockDim.x >> 5) - n_geo_warps - n_copy_warps;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < n_stages; ++i) {
-      tc::mbar_init(&full[i], n_prod_warps * 32);
+      tc::mbar_init(&full[i], n_copy_warps * 32);
       tc::mbar_init(&empty[i], n_cons_warps);
+      tc::mbar_init(&ready[i], n_geo_warps * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -505,19 +507,42 @@ corr_lookup_packed_ws_kernel(const __grid_constant__ PackedLookupParams p, int b
     npos = min(Ph::PB, P - i0);
   };
   const int first = blockIdx.x, step = gridDim.x;
-  if (warp >= n_cons_warps) {
-    // ===== producers =====
-    const int ptid = (int)threadIdx.x - n_cons_warps * 32, pn = n_prod_warps * 32;
-    int s = 0, prev_s = -1;
+  if (warp < n_cons_warps) {
+    // ===== consumers =====
+    int s = 0;
+    uint32_t parity = 0;
+    for (int bid = first; bid < n_batches; bid += step) {
+      int b, i0, npos;
+      decode(bid, b, i0, npos);
+      tc::mbar_wait(&full[s], parity);
+      Ph::interp(p, smem_raw + (size_t)s * stage_bytes, b, i0, npos, 0, p.L, warp, n_cons_warps);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&empty[s]);
+      if (++s == n_stages) { s = 0; parity ^= 1; }
+    }
+  } else if (warp < n_cons_warps + n_geo_warps) {
+    // ===== geometry =====
+    const int gtid = (int)threadIdx.x - n_cons_warps * 32, gn = n_geo_warps * 32;
+    int s = 0;
     uint32_t parity = 1;                       // a fresh barrier passes a wait on the phase "before" its first one
     for (int bid = first; bid < n_batches; bid += step) {
       int b, i0, npos;
       decode(bid, b, i0, npos);
       tc::mbar_wait(&empty[s], parity);
-      unsigned char* st = smem_raw + (size_t)s * stage_bytes;
-      Ph::geometry(p, st, b, i0, npos, 0, p.L, ptid, pn);
-      asm volatile("bar.sync 1, %0;" ::"r"(pn) : "memory");      // records complete before the copies read them
-      Ph::gather(p, st, b, i0, npos, 0, p.L, ptid, pn);
+      Ph::geometry(p, smem_raw + (size_t)s * stage_bytes, b, i0, npos, 0, p.L, gtid, gn);
+      tc::mbar_arrive(&ready[s]);              // release: this thread's records / fractions are visible to the waiters
+      if (++s == n_stages) { s = 0; parity ^= 1; }
+    }
+  } else {
+    // ===== tile copies =====
+    const int ctid = (int)threadIdx.x - (n_cons_warps + n_geo_warps) * 32, cn = n_copy_warps * 32;
+    int s = 0, prev_s = -1;
+    uint32_t parity = 0;
+    for (int bid = first; bid < n_batches; bid += step) {
+      int b, i0, npos;
+      decode(bid, b, i0, npos);
+      tc::mbar_wait(&ready[s], parity);
+      Ph::gather(p, smem_raw + (size_t)s * stage_bytes, b, i0, npos, 0, p.L, ctid, cn);
       if (prev_s >= 0) {
         asm volatile("cp.async.wait_group 1;" ::: "memory");                     // the previous batch's copies have landed
         __threadfence_block();
@@ -531,20 +556,27 @@ corr_lookup_packed_ws_kernel(const __grid_constant__ PackedLookupParams p, int b
       __threadfence_block();
       tc::mbar_arrive(&full[prev_s]);
     }
-  } else {
-    // ===== consumers =====
-    int s = 0;
-    uint32_t parity = 0;
-    for (int bid = first; bid < n_batches; bid += step) {
-      int b, i0, npos;
-      decode(bid, b, i0, npos);
-      tc::mbar_wait(&full[s], parity);
-      Ph::interp(p, smem_raw + (size_t)s * stage_bytes, b, i0, npos, 0, p.L, warp, n_cons_warps);
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&empty[s]);
-      if (++s == n_stages) { s = 0; parity ^= 1; }
-    }
   }
+}
+
+// EEM_LOOKUP_PACKED_WS = "<stages>x<CTAs per SM>x<geometry warps>x<copy warps>" selects a configuration of the persistent
+// kernel, "0" the one-batch kernel; read per call (tests switch between the kernels inside one process).
+inline WsConfig ws_config() {
+  // default.  Measured on B200 (MVSEC B = 32, graph of 12 launches, us per launch): one-batch kernel 34.7; two roles
+  // (geometry + copies on the same 4 / 8 / 12 warps) 37.1 / 32.3 / 31.6; three roles, 3 stages x 1 CTA per SM, geometry x
+  // copy warps 8x10 28.4, 8x5 28.4, 4x5 31.6, 4x10 31.6; 4 stages 37.3 (213 KiB of shared memory leave the 8-byte
+  // tile-row copies too little L1); 2 stages x 2 CTAs per SM 42.4.  At 28.4 us the kernel moves its 143 MB of DRAM
+  // traffic at 5.0 TB/s (77 % of the measured peak).
+  WsConfig c{3, 1, 8, 5};
+  if (const char* v = getenv("EEM_LOOKUP_PACKED_WS")) {
+    WsConfig e{0, 1, 8, 5};
+    const int n = sscanf(v, "%dx%dx%dx%d", &e.stages, &e.per_sm, &e.geo_warps, &e.copy_warps);
+    if (n >= 1 && e.stages == 0) return e;
+    if (n >= 2 && e.stages >= 2 && e.stages <= 8 && e.per_sm >= 1 && e.per_sm <= 4 && e.geo_warps >= 1 && e.copy_warps >= 1 &&
+        e.geo_warps + e.copy_warps <= kWsMaxProdWarps)
+      return e;                                // >= 2 stages: full[k-1] is signalled after the copies of batch k are issued
+  }
+  return c;
 }
 
 template <int R>
@@ -553,29 +585,27 @@ int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
   const size_t stage = (size_t)p.L * S::kPerLevelBytes;
   const int bps = (int)ceil_div(p.H * p.W, S::PB);
   const int64_t n_batches = (int64_t)bps * p.B;
-  // EEM_LOOKUP_PACKED_WS = "<stages>x<CTAs per SM>" (e.g. 2x2, 4x1) selects the persistent warp-specialised kernel, 0 the
-  // one-batch kernel.
-  const int ws_cfg = [] {                  // read per call (tests switch between the two kernels inside one process)
-    const char* v = getenv("EEM_LOOKUP_PACKED_WS");
-    if (v == nullptr) return kWsDefault;
-    int a = 0, c = 0, w = 4;
-    const int n = sscanf(v, "%dx%dx%d", &a, &c, &w);            // stages x CTAs per SM [x producer warps]
-    if (n >= 2 && a >= 2 && a <= 8 && c >= 1 && c <= 4 && w >= 1 && w <= kWsMaxProdWarps)
-      return (w * 16 + a) * 16 + c;                            // >= 2 stages: full[k-1] is signalled after batch k is issued
-    return 0;
-  }();
-  if (ws_cfg != 0 && p.debug == 0 && n_batches < (int64_t)0x7fffffff) {
-    const int n_stages = (ws_cfg / 16) % 16, per_sm = ws_cfg % 16, prod = ws_cfg / 256;
-    const size_t smem = (size_t)n_stages * stage + 2 * (size_t)n_stages * sizeof(uint64_t);
+  const WsConfig ws = ws_config();
+  if (ws.stages != 0 && n_batches < (int64_t)0x7fffffff) {
+    const size_t smem = (size_t)ws.stages * stage + 3 * (size_t)ws.stages * sizeof(uint64_t);
     const int sms = sm_count();
     if (smem <= 227 * 1024 && sms > 0) {
-      static DynSmemOptIn optin;
-      EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_ws_kernel<R>, smem));
       int cons = p.L * S::kGroups;
       if (cons > S::kThreads / 32) cons = S::kThreads / 32;
-      int64_t grid = (int64_t)sms * per_sm;
+      const int threads = (cons + ws.geo_warps + ws.copy_warps) * 32;
+      int64_t grid = (int64_t)sms * ws.per_sm;
       if (grid > n_batches) grid = n_batches;
-      corr_lookup_packed_ws_kernel<R><<<(unsigned)grid, (cons + prod) * 32, smem, stream>>>(p, bps, (int)n_batches, (int)stage, n_stages, prod);
+      if (p.debug != 0) {                  // phase-ablation build (EEM_LOOKUP_DEBUG, timing experiments only)
+        static DynSmemOptIn optin_dbg;
+        EEM_CHECK_CUDA(optin_dbg.ensure(corr_lookup_packed_ws_kernel<R, true>, smem));
+        corr_lookup_packed_ws_kernel<R, true><<<(unsigned)grid, threads, smem, stream>>>(p, bps, (int)n_batches, (int)stage, ws.stages,
+                                                                                       ws.geo_warps, ws.copy_warps);
+        return EEM_OK;
+      }
+      static DynSmemOptIn optin;
+      EEM_CHECK_CUDA(optin.ensure(corr_lookup_packed_ws_kernel<R, false>, smem));
+      corr_lookup_packed_ws_kernel<R, false><<<(unsigned)grid, threads, smem, stream>>>(p, bps, (int)n_batches, (int)stage, ws.stages,
+                                                                                      ws.geo_warps, ws.copy_warps);
       return EEM_OK;
     }
   }

@@ -164,9 +164,8 @@ def test_packed_fp16_pyramid_and_lookup(E, B, D, H, W, L):
 
 @pytest.mark.parametrize("B,H,W,L,r", [(12, 36, 44, 4, 4), (3, 17, 20, 4, 4), (2, 92, 160, 4, 4), (5, 24, 31, 3, 2), (1, 8, 8, 4, 1)])
 def test_packed_lookup_warp_specialised_equals_one_batch_kernel(E, B, H, W, L, r):
-    """The persistent warp-specialised lookup (producer warps: window geometry + tile copies, consumer warps: interpolation,
-    coupled by mbarriers over a ring of stages -- the default) runs the same per-element arithmetic as the one-batch
-    kernel, so the two must agree BIT FOR BIT; (12, 36, 44) has more batches than 3 x SMs, so the stage ring wraps and
+    """The persistent warp-specialised lookup (geometry warps -> tile-copy warps -> interpolation warps, coupled by
+    mbarriers over a ring of stages -- the default) runs the same per-element arithmetic as the one-batch kernel, so the two must agree BIT FOR BIT; (12, 36, 44) has more batches than 3 x SMs, so the stage ring wraps and
     the barrier phases flip; the other shapes have ragged last batches, three levels, small radii, degenerate levels."""
     import os
     from eemflow_b200 import ops
@@ -178,7 +177,7 @@ def test_packed_lookup_warp_specialised_equals_one_batch_kernel(E, B, H, W, L, r
     coords = (base[None] + 4.0 * torch.randn(B, 2, H, W, generator=gen)).cuda()
     packed = ops.corr_pyramid_packed(f1, f2, L)
     outs = {}
-    for cfg in ("0", "3x1x8", "2x2x4", "3x1x12"):
+    for cfg in ("0", "3x1x8x10", "2x1x4x5", "4x1x2x3"):   # stages x CTAs per SM x geometry warps x copy warps
         os.environ["EEM_LOOKUP_PACKED_WS"] = cfg
         try:
             outs[cfg] = ops.corr_lookup_packed(packed, coords, L, r).clone()

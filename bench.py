@@ -736,8 +736,8 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
     if dominant not in ("voxelize", "corr_lookup"):
         dominant = "voxelize" if fam_ms["voxelize"] >= fam_ms["corr_lookup"] else "corr_lookup"
     if dominant == "corr_lookup":
-        kernel = "corr_lookup_packed_kernel<4>" if args.corr == "tf32_f16" else "corr_lookup_kernel<4>"
-        ncu_key = "corr_lookup_packed_kernel" if args.corr == "tf32_f16" else "corr_lookup_kernel"
+        kernel = "corr_lookup_packed_ws_kernel<4>" if args.corr == "tf32_f16" else "corr_lookup_kernel<4>"
+        ncu_key = "corr_lookup_packed_ws_kernel" if args.corr == "tf32_f16" else "corr_lookup_kernel"
         launch_ms = fam_ms["corr_lookup"] / args.lookups
         algo = lookup_algorithmic_bytes(wl, B, args.corr)
         timing = f"CUDA events around a graph replay of the {args.lookups} lookups, K steps, same inputs as the timed region"

@@ -135,11 +135,17 @@ pool_pyramid_packed_kernel(const __grid_constant__ PoolPackedParams p) {
     for (int l = 1; l < pl.L; ++l) {
       const int hi = pl.h[l - 1], wi = pl.w[l - 1], ho = pl.h[l], wo = pl.w[l];
       float* nxt = cur + hi * wi;
+      const bool even_in = ((wi & 1) == 0) && ((reinterpret_cast<uintptr_t>(cur) & 7) == 0);
       if (ho * wo > 0) {
         int y = t / wo, x = t - y * wo;                          // once per level, then incremental
         for (int r = t; r < ho * wo; r += gsize) {
           const float* s4 = cur + (2 * y) * wi + 2 * x;
-          nxt[r] = (((s4[0] + s4[1]) + s4[wi]) + s4[wi + 1]) * 0.25f;
+          if (even_in) {                                           // even row pitch on an 8-byte aligned level: two 8-byte reads
+            const float2 a = *reinterpret_cast<const float2*>(s4), c2 = *reinterpret_cast<const float2*>(s4 + wi);
+            nxt[r] = (((a.x + a.y) + c2.x) + c2.y) * 0.25f;
+          } else {
+            nxt[r] = (((s4[0] + s4[1]) + s4[wi]) + s4[wi + 1]) * 0.25f;
+          }
           x += gsize;
           while (x >= wo) { x -= wo; ++y; }
         }
@@ -158,6 +164,7 @@ pool_pyramid_packed_kernel(const __grid_constant__ PoolPackedParams p) {
       const int h = pl.h[l], w = pl.w[l], tx = pl.tx[l];
       const int n_tiles = tx * pl.ty[l];
       float* d = dst + pl.off[l];
+      const bool vec_rows = ((w & 3) == 0) && ((reinterpret_cast<uintptr_t>(cur) & 15) == 0);
       if (n_tiles > 0) {
         int tile = t >> 2;
         int tyi = tile / tx, txi = tile - tyi * tx;            // once per level
@@ -166,7 +173,9 @@ pool_pyramid_packed_kernel(const __grid_constant__ PoolPackedParams p) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (y < h) {
             const float* sp = cur + y * w + x;
-            if (x + 3 < w) {
+            if (vec_rows) {                                        // w % 4 == 0 on a 16-byte aligned level: one 16-byte read
+              v = *reinterpret_cast<const float4*>(sp);
+            } else if (x + 3 < w) {
               v = make_float4(sp[0], sp[1], sp[2], sp[3]);
             } else {
               if (x < w) v.x = sp[0];

@@ -1850,16 +1850,21 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
     const int per_group = (int)(l2_group_bytes() / (vox * (int64_t)sizeof(float)));
     const int n_groups = (int)ceil_div(n_windows, per_group);
     const int even = (int)ceil_div(n_windows, n_groups);             // equal-sized groups
+    // The cluster-resident normalisation runs in rounds of as many windows as clusters are co-resident (15 on a B200):
+    // one launch over ALL windows after the last group's votes needs ceil(64 / 15) = 5 rounds where two launches over
+    // 32 windows need 2 x 3, and the grids it reads are still largely in L2.
+    const bool norm_at_end = normalize && !tiled && norm_cluster_plan(grid, vox).ok;
     for (int w0 = 0; w0 < n_windows; w0 += even) {
       const int nw = n_windows - w0 < even ? n_windows - w0 : even;
       // upper bound of the group's event count (sizes its scratch): never more than the whole call
       int64_t n_est = (int64_t)nw * max_events_per_window;
       if (n_est > n_total) n_est = n_total;
       const int rc = voxelize_impl<Src>(events, offsets + w0, nw, n_est, max_events_per_window, num_bins, height, width, mode,
-                                        normalize, grid + (int64_t)w0 * vox, dropped, stats_out ? stats_out + 3 * w0 : nullptr,
-                                        workspace, workspace_bytes, stream_);
+                                        norm_at_end ? 0 : normalize, grid + (int64_t)w0 * vox, dropped,
+                                        stats_out ? stats_out + 3 * w0 : nullptr, workspace, workspace_bytes, stream_);
       if (rc != EEM_OK) return rc;
     }
+    if (norm_at_end) return launch_normalize(grid, n_windows, vox, stats_out, static_cast<char*>(workspace), stream);
     return EEM_OK;
   }
   char* ws = static_cast<char*>(workspace);

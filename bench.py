@@ -838,7 +838,9 @@ def cpu_model_forward(model, events1, events2):
 def run_sweep(args):
     from eemflow_b200 import dist as edist
     from eemflow_b200.models import EEMFlow_cdc
+    import eemflow_b200
     assert torch.cuda.is_available(), "bench.py --sweep needs a CUDA device"
+    eemflow_b200.set_local_corr_precision(args.local_corr)
     rank, world, local_rank = edist.init_from_env("nccl")
     dev = torch.device("cuda", local_rank if world > 1 else 0)
     torch.cuda.set_device(dev)
@@ -900,7 +902,8 @@ def run_sweep(args):
                "sample": f"batch 1, {n} forwards, the model's ATen CPU convolutions + oracle/ref_ops.py hot-path ops"}
     if rank == 0:
         print(json.dumps({"metric": "frame-pairs/sec (end-to-end EEMFlow_cdc inference, HREM 720x1280, 15 bins)", "unit": "frame-pairs/s",
-                          "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                          "n_gpus": world, "higher_is_better": True, "scaling": "strong",
+                          "dtype": "f32" + (" (tf32 tensor-core local correlation)" if args.local_corr == "tf32" else ""), "data": "synthetic",
                           "config": {"workload": "eemflow_cdc_inference_sweep_hrem_720x1280", "model": "EEMFlow_cdc(groups=3), random init",
                                      "input": "voxel grids resident on the device", "micro_batch": micro,
                                      "parallelism": f"batch-sharded x{world}"},

@@ -88,9 +88,11 @@ def parse_args():
     ap.add_argument("--sweep-max-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--events-format", default="rows", choices=["rows", "columns"],
-                    help="host layout of the events in the end-to-end arm: the reference's [N,4] float64 rows (32 B/event) "
-                         "or packed columns as in the HREM .npz files (t f64, x/y int16, p int8 = 13 B/event)")
+    ap.add_argument("--events-format", default="auto", choices=["auto", "rows", "columns"],
+                    help="host layout of the events in the end-to-end arm: the [N,4] float64 rows of EventSequence.features "
+                         "(32 B/event; what the MVSEC loader holds: loader/loader_utils.py:44-52) or packed columns as in the HREM "
+                         "events{1,2}.npz files (x/y int16, t f64, p int8 = 13 B/event; loader/loader_utils.py:26-37 stacks them "
+                         "into rows on the host).  auto: each dataset's own format -- rows for mvsec_*, columns for hrem_*")
     return ap.parse_args()
 
 
@@ -612,7 +614,8 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
     B = wl.batch
     inp = make_host_inputs(wl, B, args.lookups, seed=100 + rank, pin=True)
     step = B200Step(wl, inp, dev, args.lookups, args.corr)
-    if args.events_format == "columns":
+    events_format = args.events_format if args.events_format != "auto" else ("columns" if wl.name.startswith("hrem") else "rows")
+    if events_format == "columns":
         step.columns = [{"t": np.ascontiguousarray(e[:, 0]), "x": e[:, 1].astype(np.int16), "y": e[:, 2].astype(np.int16),
                          "p": e[:, 3].astype(np.int8)} for e in inp["events"]]
 
@@ -781,9 +784,9 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
             torch.cuda.synchronize()
             reps.append(edist.max_over_ranks(time.perf_counter() - t0, dev))
         dt = statistics.median(reps)
-        total_b, ev_b = h2d_bytes(inp, args.events_format == "columns")
+        total_b, ev_b = h2d_bytes(inp, events_format == "columns")
         e2e = {"value": B * world * k / dt, "unit": "frame-pairs/s", "h2d_bytes_per_step": total_b,
-               "h2d_event_bytes_per_step": ev_b, "events_format": args.events_format,
+               "h2d_event_bytes_per_step": ev_b, "events_format": events_format,
                "d2h_bytes_per_step": step.d2h_bytes(), "steps": k, "ms_per_step": 1e3 * dt / k,
                "h2d_gbs_per_rank": total_b / (dt / k) / 1e9, "repetitions_ms_per_step": [1e3 * r / k for r in reps],
                "timer": "host perf_counter around synchronize (host staging + H2D + kernels + D2H)"}

@@ -1216,23 +1216,137 @@ voxel_deinterleave_kernel(const float* __restrict__ T, int nb, int nbp, int64_t 
 }
 
 // ---- cluster-resident path (windows whose grid fits the shared memory of one 8-CTA cluster) -------------------
-// (Experiment, off by default -- see cluster_plan() for the measurement.)
 // MVSEC-sized windows (5 x 260 x 346 fp32 = 1.8 MB) fit the distributed shared memory of a cluster of 8 CTAs
 // (8 x 225 KB).  One cluster then owns a window from the first vote to the normalised result: every CTA keeps
-// one eighth of the grid in its shared memory, votes are float atomics into the owning CTA's slice over DSMEM,
-// the non-zero statistics are reduced inside the cluster, and the finished grid goes to HBM exactly once.  HBM
-// traffic per window = 32 N bytes of events + one grid write, instead of memset + L2 atomics + a statistics read
-// + a read-modify-write for the normalisation; four launches (and the 2 us floor each has) become one.
+// one eighth of the grid in its shared memory, votes are atomics into the owning CTA's slice over DSMEM, the non-zero
+// statistics are reduced inside the cluster, and the finished grid goes to HBM exactly once.  HBM traffic per window
+// = 32 N bytes of events + one grid write, instead of memset + L2 atomics + a statistics read + a read-modify-write for
+// the normalisation; five launches (and the 2 us floor each has) become one.
+// Shared memory has no float RED on sm_100a (atomicAdd(float) is a compare-and-swap loop, over the cluster network a
+// remote round trip each: measured 277 us against 156 us for the L2 path in round 1), but INTEGER adds are native.  The
+// votes are therefore accumulated in fixed point, 2^-22 per unit (rounding error <= 1.2e-7 per vote, the size of the
+// fp32 rounding of the vote itself; the order-free mode's gate is 1e-5).  An int32 cell overflows at |sum| = 512, so
+// every add is issued with return and checked: a cell that ever reaches half the range (or a vote larger than 64)
+// raises a flag, and the cluster then REDOES that window with the float compare-and-swap adds -- slow, correct, and
+// only taken by windows with > 256 net votes on one voxel.
 namespace cg = cooperative_groups;
 constexpr int kClusterSize = 8;
 constexpr int kClusterThreads = 1024;
 constexpr int kClusterScratchBytes = 1024;   // [3][32] warp partials + 3 doubles CTA partial + mean/std
 
+// Tail shared by the cluster-resident kernels: the CTA's statistics (count, sum, sum of squares of its slice's non-zero
+// voxels) are reduced in the block, exchanged over distributed shared memory (rank-ordered sum: every CTA derives the
+// same mean / std, independent of scheduling), and the slice is normalised out of shared memory into `g`.
+__device__ __forceinline__ void cluster_stats_apply(cg::cluster_group& cluster, int rank, const float* mine, int valid, float* __restrict__ g,
+                                                    double c, double s, double q, bool normalize, double* red, double* partial, float* ms,
+                                                    double* __restrict__ stats_out, int w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = valid / 4;
+  float mean = 0.f, sd = 0.f;
+  if (normalize) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      red[warp] = c;
+      red[32 + warp] = s;
+      red[64 + warp] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double bc = 0, bs = 0, bq = 0;
+      for (int k = 0; k < kClusterThreads / 32; ++k) {
+        bc += red[k];
+        bs += red[32 + k];
+        bq += red[64 + k];
+      }
+      partial[0] = bc;
+      partial[1] = bs;
+      partial[2] = bq;
+    }
+    cluster.sync();
+    if (threadIdx.x == 0) {
+      double tc = 0, ts = 0, tq = 0;
+      for (int r = 0; r < kClusterSize; ++r) {       // rank order: every CTA derives identical statistics
+        const double* pr = cluster.map_shared_rank(partial, r);
+        tc += pr[0];
+        ts += pr[1];
+        tq += pr[2];
+      }
+      float m_ = 0.0f, sd_ = 0.0f;                    // same arithmetic as finish_stats_at
+      if (tc > 0) {
+        const double m = ts / tc;
+        m_ = (float)m;
+        if (tc > 1) {
+          double var = (tq - ts * m) / (tc - 1.0);
+          if (var < 0) var = 0;
+          sd_ = (float)sqrt(var);
+        } else {
+          sd_ = __int_as_float(0x7fc00000);
+        }
+      }
+      ms[0] = m_;
+      ms[1] = sd_;
+      if (stats_out != nullptr && rank == 0) {
+        stats_out[3 * w + 0] = tc;
+        stats_out[3 * w + 1] = (double)m_;
+        stats_out[3 * w + 2] = (double)sd_;
+      }
+    }
+    __syncthreads();
+    mean = ms[0];
+    sd = ms[1];
+  }
+  const bool divide = sd > 0.0f;
+  // (v - mean) / sd as q0 = c * r, rem = c - q0 * sd (exact, one FMA), q = q0 + rem * r with r = RN(1 / sd): the
+  // correctly rounded quotient (Markstein), i.e. the bits of __fdiv_rn in 3 instructions; huge / tiny operands (where the
+  // intermediate products could leave the normal range) take the IEEE division
+  const bool fast_div = divide && sd > 1.0e-15f && sd < 1.0e15f;
+  const float rcp = fast_div ? __frcp_rn(sd) : 0.0f;
+  auto norm = [&](float v) {
+    if (!normalize || v == 0.0f) return v;
+    const float cv = __fsub_rn(v, mean);
+    if (!divide) return cv;
+    if (!fast_div || !(fabsf(cv) < 1.0e15f && fabsf(cv) > 1.0e-15f)) return __fdiv_rn(cv, sd);
+    const float q0 = __fmul_rn(cv, rcp);
+    return __fmaf_rn(__fmaf_rn(-q0, sd, cv), rcp, q0);
+  };
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  const int nv = vec_ok ? nvec : 0;
+  for (int i = threadIdx.x; i < nv; i += kClusterThreads) {
+    float4 v = *reinterpret_cast<const float4*>(mine + 4 * i);
+    v.x = norm(v.x);
+    v.y = norm(v.y);
+    v.z = norm(v.z);
+    v.w = norm(v.w);
+    st_stream4(g + 4 * i, v);
+  }
+  for (int i = nv * 4 + threadIdx.x; i < valid; i += kClusterThreads) g[i] = norm(mine[i]);
+}
+
+// statistics of a slice that already sits in shared memory (four voxels summed in fp32, running sums in fp64)
+__device__ __forceinline__ void slice_stats(const float* mine, int valid, double& c, double& s, double& q) {
+  const int nvec = valid / 4;
+  for (int i = threadIdx.x; i < nvec; i += kClusterThreads) {
+    const float4 f = *reinterpret_cast<const float4*>(mine + 4 * i);
+    c += (double)((f.x != 0.0f) + (f.y != 0.0f) + (f.z != 0.0f) + (f.w != 0.0f));
+    s += (double)((f.x + f.y) + (f.z + f.w));
+    q += (double)fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, f.w * f.w)));
+  }
+  for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads) accum_stat(mine[i], c, s, q);
+}
+
+constexpr float kFixScale = 4194304.0f;          // 2^22 units per 1.0
+constexpr int kFixGuard = 1 << 30;               // half of the int32 range
+
 template <class Src>
 __global__ void __launch_bounds__(kClusterThreads, 1)
 voxel_cluster_kernel(const Src ev, const int64_t* __restrict__ offsets, int n_windows, int nb, int H, int W,
                      int slice, int normalize, float* __restrict__ grid, int64_t* __restrict__ dropped,
-                     double* __restrict__ stats_out) {
+                     double* __restrict__ stats_out, int noret) {
   extern __shared__ __align__(16) float cl_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -1241,137 +1355,87 @@ voxel_cluster_kernel(const Src ev, const int64_t* __restrict__ offsets, int n_wi
   double* red = reinterpret_cast<double*>(cl_smem + slice);     // slice is a multiple of 4 floats
   double* partial = red + 96;
   float* ms = reinterpret_cast<float*>(partial + 3);
-  float* peer[kClusterSize];
-#pragma unroll
-  for (int r = 0; r < kClusterSize; ++r) peer[r] = cluster.map_shared_rank(mine, r);
+  auto dsmem_addr = [](const void* local, int cta) {            // shared::cluster address of `local` in CTA `cta` of the cluster
+    uint32_t a;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(cta));
+    return a;
+  };
+  int* ovf = reinterpret_cast<int*>(ms + 2);                    // this CTA saw a cell near the fixed-point range
   const int64_t HW = (int64_t)H * W, vox = HW * nb;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   for (int w = cluster_id; w < n_windows; w += n_clusters) {
-    for (int i = threadIdx.x * 4; i < slice; i += kClusterThreads * 4)
-      *reinterpret_cast<float4*>(mine + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    cluster.sync();
-
     const int64_t begin = offsets[w], end = offsets[w + 1];
     const int64_t n = end - begin;
-    int ndrop = 0;
-    if (n > 0) {
-      const WindowTimes wt = window_times(ev, begin, end);
-      constexpr int kE = 4;
-      const int64_t stride = (int64_t)kClusterSize * kClusterThreads;
-      for (int64_t i0 = (int64_t)rank * kClusterThreads + threadIdx.x; i0 < n; i0 += stride * kE) {
-        EventRow rows[kE];
-#pragma unroll
-        for (int k = 0; k < kE; ++k)
-          if (i0 + k * stride < n) rows[k] = ev.load(begin + i0 + k * stride);
-#pragma unroll
-        for (int k = 0; k < kE; ++k) {
-          if (i0 + k * stride < n) {
-            const Vote v = make_vote(rows[k], wt.t_first, wt.dT, nb, W, HW, vox);
-            if (v.idx_left >= 0) {                    // vox < 2^31 on this path: 32-bit index arithmetic
-              const int il = (int)v.idx_left, r = il / slice;
-              atomicAdd(peer[r] + (il - r * slice), v.val_left);
-            }
-            if (v.idx_right >= 0) {
-              const int ir = (int)v.idx_right, r = ir / slice;
-              atomicAdd(peer[r] + (ir - r * slice), v.val_right);
-            }
-            ndrop += (int)v.oob_left + (int)v.oob_right;
-          }
-        }
-      }
-    }
-    if (dropped != nullptr && ndrop != 0)
-      atomicAdd(reinterpret_cast<unsigned long long*>(dropped), (unsigned long long)ndrop);
-    cluster.sync();
-
-    float mean = 0.f, sd = 0.f;
-    if (normalize) {
-      double c = 0, s = 0, q = 0;
-      for (int i = threadIdx.x * 4; i < slice; i += kClusterThreads * 4) {
-        const float4 v = *reinterpret_cast<const float4*>(mine + i);   // cells past the window's end stay zero
-        accum_stat(v.x, c, s, q);
-        accum_stat(v.y, c, s, q);
-        accum_stat(v.z, c, s, q);
-        accum_stat(v.w, c, s, q);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
-      }
-      if (lane == 0) {
-        red[warp] = c;
-        red[32 + warp] = s;
-        red[64 + warp] = q;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double bc = 0, bs = 0, bq = 0;
-        for (int k = 0; k < kClusterThreads / 32; ++k) {
-          bc += red[k];
-          bs += red[32 + k];
-          bq += red[64 + k];
-        }
-        partial[0] = bc;
-        partial[1] = bs;
-        partial[2] = bq;
-      }
+    bool use_float = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {             // cluster-uniform: 0 fixed point, 1 float redo
+      for (int i = threadIdx.x * 4; i < slice; i += kClusterThreads * 4)
+        *reinterpret_cast<float4*>(mine + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       cluster.sync();
-      if (threadIdx.x == 0) {
-        double tc = 0, ts = 0, tq = 0;
-        for (int r = 0; r < kClusterSize; ++r) {       // rank order: every CTA derives identical statistics
-          const double* pr = cluster.map_shared_rank(partial, r);
-          tc += pr[0];
-          ts += pr[1];
-          tq += pr[2];
-        }
-        float m_ = 0.0f, sd_ = 0.0f;                    // same arithmetic as finish_stats
-        if (tc > 0) {
-          const double m = ts / tc;
-          m_ = (float)m;
-          if (tc > 1) {
-            double var = (tq - ts * m) / (tc - 1.0);
-            if (var < 0) var = 0;
-            sd_ = (float)sqrt(var);
-          } else {
-            sd_ = __int_as_float(0x7fc00000);
+      int ndrop = 0;
+      bool bad = false;
+      if (n > 0) {
+        const WindowTimes wt = window_times(ev, begin, end);
+        constexpr int kE = 2;                                     // (64 registers per thread at 1024 threads)
+        const int64_t stride = (int64_t)kClusterSize * kClusterThreads;
+        for (int64_t i0 = (int64_t)rank * kClusterThreads + threadIdx.x; i0 < n; i0 += stride * kE) {
+          EventRow rows[kE];
+#pragma unroll
+          for (int k = 0; k < kE; ++k)
+            if (i0 + k * stride < n) rows[k] = ev.load(begin + i0 + k * stride);
+#pragma unroll
+          for (int k = 0; k < kE; ++k) {
+            if (i0 + k * stride < n) {
+              const Vote v = make_vote(rows[k], wt.t_first, wt.dT, nb, W, HW, vox);
+              auto add = [&](int64_t idx, float val) {          // vox < 2^31 on this path: 32-bit index arithmetic
+                const int il = (int)idx, r = il / slice;
+                float* cell = cluster.map_shared_rank(mine + (il - r * slice), r);
+                if (use_float) {
+                  atomicAdd(cell, val);
+                } else {
+                  if (noret) {            // timing experiment (EEM_VOXEL_CLUSTER_NORET=1): fire-and-forget adds, no range check
+                    asm volatile("red.shared::cluster.add.s32 [%0], %1;" ::"r"(dsmem_addr(mine + (il - r * slice), r)), "r"(__float2int_rn(val * kFixScale)) : "memory");
+                  } else {
+                    const int old = atomicAdd(reinterpret_cast<int*>(cell), __float2int_rn(val * kFixScale));
+                    bad = bad || !(fabsf(val) < 64.0f) || old >= kFixGuard || old <= -kFixGuard;
+                  }
+                }
+              };
+              if (v.idx_left >= 0) add(v.idx_left, v.val_left);
+              if (v.idx_right >= 0) add(v.idx_right, v.val_right);
+              ndrop += (int)v.oob_left + (int)v.oob_right;
+            }
           }
         }
-        ms[0] = m_;
-        ms[1] = sd_;
-        if (stats_out != nullptr && rank == 0) {
-          stats_out[3 * w + 0] = tc;
-          stats_out[3 * w + 1] = (double)m_;
-          stats_out[3 * w + 2] = (double)sd_;
-        }
       }
-      __syncthreads();
-      mean = ms[0];
-      sd = ms[1];
+      if (attempt == 0 && dropped != nullptr && ndrop != 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(dropped), (unsigned long long)ndrop);
+      const int any_bad = __syncthreads_or(bad ? 1 : 0);
+      if (threadIdx.x == 0) *ovf = any_bad;
+      cluster.sync();                                           // all votes of the window have landed; flags are visible
+      if (use_float) break;
+      int redo = 0;
+      for (int r = 0; r < kClusterSize; ++r) redo |= *cluster.map_shared_rank(ovf, r);
+      if (!redo) break;
+      use_float = true;
+      cluster.sync();                                           // every CTA has read the flags before they are rewritten
     }
-    const bool divide = sd > 0.0f;
-    float* out = grid + (int64_t)w * vox + (int64_t)rank * slice;
+
     const int64_t left = vox - (int64_t)rank * slice;             // cells of this slice inside the window
     const int valid = (int)(left < 0 ? 0 : (left < slice ? left : slice));
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const int nvec = vec_ok ? valid / 4 : 0;
-    for (int i = threadIdx.x; i < nvec; i += kClusterThreads) {
-      float4 v = *reinterpret_cast<const float4*>(mine + 4 * i);
-      if (normalize) {
-        v.x = normalize_one(v.x, mean, sd, divide);
-        v.y = normalize_one(v.y, mean, sd, divide);
-        v.z = normalize_one(v.z, mean, sd, divide);
-        v.w = normalize_one(v.w, mean, sd, divide);
+    if (!use_float) {                                             // fixed point -> fp32, in place (exact below |v| = 4)
+      constexpr float kInv = 1.0f / kFixScale;
+      for (int i = threadIdx.x * 4; i < slice; i += kClusterThreads * 4) {
+        const int4 q = *reinterpret_cast<const int4*>(mine + i);
+        *reinterpret_cast<float4*>(mine + i) = make_float4((float)q.x * kInv, (float)q.y * kInv, (float)q.z * kInv, (float)q.w * kInv);
       }
-      st_stream4(out + 4 * i, v);
+      __syncthreads();
     }
-    for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads)
-      out[i] = normalize ? normalize_one(mine[i], mean, sd, divide) : mine[i];
-    // no barrier needed here: the next window's first cluster.sync() orders this slice's reuse
+    double c = 0, s = 0, q = 0;
+    if (normalize) slice_stats(mine, valid, c, s, q);
+    float* out = grid + (int64_t)w * vox + (int64_t)rank * slice;
+    cluster_stats_apply(cluster, rank, mine, valid, out, c, s, q, normalize != 0, red, partial, ms, stats_out, w);
+    cluster.sync();   // the slice / `partial` / `ms` are rewritten for the next window only after every peer is done with them
   }
-  cluster.sync();   // keep every CTA's shared memory alive until all peers are done with it
 }
 
 // ---- cluster-resident NORMALISATION (windows whose grid fits the shared memory of one 8-CTA cluster) ------------------
@@ -1428,83 +1492,7 @@ voxel_normalize_cluster_kernel(float* __restrict__ grid, int n_windows, int64_t 
       mine[i] = v;
       accum_stat(v, c, s, q);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      c += __shfl_xor_sync(0xffffffffu, c, o);
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (lane == 0) {
-      red[warp] = c;
-      red[32 + warp] = s;
-      red[64 + warp] = q;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double bc = 0, bs = 0, bq = 0;
-      for (int k = 0; k < kClusterThreads / 32; ++k) {
-        bc += red[k];
-        bs += red[32 + k];
-        bq += red[64 + k];
-      }
-      partial[0] = bc;
-      partial[1] = bs;
-      partial[2] = bq;
-    }
-    cluster.sync();
-    if (threadIdx.x == 0) {
-      double tc = 0, ts = 0, tq = 0;
-      for (int r = 0; r < kClusterSize; ++r) {       // rank order: every CTA derives identical statistics
-        const double* pr = cluster.map_shared_rank(partial, r);
-        tc += pr[0];
-        ts += pr[1];
-        tq += pr[2];
-      }
-      float m_ = 0.0f, sd_ = 0.0f;                    // same arithmetic as finish_stats_at
-      if (tc > 0) {
-        const double m = ts / tc;
-        m_ = (float)m;
-        if (tc > 1) {
-          double var = (tq - ts * m) / (tc - 1.0);
-          if (var < 0) var = 0;
-          sd_ = (float)sqrt(var);
-        } else {
-          sd_ = __int_as_float(0x7fc00000);
-        }
-      }
-      ms[0] = m_;
-      ms[1] = sd_;
-      if (stats_out != nullptr && rank == 0) {
-        stats_out[3 * w + 0] = tc;
-        stats_out[3 * w + 1] = (double)m_;
-        stats_out[3 * w + 2] = (double)sd_;
-      }
-    }
-    __syncthreads();
-    const float mean = ms[0], sd = ms[1];
-    const bool divide = sd > 0.0f;
-    // (v - mean) / sd as q0 = c * r, rem = c - q0 * sd (exact, one FMA), q = q0 + rem * r with r = RN(1 / sd): the
-    // correctly rounded quotient (Markstein), i.e. the bits of __fdiv_rn in 3 instructions; huge / tiny sd (where the
-    // intermediate products could leave the normal range) take the IEEE division
-    const bool fast_div = divide && sd > 1.0e-15f && sd < 1.0e15f;
-    const float rcp = fast_div ? __frcp_rn(sd) : 0.0f;
-    auto norm = [&](float v) {
-      if (v == 0.0f) return v;
-      const float cv = __fsub_rn(v, mean);
-      if (!divide) return cv;
-      if (!fast_div || !(fabsf(cv) < 1.0e15f && fabsf(cv) > 1.0e-15f)) return __fdiv_rn(cv, sd);
-      const float q0 = __fmul_rn(cv, rcp);
-      return __fmaf_rn(__fmaf_rn(-q0, sd, cv), rcp, q0);
-    };
-    for (int i = threadIdx.x; i < nvec; i += kClusterThreads) {
-      float4 v = *reinterpret_cast<const float4*>(mine + 4 * i);
-      v.x = norm(v.x);
-      v.y = norm(v.y);
-      v.z = norm(v.z);
-      v.w = norm(v.w);
-      st_stream4(g + 4 * i, v);
-    }
-    for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads) g[i] = normalize_one(mine[i], mean, sd, divide);
+    cluster_stats_apply(cluster, rank, mine, valid, g, c, s, q, true, red, partial, ms, stats_out, w);
     cluster.sync();   // `partial` / `ms` are rewritten for the next window only after every peer has read them
   }
 }
@@ -1709,12 +1697,14 @@ int time_lanes(int dflt) {
   return dflt;
 }
 
-// Cluster-resident path: possible when one window's grid fits the shared memory of an 8-CTA cluster.
-// MEASURED SLOWER than the L2-atomic path and therefore only taken when forced (EEM_VOXEL_PATH=cluster):
-// sm_100a has no native fp32 add on shared memory -- atomicAdd on (distributed) shared memory compiles to
-// ATOMS.CAST.SPIN / ATOM.E.CAST.SPIN compare-and-swap loops, and over the cluster network each one is a remote
-// round trip: MVSEC x64 windows take 277 us here against 156 us for memset + RED.ADD.F32 in L2 + stats + apply
-// (profiles/r01/README.md).  Kept as a tested experiment for parts that get a native shared-memory float RED.
+// Cluster-resident path: possible when one window's grid fits the shared memory of an 8-CTA cluster.  MEASURED SLOWER
+// than the L2-atomic path in both of its forms and therefore only taken when forced (EEM_VOXEL_PATH=cluster; tested):
+// round 1, float compare-and-swap adds over DSMEM: 277 us against 156 us for MVSEC x64 windows; round 2, fixed-point
+// integer adds (native): voxelize family of the bench 0.194 ms (adds with return + range check) / 0.185 ms
+// (fire-and-forget red.shared::cluster, EEM_VOXEL_CLUSTER_NORET=1) against 0.135 ms -- so the adds are not what costs:
+// only 15 clusters are co-resident on a B200 (5 rounds for 64 windows) and inside a cluster the phases (zero, stamps,
+// two batches of event loads, votes, conversion, statistics, exchange, apply) run strictly one after the other at
+// ~37 us per window, where the L2 kernels keep every SM busy with thousands of independent CTAs.
 struct ClusterPlan {
   bool ok;
   int slice;          // floats of the window grid held by each CTA
@@ -1725,9 +1715,8 @@ struct ClusterPlan {
 template <class Src>
 ClusterPlan cluster_plan(int64_t vox, int n_windows, int64_t n_total) {
   ClusterPlan pl{false, 0, 0, 0};
-  if (const char* v = getenv("EEM_VOXEL_PATH")) {   // timing experiments only
-    if (v[0] == 'd' || v[0] == 'p') return pl;
-  }
+  const char* forced = getenv("EEM_VOXEL_PATH");
+  if (forced == nullptr || forced[0] != 'c') return pl;         // opt-in
   if (vox >= (1ll << 31)) return pl;
   pl.slice = (int)align_up((size_t)ceil_div(vox, kClusterSize), 4);
   pl.smem = (size_t)pl.slice * sizeof(float) + kClusterScratchBytes;
@@ -1770,7 +1759,7 @@ ClusterPlan cluster_plan(int64_t vox, int n_windows, int64_t n_total) {
   const int active = n_windows < pl.max_clusters ? n_windows : pl.max_clusters;
   (void)active;
   (void)n_total;
-  pl.ok = getenv("EEM_VOXEL_PATH") != nullptr && getenv("EEM_VOXEL_PATH")[0] == 'c';
+  pl.ok = true;
   return pl;
 }
 
@@ -1845,6 +1834,32 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
   // 126 MB L2), so the memset, the L2-resolved votes, the statistics read and the normalisation read-modify-write
   // of a group all hit L2 and HBM only sees the events and one write-back of each grid.
   const bool tiled = tiled_path_enabled(mode) && tiled_path_fits(num_bins, height, width, vox);
+  // Order-free mode, windows that fit a cluster's shared memory: one launch from the first vote to the normalised grid.
+  // Checked before the L2 grouping below: the grids never live in L2 on this path.
+  if (mode == EEM_VOXEL_ATOMIC && !tiled && n_total > 0 && max_events_per_window > 0 && !use_pair_path(n_total, total_vox) &&
+      (reinterpret_cast<uintptr_t>(grid) & 15) == 0 && vox % 4 == 0) {
+    const ClusterPlan pl = cluster_plan<Src>(vox, n_windows, n_total);
+    if (pl.ok) {
+      const int n_clusters = n_windows < pl.max_clusters ? n_windows : pl.max_clusters;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(n_clusters * kClusterSize), 1, 1);
+      cfg.blockDim = dim3(kClusterThreads, 1, 1);
+      cfg.dynamicSmemBytes = pl.smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = kClusterSize;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      EEM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, voxel_cluster_kernel<Src>, events, offsets, n_windows, num_bins, height, width,
+                                        pl.slice, normalize, grid, dropped, stats_out,
+                                        getenv("EEM_VOXEL_CLUSTER_NORET") != nullptr ? 1 : 0));
+      EEM_CHECK_LAUNCH("voxel_cluster_kernel");
+      return EEM_OK;
+    }
+  }
   if ((mode == EEM_VOXEL_ATOMIC || tiled) && n_windows > 1 && total_vox * (int64_t)sizeof(float) > l2_group_bytes() &&
       vox * (int64_t)sizeof(float) <= l2_group_bytes()) {
     const int per_group = (int)(l2_group_bytes() / (vox * (int64_t)sizeof(float)));
@@ -1924,28 +1939,6 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
     return EEM_OK;
   }
   const bool pair = !no_events && mode == EEM_VOXEL_ATOMIC && use_pair_path(n_total, total_vox);
-  if (!no_events && mode == EEM_VOXEL_ATOMIC && !pair && (reinterpret_cast<uintptr_t>(grid) & 15) == 0) {
-    const ClusterPlan pl = cluster_plan<Src>(vox, n_windows, n_total);
-    if (pl.ok) {
-      const int n_clusters = n_windows < pl.max_clusters ? n_windows : pl.max_clusters;
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(n_clusters * kClusterSize), 1, 1);
-      cfg.blockDim = dim3(kClusterThreads, 1, 1);
-      cfg.dynamicSmemBytes = pl.smem;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr{};
-      attr.id = cudaLaunchAttributeClusterDimension;
-      attr.val.clusterDim.x = kClusterSize;
-      attr.val.clusterDim.y = 1;
-      attr.val.clusterDim.z = 1;
-      cfg.attrs = &attr;
-      cfg.numAttrs = 1;
-      EEM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, voxel_cluster_kernel<Src>, events, offsets, n_windows, num_bins, height, width,
-                                        pl.slice, normalize, grid, dropped, stats_out));
-      EEM_CHECK_LAUNCH("voxel_cluster_kernel");
-      return EEM_OK;
-    }
-  }
   if (!no_events && mode == EEM_VOXEL_ATOMIC && !pair && use_interleaved_path(num_bins) && vox < (1ll << 31)) {
     const int nbp = (num_bins + 1) & ~1;
     const int64_t HW = (int64_t)height * width, vox_p = HW * nbp;

@@ -135,6 +135,53 @@ def test_normalize_cluster_path_matches_split_path(n_windows, shape):
         assert a[1].abs().max().item() == 0.0 and a[2].view(-1)[3].item() == 0.0     # 2.5 - mean(2.5)
 
 
+def test_cluster_path_fixed_point_and_overflow_redo(V):
+    """The opt-in cluster-resident voxelizer (EEM_VOXEL_PATH=cluster; measured slower than the L2-atomic kernels, kept as a
+    tested experiment): votes are integer adds (2^-22 units) into the distributed shared memory of 8 CTAs.  (1) ordinary
+    windows: <= 1e-5 relative against the C oracle and against the default L2-atomic kernels; (2) a hot pixel collecting
+    ~1500 same-sign votes per bin exceeds half the int32 range: the cluster must notice and redo the window with float
+    adds (gate scaled by the vote mass like every order-free sum); (3) a polarity of 100 is outside the fixed-point
+    vote range and takes the same redo."""
+    import os
+    rng = np.random.default_rng(77)
+    nb, h, w = 5, 260, 346
+    enc = V(nb, gpu=True, normalize=False, forkserver=False)
+    ev = make_events(rng, 30_000, h, w)
+    ref, _, _ = c_oracle.voxelize(ev, nb, h, w, normalize=False)
+    out_l2 = enc(Seq(ev, h, w)).cpu().numpy()
+    os.environ["EEM_VOXEL_PATH"] = "cluster"
+    try:
+        _cluster_path_checks(V, enc, ev, ref, out_l2, rng, nb, h, w)
+    finally:
+        os.environ.pop("EEM_VOXEL_PATH", None)
+
+
+def _cluster_path_checks(V, enc, ev, ref, out_l2, rng, nb, h, w):
+    out = enc(Seq(ev, h, w)).cpu().numpy()
+    assert rel_close(out, ref).all(), np.abs(out - ref).max()
+    assert rel_close(out, out_l2).all()
+    # (2) hot pixel: 6000 events, all polarity +1, at (x, y) = (17, 33), inside a window of uniform events
+    hot = make_events(rng, 26_000, h, w)
+    hot[::4, 1], hot[::4, 2], hot[::4, 3] = 17.0, 33.0, 1.0
+    ref, _, _ = c_oracle.voxelize(hot, nb, h, w, normalize=False)
+    assert np.abs(ref).max() > 600.0                       # far beyond the +-256 the fixed-point cells may reach
+    mass = _vote_mass(hot, nb, h, w)
+    batch = enc.voxelize_batch([Seq(ev, h, w), Seq(hot, h, w), Seq(ev, h, w)]).cpu().numpy()
+    assert order_free_close(batch[1], ref, mass).all(), np.abs(batch[1] - ref).max()
+    assert rel_close(batch[0], out).all()
+    assert rel_close(batch[2], batch[0]).all()
+    # normalised: same window through the fused statistics
+    ref_n = ref_ops.voxelize(hot, nb, h, w, normalize=True).numpy()
+    out_n = V(nb, gpu=True, normalize=True, forkserver=False)(Seq(hot, h, w)).cpu().numpy()
+    assert np.abs(out_n - ref_n).max() <= 1e-4 * np.abs(ref_n).max()
+    # (3) a large polarity value
+    big = ev.copy()
+    big[5, 3] = 100.0
+    ref, _, _ = c_oracle.voxelize(big, nb, h, w, normalize=False)
+    out = enc(Seq(big, h, w)).cpu().numpy()
+    assert rel_close(out, ref).all(), np.abs(out - ref).max()
+
+
 def test_batched_windows_ragged(V):
     rng = np.random.default_rng(5)
     h, w, nb = 64, 96, 5

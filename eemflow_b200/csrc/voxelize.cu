@@ -1258,7 +1258,7 @@ __device__ __forceinline__ void cluster_stats_apply(cg::cluster_group& cluster, 
     __syncthreads();
     if (threadIdx.x == 0) {
       double bc = 0, bs = 0, bq = 0;
-      for (int k = 0; k < kClusterThreads / 32; ++k) {
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
         bc += red[k];
         bs += red[32 + k];
         bq += red[64 + k];
@@ -1316,7 +1316,8 @@ __device__ __forceinline__ void cluster_stats_apply(cg::cluster_group& cluster, 
   };
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
   const int nv = vec_ok ? nvec : 0;
-  for (int i = threadIdx.x; i < nv; i += kClusterThreads) {
+  #pragma unroll 4
+  for (int i = threadIdx.x; i < nv; i += (int)blockDim.x) {
     float4 v = *reinterpret_cast<const float4*>(mine + 4 * i);
     v.x = norm(v.x);
     v.y = norm(v.y);
@@ -1324,19 +1325,20 @@ __device__ __forceinline__ void cluster_stats_apply(cg::cluster_group& cluster, 
     v.w = norm(v.w);
     st_stream4(g + 4 * i, v);
   }
-  for (int i = nv * 4 + threadIdx.x; i < valid; i += kClusterThreads) g[i] = norm(mine[i]);
+  for (int i = nv * 4 + threadIdx.x; i < valid; i += (int)blockDim.x) g[i] = norm(mine[i]);
 }
 
 // statistics of a slice that already sits in shared memory (four voxels summed in fp32, running sums in fp64)
 __device__ __forceinline__ void slice_stats(const float* mine, int valid, double& c, double& s, double& q) {
   const int nvec = valid / 4;
-  for (int i = threadIdx.x; i < nvec; i += kClusterThreads) {
+#pragma unroll 4
+  for (int i = threadIdx.x; i < nvec; i += (int)blockDim.x) {
     const float4 f = *reinterpret_cast<const float4*>(mine + 4 * i);
     c += (double)((f.x != 0.0f) + (f.y != 0.0f) + (f.z != 0.0f) + (f.w != 0.0f));
     s += (double)((f.x + f.y) + (f.z + f.w));
     q += (double)fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, f.w * f.w)));
   }
-  for (int i = nvec * 4 + threadIdx.x; i < valid; i += kClusterThreads) accum_stat(mine[i], c, s, q);
+  for (int i = nvec * 4 + threadIdx.x; i < valid; i += (int)blockDim.x) accum_stat(mine[i], c, s, q);
 }
 
 constexpr float kFixScale = 4194304.0f;          // 2^22 units per 1.0
@@ -1438,6 +1440,35 @@ voxel_cluster_kernel(const Src ev, const int64_t* __restrict__ offsets, int n_wi
   }
 }
 
+// ---- cluster-synchronised STREAMING normalisation (EEM_VOXEL_NORM=stream; measured, not the default) -----------------
+// The kernel boundary between K2's statistics and apply passes exists only because the statistics are a whole-window
+// reduction.  Here a window is owned by a cluster of 8 CTAs without shared-memory residency: pass 1 reads the CTA's
+// eighth of the window and accumulates the non-zero statistics, a cluster barrier + distributed shared memory exchange
+// gives every CTA the window's mean / std, pass 2 re-reads the slice (from L2) and writes the normalised values.  Every
+// window proceeds on its own and all windows of a call are in flight at once -- but it moves 12 bytes per voxel like
+// the two-kernel path, and that traffic is what bounds all forms (see norm_mode()).
+constexpr int kStreamThreads = 1024;
+constexpr int64_t kStreamNormMaxBytes = 8ll << 20;   // windows up to 8 MB: the second pass should find the first one's lines in L2
+
+__global__ void __launch_bounds__(kStreamThreads)
+voxel_normalize_stream_kernel(float* __restrict__ grid, int n_windows, int64_t vox, int slice, double* __restrict__ stats_out) {
+  __shared__ double red[96];
+  __shared__ double partial[3];
+  __shared__ float ms[2];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / kClusterSize, n_clusters = gridDim.x / kClusterSize;
+  for (int w = cluster_id; w < n_windows; w += n_clusters) {
+    float* g = grid + (int64_t)w * vox + (int64_t)rank * slice;
+    const int64_t left = vox - (int64_t)rank * slice;             // cells of this slice inside the window
+    const int valid = (int)(left < 0 ? 0 : (left < slice ? left : slice));
+    double c = 0, s = 0, q = 0;
+    slice_stats(g, valid, c, s, q);
+    cluster_stats_apply(cluster, rank, g, valid, g, c, s, q, true, red, partial, ms, stats_out, w);
+    cluster.sync();   // `partial` / `ms` are rewritten for the next window only after every peer has read them
+  }
+}
+
 // ---- cluster-resident NORMALISATION (windows whose grid fits the shared memory of one 8-CTA cluster) ------------------
 // K2 as two kernels reads every voxel twice and writes it once, with a launch boundary in between because the
 // statistics are a whole-window reduction.  For MVSEC-sized windows (5 x 260 x 346 fp32 = 1.8 MB) one 8-CTA cluster
@@ -1508,9 +1539,6 @@ struct NormClusterPlan {
 // forces the two-kernel path (comparisons).
 NormClusterPlan norm_cluster_plan(const float* grid, int64_t vox) {
   NormClusterPlan pl{false, 0, 0, 0};
-  if (const char* v = getenv("EEM_VOXEL_NORM")) {
-    if (v[0] == 's') return pl;
-  }
   if (vox >= (1ll << 31) || vox % 4 != 0 || (reinterpret_cast<uintptr_t>(grid) & 15) != 0) return pl;
   pl.slice = (int)align_up((size_t)ceil_div(vox, kClusterSize), 4);
   pl.smem = (size_t)pl.slice * sizeof(float) + kClusterScratchBytes;
@@ -1763,8 +1791,66 @@ ClusterPlan cluster_plan(int64_t vox, int n_windows, int64_t n_total) {
   return pl;
 }
 
-int launch_normalize(float* grid, int n_windows, int64_t vox, double* stats_out, char* ws, cudaStream_t stream) {
+// EEM_VOXEL_NORM: "cluster" (shared-memory resident; the default where it applies), "stream" (cluster-synchronised, two
+// passes from L2), "split" (two kernels).  Measured in the MVSEC step (voxelize family / whole step, ms): cluster 0.135 /
+// 0.795, stream 0.158 / 0.807 (256-thread CTAs: 0.163 / 0.834), split 0.129 / 0.850 -- all three are within 1.7x of the
+// two L2 passes over 115 MB that any normalisation needs; the resident form moves the fewest bytes and leaves 28 SMs to
+// the other branches of the step.
+inline int norm_mode() {
+  const char* v = getenv("EEM_VOXEL_NORM");
+  if (v == nullptr || v[0] == 'c') return 1;
+  return (v[0] == 's' && v[1] == 't') ? 0 : 2;
+}
+
+// Windows of up to 8 x 2^22 voxels whose slices are 16-byte aligned; grid = min(windows, co-resident clusters) x 8 CTAs.
+int launch_normalize_stream(float* grid, int n_windows, int64_t vox, double* stats_out, cudaStream_t stream, bool* done) {
+  *done = false;
+  if (vox % 4 != 0 || (reinterpret_cast<uintptr_t>(grid) & 15) != 0 || vox > ((int64_t)kClusterSize << 22)) return EEM_OK;
+  const int slice = (int)align_up((size_t)ceil_div(vox, kClusterSize), 4);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return EEM_OK;
+  static std::mutex mu;
+  static int clusters_dev[kMaxDevices] = {};
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kStreamThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = kClusterSize;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
   {
+    std::lock_guard<std::mutex> lock(mu);
+    if (clusters_dev[dev] == 0) {
+      cfg.gridDim = dim3(kClusterSize, 1, 1);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, voxel_normalize_stream_kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return EEM_OK;
+      }
+      clusters_dev[dev] = n;
+    }
+    max_clusters = clusters_dev[dev];
+  }
+  const int n_clusters = n_windows < max_clusters ? n_windows : max_clusters;
+  cfg.gridDim = dim3((unsigned)(n_clusters * kClusterSize), 1, 1);
+  EEM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, voxel_normalize_stream_kernel, grid, n_windows, vox, slice, stats_out));
+  EEM_CHECK_LAUNCH("voxel_normalize_stream_kernel");
+  *done = true;
+  return EEM_OK;
+}
+
+int launch_normalize(float* grid, int n_windows, int64_t vox, double* stats_out, char* ws, cudaStream_t stream) {
+  if (norm_mode() == 0 && vox * (int64_t)sizeof(float) <= kStreamNormMaxBytes) {
+    bool done = false;
+    const int rc = launch_normalize_stream(grid, n_windows, vox, stats_out, stream, &done);
+    if (rc != EEM_OK || done) return rc;
+  }
+  if (norm_mode() == 1) {
     const NormClusterPlan pl = norm_cluster_plan(grid, vox);
     if (pl.ok) {
       const int n_clusters = n_windows < pl.max_clusters ? n_windows : pl.max_clusters;
@@ -1865,10 +1951,11 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
     const int per_group = (int)(l2_group_bytes() / (vox * (int64_t)sizeof(float)));
     const int n_groups = (int)ceil_div(n_windows, per_group);
     const int even = (int)ceil_div(n_windows, n_groups);             // equal-sized groups
-    // The cluster-resident normalisation runs in rounds of as many windows as clusters are co-resident (15 on a B200):
-    // one launch over ALL windows after the last group's votes needs ceil(64 / 15) = 5 rounds where two launches over
-    // 32 windows need 2 x 3, and the grids it reads are still largely in L2.
-    const bool norm_at_end = normalize && !tiled && norm_cluster_plan(grid, vox).ok;
+    // The shared-memory-resident normalisation (EEM_VOXEL_NORM=cluster) runs in rounds of as many windows as clusters are
+    // co-resident (15 on a B200): one launch over ALL windows after the last group's votes needs ceil(64 / 15) = 5 rounds
+    // where two launches over 32 windows need 2 x 3.  The streaming form (default) has every window in flight at once and
+    // normalises each group right after its votes, while its grids are L2-hot.
+    const bool norm_at_end = normalize && !tiled && norm_mode() == 1 && norm_cluster_plan(grid, vox).ok;
     for (int w0 = 0; w0 < n_windows; w0 += even) {
       const int nw = n_windows - w0 < even ? n_windows - w0 : even;
       // upper bound of the group's event count (sizes its scratch): never more than the whole call

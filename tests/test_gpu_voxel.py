@@ -97,8 +97,9 @@ def test_oracle_parity(V, n, nb, h, w, clustered):
 
 @pytest.mark.parametrize("n_windows,shape", [(40, (5, 64, 96)), (3, (5, 260, 346)), (2, (15, 60, 62)), (1, (1, 1, 4))])
 def test_normalize_cluster_path_matches_split_path(n_windows, shape):
-    """K2 for windows that fit one 8-CTA cluster's shared memory (one launch: load + statistics, DSMEM exchange, apply)
-    against the two-kernel path (EEM_VOXEL_NORM=split) and the oracle's formula: non-zero count exact, mean / std and the
+    """K2 as ONE launch per call -- a cluster of 8 CTAs per window, statistics exchanged over distributed shared memory:
+    the streaming form (default: two passes over the slice, every window in flight) and the shared-memory-resident form
+    (EEM_VOXEL_NORM=cluster) -- against the two-kernel path (EEM_VOXEL_NORM=split) and the oracle's formula: non-zero count exact, mean / std and the
     normalised voxels <= 1e-6 relative (the two paths add the same fp64 terms in a different order).  40 windows: more
     than the resident clusters, so clusters loop; all-zero, one-non-zero (std = NaN -> v - mean) and dense windows."""
     import os
@@ -111,7 +112,7 @@ def test_normalize_cluster_path_matches_split_path(n_windows, shape):
         grid[2].zero_()
         grid[2].view(-1)[3] = 2.5                         # a single non-zero voxel
     outs, stats = {}, {}
-    for mode in ("cluster", "split"):
+    for mode in ("stream", "cluster", "split"):
         os.environ["EEM_VOXEL_NORM"] = mode
         try:
             g = grid.cuda()
@@ -120,7 +121,8 @@ def test_normalize_cluster_path_matches_split_path(n_windows, shape):
             outs[mode], stats[mode] = g.cpu(), st.cpu()
         finally:
             os.environ.pop("EEM_VOXEL_NORM", None)
-    assert torch.equal(stats["cluster"][:, 0], stats["split"][:, 0])
+    assert torch.equal(stats["cluster"][:, 0], stats["split"][:, 0]) and torch.equal(stats["stream"][:, 0], stats["split"][:, 0])
+    assert torch.equal(torch.nan_to_num(outs["stream"], nan=-7.0), torch.nan_to_num(outs["cluster"], nan=-7.0))   # same arithmetic, same order
     assert torch.equal(stats["cluster"][:, 0], (grid.flatten(1) != 0).sum(1).double())
     for k in range(n_windows):
         nz = grid[k][grid[k] != 0].double()

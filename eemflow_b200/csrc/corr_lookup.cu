@@ -597,6 +597,10 @@ int launch_lookup_packed(const PackedLookupParams& p, cudaStream_t stream) {
       if (cons > S::kThreads / 32) cons = S::kThreads / 32;
       const int threads = (cons + ws.geo_warps + ws.copy_warps) * 32;
       int64_t grid = (int64_t)sms * ws.per_sm;
+      if (const char* v = getenv("EEM_LOOKUP_WS_CTAS")) {      // timing experiments: leave SMs to concurrent kernels
+        const int cap = atoi(v);
+        if (cap >= 1 && cap < grid) grid = cap;
+      }
       if (grid > n_batches) grid = n_batches;
       if (p.debug != 0) {                  // phase-ablation build (EEM_LOOKUP_DEBUG, timing experiments only)
         static DynSmemOptIn optin_dbg;

@@ -616,8 +616,12 @@ def run_b200(wl, args, rank, world, dev, steps, warmup, do_e2e, do_cpu, sample_c
     step = B200Step(wl, inp, dev, args.lookups, args.corr)
     events_format = args.events_format if args.events_format != "auto" else ("columns" if wl.name.startswith("hrem") else "rows")
     if events_format == "columns":
-        step.columns = [{"t": np.ascontiguousarray(e[:, 0]), "x": e[:, 1].astype(np.int16), "y": e[:, 2].astype(np.int16),
-                         "p": e[:, 3].astype(np.int8)} for e in inp["events"]]
+        def pinned(a, dtype):          # like the rows: page-locked host memory (a loader with pin_memory=True)
+            t = torch.empty(a.shape, dtype=dtype, pin_memory=True)
+            t.numpy()[...] = a
+            return t.numpy()
+        step.columns = [{"t": pinned(e[:, 0], torch.float64), "x": pinned(e[:, 1], torch.int16), "y": pinned(e[:, 2], torch.int16),
+                         "p": pinned(e[:, 3], torch.int8)} for e in inp["events"]]
 
     # N > 1: nothing on the data path is exchanged.  The result flows go to rank 0 every step, on a communication
     # stream that overlaps the next step: a device-to-peer copy into rank 0's result buffer (peer memory over NVLink,

@@ -378,10 +378,48 @@ class _ColumnStage:
         self.done = None
         self.t_dtype = None
 
+    @staticmethod
+    def _pinned_exact(window, t_dtype) -> bool:
+        """All four columns already page-locked and in the device layout (t int64 / float64, x / y int16, p int8)."""
+        want = (t_dtype, numpy.int16, numpy.int16, numpy.int8)
+        try:
+            return all(c.dtype == d and c.flags.c_contiguous and torch.from_numpy(c).is_pinned() for c, d in zip(window, want))
+        except (TypeError, ValueError, RuntimeError):
+            return False
+
+    def _upload_pinned(self, cols, counts, t_dtype, device):
+        """Page-locked caller columns (a loader with pin_memory=True): no staging pass -- one DMA per column and window
+        straight from the caller's memory, and the sortedness scan of EventSequence.is_sorted runs on the staging
+        threads WHILE the copies are on the link (the kernels that consume them are enqueued after this returns)."""
+        total = sum(counts)
+        tt = torch.int64 if t_dtype == numpy.int64 else torch.float64
+        if self.off is None or self.off.numel() < len(counts) + 1:
+            self.off = torch.empty(max(len(counts) + 1, 64), dtype=torch.int64, pin_memory=True)
+        off_host = self.off.numpy()
+        off_host[0] = 0
+        numpy.cumsum(counts, out=off_host[1:len(counts) + 1])
+        with torch.cuda.device(device):
+            off = self.off[:len(counts) + 1].to(device, non_blocking=True)
+            out = [torch.empty(total, dtype=d, device=device) for d in (tt, torch.int16, torch.int16, torch.int8)]
+            pos = 0
+            for window, n in zip(cols, counts):
+                for o, col in zip(out, window):
+                    o[pos:pos + n].copy_(torch.from_numpy(col), non_blocking=True)
+                pos += n
+            self.done = torch.cuda.Event()
+            self.done.record()
+        tasks = [(k, lo, min(n, lo + 4 * _STAGE_CHUNK_ROWS)) for k, n in enumerate(counts) for lo in range(0, n, 4 * _STAGE_CHUNK_ROWS)]
+        scan = (lambda task: task[0] if not _chunk_is_sorted(cols[task[0]][0], task[1], task[2]) else -1)
+        results = map(scan, tasks) if total <= _STAGE_CHUNK_ROWS else _staging_pool().map(scan, tasks)
+        unsorted = sorted({k for k in results if k >= 0})
+        return (*out, off, unsorted)
+
     def upload(self, cols, counts, t_dtype, device):
         total = sum(counts)
         if self.done is not None:
             self.done.synchronize()
+        if total > 0 and all(self._pinned_exact(w, t_dtype) for w in cols):
+            return self._upload_pinned(cols, counts, t_dtype, device)
         if self.host is None or self.host[1].shape[0] < total or self.t_dtype != t_dtype:
             cap = max(total, 1024)
             tt = torch.int64 if t_dtype == numpy.int64 else torch.float64

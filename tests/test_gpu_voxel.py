@@ -440,6 +440,20 @@ def test_packed_columns_match_reference_loader_chain(V):
         assert np.array_equal(det[k], ref_raw), k
         ref_norm = ref_ops.voxelize(s.features, nb, h, w, normalize=True).numpy()
         assert rel_close(atom[k], ref_norm).all(), k
+    # page-locked columns in the device layout (a loader with pin_memory=True) take the staging-free upload: same bits
+    def pin(a, dtype):
+        t = torch.empty(a.shape, dtype=dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
+    pinned = [{"t": pin(c["t"], torch.int64), "x": pin(c["x"], torch.int16), "y": pin(c["y"], torch.int16),
+               "p": pin(c["p"], torch.int8)} for c in windows]
+    from eemflow_b200.event_utils import _ColumnStage
+    assert all(_ColumnStage._pinned_exact(tuple(c[k] for k in ("t", "x", "y", "p")), np.int64) for c in pinned)
+    det_p = V(nb, gpu=True, normalize=False, forkserver=False, deterministic=True).voxelize_columns(pinned, h, w).cpu().numpy()
+    assert np.array_equal(det_p, det)
+    pinned[2] = {k: pin(v[::-1].copy(), torch.from_numpy(v).dtype) for k, v in pinned[2].items()}      # unsorted pinned window
+    atom_p = V(nb, gpu=True, normalize=True, forkserver=False).voxelize_columns(pinned, h, w).cpu().numpy()
+    assert rel_close(atom_p[2], atom[2]).all() and rel_close(atom_p[0], atom[0]).all()
     # unsorted columns are sorted by time stamp first, as EventSequence does (loader/loader_utils.py:365-366)
     perm = rng.permutation(windows[2]["t"].shape[0])
     shuffled = [windows[0], windows[1], {k: v[perm] for k, v in windows[2].items()}]

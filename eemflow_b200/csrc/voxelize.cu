@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <mutex>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace eem {
@@ -2033,7 +2035,7 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
     EEM_CHECK_CUDA(cudaMemsetAsync(T, 0, (size_t)n_windows * vox_p * sizeof(float), stream));
     const int64_t per_block = (int64_t)kVoteThreads * kVoteEventsPerThread;
     const int64_t chunks = ceil_div(max_events_per_window, per_block);
-    const int lanes = time_lanes(64);
+    const int lanes = (int)std::min<int64_t>(time_lanes(64), chunks);   // short windows: no CTAs without a chunk
     dim3 g((unsigned)(ceil_div(chunks, lanes) * lanes), (unsigned)n_windows);
     voxel_vote_interleaved_kernel<Src><<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, nbp, height, width, lanes, T, dropped);
     EEM_CHECK_LAUNCH("voxel_vote_interleaved_kernel");
@@ -2061,7 +2063,7 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
   } else if (mode == EEM_VOXEL_ATOMIC && !pair) {
     const int64_t per_block = (int64_t)kVoteThreads * kVoteEventsPerThread;
     const int64_t chunks = ceil_div(max_events_per_window, per_block);
-    const int lanes = time_lanes(64);
+    const int lanes = (int)std::min<int64_t>(time_lanes(64), chunks);   // short windows: no CTAs without a chunk
     dim3 g((unsigned)(ceil_div(chunks, lanes) * lanes), (unsigned)n_windows);
     voxel_vote_atomic_kernel<Src><<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height,
                                                              width, lanes, grid, dropped);
@@ -2072,7 +2074,7 @@ int voxelize_impl(const Src events, const int64_t* offsets, int n_windows, int64
     const int64_t per_block = (int64_t)kVoteThreads * kVoteEventsPerThread;
     const int64_t chunks = ceil_div(max_events_per_window, per_block);
     // the scratch is 2x the grid: keep the set of concurrently active bin planes small enough for L2
-    const int lanes = time_lanes(4);
+    const int lanes = (int)std::min<int64_t>(time_lanes(4), chunks);
     dim3 g((unsigned)(ceil_div(chunks, lanes) * lanes), (unsigned)n_windows);
     voxel_vote_pair_kernel<Src><<<g, kVoteThreads, 0, stream>>>(events, offsets, num_bins, height, width, lanes, scratch, dropped);
     EEM_CHECK_LAUNCH("voxel_vote_pair_kernel");

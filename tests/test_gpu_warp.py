@@ -205,7 +205,9 @@ def test_upsample2d_flows_as_equals_the_list_of_calls():
     gen = torch.Generator().manual_seed(12)
     shapes = [(5, 6), (10, 12), (20, 24), (40, 48), (80, 96)]
     for if_rate in (True, False):
-        for (H, W) in ((260, 346), (64, 96)):
+        # (260, 346), (64, 96): upsampling or mixed targets -> row-walking kernel where every map is upsampled in y,
+        # per-pixel kernel otherwise; (7, 9): a target smaller than most maps (source rows skip)
+        for (H, W) in ((260, 346), (64, 96), (7, 9), (80, 8)):
             flows = [2.0 * torch.randn(3, 2, h, w, generator=gen) for (h, w) in shapes]
             tgt = torch.zeros(3, 1, H, W)
             ref_in = [f.clone() for f in flows]

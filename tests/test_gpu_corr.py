@@ -111,8 +111,9 @@ def test_bench_config_b32_tf32_full(E):
 
 
 @pytest.mark.parametrize("B,D,H,W,L", [(2, 256, 36, 44, 4), (1, 256, 32, 32, 4), (1, 128, 23, 40, 4), (3, 64, 17, 20, 4),
-                                       (1, 32, 12, 20, 2), (1, 32, 8, 2, 2), (32, 256, 36, 44, 4)])
-def test_packed_fp16_pyramid_and_lookup(E, B, D, H, W, L):
+                                       (1, 32, 12, 20, 2), (1, 32, 8, 2, 2), (32, 256, 36, 44, 4),
+                                       (1, 32, 64, 64, 6), (2, 32, 32, 44, 1)])      # 6 levels: three lookup stages exceed the
+def test_packed_fp16_pyramid_and_lookup(E, B, D, H, W, L):                           # shared memory -> one-batch kernel; 1 level
     """precision="tf32_f16": TF32 contraction stored as the fp16 working pyramid (4x4-pixel tiles, csrc/packed_layout.cuh).
     (1) the lazily materialised `corr_pyramid` against the CPU oracle, every element: <= 1e-2 sigma max and
     <= 2e-3 sigma RMS (TF32 inputs + one fp16 rounding of the fp32 accumulator); (2) the packed lookup against the

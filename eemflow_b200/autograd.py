@@ -7,6 +7,8 @@ resize, and the all-pairs CorrBlock (pyramid + lookup).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -57,19 +59,33 @@ class ResizeFn(torch.autograd.Function):
         return ops.bilinear_resize_backward(grad_out.contiguous(), in_size, align, s0, s1, sr), None, None, None, None, None
 
 
+def _backward_precision(forward_precision: str) -> str:
+    """Precision of the pyramid's backward GEMMs: that of the forward unless EEMFLOW_B200_CORR_BACKWARD says otherwise."""
+    forced = os.environ.get("EEMFLOW_B200_CORR_BACKWARD", "").strip().lower()
+    if forced:
+        if forced not in ("fp32", "tf32"):
+            raise ValueError(f"EEMFLOW_B200_CORR_BACKWARD must be fp32 or tf32, got {forced!r}")
+        return forced
+    return "tf32" if forward_precision in ("tf32", "tf32_f16") else "fp32"
+
+
 class CorrPyramidFn(torch.autograd.Function):
     """CorrBlock.__init__ under autograd (model/corr.py:13-27, 52-60): fmaps -> pyramid levels.
 
     Forward is the one fused kernel (level_l = fmap1^T pool^l(fmap2) / sqrt(D)).  Backward uses the same
     linearity: d fmap1 = sum_l pool^l(fmap2) . dV_l^T, d pool^l(fmap2) = fmap1 . dV_l, folded back through
-    the pooling by the avg-pool backward kernel.  The products are exact-fp32 batched GEMMs in this library's own
-    kernel (eem_batched_gemm_f32; the 1/sqrt(D) scale and the sum over the levels are fused into it).
+    the pooling by the avg-pool backward kernel.  The products are batched GEMMs in this library's own kernels (the
+    1/sqrt(D) scale and the sum over the levels are fused into them): exact fp32 FFMA (eem_batched_gemm_f32) after an
+    fp32 forward; after a TF32 forward the tcgen05 kernel (eem_batched_gemm_tf32: TF32 operands, fp32 accumulate, the
+    precision torch gives the backward of a TF32 matmul) for every level whose row pitch TMA can address, FFMA for
+    the others.  EEMFLOW_B200_CORR_BACKWARD=fp32|tf32 overrides the choice.
     """
 
     @staticmethod
     def forward(ctx, fmap1, fmap2, num_levels, precision):
         ctx.save_for_backward(fmap1, fmap2)
         ctx.num_levels = num_levels
+        ctx.backward_precision = _backward_precision(precision)
         return tuple(ops.corr_pyramid(fmap1, fmap2, num_levels, precision=precision))
 
     @staticmethod
@@ -79,6 +95,7 @@ class CorrPyramidFn(torch.autograd.Function):
         P = H * W
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         scale = ops.inv_sqrt_dim(D)
+        bp = ctx.backward_precision
         f1m = f1.contiguous().reshape(B, D, P)
         d1 = None
         d2_levels = []
@@ -92,10 +109,11 @@ class CorrPyramidFn(torch.autograd.Function):
                     first = d1 is None
                     if first:
                         d1 = torch.empty((B, D, P), dtype=torch.float32, device=f1.device)
-                    ops.batched_gemm_(d1, f2l.reshape(B, D, hl * wl), G, b_transposed=True, alpha=scale, accumulate=not first)
+                    ops.batched_gemm_(d1, f2l.reshape(B, D, hl * wl), G, b_transposed=True, alpha=scale, accumulate=not first,
+                                      precision=bp)
                 if need2:            # d2[b,d,j] = s * sum_i f1[b,d,i] * G[b,i,j]
                     d2 = torch.empty((B, D, hl * wl), dtype=torch.float32, device=f1.device)
-                    ops.batched_gemm_(d2, f1m, G, b_transposed=False, alpha=scale)
+                    ops.batched_gemm_(d2, f1m, G, b_transposed=False, alpha=scale, precision=bp)
                     d2 = d2.view(B, D, hl, wl)
             d2_levels.append((d2, (hl, wl)))
             if l + 1 < len(grad_levels):

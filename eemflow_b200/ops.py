@@ -515,17 +515,36 @@ def avg_pool2x2_backward_(grad_fine: torch.Tensor, grad_coarse: torch.Tensor, ac
     return grad_fine
 
 
+def batched_gemm_tf32_supported(A: torch.Tensor, B: torch.Tensor, b_transposed: bool) -> bool:
+    """True when `batched_gemm_(..., precision="tf32")` can run this product on the tcgen05 kernel (shape and
+    alignment rules of eem_batched_gemm_tf32; contiguous [batch, rows, cols] operands assumed)."""
+    batch, M, K = A.shape
+    N = B.shape[1] if b_transposed else B.shape[2]
+    if A.data_ptr() % 16 or B.data_ptr() % 16:
+        return False
+    return bool(L.lib().eem_batched_gemm_tf32_supported(batch, M, N, K, A.shape[2], B.shape[2], M * K,
+                                                        B.shape[1] * B.shape[2], int(b_transposed)))
+
+
 def batched_gemm_(C_: torch.Tensor, A: torch.Tensor, B: torch.Tensor, *, b_transposed: bool, alpha: float = 1.0,
-                  accumulate: bool = False) -> torch.Tensor:
-    """C_[b] = alpha * A[b] @ (B[b].T if b_transposed else B[b]) (+ C_[b]), exact fp32, all [batch, rows, cols] contiguous."""
+                  accumulate: bool = False, precision: str = "fp32") -> torch.Tensor:
+    """C_[b] = alpha * A[b] @ (B[b].T if b_transposed else B[b]) (+ C_[b]), all [batch, rows, cols] contiguous.
+
+    precision "fp32": exact FFMA kernel; "tf32": the tcgen05 kernel (TF32 operands, fp32 accumulate) where its shape
+    rules hold, the FFMA kernel otherwise (e.g. a 9x11 level whose row pitch is not a multiple of 16 bytes)."""
+    if precision not in ("fp32", "tf32"):
+        raise ValueError(f"eemflow_b200.batched_gemm_: unknown precision {precision!r}")
     A = L.require_cuda(A, "A")
     B = L.require_cuda(B, "B")
     assert C_.is_cuda and C_.dtype == torch.float32 and C_.is_contiguous() and A.dim() == B.dim() == C_.dim() == 3
     batch, M, K = A.shape
     N = B.shape[1] if b_transposed else B.shape[2]
     assert B.shape[0] == batch and (B.shape[2] if b_transposed else B.shape[1]) == K and tuple(C_.shape) == (batch, M, N)
+    fn = L.lib().eem_batched_gemm_f32
+    if precision == "tf32" and batched_gemm_tf32_supported(A, B, b_transposed):
+        fn = L.lib().eem_batched_gemm_tf32
     with torch.cuda.device(A.device):
-        L.check(L.lib().eem_batched_gemm_f32(A.data_ptr(), B.data_ptr(), C_.data_ptr(), batch, M, N, K, A.shape[2], B.shape[2],
-                                             N, M * K, B.shape[1] * B.shape[2], M * N, int(b_transposed), float(alpha),
-                                             int(accumulate), L.stream_ptr(A.device)))
+        L.check(fn(A.data_ptr(), B.data_ptr(), C_.data_ptr(), batch, M, N, K, A.shape[2], B.shape[2],
+                   N, M * K, B.shape[1] * B.shape[2], M * N, int(b_transposed), float(alpha),
+                   int(accumulate), L.stream_ptr(A.device)))
     return C_

@@ -317,6 +317,18 @@ EEM_API int eem_batched_gemm_f32(const float* A, const float* B, float* C, int b
                                  int64_t strideC, int b_transposed, float alpha, int accumulate,
                                  eem_stream_t stream);
 
+/* The same product on the tensor cores (tcgen05 kind::tf32: 10-bit-mantissa operands, fp32 accumulate; TMA-staged
+ * operands, TMEM accumulators) -- the precision torch gives the backward of torch.matmul (model/corr.py:58) when TF32
+ * is allowed, and what the TF32 forward (EEM_CORR_TF32) uses.  Same arguments as eem_batched_gemm_f32.  Requirements
+ * (EEM_ERR_UNSUPPORTED otherwise; eem_batched_gemm_tf32_supported answers without touching the GPU): M % 32 == 0,
+ * M <= 256, lda / ldb / strideA / strideB multiples of 4 elements, A and B 16-byte aligned. */
+EEM_API int eem_batched_gemm_tf32(const float* A, const float* B, float* C, int batch, int M, int N, int K,
+                                  int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                                  int64_t strideC, int b_transposed, float alpha, int accumulate,
+                                  eem_stream_t stream);
+EEM_API int eem_batched_gemm_tf32_supported(int batch, int M, int N, int K, int64_t lda, int64_t ldb,
+                                            int64_t strideA, int64_t strideB, int b_transposed);
+
 /* grad_out [B,n_out,H,W] -> grad_f1, grad_f2 [B,C,H,W]; same index/scale meaning as eem_local_corr. */
 EEM_API int eem_local_corr_backward(const float* f1, const float* f2, const float* grad_out, int B,
                                     int C, int H, int W, int max_disp, const int* index, int n_out,

@@ -72,6 +72,7 @@ SIGNATURES = {
     "eem_batched_gemm_tf32_supported": (_i, [_i, _i, _i, _i, _i64, _i64, _i64, _i64, _i]),
     "eem_local_corr_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, _vp, _vp, _vp]),
     "eem_backwarp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "eem_bilinear_sample_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "eem_bilinear_resize_backward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp]),
     "eem_event_mask": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp]),
     "eem_voxel_bin_sum": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),

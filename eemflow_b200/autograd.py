@@ -153,6 +153,27 @@ class CorrLookupFn(torch.autograd.Function):
         return (None, None, *ops.corr_lookup_backward(grad_out.contiguous(), coords, radius, n))
 
 
+class BilinearSampleFn(torch.autograd.Function):
+    """bilinear_sampler (model/model_utils.py:7-21) under autograd: gradients to the image and to the pixel
+    coordinates, as F.grid_sample gives them in the reference; the optional in-range mask is not differentiable."""
+
+    @staticmethod
+    def forward(ctx, img, coords, mask):
+        ctx.save_for_backward(img, coords)
+        res = ops.bilinear_sample(img, coords, mask=mask)
+        if mask:
+            ctx.mark_non_differentiable(res[1])
+            return res
+        return res
+
+    @staticmethod
+    def backward(ctx, grad_out, *unused):
+        img, coords = ctx.saved_tensors
+        g_img, g_coords = ops.bilinear_sample_backward(img, coords, grad_out.contiguous(), need_img=ctx.needs_input_grad[0],
+                                                       need_coords=ctx.needs_input_grad[1])
+        return g_img, g_coords, None
+
+
 def needs_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -178,3 +199,10 @@ def bilinear_resize(x, size, align_corners, scale0=1.0, scale1=1.0, scale_rest=1
         return ResizeFn.apply(x, tuple(size), align_corners, scale0, scale1, scale_rest)
     with torch.no_grad():
         return ops.bilinear_resize(x, size, align_corners, scale0, scale1, scale_rest, out=out)
+
+
+def bilinear_sample(img, coords, mask=False):
+    if needs_grad(img, coords):
+        return BilinearSampleFn.apply(img, coords, bool(mask))
+    with torch.no_grad():
+        return ops.bilinear_sample(img, coords, mask=mask)

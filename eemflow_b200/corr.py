@@ -76,9 +76,7 @@ class CorrBlock:
 
     def __call__(self, coords):
         if torch.is_grad_enabled() and coords.requires_grad:     # never a silent zero gradient
-            raise NotImplementedError(
-                "eemflow_b200.CorrBlock gives no gradient to the lookup coordinates; detach them as the "
-                "reference's callers do (model/eraft.py:141)")
+            return self._lookup_differentiable_coords(coords)
         if self._packed is not None:
             with torch.no_grad():
                 return ops.corr_lookup_packed(self._packed, coords, self.num_levels, self.radius)
@@ -86,6 +84,24 @@ class CorrBlock:
             return ag.CorrLookupFn.apply(coords, self.radius, *self.corr_pyramid)
         with torch.no_grad():
             return ops.corr_lookup(self.corr_pyramid, coords, self.radius)
+
+    def _lookup_differentiable_coords(self, coords):
+        """Coordinates that require grad: the reference's own composition (model/corr.py:29-50) over the differentiable
+        bilinear sampler, so they receive the gradient F.grid_sample gives them there (and the pyramid its own).  Every
+        shipped caller detaches the coordinates (model/eraft.py:141) and takes the fused lookup kernel instead."""
+        r = self.radius
+        coords = coords.permute(0, 2, 3, 1)
+        batch, h1, w1, _ = coords.shape
+        d = torch.linspace(-r, r, 2 * r + 1, device=coords.device)
+        delta = torch.stack(torch.meshgrid(d, d, indexing='ij'), dim=-1).view(1, 2 * r + 1, 2 * r + 1, 2)
+        out_pyramid = []
+        for i, corr in enumerate(self.corr_pyramid):
+            if corr.numel() == 0:                           # a level pooled away entirely: zeros, like the fused lookup
+                out_pyramid.append(coords.new_zeros(batch, h1, w1, (2 * r + 1) ** 2))
+                continue
+            coords_lvl = coords.reshape(batch * h1 * w1, 1, 1, 2) / 2 ** i + delta
+            out_pyramid.append(ag.bilinear_sample(corr, coords_lvl).view(batch, h1, w1, -1))
+        return torch.cat(out_pyramid, dim=-1).permute(0, 3, 1, 2).contiguous().float()
 
     @staticmethod
     def corr(fmap1, fmap2, precision=None):
@@ -104,10 +120,7 @@ def bilinear_sampler(img, coords, mode='bilinear', mask=False):
     """ Wrapper for grid_sample, uses pixel coordinates """
     if mode != 'bilinear':
         raise NotImplementedError("eemflow_b200.bilinear_sampler implements mode='bilinear' only")
-    if ag.needs_grad(img, coords):      # never a silent zero gradient: CorrBlock is the differentiable user of this op
-        raise NotImplementedError("eemflow_b200.bilinear_sampler has no backward; use CorrBlock (differentiable) or detach the inputs")
-    with torch.no_grad():
-        return ops.bilinear_sample(img, coords, mask=mask)
+    return ag.bilinear_sample(img, coords, mask=mask)     # differentiable w.r.t. img and coords, like F.grid_sample
 
 
 def coords_grid(batch, ht, wd, device=None):

@@ -166,6 +166,46 @@ backwarp_backward_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
+// ---- bilinear_sampler backward (model/model_utils.py:7-21 under autograd) -----------------------------------
+// out[n,c,r] = bilinear(img[n,c], coords[n,r]) with zeros outside: thread = one sampling location, loop over the
+// channels; d img by RED scatter of the 4 taps, d coords analytically (the normalise / un-normalise round trip has
+// slope 1).  The optional in-range mask of the forward is piecewise constant and gets no gradient.
+__global__ void __launch_bounds__(256)
+bilinear_sample_backward_kernel(const float* __restrict__ img, const float* __restrict__ coords, const float* __restrict__ gout,
+                                int N, int C, int H, int W, int Ho, int Wo, float* __restrict__ dimg,
+                                float* __restrict__ dcoords) {
+  const int64_t per = (int64_t)Ho * Wo, total = (int64_t)N * per, plane = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / per, r = i - n * per;
+    const Geo q = make_geo(coords[2 * i + 0], coords[2 * i + 1], H, W, EEM_WARP_EXACT);
+    const float nw = q.s * q.e, ne = q.s * q.w, sw = q.n * q.e, se = q.n * q.w;
+    const int64_t tap = (int64_t)q.y0 * W + q.x0;
+    float gx = 0.f, gy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const int64_t off = (n * C + c) * plane;
+      const float g = gout[(n * C + c) * per + r];
+      if (dimg != nullptr && g != 0.f) {
+        if (q.in_nw) red_add_f32(dimg + off + tap, g * nw);
+        if (q.in_ne) red_add_f32(dimg + off + tap + 1, g * ne);
+        if (q.in_sw) red_add_f32(dimg + off + tap + W, g * sw);
+        if (q.in_se) red_add_f32(dimg + off + tap + W + 1, g * se);
+      }
+      if (dcoords != nullptr) {
+        const float v_nw = q.in_nw ? __ldg(img + off + tap) : 0.f;
+        const float v_ne = q.in_ne ? __ldg(img + off + tap + 1) : 0.f;
+        const float v_sw = q.in_sw ? __ldg(img + off + tap + W) : 0.f;
+        const float v_se = q.in_se ? __ldg(img + off + tap + W + 1) : 0.f;
+        gx += g * (q.s * (v_ne - v_nw) + q.n * (v_se - v_sw));
+        gy += g * (q.e * (v_sw - v_nw) + q.w * (v_se - v_ne));
+      }
+    }
+    if (dcoords != nullptr) {
+      dcoords[2 * i + 0] = gx * q.dix;
+      dcoords[2 * i + 1] = gy * q.diy;
+    }
+  }
+}
+
 // ---- bilinear resize backward ---------------------------------------------------------------------
 __device__ __forceinline__ void source_index(int dst, int in_size, int out_size, int align_corners, int& i0, int& i1,
                                              float& l0, float& l1) {
@@ -373,6 +413,22 @@ int eem_backwarp_backward(const float* x, const float* flow, const float* grad_o
   dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(H, 8), (unsigned)B);
   backwarp_backward_kernel<<<grid, 256, 0, stream>>>(x, flow, grad_out, B, C, H, W, convention, mask_mode, grad_x, grad_flow);
   EEM_CHECK_LAUNCH("backwarp_backward_kernel");
+  return EEM_OK;
+}
+
+int eem_bilinear_sample_backward(const float* img, const float* coords, const float* grad_out, int N, int C, int H, int W,
+                                 int Ho, int Wo, float* grad_img, float* grad_coords, eem_stream_t stream_) {
+  EEM_CHECK_ARG(img && coords && grad_out, "eem_bilinear_sample_backward: NULL pointer");
+  EEM_CHECK_ARG(grad_img || grad_coords, "eem_bilinear_sample_backward: at least one gradient output is required");
+  EEM_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "eem_bilinear_sample_backward: sizes must be > 0");
+  cudaStream_t stream = as_stream(stream_);
+  if (grad_img) EEM_CHECK_CUDA(cudaMemsetAsync(grad_img, 0, (size_t)N * C * H * W * sizeof(float), stream));
+  const int64_t total = (int64_t)N * Ho * Wo;
+  int64_t blocks = ceil_div(total, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (cap > 0 && blocks > cap) blocks = cap;
+  bilinear_sample_backward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, coords, grad_out, N, C, H, W, Ho, Wo, grad_img, grad_coords);
+  EEM_CHECK_LAUNCH("bilinear_sample_backward_kernel");
   return EEM_OK;
 }
 

@@ -249,6 +249,25 @@ def bilinear_sample(img: torch.Tensor, coords: torch.Tensor, mask: bool = False)
     return (out, m) if mask else out
 
 
+def bilinear_sample_backward(img: torch.Tensor, coords: torch.Tensor, grad_out: torch.Tensor, need_img: bool = True,
+                             need_coords: bool = True):
+    """Gradients of bilinear_sample w.r.t. img [N,C,H,W] and coords [N,Ho,Wo,2] (None where not needed)."""
+    img = L.require_cuda(img, "img")
+    coords = L.require_cuda(coords, "coords")
+    grad_out = L.require_cuda(grad_out, "grad_out")
+    N, Cc, H, W = img.shape
+    _, Ho, Wo, _ = coords.shape
+    assert tuple(grad_out.shape) == (N, Cc, Ho, Wo)
+    g_img = torch.empty_like(img) if need_img else None
+    g_coords = torch.empty_like(coords) if need_coords else None
+    if not (need_img or need_coords):
+        return None, None
+    with torch.cuda.device(img.device):
+        L.check(L.lib().eem_bilinear_sample_backward(img.data_ptr(), coords.data_ptr(), grad_out.data_ptr(), N, Cc, H, W, Ho, Wo,
+                                                     L.ptr(g_img), L.ptr(g_coords), L.stream_ptr(img.device)))
+    return g_img, g_coords
+
+
 # ------------------------------------------------------------------------------------------ K6
 LOCAL_CORR_PRECISIONS = ("fp32", "tf32")
 _local_corr_precision: str | None = None

@@ -80,9 +80,6 @@ def patch_reference(reference_root: str | None = None) -> dict:
     patch("utils_luo.event_utils", EventSequenceToVoxelGrid_Pytorch=voxel, EventSequence=_event_utils.EventSequence)
     patch("model.model_utils", bilinear_sampler=_corr.bilinear_sampler, upflow8=_corr.upflow8)
     patch("model.corr", CorrBlock=_corr.CorrBlock, bilinear_sampler=_corr.bilinear_sampler)
-    # restriction callers should know about: the patched sampler is inference-only (it raises for inputs that
-    # require grad instead of returning a detached result); CorrBlock is the differentiable user of the op
-    report["note: model.model_utils.bilinear_sampler"] = "no backward: raises NotImplementedError for grad-requiring inputs"
     patch("utils.image_utils", InputPadder=_warp.InputPadder)
     patch("model.EEMFlow.cdc_utils", WarpingLayer_no_div=_warp.WarpingLayer_no_div,
           upsample2d_flow_as=_warp.upsample2d_flow_as)

@@ -338,6 +338,13 @@ EEM_API int eem_local_corr_backward(const float* f1, const float* f2, const floa
 EEM_API int eem_backwarp_backward(const float* x, const float* flow, const float* grad_out, int B,
                                   int C, int H, int W, int convention, int mask_mode, float* grad_x,
                                   float* grad_flow, eem_stream_t stream);
+/* Backward of eem_bilinear_sample (model/model_utils.py:7-21 under autograd; the reference differentiates
+ * F.grid_sample): grad_out [N,C,Ho,Wo] -> grad_img [N,C,H,W] (zero-filled here, 4-tap scatter) and / or
+ * grad_coords [N,Ho,Wo,2] (pixel units).  Either output may be NULL. */
+EEM_API int eem_bilinear_sample_backward(const float* img, const float* coords, const float* grad_out, int N, int C,
+                                         int H, int W, int Ho, int Wo, float* grad_img, float* grad_coords,
+                                         eem_stream_t stream);
+
 /* grad_out [B,C,H,W] -> grad_in [B,C,h,w]; adjoint of eem_bilinear_resize with the same scales. */
 EEM_API int eem_bilinear_resize_backward(const float* grad_out, int B, int C, int h, int w, int H,
                                          int W, int align_corners, float scale0, float scale1,

@@ -180,9 +180,8 @@ def test_corrblock_backward_partial_and_guards(E):
     # CorrBlock.corr static method is differentiable too
     v = E.CorrBlock.corr(f1.cuda(), b, precision="fp32")
     assert v.requires_grad and v.shape == (1, 16, 24, 1, 16, 24)
-    # coordinates must be detached
-    with pytest.raises(NotImplementedError):
-        blk(coords.cuda().requires_grad_(True))
+    # coordinates that require grad take the differentiable composition (test_corrblock_coords_gradient)
+    assert blk(coords.cuda().requires_grad_(True)).requires_grad
     # no gradient requested: plain inference path
     with torch.no_grad():
         assert not E.CorrBlock(f1.cuda(), b)(coords.cuda()).requires_grad
@@ -303,3 +302,59 @@ def test_corrblock_backward_tf32_gemms(E, monkeypatch, B, D, H, W, levels):
     ok1, e1 = close(a.grad, f1.grad, 3e-3)
     ok2, e2 = close(b.grad, f2.grad, 3e-3)
     assert ok1 and ok2, (e1, e2)
+
+
+@pytest.mark.parametrize("N,C,H,W,Ho,Wo", [(2, 3, 9, 13, 7, 5), (6, 1, 12, 16, 9, 9), (1, 8, 5, 4, 33, 3)])
+def test_bilinear_sampler_backward(E, N, C, H, W, Ho, Wo):
+    """bilinear_sampler (model/model_utils.py:7-21) under autograd: gradients to the image and to the coordinates vs
+    torch autograd through the oracle's F.grid_sample composition; samples outside the map included."""
+    gen = torch.Generator().manual_seed(N * H + W)
+    img = torch.randn(N, C, H, W, generator=gen, requires_grad=True)
+    coords = torch.stack([torch.rand(N, Ho, Wo, generator=gen) * (W + 3) - 2, torch.rand(N, Ho, Wo, generator=gen) * (H + 3) - 2], -1)
+    coords.requires_grad_(True)
+    ref, ref_mask = ref_ops.bilinear_sampler(img, coords, mask=True)
+    g = torch.randn(ref.shape, generator=gen)
+    ref.backward(g)
+    a = img.detach().cuda().requires_grad_(True)
+    c = coords.detach().cuda().requires_grad_(True)
+    out, mask = E.bilinear_sampler(a, c, mask=True)
+    assert out.requires_grad and not mask.requires_grad
+    assert close(out, ref, 1e-5)[0] and torch.equal(mask.cpu(), ref_mask.float())
+    out.backward(g.cuda())
+    ok1, e1 = close(a.grad, img.grad)
+    ok2, e2 = close(c.grad, coords.grad)
+    assert ok1 and ok2, (e1, e2)
+    # one-sided: only the coordinates need a gradient
+    c2 = coords.detach().cuda().requires_grad_(True)
+    E.bilinear_sampler(img.detach().cuda(), c2).backward(g.cuda())
+    assert close(c2.grad, coords.grad)[0]
+
+
+def test_corrblock_coords_gradient(E):
+    """CorrBlock.__call__ with coordinates that require grad (the reference differentiates them through grid_sample;
+    its shipped callers detach them, model/eraft.py:141): value and all three gradients vs the oracle."""
+    gen = torch.Generator().manual_seed(11)
+    B, D, H, W, levels, radius = 2, 32, 8, 12, 3, 3
+    f1 = torch.randn(B, D, H, W, generator=gen, requires_grad=True)
+    f2 = torch.randn(B, D, H, W, generator=gen, requires_grad=True)
+    base = torch.stack(torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")[::-1], 0).float()[None]
+    coords = (base + 1.5 * torch.randn(B, 2, H, W, generator=gen) + 0.25).requires_grad_(True)
+    ref = ref_ops.corr_lookup(ref_ops.corr_pyramid(f1, f2, levels), coords, radius)
+    g = torch.randn(ref.shape, generator=gen)
+    ref.backward(g)
+    a = f1.detach().cuda().requires_grad_(True)
+    b = f2.detach().cuda().requires_grad_(True)
+    c = coords.detach().cuda().requires_grad_(True)
+    blk = E.CorrBlock(a, b, num_levels=levels, radius=radius, precision="fp32")
+    out = blk(c)
+    assert close(out, ref, 1e-5)[0]
+    with torch.no_grad():                                   # the same values as the fused lookup kernel
+        assert close(out, blk(c.detach()), 1e-5)[0]
+    out.backward(g.cuda())
+    for name, mine, theirs in (("coords", c.grad, coords.grad), ("fmap1", a.grad, f1.grad), ("fmap2", b.grad, f2.grad)):
+        ok, e = close(mine, theirs)
+        assert ok, (name, e)
+    # pyramid without grad, coordinates with: the gradient still arrives (round 1 returned a detached result)
+    c2 = coords.detach().cuda().requires_grad_(True)
+    E.CorrBlock(f1.detach().cuda(), f2.detach().cuda(), num_levels=levels, radius=radius, precision="fp32")(c2).backward(g.cuda())
+    assert close(c2.grad, coords.grad)[0]

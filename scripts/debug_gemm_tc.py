@@ -5,6 +5,7 @@ the MVSEC / HREM backward shapes against the exact FFMA kernel.
 
     python scripts/debug_gemm_tc.py            # all cases
     python scripts/debug_gemm_tc.py all | timing   (the children)
+    ncu --set full -k regex:gemm_tf32 -c 2 ... python scripts/debug_gemm_tc.py ncu
 """
 import subprocess
 import sys
@@ -154,6 +155,16 @@ if __name__ == "__main__":
         sys.exit(1 if failed else 0)
     if len(sys.argv) > 1 and sys.argv[1] == "timing":
         timing()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ncu":        # one d_fmap1 and one d_fmap2 launch at MVSEC B = 32, level 0
+        import torch
+        from eemflow_b200 import ops
+        f = torch.randn(32, 256, 1584, device="cuda")
+        G = torch.randn(32, 1584, 1584, device="cuda")
+        d = torch.empty(32, 256, 1584, device="cuda")
+        ops.batched_gemm_(d, f, G, b_transposed=True, alpha=0.0625, precision="tf32")
+        ops.batched_gemm_(d, f, G, b_transposed=False, alpha=0.0625, precision="tf32")
+        torch.cuda.synchronize()
         sys.exit(0)
     t0 = time.time()
     try:

@@ -69,6 +69,8 @@ SIGNATURES = {
     "eem_avg_pool2x2_backward": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp]),
     "eem_batched_gemm_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _f, _i, _vp]),
     "eem_batched_gemm_tf32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _f, _i, _vp]),
+    "eem_batched_gemm_tf32_multi": (_i, [C.POINTER(_vp), C.POINTER(_vp), _vp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i64),
+                                         C.POINTER(_i64), _i64, C.POINTER(_i64), C.POINTER(_i64), _i64, _i, _f, _i, _vp]),
     "eem_batched_gemm_tf32_supported": (_i, [_i, _i, _i, _i, _i64, _i64, _i64, _i64, _i]),
     "eem_local_corr_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, _vp, _vp, _vp]),
     "eem_backwarp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

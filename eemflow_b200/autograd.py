@@ -69,6 +69,15 @@ def _backward_precision(forward_precision: str) -> str:
     return "tf32" if forward_precision in ("tf32", "tf32_f16") else "fp32"
 
 
+def _tc_operand(t: torch.Tensor) -> torch.Tensor:
+    """[batch, rows, cols] operand as the tcgen05 GEMM can address it: the column count (row pitch) a multiple of 4
+    elements and a 16-byte aligned base; a zero-padded copy only where needed."""
+    pad_c = (-t.shape[2]) % 4
+    if pad_c:
+        return torch.nn.functional.pad(t, (0, pad_c))
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 class CorrPyramidFn(torch.autograd.Function):
     """CorrBlock.__init__ under autograd (model/corr.py:13-27, 52-60): fmaps -> pyramid levels.
 
@@ -77,8 +86,9 @@ class CorrPyramidFn(torch.autograd.Function):
     the pooling by the avg-pool backward kernel.  The products are batched GEMMs in this library's own kernels (the
     1/sqrt(D) scale and the sum over the levels are fused into them): exact fp32 FFMA (eem_batched_gemm_f32) after an
     fp32 forward; after a TF32 forward the tcgen05 kernel (eem_batched_gemm_tf32: TF32 operands, fp32 accumulate, the
-    precision torch gives the backward of a TF32 matmul) for every level whose row pitch TMA can address, FFMA for
-    the others.  EEMFLOW_B200_CORR_BACKWARD=fp32|tf32 overrides the choice.
+    precision torch gives the backward of a TF32 matmul): d fmap1 as ONE launch whose K loop runs over all levels,
+    d pool^l(fmap2) one launch per level; a level whose row pitch TMA cannot address (9 x 11) goes through a zero-padded
+    copy.  EEMFLOW_B200_CORR_BACKWARD=fp32|tf32 overrides the choice.
     """
 
     @staticmethod
@@ -95,29 +105,46 @@ class CorrPyramidFn(torch.autograd.Function):
         P = H * W
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         scale = ops.inv_sqrt_dim(D)
-        bp = ctx.backward_precision
+        # the tcgen05 kernel's rules: M = D in whole 32-column TMEM chunks, 16-byte row pitch of the feature maps
+        tc = ctx.backward_precision == "tf32" and D % 32 == 0 and D <= 256 and P % 4 == 0
         f1m = f1.contiguous().reshape(B, D, P)
-        d1 = None
         d2_levels = []
+        a_segs, b_segs = [], []                                                 # d fmap1: one K segment per level
         f2l = f2.contiguous()
         for l, g in enumerate(grad_levels):
             hl, wl = f2l.shape[-2:]
+            Pl = hl * wl
             d2 = None
-            if g is not None and hl * wl > 0:
-                G = g.contiguous().reshape(B, P, hl * wl)
-                if need1:            # d1[b,d,i] (+)= s * sum_j f2l[b,d,j] * G[b,i,j]
-                    first = d1 is None
-                    if first:
-                        d1 = torch.empty((B, D, P), dtype=torch.float32, device=f1.device)
-                    ops.batched_gemm_(d1, f2l.reshape(B, D, hl * wl), G, b_transposed=True, alpha=scale, accumulate=not first,
-                                      precision=bp)
+            if g is not None and Pl > 0:
+                G = g.contiguous().reshape(B, P, Pl)
+                f2m = f2l.reshape(B, D, Pl)
+                if tc:
+                    # TMA needs 16-byte row pitches: a level such as 9 x 11 goes through zero-padded copies (its dV is a
+                    # few percent of the pyramid's bytes); the zero columns add nothing to the sums
+                    G, f2m = _tc_operand(G), _tc_operand(f2m)
+                if need1:            # d1[b,d,i] = s * sum_l sum_j f2l[b,d,j] * G_l[b,i,j]
+                    a_segs.append(f2m)
+                    b_segs.append(G)
                 if need2:            # d2[b,d,j] = s * sum_i f1[b,d,i] * G[b,i,j]
-                    d2 = torch.empty((B, D, hl * wl), dtype=torch.float32, device=f1.device)
-                    ops.batched_gemm_(d2, f1m, G, b_transposed=False, alpha=scale, precision=bp)
+                    d2 = torch.empty((B, D, G.shape[2]), dtype=torch.float32, device=f1.device)
+                    ops.batched_gemm_(d2, _tc_operand(f1m) if tc else f1m, G, b_transposed=False, alpha=scale,
+                                      precision="tf32" if tc else "fp32")
+                    if d2.shape[2] != Pl:
+                        d2 = d2[:, :, :Pl].contiguous()
                     d2 = d2.view(B, D, hl, wl)
             d2_levels.append((d2, (hl, wl)))
             if l + 1 < len(grad_levels):
                 f2l = ops.avg_pool2x2(f2l)
+        d1 = None
+        if need1 and a_segs:
+            d1 = torch.empty((B, D, P), dtype=torch.float32, device=f1.device)
+            if tc:                   # all levels in one launch: one K loop, d fmap1 written once
+                for k in range(0, len(a_segs), 6):
+                    ops.batched_gemm_tf32_multi_(d1, a_segs[k:k + 6], b_segs[k:k + 6], b_transposed=True, alpha=scale,
+                                                 accumulate=k > 0)
+            else:
+                for k, (a_, b_) in enumerate(zip(a_segs, b_segs)):
+                    ops.batched_gemm_(d1, a_, b_, b_transposed=True, alpha=scale, accumulate=k > 0)
         g2 = None
         if need2:
             for d2, (hl, wl) in reversed(d2_levels):         # fold the coarse gradients down to level 0

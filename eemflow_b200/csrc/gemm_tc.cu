@@ -42,12 +42,15 @@ constexpr int kEpiWarps = 8;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kTmemCols = 2 * kMaxM;
+constexpr int kMaxSeg = 6;                       // K segments summed into one product (the pyramid's levels)
 
 struct GemmTcParams {
-  CUtensorMap map_a;                 // tcgen05 A operand (API B)
-  CUtensorMap map_b;                 // tcgen05 B operand (API A)
+  CUtensorMap map_a[kMaxSeg];        // tcgen05 A operand (API B), one map per K segment
+  CUtensorMap map_b[kMaxSeg];        // tcgen05 B operand (API A)
   float* C;
-  int M, N, K;
+  int M, N;
+  int K[kMaxSeg];
+  int n_seg;
   int64_t ldc, strideC;
   int n_tiles;                       // ceil(N / 128)
   int total_tiles;                   // batch * n_tiles
@@ -80,7 +83,6 @@ gemm_tf32_kernel(const __grid_constant__ GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   GemmTcSmem& s = *reinterpret_cast<GemmTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = (p.K + kBK - 1) / kBK;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
@@ -106,22 +108,28 @@ gemm_tf32_kernel(const __grid_constant__ GemmTcParams p) {
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.n_tiles;
       const int n0 = (tile - b * p.n_tiles) * kTileN;
-      for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(&s.empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&s.full[stage], kABytes + b_bytes);
-          const int k0 = kb * kBK;
-          if constexpr (kAMn) {
+      for (int seg = 0; seg < p.n_seg; ++seg) {
+        const int KB = (p.K[seg] + kBK - 1) / kBK;
+        const CUtensorMap* map_a = &p.map_a[seg];
+        const CUtensorMap* map_b = &p.map_b[seg];
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&s.empty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&s.full[stage], kABytes + b_bytes);
+            const int k0 = kb * kBK;
+            if constexpr (kAMn) {
 #pragma unroll
-            for (int ch = 0; ch < kTileN / 32; ++ch)
-              tma_load_3d(s.a[stage] + ch * (32 * kBK * 4), &p.map_a, n0 + ch * 32, k0, b, &s.full[stage], pol_a);
-          } else {
-            tma_load_3d(s.a[stage], &p.map_a, k0, n0, b, &s.full[stage], pol_a);
+              for (int ch = 0; ch < kTileN / 32; ++ch)
+                tma_load_3d(s.a[stage] + ch * (32 * kBK * 4), map_a, n0 + ch * 32, k0, b, &s.full[stage], pol_a);
+            } else {
+              tma_load_3d(s.a[stage], map_a, k0, n0, b, &s.full[stage], pol_a);
+            }
+            tma_load_3d(s.b[stage], map_b, k0, 0, b, &s.full[stage], pol_b);
           }
-          tma_load_3d(s.b[stage], &p.map_b, k0, 0, b, &s.full[stage], pol_b);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -134,20 +142,26 @@ gemm_tf32_kernel(const __grid_constant__ GemmTcParams p) {
       mbar_wait(&s.acc_empty[acc], ((t >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem + acc * kMaxM;
-      for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(&s.full[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(s.a[stage]);
-        const uint32_t b_addr = smem_u32(s.b[stage]);
-        if (elect_one()) {
+      uint32_t issued = 0;                       // 0 only for the first MMA of the tile: it overwrites the accumulator
+      for (int seg = 0; seg < p.n_seg; ++seg) {
+        const int KB = (p.K[seg] + kBK - 1) / kBK;
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s.a[stage]);
+          const uint32_t b_addr = smem_u32(s.b[stage]);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kBK / kUK; ++ks)
-            tc_mma_tf32(d_tmem, make_desc(a_addr + ks * p.a_kstep, p.a_lo, p.a_hi),
-                        make_desc(b_addr + ks * (kUK * 4), p.b_lo, p.b_hi), p.idesc, (kb | ks) != 0);
-          tc_commit(&s.empty[stage]);
+            for (int ks = 0; ks < kBK / kUK; ++ks)
+              tc_mma_tf32(d_tmem, make_desc(a_addr + ks * p.a_kstep, p.a_lo, p.a_hi),
+                          make_desc(b_addr + ks * (kUK * 4), p.b_lo, p.b_hi), p.idesc, issued | (uint32_t)ks);
+            tc_commit(&s.empty[stage]);
+          }
+          __syncwarp();
+          issued = 1;
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (elect_one()) tc_commit(&s.acc_full[acc]);
       __syncwarp();
@@ -243,24 +257,20 @@ extern "C" int eem_batched_gemm_tf32_supported(int batch, int M, int N, int K, i
   return shape_ok(batch, M, N, K, lda, ldb, strideA, strideB, b_transposed) ? 1 : 0;
 }
 
-extern "C" int eem_batched_gemm_tf32(const float* A, const float* B, float* C, int batch, int M, int N, int K, int64_t lda,
-                                     int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC,
-                                     int b_transposed, float alpha, int accumulate, eem_stream_t stream_) {
-  EEM_CHECK_ARG(A && B && C, "eem_batched_gemm_tf32: NULL pointer");
-  EEM_CHECK_ARG(batch > 0 && M > 0 && N > 0 && K > 0, "eem_batched_gemm_tf32: sizes must be > 0");
-  if (!shape_ok(batch, M, N, K, lda, ldb, strideA, strideB, b_transposed))
-    return fail(EEM_ERR_UNSUPPORTED,
-                "eem_batched_gemm_tf32: needs M %% 32 == 0, M <= %d and row pitches / batch strides that are multiples of 4 "
-                "elements (got M=%d, lda=%lld, ldb=%lld); use eem_batched_gemm_f32",
-                kMaxM, M, (long long)lda, (long long)ldb);
-  EEM_CHECK_ARG(ldc >= N, "eem_batched_gemm_tf32: ldc < N");
-  EEM_CHECK_ALIGNED(A, 16);
-  EEM_CHECK_ALIGNED(B, 16);
+extern "C" int eem_batched_gemm_tf32_multi(const float* const* A, const float* const* B, float* C, int n_seg, int batch, int M,
+                                           int N, const int* K, const int64_t* lda, const int64_t* ldb, int64_t ldc,
+                                           const int64_t* strideA, const int64_t* strideB, int64_t strideC, int b_transposed,
+                                           float alpha, int accumulate, eem_stream_t stream_) {
+  EEM_CHECK_ARG(A && B && C && K && lda && ldb && strideA && strideB, "eem_batched_gemm_tf32_multi: NULL pointer");
+  EEM_CHECK_ARG(n_seg > 0 && n_seg <= kMaxSeg, "eem_batched_gemm_tf32_multi: n_seg must be in [1,%d]", kMaxSeg);
+  EEM_CHECK_ARG(batch > 0 && M > 0 && N > 0, "eem_batched_gemm_tf32_multi: sizes must be > 0");
+  EEM_CHECK_ARG(ldc >= N, "eem_batched_gemm_tf32_multi: ldc < N");
   const bool a_mn = b_transposed == 0;   // API B given K x N (n contiguous): the tcgen05 A operand is MN-major
 
   GemmTcParams p{};
   p.C = C;
-  p.M = M; p.N = N; p.K = K;
+  p.M = M; p.N = N;
+  p.n_seg = n_seg;
   p.ldc = ldc; p.strideC = strideC;
   p.n_tiles = (int)ceil_div(N, kTileN);
   p.total_tiles = batch * p.n_tiles;
@@ -279,14 +289,25 @@ extern "C" int eem_batched_gemm_tf32(const float* A, const float* B, float* C, i
     p.a_hi = p.b_hi;
     p.a_kstep = kUK * 4;
   }
-  int rc;
-  if (a_mn)
-    rc = encode_3d(&p.map_a, B, N, K, batch, ldb, strideB, 32, kBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  else
-    rc = encode_3d(&p.map_a, B, K, N, batch, ldb, strideB, kBK, kTileN, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc != EEM_OK) return rc;
-  rc = encode_3d(&p.map_b, A, K, M, batch, lda, strideA, kBK, M, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc != EEM_OK) return rc;
+  for (int sgm = 0; sgm < n_seg; ++sgm) {
+    EEM_CHECK_ARG(A[sgm] && B[sgm] && K[sgm] > 0, "eem_batched_gemm_tf32_multi: segment %d: NULL pointer or K <= 0", sgm);
+    if (!shape_ok(batch, M, N, K[sgm], lda[sgm], ldb[sgm], strideA[sgm], strideB[sgm], b_transposed))
+      return fail(EEM_ERR_UNSUPPORTED,
+                  "eem_batched_gemm_tf32: needs M %% 32 == 0, M <= %d and row pitches / batch strides that are multiples of 4 "
+                  "elements (got M=%d, lda=%lld, ldb=%lld); use eem_batched_gemm_f32",
+                  kMaxM, M, (long long)lda[sgm], (long long)ldb[sgm]);
+    EEM_CHECK_ALIGNED(A[sgm], 16);
+    EEM_CHECK_ALIGNED(B[sgm], 16);
+    p.K[sgm] = K[sgm];
+    int rc;
+    if (a_mn)
+      rc = encode_3d(&p.map_a[sgm], B[sgm], N, K[sgm], batch, ldb[sgm], strideB[sgm], 32, kBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    else
+      rc = encode_3d(&p.map_a[sgm], B[sgm], K[sgm], N, batch, ldb[sgm], strideB[sgm], kBK, kTileN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != EEM_OK) return rc;
+    rc = encode_3d(&p.map_b[sgm], A[sgm], K[sgm], M, batch, lda[sgm], strideA[sgm], kBK, M, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != EEM_OK) return rc;
+  }
 
   const int sms = sm_count();
   if (sms <= 0) return fail(EEM_ERR_CUDA, "eem_batched_gemm_tf32: cannot query SM count");
@@ -304,4 +325,13 @@ extern "C" int eem_batched_gemm_tf32(const float* A, const float* B, float* C, i
   }
   EEM_CHECK_LAUNCH("gemm_tf32_kernel");
   return EEM_OK;
+}
+
+extern "C" int eem_batched_gemm_tf32(const float* A, const float* B, float* C, int batch, int M, int N, int K, int64_t lda,
+                                     int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC,
+                                     int b_transposed, float alpha, int accumulate, eem_stream_t stream_) {
+  EEM_CHECK_ARG(A && B && C, "eem_batched_gemm_tf32: NULL pointer");
+  EEM_CHECK_ARG(batch > 0 && M > 0 && N > 0 && K > 0, "eem_batched_gemm_tf32: sizes must be > 0");
+  return eem_batched_gemm_tf32_multi(&A, &B, C, 1, batch, M, N, &K, &lda, &ldb, ldc, &strideA, &strideB, strideC, b_transposed,
+                                     alpha, accumulate, stream_);
 }

@@ -545,6 +545,34 @@ def batched_gemm_tf32_supported(A: torch.Tensor, B: torch.Tensor, b_transposed: 
                                                         B.shape[1] * B.shape[2], int(b_transposed)))
 
 
+def batched_gemm_tf32_multi_(C_: torch.Tensor, As, Bs, *, b_transposed: bool, alpha: float = 1.0,
+                             accumulate: bool = False) -> torch.Tensor:
+    """C_[b] = alpha * sum_s As[s][b] @ (Bs[s][b].T if b_transposed else Bs[s][b]) (+ C_[b]) in ONE launch of the tcgen05
+    kernel (one K loop over the segments); every segment must satisfy batched_gemm_tf32_supported."""
+    As = [L.require_cuda(a, "A") for a in As]
+    Bs = [L.require_cuda(b, "B") for b in Bs]
+    n = len(As)
+    assert n == len(Bs) and 1 <= n <= 6
+    batch, M, N = C_.shape
+    assert C_.is_cuda and C_.dtype == torch.float32 and C_.is_contiguous()
+    Ks = []
+    for a, b in zip(As, Bs):
+        assert a.dim() == b.dim() == 3 and a.shape[0] == b.shape[0] == batch and a.shape[1] == M
+        K = a.shape[2]
+        assert tuple(b.shape[1:]) == ((N, K) if b_transposed else (K, N))
+        if not batched_gemm_tf32_supported(a, b, b_transposed):
+            raise NotImplementedError("eemflow_b200.batched_gemm_tf32_multi_: a segment is not addressable by the tcgen05 kernel")
+        Ks.append(K)
+    i64 = C.c_int64 * n
+    with torch.cuda.device(C_.device):
+        L.check(L.lib().eem_batched_gemm_tf32_multi(
+            L.ptr_array(As), L.ptr_array(Bs), C_.data_ptr(), n, batch, M, N, (C.c_int * n)(*Ks),
+            i64(*[a.shape[2] for a in As]), i64(*[b.shape[2] for b in Bs]), N,
+            i64(*[a.shape[1] * a.shape[2] for a in As]), i64(*[b.shape[1] * b.shape[2] for b in Bs]), M * N,
+            int(b_transposed), float(alpha), int(accumulate), L.stream_ptr(C_.device)))
+    return C_
+
+
 def batched_gemm_(C_: torch.Tensor, A: torch.Tensor, B: torch.Tensor, *, b_transposed: bool, alpha: float = 1.0,
                   accumulate: bool = False, precision: str = "fp32") -> torch.Tensor:
     """C_[b] = alpha * A[b] @ (B[b].T if b_transposed else B[b]) (+ C_[b]), all [batch, rows, cols] contiguous.

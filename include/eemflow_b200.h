@@ -326,6 +326,13 @@ EEM_API int eem_batched_gemm_tf32(const float* A, const float* B, float* C, int 
                                   int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
                                   int64_t strideC, int b_transposed, float alpha, int accumulate,
                                   eem_stream_t stream);
+/* Several products summed into ONE result in one launch (one K loop over the segments, no read-modify-write of C):
+ *   C[b] = alpha * sum_s A_s[b] (M x K_s) * op(B_s[b])   (+ C[b]);   n_seg <= 6; every segment obeys the rules above.
+ * This is d fmap1 = sum_l pool^l(fmap2) . dV_l^T over the pyramid levels (model/corr.py:13-27 under autograd). */
+EEM_API int eem_batched_gemm_tf32_multi(const float* const* A, const float* const* B, float* C, int n_seg, int batch,
+                                        int M, int N, const int* K, const int64_t* lda, const int64_t* ldb,
+                                        int64_t ldc, const int64_t* strideA, const int64_t* strideB, int64_t strideC,
+                                        int b_transposed, float alpha, int accumulate, eem_stream_t stream);
 EEM_API int eem_batched_gemm_tf32_supported(int batch, int M, int N, int K, int64_t lda, int64_t ldb,
                                             int64_t strideA, int64_t strideB, int b_transposed);
 

@@ -124,6 +124,19 @@ def timing():
                     else:
                         ms2 += ms
                 del f2l, G, d2
+            if prec == "tf32":                     # d_fmap1 as ONE launch over all levels
+                As = [torch.randn(batch, D, Pl, device="cuda") for Pl in levels]
+                Bs = [torch.randn(batch, P, Pl, device="cuda") for Pl in levels]
+                ops.batched_gemm_tf32_multi_(d1, As, Bs, b_transposed=True, alpha=0.0625)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    ops.batched_gemm_tf32_multi_(d1, As, Bs, b_transposed=True, alpha=0.0625)
+                e1.record()
+                torch.cuda.synchronize()
+                print(f"  {tag}: d_fmap1, all levels in one launch {e0.elapsed_time(e1) / 3:.3f} ms")
+                del As, Bs
             flop = 2.0 * batch * D * P * sum(levels)
             print(f"  {tag} {prec}: d_fmap1 {ms1:.3f} ms ({flop / ms1 / 1e9:.0f} TFLOP/s)  d_fmap2 {ms2:.3f} ms ({flop / ms2 / 1e9:.0f} TFLOP/s)")
 

@@ -358,3 +358,30 @@ def test_corrblock_coords_gradient(E):
     c2 = coords.detach().cuda().requires_grad_(True)
     E.CorrBlock(f1.detach().cuda(), f2.detach().cuda(), num_levels=levels, radius=radius, precision="fp32")(c2).backward(g.cuda())
     assert close(c2.grad, coords.grad)[0]
+
+
+def test_batched_gemm_tf32_multi_segments(E):
+    """One launch, K loop over several segments (the pyramid's levels): C = alpha * sum_s A_s . B_s^T (+ C)."""
+    from eemflow_b200 import ops as O
+    gen = torch.Generator().manual_seed(9)
+    batch, M, N = 3, 256, 1000
+    Ks = (1584, 396, 100, 20)
+    As = [torch.randn(batch, M, K, generator=gen).cuda() for K in Ks]
+    Bs = [torch.randn(batch, N, K, generator=gen).cuda() for K in Ks]
+    ref = sum(torch.bmm(a.double(), b.double().transpose(1, 2)) for a, b in zip(As, Bs))
+    launches = E._lib.lib().eem_launch_count()
+    C = torch.full((batch, M, N), float("nan"), device="cuda")
+    O.batched_gemm_tf32_multi_(C, As, Bs, b_transposed=True, alpha=0.5)
+    assert E._lib.lib().eem_launch_count() == launches + 1
+    ok, e = close(C, 0.5 * ref, 3e-3)
+    assert ok, e
+    O.batched_gemm_tf32_multi_(C, As[1:3], Bs[1:3], b_transposed=True, alpha=1.0, accumulate=True)
+    ref2 = 0.5 * ref + sum(torch.bmm(a.double(), b.double().transpose(1, 2)) for a, b in zip(As[1:3], Bs[1:3]))
+    ok, e = close(C, ref2, 3e-3)
+    assert ok, e
+    Bn = [b.transpose(1, 2).contiguous() for b in Bs]                    # the MN-major operand form
+    O.batched_gemm_tf32_multi_(C, As, Bn, b_transposed=False, alpha=0.5)
+    ok, e = close(C, 0.5 * ref, 3e-3)
+    assert ok, e
+    with pytest.raises(NotImplementedError):
+        O.batched_gemm_tf32_multi_(C, [torch.randn(batch, M, 99).cuda()], [torch.randn(batch, N, 99).cuda()], b_transposed=True)

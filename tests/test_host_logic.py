@@ -187,3 +187,66 @@ def test_center_crop_matches_the_mvsec_cropper():
     top, left = int(round((260 - 256) / 2.0)), int(round((346 - 256) / 2.0))
     assert tuple(out.shape) == (2, 256, 256) and torch.equal(out, x[:, top:top + 256, left:left + 256])
     assert out.data_ptr() == x[:, top:, left:].data_ptr()          # a view, no copy
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_corr_pyramid_backward_plumbing(monkeypatch, mode):
+    """Host logic of CorrPyramidFn.backward -- level loop, zero-padded copies of the 9 x 11 level for the tcgen05 GEMM,
+    ONE multi-segment product for d fmap1, pooling fold -- with the kernels replaced by torch stand-ins on the CPU,
+    against autograd through the oracle's pyramid.  (The kernels themselves are covered by the GPU tests.)"""
+    import torch.nn.functional as F
+    from eemflow_b200 import autograd as ag, ops
+    from oracle import ref_ops
+    calls = {"multi": 0, "tf32": 0, "fp32": 0}
+
+    def mm(A, B, bt):
+        return torch.bmm(A, B.transpose(1, 2) if bt else B)
+
+    def gemm(C, A, B, *, b_transposed, alpha=1.0, accumulate=False, precision="fp32"):
+        if precision == "tf32":
+            assert A.shape[2] % 4 == 0 and B.shape[2] % 4 == 0 and A.shape[1] % 32 == 0   # the tcgen05 kernel's rules
+        calls[precision] += 1
+        C.copy_(alpha * mm(A, B, b_transposed) + (C if accumulate else 0))
+        return C
+
+    def gemm_multi(C, As, Bs, *, b_transposed, alpha=1.0, accumulate=False):
+        assert 1 <= len(As) <= 6 and all(a.shape[2] % 4 == 0 and b.shape[2] % 4 == 0 for a, b in zip(As, Bs))
+        calls["multi"] += 1
+        C.copy_(alpha * sum(mm(a, b, b_transposed) for a, b in zip(As, Bs)) + (C if accumulate else 0))
+        return C
+
+    def pool_bwd(gin, gout, accumulate=False):
+        h, w = gin.shape[-2:]
+        up = torch.zeros_like(gin)
+        up[..., : 2 * (h // 2), : 2 * (w // 2)] = 0.25 * gout.repeat_interleave(2, -2).repeat_interleave(2, -1)
+        gin.copy_(up + (gin if accumulate else 0))
+        return gin
+
+    monkeypatch.setattr(ops, "corr_pyramid", lambda a, b, L, precision="fp32": [t.detach() for t in ref_ops.corr_pyramid(a, b, L)])
+    monkeypatch.setattr(ops, "batched_gemm_", gemm)
+    monkeypatch.setattr(ops, "batched_gemm_tf32_multi_", gemm_multi)
+    monkeypatch.setattr(ops, "avg_pool2x2", lambda x: F.avg_pool2d(x, 2, 2))
+    monkeypatch.setattr(ops, "avg_pool2x2_backward_", pool_bwd)
+    monkeypatch.setenv("EEMFLOW_B200_CORR_BACKWARD", mode)
+    gen = torch.Generator().manual_seed(2)
+    f1 = torch.randn(1, 32, 36, 44, generator=gen, requires_grad=True)
+    f2 = torch.randn(1, 32, 36, 44, generator=gen, requires_grad=True)
+    ref = ref_ops.corr_pyramid(f1, f2, 4)                     # 36x44, 18x22, 9x11 (99 columns: padded), 4x5
+    gs = [torch.randn(t.shape, generator=gen) for t in ref]
+    sum((t * g).sum() for t, g in zip(ref, gs)).backward()
+    a = f1.detach().clone().requires_grad_(True)
+    b = f2.detach().clone().requires_grad_(True)
+    mine = ag.CorrPyramidFn.apply(a, b, 4, "fp32")
+    sum((t * g).sum() for t, g in zip(mine, gs)).backward()
+    for x, y in ((a.grad, f1.grad), (b.grad, f2.grad)):
+        assert (x - y).abs().max().item() <= 1e-4 * y.abs().max().item()
+    if mode == "tf32":
+        assert calls == {"multi": 1, "tf32": 4, "fp32": 0}      # d fmap1 in one launch, d fmap2 one per level, no FFMA
+    else:
+        assert calls == {"multi": 0, "tf32": 0, "fp32": 8}
+    # only fmap2 needs a gradient: no d fmap1 product at all
+    calls.update(multi=0, tf32=0, fp32=0)
+    b2 = f2.detach().clone().requires_grad_(True)
+    sum((t * g).sum() for t, g in zip(ag.CorrPyramidFn.apply(f1.detach(), b2, 4, "fp32"), gs)).backward()
+    assert (b2.grad - f2.grad).abs().max().item() <= 1e-4 * f2.grad.abs().max().item()
+    assert calls["multi"] == 0 and calls["tf32"] + calls["fp32"] == 4

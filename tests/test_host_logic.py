@@ -250,3 +250,37 @@ def test_corr_pyramid_backward_plumbing(monkeypatch, mode):
     sum((t * g).sum() for t, g in zip(ag.CorrPyramidFn.apply(f1.detach(), b2, 4, "fp32"), gs)).backward()
     assert (b2.grad - f2.grad).abs().max().item() <= 1e-4 * f2.grad.abs().max().item()
     assert calls["multi"] == 0 and calls["tf32"] + calls["fp32"] == 4
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/eemflow_b200.h against the ctypes table of eemflow_b200/_lib.py: same number of
+    arguments, same class per argument (pointer / int / int64 / size_t / float / double) and the same return class --
+    a drifted binding would otherwise only show up as garbage arguments on the GPU."""
+    from eemflow_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", " ", (ROOT / "include" / "eemflow_b200.h").read_text(), flags=re.S)
+    protos = re.findall(r"EEM_API\s+([\w\s\*]+?)\b(eem_\w+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def c_class(decl: str) -> str:
+        decl = decl.strip()
+        if "*" in decl or "eem_stream_t" in decl:
+            return "ptr"
+        base = re.sub(r"\bconst\b", "", decl).split()
+        kind = base[0] if len(base) <= 2 else " ".join(base[:-1])
+        return {"int": "int", "int64_t": "i64", "size_t": "size", "float": "float", "double": "double",
+                "long long": "i64", "void": "void"}[kind]
+
+    def ct_class(t) -> str:
+        if t is None:
+            return "void"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type(ctypes.POINTER(ctypes.c_int))):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_int64: "i64", ctypes.c_longlong: "i64", ctypes.c_size_t: "size",
+                ctypes.c_float: "float", ctypes.c_double: "double"}[t]
+
+    for ret, name, args in protos:
+        res, argtypes = _lib.SIGNATURES[name]
+        want = [] if args.strip() in ("", "void") else [c_class(a) for a in args.split(",")]
+        got = [ct_class(t) for t in argtypes]
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
+        assert ct_class(res) == c_class(ret + " x"), f"{name}: return type"

@@ -207,24 +207,6 @@ bilinear_sample_backward_kernel(const float* __restrict__ img, const float* __re
 }
 
 // ---- bilinear resize backward ---------------------------------------------------------------------
-__device__ __forceinline__ void source_index(int dst, int in_size, int out_size, int align_corners, int& i0, int& i1,
-                                             float& l0, float& l1) {
-  float src;
-  if (align_corners) {
-    const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
-    src = scale * (float)dst;
-  } else {
-    const float scale = (float)in_size / (float)out_size;
-    src = scale * ((float)dst + 0.5f) - 0.5f;
-    if (src < 0.f) src = 0.f;
-  }
-  i0 = (int)src;
-  if (i0 > in_size - 1) i0 = in_size - 1;
-  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
-  l1 = src - (float)i0;
-  l0 = 1.f - l1;
-}
-
 // ATen's source index with the scale hoisted (same value: it is formed by the same fp32 division).
 __device__ __forceinline__ void source_index_s(int dst, int in_size, float scale, int align_corners, int& i0, int& i1,
                                                float& l0, float& l1) {

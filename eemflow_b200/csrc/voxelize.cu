@@ -741,11 +741,6 @@ __device__ __forceinline__ TileRec make_tile_rec(const EventRow& e, double t_fir
   return off_sensor_rec(e.x, e.y, ti, ok_right, flags, rec.dt, nb, H, W, tiles_x);
 }
 
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -1489,7 +1484,6 @@ voxel_normalize_cluster_kernel(float* __restrict__ grid, int n_windows, int64_t 
   double* red = reinterpret_cast<double*>(cl_smem + slice);     // slice is a multiple of 4 floats
   double* partial = red + 96;
   float* ms = reinterpret_cast<float*>(partial + 3);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   for (int w = cluster_id; w < n_windows; w += n_clusters) {
     float* g = grid + (int64_t)w * vox + (int64_t)rank * slice;
